@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's metric on BASELINE.json's workload.
+
+    python bench.py --gpus 1 --steps K --warmup W            # our arm (CUDA, libqsv.so)
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU algorithm
+
+metric  amplitude-updates/s = (#gates * 2^n) per circuit execution / time  (SURVEY.md §8d:
+        every gate "updates" all amplitudes, the reference's own bench accounting,
+        wenbo_engine/bench/kernel.py:21)
+step    one execution of the whole circuit from |0...0>: init + every compiled pass.
+N=1     configs[2]: random depth-20 (1q+CZ layers) circuit, 30 qubits, complex128, one B200.
+value   device-timed (CUDA events on the library's stream), state resident in HBM.
+e2e     the public call ``kernel.cuda_dense.simulate(circuit, out=host_buffer)``: compile,
+        allocate, run, and copy the full 2^n state back into pinned HOST memory, host-timed.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+from quantum_simulations_b200 import workloads as W                      # noqa: E402
+from quantum_simulations_b200.circuit.io import levelize, validate_circuit_dict   # noqa: E402
+
+METRIC = "amplitude-updates/s"
+UNIT = "amp-updates/s"
+
+
+def _peaks() -> tuple[float, str]:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int = 0):
+        self.rows: list[list[str]] = []
+        self.proc = None
+        self.device = device
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for nm, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def workload(n: int) -> tuple[dict, dict]:
+    cd = validate_circuit_dict(W.random_1q_cz(n, 20, 1234))
+    info = {"workload": f"random_1q_cz(n={n}, depth=20, seed=1234): alternating 1-qubit "
+                        f"{{H,X,Y,S,T,RY}} and brickwork CZ layers",
+            "n_qubits": n, "gates": len(cd["gates"]), "levels": len(levelize(cd))}
+    return cd, info
+
+
+# ----------------------------------------------------------------------- CPU arms
+def _cpu_numpy_rate(cd: dict) -> tuple[float, float]:
+    """The reference's formulation (index arrays + gather/scatter, ref_dense.py:13-41)
+    restated in oracle/ref_dense.py; returns (amp-updates/s, seconds)."""
+    from oracle import ref_dense as O
+    t0 = time.perf_counter()
+    O.simulate(cd, indexed=True)
+    dt = time.perf_counter() - t0
+    return len(cd["gates"]) * (1 << cd["number_of_qubits"]) / dt, dt
+
+
+def _cpu_c_rate(cd: dict) -> tuple[float, float, int]:
+    from oracle import c_oracle as CO
+    CO.lib()
+    t0 = time.perf_counter()
+    CO.simulate_c(cd)
+    dt = time.perf_counter() - t0
+    return len(cd["gates"]) * (1 << cd["number_of_qubits"]) / dt, dt, CO.n_threads()
+
+
+def cpu_baseline(n_sample: int = 20) -> dict:
+    cd, _ = workload(n_sample)
+    rate, dt = _cpu_numpy_rate(cd)
+    out = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
+           "sample": f"same circuit family at n={n_sample} (random_1q_cz depth 20, {len(cd['gates'])} gates), "
+                     f"oracle/ref_dense.py simulate(indexed=True) = the reference's NumPy gather/scatter "
+                     f"formulation, complex128, {dt:.1f} s",
+           "host_cores_available": os.cpu_count()}
+    try:
+        cdc, _ = workload(min(n_sample + 4, 24))
+        crate, cdt, thr = _cpu_c_rate(cdc)
+        out["c_openmp_port"] = {"value": crate, "unit": UNIT, "cores": thr,
+                                "sample": f"oracle/ref_dense_c.c at n={cdc['number_of_qubits']}, {cdt:.1f} s"}
+    except Exception as e:  # the C port is optional context
+        out["c_openmp_port"] = {"error": str(e)[:100]}
+    return out
+
+
+def reference_arm(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    budget = 150.0 / max(args.steps + args.warmup, 1)          # seconds per step
+    from oracle import ref_dense as O
+    probe = np.zeros(1 << 18, dtype=np.complex128); probe[0] = 1
+    t0 = time.perf_counter()
+    for q in (0, 9, 17):
+        O.apply_1q_indexed(probe, q, O.gate_matrix("H"))
+    rate_guess = 3 * (1 << 18) / (time.perf_counter() - t0)
+    n_sample = 16
+    for n in range(16, 25):
+        cd, _ = workload(n)
+        if len(cd["gates"]) * (1 << n) / rate_guess <= budget:
+            n_sample = n
+    cd, info = workload(n_sample)
+    for _ in range(args.warmup):
+        _cpu_numpy_rate(cd)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _cpu_numpy_rate(cd)
+    dt = time.perf_counter() - t0
+    value = args.steps * len(cd["gates"]) * (1 << n_sample) / dt
+    sample = (f"bounded sample: same circuit family at n={n_sample} ({len(cd['gates'])} gates, complex128), "
+              "oracle/ref_dense.py simulate(indexed=True): the reference's NumPy index-array formulation; "
+              "NumPy elementwise kernels are single-threaded")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "complex128",
+            "data": "synthetic", "config": {**info, "note": "CPU arm runs a bounded sample of the GPU arm's workload"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                             "host_cores_available": os.cpu_count()},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------- GPU arm
+def bench_single(args) -> None:
+    from quantum_simulations_b200.kernel.cuda import DeviceState
+    from quantum_simulations_b200.kernel.cuda_dense import circuit_ops, simulate
+    from quantum_simulations_b200.circuit.passes import PassCompiler
+    from quantum_simulations_b200.storage.pinned import PinnedBuffer
+
+    n, dtype = args.qubits, args.dtype
+    cd, info = workload(n)
+    amp_bytes = np.dtype(dtype).itemsize
+    t0 = time.perf_counter()
+    prog = PassCompiler(n, dtype=dtype, tile_bits=args.tile_bits, low_bits=args.low_bits,
+                        max_rounds=args.max_rounds).compile(circuit_ops(cd))
+    compile_s = time.perf_counter() - t0
+    n_pass = len(prog.passes)
+    updates_per_step = len(cd["gates"]) * (1 << n)
+
+    with DeviceState(n, dtype, args.device) as st:
+        handle = st.upload_program(prog)
+        for _ in range(args.warmup):
+            st.init_zero(); st.replay(handle)
+        st.sync()
+        clocks = ClockSampler(args.device).start()
+        st.timing(True)
+        st.timer_start()
+        for _ in range(args.steps):
+            st.init_zero(); st.replay(handle)
+        total_ms = st.timer_stop()
+        per_launch = st.take_timings()
+        st.timing(False)
+        clk = clocks.stop()
+        norm = st.norm2()
+    if abs(norm - 1.0) > 1e-9:
+        raise SystemExit(f"bench: state norm {norm} != 1 — result invalid")
+
+    ms_per_step = total_ms / args.steps
+    value = updates_per_step / (ms_per_step * 1e-3)
+    pass_ms = [ms for ms, kind, _ in per_launch if kind == 10]
+    avg_pass_ms = float(np.mean(pass_ms)) if pass_ms else float("nan")
+    alg_bytes = 2 * amp_bytes * (1 << n)                       # one read + one write of the state
+    peak, peak_src = _peaks()
+    achieved = alg_bytes / (avg_pass_ms * 1e-3) / 1e9
+    pass_share = sum(pass_ms) / total_ms if total_ms else None
+
+    # ---- end to end through the public API, result in pinned HOST memory ----
+    e2e = None
+    if not args.no_e2e:
+        host = PinnedBuffer((1 << n) * amp_bytes)
+        out = host.array(dtype, 1 << n)
+        simulate(cd, dtype=dtype, device=args.device, out=out, tile_bits=args.tile_bits,
+                 low_bits=args.low_bits, max_rounds=args.max_rounds)       # warm-up
+        reps = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            simulate(cd, dtype=dtype, device=args.device, out=out, tile_bits=args.tile_bits,
+                     low_bits=args.low_bits, max_rounds=args.max_rounds)
+        e2e_s = (time.perf_counter() - t0) / reps
+        import ctypes
+        from quantum_simulations_b200 import _lib as L
+        prog_bytes = n_pass * ctypes.sizeof(L.QsvPass) + prog.stats["micro_ops"] * ctypes.sizeof(L.QsvOp)
+        e2e = {"value": updates_per_step / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3,
+               "h2d_bytes_per_step": int(prog_bytes), "d2h_bytes_per_step": int((1 << n) * amp_bytes),
+               "what": "kernel.cuda_dense.simulate(circuit, out=pinned host array): validate + compile + "
+                       "cudaMalloc + |0> + passes + D2H of the full state, host perf_counter"}
+        nrm = float(np.vdot(out[: 1 << 20], out[: 1 << 20]).real)
+        e2e["host_prefix_norm"] = nrm
+        host.free()
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+        "config": {**info, "passes_per_step": n_pass, "rounds_per_step": prog.stats["rounds"],
+                   "tile_bits": prog.stats["tile_bits"], "low_bits": prog.stats["low_bits"],
+                   "l2_hygiene": f"state {(1 << n) * amp_bytes / 2**30:.0f} GiB >> 126 MB L2: every pass streams from HBM",
+                   "host_compile_s": compile_s},
+        "gate_layers_per_s": info["levels"] / (ms_per_step * 1e-3),
+        "hbm_gbs_per_gate_layer": info["levels"] * alg_bytes / (ms_per_step * 1e-3) / 1e9,
+        "roofline": {"bound": "hbm", "kernel": f"k_pass<{'double' if dtype == 'complex128' else 'float'}>",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "peak_source": peak_src, "traffic": None,
+                     "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_pass_ms,
+                     "launches_timed": len(pass_ms), "share_of_step": pass_share},
+        "gpu_launches": len(per_launch) + 2 * args.steps,        # + memset & set-amp of |0>
+        "clocks": clk,
+        "e2e": e2e,
+    }
+    if not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline(args.cpu_qubits)
+    print(json.dumps(line), flush=True)
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--qubits", type=int, default=None)
+    ap.add_argument("--dtype", default="complex128", choices=["complex64", "complex128"])
+    ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--tile-bits", type=int, default=None)
+    ap.add_argument("--low-bits", type=int, default=None)
+    ap.add_argument("--max-rounds", type=int, default=6)
+    ap.add_argument("--cpu-qubits", type=int, default=20)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+    world = int(os.environ.get("WORLD_SIZE", args.gpus))
+    if world == 1:
+        if args.qubits is None:
+            args.qubits = 30
+        bench_single(args)
+    else:
+        from quantum_simulations_b200.runner.multi_gpu_bench import bench_multi
+        bench_multi(args)
+
+
+if __name__ == "__main__":
+    main()

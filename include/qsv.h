@@ -1,0 +1,187 @@
+/* qsv.h — C ABI of libqsv.so, the sm_100a state-vector gate-application library.
+ *
+ * This is the drop-in boundary for the reference's hot path.  The
+ * reference (onofreiandrea/quantum_simulations, package wenbo_engine) has no FFI layer;
+ * its seam is the pair of Python callables the runner dispatches to
+ *     a1(chunk, qubit, U)            wenbo_engine/kernel/cpu_scalar.py:21  (cpu_batched.py:12)
+ *     a2(chunk, qa, qb, U)           wenbo_engine/kernel/cpu_scalar.py:35  (cpu_batched.py:28)
+ * chosen by string in wenbo_engine/runner/single_node.py:103-106, plus the four butterfly
+ * functions of wenbo_engine/kernel/cpu_nonlocal.py:22-67 and the chunk store
+ * (wenbo_engine/storage/block_store.py:18-65).  Every entry point below names the
+ * reference interface it replaces.  INTEGRATION.md shows the ctypes stub a maintainer
+ * adds to wenbo_engine to bind them (kernel="cuda").
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; every function returns 0 on success and a negative
+ *     QSV_E* code on failure; qsv_last_error() gives the message.
+ *   - amplitudes are interleaved (re, im): float[2] (QSV_C64) or double[2] (QSV_C128),
+ *     exactly numpy complex64 / complex128 memory.
+ *   - LITTLE-ENDIAN qubits (wenbo_engine/circuit/io.py:3-6): qubit q is bit q of the
+ *     amplitude index.
+ *   - matrices are row-major complex, interleaved doubles: U[2*(r*dim+c)] = Re U[r][c].
+ *     2-qubit matrices use the reference's sub-space order row = 2*bit(qa) + bit(qb)
+ *     (wenbo_engine/kernel/gates.py:3-11).
+ *   - a handle owns ONE shard: the 2^(n_qubits - log2(world)) amplitudes whose top
+ *     log2(world) index bits equal `rank` (the reference's "chunk" with
+ *     chunk_size = 2^n/world, wenbo_engine/docs/architecture.md:153-154).  Qubit numbers
+ *     passed to the apply functions are PHYSICAL bit positions of the full index;
+ *     positions >= n_local are rank bits.
+ *   - all work is enqueued on the handle's stream; qsv_sync() waits for it.
+ */
+#ifndef QSV_H
+#define QSV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QSV_ABI_VERSION 1
+
+/* dtypes (wenbo_engine/storage/block_store.py:11 fixes complex64; the oracle is complex128) */
+#define QSV_C64  0
+#define QSV_C128 1
+
+/* error codes */
+#define QSV_OK            0
+#define QSV_EINVAL       -1   /* bad argument */
+#define QSV_ENONLOCAL    -2   /* gate mixes a qubit that is a rank bit: remap first
+                                 (NotImplementedError "non-local" of cpu_scalar.py:13-18) */
+#define QSV_ECUDA        -3   /* CUDA runtime error (message has the cudaError string) */
+#define QSV_ENOMEM       -4
+#define QSV_ECOMM        -5   /* NCCL / peer-exchange error */
+#define QSV_EIO          -6
+
+typedef struct qsv_handle qsv_handle;
+typedef struct qsv_program qsv_program;
+
+/* ---------------------------------------------------------------- lifecycle ---- */
+int qsv_abi_version(void);
+/* Number of visible CUDA devices (0 => the library cannot run; there is no CPU path). */
+int qsv_device_count(void);
+/* Allocate the shard `rank` of `world` (power of two) of an n_qubits state on `device`. */
+int qsv_create(qsv_handle **out, int n_qubits, int dtype, int device, int rank, int world);
+int qsv_destroy(qsv_handle *h);
+/* Message of the last failure on h (h == NULL: last failure of qsv_create). */
+const char *qsv_last_error(const qsv_handle *h);
+int qsv_sync(qsv_handle *h);
+/* Raw device pointer + CUDA stream of the shard (for zero-copy hand-off to NCCL/torch plumbing). */
+int qsv_device_ptr(qsv_handle *h, void **ptr, size_t *n_amps_local, void **stream);
+
+/* ---------------------------------------------------------------- state I/O ----
+ * replaces init_zero_state / read_chunk / write_chunk_atomic (block_store.py:18-65) and
+ * collect_state (single_node.py:326-346): offsets and counts are in amplitudes of the
+ * LOCAL shard. */
+int qsv_init_zero(qsv_handle *h);                      /* |0...0>: amp[0]=1 on rank 0 */
+int qsv_init_basis(qsv_handle *h, uint64_t index);     /* |index> (global index)      */
+int qsv_upload(qsv_handle *h, const void *host, size_t off_amps, size_t n_amps);
+int qsv_download(qsv_handle *h, void *host, size_t off_amps, size_t n_amps);
+/* Async variants for pinned host buffers (checkpoint path); complete at qsv_sync(). */
+int qsv_upload_async(qsv_handle *h, const void *pinned_host, size_t off_amps, size_t n_amps);
+int qsv_download_async(qsv_handle *h, void *pinned_host, size_t off_amps, size_t n_amps);
+int qsv_host_alloc(void **ptr, size_t bytes);          /* cudaHostAlloc: pinned staging */
+int qsv_host_free(void *ptr);
+
+/* ------------------------------------------------------ per-gate operators ----
+ * qsv_apply_1q  replaces a1 = cpu_scalar.apply_1q / cpu_batched.apply_1q and
+ *               cpu_nonlocal.apply_1q_pair (any q < n_local is just a stride on a GPU).
+ * qsv_apply_2q  replaces a2 = cpu_scalar.apply_2q / cpu_batched.apply_2q and
+ *               cpu_nonlocal.apply_2q_pair_qa_local / _qb_local / apply_2q_quad.
+ * Both return QSV_ENONLOCAL if a qubit they must mix is >= n_local. */
+int qsv_apply_1q(qsv_handle *h, int q, const double U[8]);
+int qsv_apply_2q(qsv_handle *h, int qa, int qb, const double U[32]);
+/* Diagonal gate on nq <= 6 qubits: amp *= phases[sum_i bit(qs[i]) << (nq-1-i)] (qs[0] is the
+ * most significant, like the 2-qubit sub-space order).  Z,S,T,R,CZ,CR of gates.py:33-40,47,64,72.
+ * Rank bits are allowed (a per-shard constant: Atlas "insular" qubits, staging.py:65-98). */
+int qsv_apply_diag(qsv_handle *h, int nq, const int *qs, const double *phases);
+/* Controlled 1-qubit gate |0><0| (x) I + |1><1| (x) U: CNOT, CY, CU (gates.py:58-82).
+ * ctrl may be a rank bit; tgt must be local. */
+int qsv_apply_ctrl_1q(qsv_handle *h, int ctrl, int tgt, const double U[8]);
+/* Dense k-qubit unitary, k <= 5, on local qubits qs[0..k) (qs[0] most significant row bit);
+ * U is 2^k x 2^k.  Used for fused gate blocks (batch_levels/fuse_1q_ops, fusion.py:41-142). */
+int qsv_apply_kq(qsv_handle *h, int k, const int *qs, const double *U);
+
+/* ------------------------------------------------------------- fused passes ----
+ * One pass = ONE read and ONE write of the shard applying a whole list of gates
+ * (batch_levels, fusion.py:86-142, moved on chip).  A pass owns a TILE: 2^n_tile
+ * amplitudes addressed by n_tile physical bit positions (tile_bits, ascending; the low
+ * ones contiguous for coalescing).  It runs as a sequence of ROUNDS; in each round every
+ * thread holds 2^QSV_REG_BITS amplitudes in registers (the round's reg_pos bits vary inside
+ * a thread, the other tile bits are fixed per thread) and applies the round's ops; between
+ * rounds amplitudes are exchanged through a swizzled shared-memory tile. */
+#define QSV_MAX_TILE_BITS 14
+#define QSV_REG_BITS       4
+#define QSV_MAX_ROUNDS    16
+
+/* op kinds */
+#define QSV_OP_MAT    0  /* general complex 2x2 on register bit `target`                 */
+#define QSV_OP_REAL   1  /* real 2x2 (m[0],m[2],m[4],m[6]) times scalar phase-free       */
+#define QSV_OP_PHASE  2  /* amp *= (m[0] + i m[1]) where all control bits are 1          */
+#define QSV_OP_SIGN   3  /* amp = -amp where all control bits are 1 (CZ, Z)              */
+#define QSV_OP_XPERM  4  /* swap the pair (X), no flops                                  */
+#define QSV_OP_HAD    5  /* (a+b, a-b) * m[0]                                            */
+#define QSV_OP_IPHASE 6  /* amp *= i^m_int where control bits are 1 (S, S^dagger)        */
+
+typedef struct {
+    int32_t  kind;         /* QSV_OP_*                                                   */
+    int32_t  target;       /* register-slot index 0..QSV_REG_BITS-1 (non-diagonal kinds) */
+    uint32_t reg_ctrl;     /* controls among register slots (bit b = slot b)             */
+    uint32_t tile_ctrl;    /* controls among thread-fixed tile positions (bit i = pos i) */
+    uint64_t glob_ctrl;    /* controls among physical bits outside the tile (rank bits ok)*/
+    double   m[8];         /* coefficients, meaning depends on kind                      */
+} qsv_op;
+
+typedef struct {
+    uint8_t  reg_pos[QSV_REG_BITS];        /* tile positions held in registers, ascending */
+    uint8_t  thr_pos[QSV_MAX_TILE_BITS];   /* tile position of each thread-index bit      */
+    int32_t  op_begin, op_end;             /* slice of the pass's op array                */
+} qsv_round;
+
+typedef struct {
+    int32_t   n_tile;                          /* tile bits (c128: 12, c64: 13 by default) */
+    int32_t   load_bits[QSV_MAX_TILE_BITS];    /* physical bit of tile position i on load  */
+    int32_t   store_bits[QSV_MAX_TILE_BITS];   /* ... on store (a permutation of load_bits:
+                                                  free qubit relabelling inside the tile)  */
+    int32_t   n_rounds;
+    qsv_round rounds[QSV_MAX_ROUNDS];
+    int32_t   n_ops;
+} qsv_pass;
+
+/* One-shot: run one pass now. */
+int qsv_apply_pass(qsv_handle *h, const qsv_pass *pass, const qsv_op *ops);
+/* Compiled circuit: upload all passes once, replay with one call (CUDA-graph replay). */
+int qsv_program_create(qsv_handle *h, const qsv_pass *passes, int n_passes,
+                       const qsv_op *ops /* concatenated */, qsv_program **out);
+int qsv_program_run(qsv_handle *h, qsv_program *p);
+int qsv_program_destroy(qsv_handle *h, qsv_program *p);
+
+/* --------------------------------------------------------------- reductions ---- */
+int qsv_norm2(qsv_handle *h, double *out);   /* sum |amp|^2 of the LOCAL shard */
+/* Deterministic sampling on the local shard (parity unpinned by the reference: it has no
+ * sampler — SURVEY.md §2.4-6; definition frozen in oracle/ref_dense.py sample_indices). */
+int qsv_sample(qsv_handle *h, uint64_t seed_unused, int shots, const double *sorted_u,
+               uint64_t *out_indices);
+
+/* ---------------------------------------------------- multi-GPU qubit remap ----
+ * HiSVSIM-style redistribution (hisvsim_repo/mpi_redistributer.hpp:265-344,
+ * svsim-mpi.hpp:123-173): swap `n_swap` rank bits with local bits. */
+int qsv_comm_unique_id(void *id128);                       /* ncclGetUniqueId, 128 bytes   */
+int qsv_comm_init(qsv_handle *h, const void *id128);       /* ncclCommInitRank(world,rank) */
+int qsv_swap_global_local(qsv_handle *h, int n_swap, const int *global_bits, const int *local_bits);
+/* Sum one double across all shards (norm, sampling offsets). world==1: no-op. */
+int qsv_allreduce_sum(qsv_handle *h, double *value);
+
+/* ------------------------------------------------------------------- timing ---- */
+typedef struct { float ms; int32_t kind; int32_t pass_index; } qsv_timing;
+int qsv_timing_enable(qsv_handle *h, int on);
+int qsv_get_timings(qsv_handle *h, qsv_timing *out, int max, int *n_out);
+/* One CUDA-event stopwatch on the handle's stream (bench.py's timed region). */
+int qsv_timer_start(qsv_handle *h);
+int qsv_timer_stop(qsv_handle *h, float *elapsed_ms);   /* records, synchronises, reads */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QSV_H */

@@ -1,0 +1,111 @@
+"""ctypes binding of libqsv.so (the C ABI declared in include/qsv.h).
+
+There is NO fallback: if the shared library is missing or no CUDA device is visible the
+product path raises — it never routes through NumPy or the oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_CSRC = Path(__file__).resolve().parent / "csrc"
+LIB_PATH = _CSRC / "libqsv.so"
+
+QSV_C64, QSV_C128 = 0, 1
+QSV_OK, QSV_EINVAL, QSV_ENONLOCAL, QSV_ECUDA, QSV_ENOMEM, QSV_ECOMM, QSV_EIO = 0, -1, -2, -3, -4, -5, -6
+QSV_MAX_TILE_BITS, QSV_REG_BITS, QSV_MAX_ROUNDS = 14, 4, 16
+OP_MAT, OP_REAL, OP_PHASE, OP_SIGN, OP_XPERM, OP_HAD, OP_IPHASE = range(7)
+
+
+class QsvOp(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("target", C.c_int32), ("reg_ctrl", C.c_uint32),
+                ("tile_ctrl", C.c_uint32), ("glob_ctrl", C.c_uint64), ("m", C.c_double * 8)]
+
+
+class QsvRound(C.Structure):
+    _fields_ = [("reg_pos", C.c_uint8 * QSV_REG_BITS), ("thr_pos", C.c_uint8 * QSV_MAX_TILE_BITS),
+                ("op_begin", C.c_int32), ("op_end", C.c_int32)]
+
+
+class QsvPass(C.Structure):
+    _fields_ = [("n_tile", C.c_int32), ("load_bits", C.c_int32 * QSV_MAX_TILE_BITS),
+                ("store_bits", C.c_int32 * QSV_MAX_TILE_BITS), ("n_rounds", C.c_int32),
+                ("rounds", QsvRound * QSV_MAX_ROUNDS), ("n_ops", C.c_int32)]
+
+
+class QsvTiming(C.Structure):
+    _fields_ = [("ms", C.c_float), ("kind", C.c_int32), ("pass_index", C.c_int32)]
+
+
+class QsvError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libqsv error {code}: {msg}")
+        self.code = code
+
+
+_H = C.c_void_p
+_P = C.c_void_p
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+# name -> (restype, argtypes); every symbol include/qsv.h declares
+SIGNATURES = {
+    "qsv_abi_version": (C.c_int, []),
+    "qsv_device_count": (C.c_int, []),
+    "qsv_create": (C.c_int, [C.POINTER(_H), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "qsv_destroy": (C.c_int, [_H]),
+    "qsv_last_error": (C.c_char_p, [_H]),
+    "qsv_sync": (C.c_int, [_H]),
+    "qsv_device_ptr": (C.c_int, [_H, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p)]),
+    "qsv_init_zero": (C.c_int, [_H]),
+    "qsv_init_basis": (C.c_int, [_H, C.c_uint64]),
+    "qsv_upload": (C.c_int, [_H, C.c_void_p, C.c_size_t, C.c_size_t]),
+    "qsv_download": (C.c_int, [_H, C.c_void_p, C.c_size_t, C.c_size_t]),
+    "qsv_upload_async": (C.c_int, [_H, C.c_void_p, C.c_size_t, C.c_size_t]),
+    "qsv_download_async": (C.c_int, [_H, C.c_void_p, C.c_size_t, C.c_size_t]),
+    "qsv_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
+    "qsv_host_free": (C.c_int, [C.c_void_p]),
+    "qsv_apply_1q": (C.c_int, [_H, C.c_int, _dp]),
+    "qsv_apply_2q": (C.c_int, [_H, C.c_int, C.c_int, _dp]),
+    "qsv_apply_diag": (C.c_int, [_H, C.c_int, _ip, _dp]),
+    "qsv_apply_ctrl_1q": (C.c_int, [_H, C.c_int, C.c_int, _dp]),
+    "qsv_apply_kq": (C.c_int, [_H, C.c_int, _ip, _dp]),
+    "qsv_apply_pass": (C.c_int, [_H, C.POINTER(QsvPass), C.POINTER(QsvOp)]),
+    "qsv_program_create": (C.c_int, [_H, C.POINTER(QsvPass), C.c_int, C.POINTER(QsvOp), C.POINTER(_P)]),
+    "qsv_program_run": (C.c_int, [_H, _P]),
+    "qsv_program_destroy": (C.c_int, [_H, _P]),
+    "qsv_norm2": (C.c_int, [_H, _dp]),
+    "qsv_sample": (C.c_int, [_H, C.c_uint64, C.c_int, _dp, C.POINTER(C.c_uint64)]),
+    "qsv_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "qsv_comm_init": (C.c_int, [_H, C.c_void_p]),
+    "qsv_swap_global_local": (C.c_int, [_H, C.c_int, _ip, _ip]),
+    "qsv_allreduce_sum": (C.c_int, [_H, _dp]),
+    "qsv_timing_enable": (C.c_int, [_H, C.c_int]),
+    "qsv_get_timings": (C.c_int, [_H, C.POINTER(QsvTiming), C.c_int, _ip]),
+    "qsv_timer_start": (C.c_int, [_H]),
+    "qsv_timer_stop": (C.c_int, [_H, C.POINTER(C.c_float)]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """dlopen libqsv.so and attach signatures; raises if it was not built."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise ImportError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; "
+                "g.build()'` (nvcc, sm_100a). There is no CPU fallback.")
+        lib = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)      # AttributeError if the .so lacks a declared symbol
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, handle=None) -> None:
+    if rc != 0:
+        msg = load().qsv_last_error(handle)
+        raise QsvError(rc, msg.decode(errors="replace") if msg else "?")

@@ -1,0 +1,542 @@
+"""Pass compiler: step-IR ops [(phys_qubits, U)] -> fused on-chip passes for libqsv.
+
+This is `batch_levels` (reference wenbo_engine/circuit/fusion.py:86-142) and the Atlas-style
+stage selection (reference circuit/staging.py:320-421) moved one level down the memory
+hierarchy.  The reference asks "which gates can run while this CHUNK FILE is in RAM?"; here
+the question is "which gates can run while this 2^t-amplitude TILE is on chip?" and, inside
+a pass, "while these 4 index bits are in a thread's REGISTERS?".  One pass costs exactly one
+read + one write of the shard in HBM, whatever it executes, so the compiler minimises passes.
+
+Vocabulary
+  content    a qubit's worth of index information.  Initially content c is IR qubit c.  SWAP
+             gates never move data: they rename which content an IR qubit refers to.
+  position   a bit of the amplitude index in device memory; pos[c] = position of content c.
+             A pass may permute the contents of its tile among the tile's positions for free
+             (store_bits), which is how layouts are rotated and finally restored.
+  micro-op   one kernel op (include/qsv.h QSV_OP_*): an optional TARGET content that is mixed
+             (must be a register bit of its round) plus CONTROL contents that are only
+             inspected (diagonal action: controls of CNOT/CY/CU and every qubit of
+             Z,S,T,R,CZ,CR — Atlas's "insular" qubits, reference staging.py:65-98).  Controls
+             may be register bits, other tile bits, bits outside the tile or rank bits.
+
+Ordering rule (this is what the reference's heuristic stager gets wrong):
+two micro-ops may be reordered iff on every shared content BOTH act diagonally.  Passes and
+rounds always execute a dependency-closed set, so per-qubit program order is preserved.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from quantum_simulations_b200 import _lib as L
+
+REG_BITS = L.QSV_REG_BITS
+_ONE = 1.0 + 0.0j
+_Z8 = (0.0,) * 8
+
+
+# --------------------------------------------------------------------------- lowering
+@dataclass
+class MicroOp:
+    kind: int
+    target: int | None                 # content that is mixed (None: purely diagonal)
+    ctrls: tuple[int, ...]             # contents that must be 1 for the op to act
+    m: tuple[float, ...] = _Z8         # coefficients (see qsv.h)
+    src: int = -1                      # IR op index it came from
+    seq: int = -1                      # position in the lowered stream (stable order key)
+
+
+@dataclass
+class Dense2Q:
+    """2-qubit op without diagonal / controlled / swap structure: runs as its own kernel."""
+    qa: int
+    qb: int
+    U: np.ndarray
+    src: int = -1
+
+
+def _flat(u) -> tuple[float, ...]:
+    out: list[float] = []
+    for z in np.asarray(u, dtype=np.complex128).ravel():
+        out += [float(z.real), float(z.imag)]
+    return tuple(out)
+
+
+def _phase(d: complex, ctrls: tuple[int, ...], src: int) -> list[MicroOp]:
+    if d == _ONE:
+        return []
+    if d == -_ONE and ctrls:
+        return [MicroOp(L.OP_SIGN, None, ctrls, _Z8, src)]
+    return [MicroOp(L.OP_PHASE, None, ctrls, (float(d.real), float(d.imag)) + (0.0,) * 6, src)]
+
+
+def lower_1q(u, q: int, ctrls: tuple[int, ...] = (), src: int = -1) -> list[MicroOp]:
+    """2x2 `u` on content q, active where all `ctrls` are 1."""
+    u = np.asarray(u, dtype=np.complex128)
+    if u[0, 1] == 0 and u[1, 0] == 0:                       # diagonal
+        d0, d1 = complex(u[0, 0]), complex(u[1, 1])
+        rel = d1 if d0 == _ONE else d1 / d0
+        return _phase(d0, ctrls, src) + _phase(rel, ctrls + (q,), src)
+    if not np.any(u.imag):
+        return [MicroOp(L.OP_REAL, q, ctrls, _flat(u), src)]
+    return [MicroOp(L.OP_MAT, q, ctrls, _flat(u), src)]
+
+
+_SWAP = np.eye(4)[[0, 2, 1, 3]]
+_I2, _O2 = np.eye(2), np.zeros((2, 2))
+
+
+def lower_op(qubits, U, src: int = -1) -> list:
+    """One step-IR op -> micro-ops | ('swap', a, b) | Dense2Q.  Structure is detected on exact
+    zeros/ones, which gate constructors and products of structured matrices preserve."""
+    U = np.asarray(U, dtype=np.complex128)
+    if len(qubits) == 1:
+        return lower_1q(U, qubits[0], (), src)
+    qa, qb = qubits
+    if qa == qb:
+        raise ValueError("2-qubit op on a repeated qubit")
+    if np.array_equal(U, _SWAP):
+        return [("swap", qa, qb)]
+    if not np.any(U - np.diag(np.diag(U))):
+        d = [complex(x) for x in np.diag(U)]                 # index = 2*bit(qa) + bit(qb)
+        s = d[0]
+        pb = d[1] if s == _ONE else d[1] / s
+        pa = d[2] if s == _ONE else d[2] / s
+        pab = d[3] if (s == _ONE and pa == _ONE and pb == _ONE) else d[3] / (s * pa * pb)
+        return (_phase(s, (), src) + _phase(pb, (qb,), src) + _phase(pa, (qa,), src)
+                + _phase(pab, (qa, qb), src))
+    if np.array_equal(U[:2, :2], _I2) and np.array_equal(U[:2, 2:], _O2) and np.array_equal(U[2:, :2], _O2):
+        return lower_1q(U[2:, 2:], qb, (qa,), src)           # control = qubits[0]
+    ev, od = [0, 2], [1, 3]
+    if np.array_equal(U[np.ix_(ev, ev)], _I2) and not np.any(U[np.ix_(ev, od)]) and not np.any(U[np.ix_(od, ev)]):
+        return lower_1q(U[np.ix_(od, od)], qa, (qb,), src)   # control = qubits[1]
+    return [Dense2Q(qa, qb, U, src)]
+
+
+# ------------------------------------------------------------------------ compiled form
+@dataclass
+class PassStep:
+    desc: L.QsvPass
+    ops: C.Array                      # (QsvOp * max(n,1))
+    n_micro_ops: int
+    src_ops: set
+    tile_contents: list
+
+
+@dataclass
+class Dense2QStep:
+    qa_pos: int
+    qb_pos: int
+    U: np.ndarray
+    src_ops: set
+
+
+@dataclass
+class Program:
+    n_qubits: int
+    n_local: int
+    dtype: str
+    steps: list = field(default_factory=list)
+    final_pos: list = field(default_factory=list)   # final_pos[q] = position of IR qubit q
+    stats: dict = field(default_factory=dict)
+
+    @property
+    def passes(self):
+        return [s for s in self.steps if isinstance(s, PassStep)]
+
+
+# -------------------------------------------------------------------- dependency scan
+def _scan(ops, mixable, lookahead: int | None = None):
+    """(run, missing): ops that can execute, in order, when exactly the contents in `mixable`
+    may be mixed; and the dependency-free ops that only lack their target in `mixable`."""
+    bt: set = set()      # contents an earlier pending op MIXES
+    bc: set = set()      # contents an earlier pending op INSPECTS
+    run: list = []
+    missing: list = []
+    for i, op in enumerate(ops):
+        if lookahead is not None and i >= lookahead:
+            break
+        t = op.target
+        free = (t is None or (t not in bt and t not in bc)) and not any(c in bt for c in op.ctrls)
+        if free and (t is None or t in mixable):
+            run.append(i)
+            continue
+        if free:
+            missing.append(i)
+        if t is not None:
+            bt.add(t)
+        bc.update(op.ctrls)
+    return run, missing
+
+
+class PassCompiler:
+    """Greedy tile / round selection (see module docstring)."""
+
+    def __init__(self, n_qubits: int, n_local: int | None = None, dtype: str = "complex128",
+                 tile_bits: int | None = None, low_bits: int | None = None,
+                 max_rounds: int = 6, restore_layout: bool = True, lookahead: int = 4096):
+        self.n = n_qubits
+        self.n_local = n_qubits if n_local is None else n_local
+        self.dtype = np.dtype(dtype).name
+        if self.dtype not in ("complex64", "complex128"):
+            raise ValueError(f"unsupported dtype {dtype}")
+        max_t = 12 if self.dtype == "complex128" else 13
+        self.W = 3 if self.dtype == "complex128" else 4      # log2(128 B / sizeof(amp))
+        self.t = min(tile_bits or max_t, max_t, self.n_local)
+        if self.t < REG_BITS:
+            raise ValueError(f"pass kernel needs n_local >= {REG_BITS} (got {self.n_local})")
+        a = 5 if low_bits is None else low_bits
+        # when the tile does not cover the whole shard, leave room for >= 4 free tile slots
+        self.a = self.t if self.t >= self.n_local else max(0, min(a, self.t - REG_BITS))
+        self.max_rounds = max(2, min(max_rounds, L.QSV_MAX_ROUNDS - 2))
+        self.restore_layout = restore_layout
+        self.lookahead = lookahead
+
+    # ---- public -----------------------------------------------------------------------
+    def compile(self, ir_ops, init_pos=None) -> Program:
+        n = self.n
+        alias = list(range(n))                      # IR qubit -> content
+        segments: list = [[]]
+        seq = 0
+        for i, (qs, U) in enumerate(ir_ops):
+            for item in lower_op([alias[q] for q in qs], U, i):
+                if isinstance(item, tuple):         # swap: rename, no data movement
+                    qa, qb = list(qs)
+                    alias[qa], alias[qb] = alias[qb], alias[qa]
+                elif isinstance(item, Dense2Q):
+                    segments.append(item)
+                    segments.append([])
+                else:
+                    item.seq = seq
+                    seq += 1
+                    segments[-1].append(item)
+        pos = list(init_pos) if init_pos is not None else list(range(n))
+        home = [0] * n                              # home[content] = position it must end at
+        for q in range(n):
+            home[alias[q]] = q if init_pos is None else init_pos[q]
+        prog = Program(n, self.n_local, self.dtype)
+        live = [s for s in segments if isinstance(s, Dense2Q) or s]
+        for k, seg in enumerate(live):
+            if isinstance(seg, Dense2Q):
+                for c in (seg.qa, seg.qb):
+                    if pos[c] >= self.n_local:
+                        raise NotImplementedError(
+                            f"non-local gate: content {c} sits on rank bit {pos[c]}")
+                prog.steps.append(Dense2QStep(pos[seg.qa], pos[seg.qb], seg.U, {seg.src}))
+            else:
+                self._plan_segment(seg, pos, home, prog, last_segment=(k == len(live) - 1))
+        if self.restore_layout:
+            self._restore(prog, pos, home)
+        prog.final_pos = [pos[alias[q]] for q in range(n)]
+        ps = prog.passes
+        prog.stats = {
+            "passes": len(ps), "dense2q_steps": len(prog.steps) - len(ps),
+            "micro_ops": sum(s.n_micro_ops for s in ps),
+            "rounds": sum(s.desc.n_rounds for s in ps),
+            "max_rounds_in_pass": max((s.desc.n_rounds for s in ps), default=0),
+            "tile_bits": self.t, "low_bits": self.a,
+        }
+        return prog
+
+    # ---- pass planning ----------------------------------------------------------------
+    def _plan_segment(self, ops, pos, home, prog, last_segment):
+        remaining = list(ops)
+        while remaining:
+            tile = self._choose_tile(remaining, pos, forced=self._low_contents(pos))
+            run, _ = _scan(remaining, set(tile), self.lookahead)
+            if not run:
+                _, missing = _scan(remaining, set(tile), self.lookahead)
+                for i in missing:
+                    c = remaining[i].target
+                    if pos[c] >= self.n_local:
+                        raise NotImplementedError(
+                            f"non-local gate: content {c} sits on rank bit {pos[c]} and must be "
+                            "mixed; swap it with a local bit first")
+                raise RuntimeError("planner made no progress")
+            chosen = [remaining[i] for i in run]
+            rounds, deferred = self._plan_rounds(chosen, tile)
+            done = {id(op) for r in rounds for op in r[1]}
+            remaining = [op for op in remaining if id(op) not in done]
+            final = not remaining and last_segment and self.restore_layout
+            park = []
+            if remaining and self.a:
+                wish = self._choose_tile(remaining, pos, forced=[], pool=set(tile))
+                park = [c for c in wish if c in set(tile)][: self.a]
+            prog.steps.append(self._emit_pass(tile, rounds, pos, home, park, final))
+
+    def _low_contents(self, pos):
+        at = {p: c for c, p in enumerate(pos)}
+        return [at[p] for p in range(self.a)]
+
+    def _choose_tile(self, remaining, pos, forced, pool=None):
+        """t contents for a pass: follow the pending targets in program order.  `forced`
+        contents (those sitting in the always-in-tile low positions) are in from the start.
+        With `pool` (peeking at the pass after next), at most t-a contents may come from
+        outside the pool, because `a` slots of that pass will hold parked pool members."""
+        tile = list(forced)
+        in_tile = set(tile)
+        outside_cap = self.t - self.a if pool is not None else self.t
+        n_outside = 0
+        while len(tile) < self.t:
+            _, missing = _scan(remaining, in_tile, self.lookahead)
+            pick = None
+            for i in missing:
+                c = remaining[i].target
+                if pos[c] >= self.n_local:
+                    continue                       # rank bit: cannot be mixed in this stage
+                if pool is not None and c not in pool and n_outside >= outside_cap:
+                    continue
+                pick = c
+                break
+            if pick is None:
+                break
+            if pool is not None and pick not in pool:
+                n_outside += 1
+            tile.append(pick)
+            in_tile.add(pick)
+        if pool is not None:
+            return tile
+        # pad with idle local contents (highest positions first)
+        if len(tile) < self.t:
+            for c in sorted((c for c in range(self.n) if pos[c] < self.n_local), key=lambda c: -pos[c]):
+                if c not in in_tile:
+                    tile.append(c)
+                    in_tile.add(c)
+                    if len(tile) >= self.t:
+                        break
+        return tile
+
+    def _plan_rounds(self, chosen, tile):
+        """Split a pass's ops into rounds of <= 4 register contents.  Returns (rounds, deferred)
+        with rounds = [(reg_contents, ops)]; ops beyond max_rounds are deferred to a later pass."""
+        pend = list(chosen)
+        rounds = []
+        while pend and len(rounds) < self.max_rounds:
+            regs: list = []
+            while len(regs) < REG_BITS:
+                _, missing = _scan(pend, set(regs))
+                if not missing:
+                    break
+                regs.append(pend[missing[0]].target)
+            run, _ = _scan(pend, set(regs))
+            if not run:
+                break
+            rs = set(run)
+            rounds.append((regs, [pend[i] for i in run]))
+            pend = [op for i, op in enumerate(pend) if i not in rs]
+        return rounds, pend
+
+    # ---- pass emission ----------------------------------------------------------------
+    def _emit_pass(self, tile, rounds, pos, home, park, final) -> PassStep:
+        t, W = self.t, min(self.W, self.t - REG_BITS)
+        load_bits = sorted(pos[c] for c in tile)
+        at = {p: c for c, p in enumerate(pos)}
+        content = [at[p] for p in load_bits]              # content at tile index i
+        idx_of = {c: i for i, c in enumerate(content)}
+        store = self._choose_store(content, load_bits, home, park, final)   # per tile index
+
+        lo_load = {i for i in range(t) if load_bits[i] < W}
+        lo_store = {i for i in range(t) if store[i] < W}
+
+        # register tile-indices of every round, padded to 4 with idle indices
+        plan = []
+        for regs_c, rops in rounds:
+            regs = [idx_of[c] for c in regs_c]
+            for i in range(t - 1, -1, -1):
+                if len(regs) >= REG_BITS:
+                    break
+                if i not in regs:
+                    regs.append(i)
+            plan.append((regs, rops))
+        if not plan:
+            plan.append((self._idle_regs(lo_load | lo_store), []))
+        if set(plan[0][0]) & lo_load:
+            plan.insert(0, (self._idle_regs(lo_load), []))
+        if set(plan[-1][0]) & lo_store:
+            plan.append((self._idle_regs(lo_store), []))
+        if len(plan) == 1:
+            # one round = same thread mapping for load and store: only coalesced on both
+            # sides if the W lowest positions hold the same tile indices before and after
+            free = [i for i in range(t) if i not in plan[0][0]]
+            by_load = sorted(free, key=lambda i: load_bits[i])[:W]
+            by_store = sorted(free, key=lambda i: store[i])[:W]
+            if by_load != by_store:
+                plan.append((self._idle_regs(lo_store), []))
+        if len(plan) > L.QSV_MAX_ROUNDS:
+            raise RuntimeError("too many rounds in one pass")
+
+        desc = L.QsvPass()
+        desc.n_tile = t
+        for i in range(t):
+            desc.load_bits[i] = load_bits[i]
+            desc.store_bits[i] = store[i]
+        desc.n_rounds = len(plan)
+        flat: list = []
+        srcs: set = set()
+        for r, (regs, rops) in enumerate(plan):
+            rd = desc.rounds[r]
+            slot_of = {}
+            for b, i in enumerate(sorted(regs)):
+                rd.reg_pos[b] = i
+                slot_of[content[i]] = b
+            free = [i for i in range(t) if i not in regs]
+            if r == 0:
+                thr = sorted(free, key=lambda i: load_bits[i])
+            elif r == len(plan) - 1:
+                thr = sorted(free, key=lambda i: store[i])
+            else:
+                thr = self._bank_friendly(free)
+            for k, i in enumerate(thr):
+                rd.thr_pos[k] = i
+            rd.op_begin = len(flat)
+            for op in rops:
+                flat.append(self._encode(op, slot_of, idx_of, pos))
+                srcs.add(op.src)
+            rd.op_end = len(flat)
+        desc.n_ops = len(flat)
+        arr = (L.QsvOp * max(len(flat), 1))(*flat)
+        for i in range(t):                                # commit the relabelling
+            pos[content[i]] = store[i]
+        return PassStep(desc, arr, len(flat), srcs, list(tile))
+
+    def _idle_regs(self, avoid) -> list:
+        regs = [i for i in range(self.t - 1, -1, -1) if i not in avoid][:REG_BITS]
+        if len(regs) < REG_BITS:
+            regs = list(range(self.t - REG_BITS, self.t))
+        return regs
+
+    def _bank_friendly(self, free) -> list:
+        """Middle rounds: the first W thread bits should drive tile indices with distinct
+        residues mod W, so a quarter-warp's 128-bit shared accesses hit distinct bank groups
+        under tile_swizzle (pass_kernel.cuh)."""
+        W = self.W
+        free = sorted(free)
+        head, seen = [], set()
+        for i in free:
+            if i % W not in seen:
+                head.append(i)
+                seen.add(i % W)
+            if len(head) == W:
+                break
+        return head + [i for i in free if i not in head]
+
+    def _choose_store(self, content, load_bits, home, park, final) -> list:
+        """New position of the content at every tile index (a permutation of load_bits)."""
+        import itertools
+        t = len(content)
+        cur = {content[i]: load_bits[i] for i in range(t)}
+        idx = {content[i]: i for i in range(t)}
+        occ = {load_bits[i]: content[i] for i in range(t)}
+        new = dict(cur)
+        if final:
+            slots = set(load_bits)
+            new = {}
+            for c in content:                             # everyone whose home is here goes home
+                if home[c] in slots:
+                    new[c] = home[c]
+            used = set(new.values())
+            for c in content:                             # others keep their slot if still free
+                if c not in new and cur[c] not in used:
+                    new[c] = cur[c]
+                    used.add(cur[c])
+            spare = sorted(slots - used)
+            for c in content:
+                if c not in new:
+                    new[c] = spare.pop(0)
+            return [new[c] for c in content]
+        low = [p for p in load_bits if p < self.a]
+        park = [c for c in park if c in cur][: len(low)]
+        parked = set(park)
+        movers = [c for c in park if cur[c] not in low]
+        vacate = [p for p in low if occ[p] not in parked][: len(movers)]
+        movers = movers[: len(vacate)]
+        if not movers:
+            return [new[c] for c in content]
+
+        def assign(order):
+            out = dict(cur)
+            for c, p in zip(order, vacate):
+                out[c], out[occ[p]] = p, cur[c]
+            return out
+
+        def score(asg):                                   # distinct bank residues at positions < W
+            byp = {p: c for c, p in asg.items()}
+            res = {idx[byp[p]] % self.W for p in range(min(self.W, self.a)) if p in byp}
+            return len(res)
+
+        best, best_s = None, -1
+        for order in itertools.islice(itertools.permutations(movers), 120):
+            asg = assign(order)
+            sc = score(asg)
+            if sc > best_s:
+                best, best_s = asg, sc
+        return [best[c] for c in content]
+
+    def _encode(self, op: MicroOp, slot_of, idx_of, pos) -> L.QsvOp:
+        o = L.QsvOp()
+        o.kind = op.kind
+        if op.target is not None:
+            o.target = slot_of[op.target]
+        reg_ctrl = tile_ctrl = glob = 0
+        for c in op.ctrls:
+            if c in slot_of:
+                reg_ctrl |= 1 << slot_of[c]
+            elif c in idx_of:
+                tile_ctrl |= 1 << idx_of[c]
+            else:
+                glob |= 1 << pos[c]
+        o.reg_ctrl, o.tile_ctrl, o.glob_ctrl = reg_ctrl, tile_ctrl, glob
+        for k in range(8):
+            o.m[k] = op.m[k]
+        return o
+
+    # ---- layout restoration -----------------------------------------------------------
+    def _restore(self, prog, pos, home) -> None:
+        """Relabel-only passes until every local content is at its home position."""
+        n_loc = self.n_local
+        for _ in range(8 * self.n + 8):
+            bad = [c for c in range(self.n) if pos[c] < n_loc and pos[c] != home[c]]
+            if not bad:
+                return
+            if any(home[c] >= n_loc for c in bad):
+                raise NotImplementedError("layout restoration across rank bits needs a global swap")
+            at = {p: c for c, p in enumerate(pos)}
+            # cycles of the position permutation p -> home[at[p]]
+            cycles, seen = [], set()
+            for p in sorted(pos[c] for c in bad):
+                if p in seen:
+                    continue
+                cyc, x = [], p
+                while x not in seen:
+                    seen.add(x)
+                    cyc.append(x)
+                    x = home[at[x]]
+                cycles.append(cyc)
+            cycles.sort(key=lambda cyc: (not any(p < self.a for p in cyc), len(cyc)))
+            chosen = set(range(self.a))
+            for cyc in cycles:
+                fresh = [p for p in cyc if p not in chosen]
+                room = self.t - len(chosen)
+                if len(fresh) <= room:
+                    chosen.update(fresh)
+                elif room >= 2:
+                    # rotate so the chain starts right after a position already chosen, if any
+                    k = next((i for i, p in enumerate(cyc) if p in chosen), -1)
+                    chain = cyc[k + 1:] + cyc[:k + 1]
+                    chosen.update([p for p in chain if p not in chosen][:room])
+                if len(chosen) >= self.t:
+                    break
+            for p in range(n_loc - 1, -1, -1):             # pad with idle positions
+                if len(chosen) >= self.t:
+                    break
+                chosen.add(p)
+            tile = [at[p] for p in sorted(chosen)]
+            prog.steps.append(self._emit_pass(tile, [], pos, home, [], True))
+        raise RuntimeError("layout restoration did not converge")
+
+
+def compile_ops(ir_ops, n_qubits: int, n_local: int | None = None, dtype: str = "complex128",
+                **kw) -> Program:
+    return PassCompiler(n_qubits, n_local, dtype, **kw).compile(ir_ops)

@@ -1,0 +1,70 @@
+// common.cuh — complex helpers, bit twiddling and the handle type shared by all kernels.
+// sm_100a only; built by __graft_entry__.build() / csrc/Makefile with
+//   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "qsv.h"
+
+// ---------------------------------------------------------------- complex math ----
+template <typename R> struct CxT;
+template <> struct CxT<float>  { using V = float2;  };
+template <> struct CxT<double> { using V = double2; };
+
+template <typename V> __device__ __forceinline__ V cx_make(decltype(V::x) re, decltype(V::x) im) {
+    V r; r.x = re; r.y = im; return r;
+}
+// a*b
+template <typename V> __device__ __forceinline__ V cx_mul(V a, V b) {
+    return cx_make<V>(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+// acc + a*b  (4 FMAs)
+template <typename V> __device__ __forceinline__ V cx_fma(V a, V b, V acc) {
+    acc.x = fma(a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x);
+    acc.y = fma(a.x, b.y, acc.y); acc.y = fma(a.y, b.x, acc.y);
+    return acc;
+}
+
+// 2x2 / 4x4 complex matrices passed by value as kernel parameters, in the compute type.
+template <typename R> struct Mat2 { typename CxT<R>::V m[4]; };
+template <typename R> struct Mat4 { typename CxT<R>::V m[16]; };
+
+// --------------------------------------------------------------- bit twiddling ----
+__host__ __device__ __forceinline__ uint64_t insert_zero_bit(uint64_t x, int pos) {
+    const uint64_t low = x & ((1ull << pos) - 1ull);
+    return ((x >> pos) << (pos + 1)) | low;
+}
+
+// ---------------------------------------------------------------------- handle ----
+struct qsv_program {
+    std::vector<qsv_pass> passes;
+    std::vector<int>      op_offset;     // first op of each pass in d_ops
+    qsv_op  *d_ops   = nullptr;          // device copy of all ops
+    qsv_pass *d_passes = nullptr;        // device copy of pass descriptors
+    cudaGraphExec_t graph = nullptr;
+};
+
+struct qsv_handle {
+    int n_qubits = 0, n_local = 0, dtype = QSV_C128, device = 0, rank = 0, world = 1;
+    size_t n_amps = 0;            // local amplitudes
+    size_t amp_bytes = 16;
+    void *d_state = nullptr;
+    cudaStream_t stream = nullptr;
+    // scratch for reductions / one-shot passes
+    double *d_partials = nullptr; size_t n_partials = 0;
+    qsv_op *d_ops_scratch = nullptr; size_t ops_scratch_cap = 0;
+    qsv_pass *d_pass_scratch = nullptr;
+    // timing
+    bool timing = false;
+    struct TimedLaunch { cudaEvent_t a, b; int kind, pass_index; };
+    std::vector<TimedLaunch> timed;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;   // qsv_timer_*
+    // comm (NCCL) — opaque here, owned by exchange.cuh
+    void *comm = nullptr;
+    std::string err;
+};

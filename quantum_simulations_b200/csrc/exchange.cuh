@@ -1,0 +1,222 @@
+// exchange.cuh — global<->local qubit swap across the shards of one box.
+//
+// Design source: HiSVSIM's bit redistribution (hisvsim_repo/mpi_redistributer.hpp:100-344,
+// svsim-mpi.hpp:123-173): "make a different set of index bits the rank bits".  Here the set
+// of local bits that leave is always the TOP n_swap local bits (the pass kernel relabels
+// qubits inside a tile for free, so the planner parks the outgoing qubits there first);
+// every peer block is then one contiguous slice of 2^(n_local - n_swap) amplitudes and the
+// exchange is an all-to-all of equal contiguous blocks among groups of 2^n_swap ranks:
+//      rank r, block d   <->   rank r' (= r with its swapped rank bits set to d), block me
+// The block d == me stays where it is.
+//
+// Memory: shards of 128 GiB (n=36 on 8 GPUs, n=34 on 2) leave no room for a second copy, so
+// the exchange is IN PLACE and chunked: chunk c of my block d goes out while the peer's chunk
+// c of its block `me` lands in a small bounce buffer, which is then copied over the slot
+// that was just sent.  NCCL (ncclSend/ncclRecv grouped) over NVLink 5 / NVSwitch carries the
+// chunks; NCCL is dlopen()ed at qsv_comm_init so single-GPU use has no NCCL dependency.
+#pragma once
+#include <dlfcn.h>
+
+#include "common.cuh"
+
+namespace qsvx {
+
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+constexpr int ncclChar = 0;   // ncclInt8
+
+struct Nccl {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    std::string why;
+
+    bool load() {
+        if (lib) return true;
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *n : names) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+        if (!lib) { why = std::string("dlopen(libnccl.so.2): ") + dlerror(); return false; }
+#define QSV_SYM(field, name) field = (decltype(field))dlsym(lib, name); if (!field) { why = std::string("missing symbol ") + name; return false; }
+        QSV_SYM(GetUniqueId, "ncclGetUniqueId");
+        QSV_SYM(CommInitRank, "ncclCommInitRank");
+        QSV_SYM(CommDestroy, "ncclCommDestroy");
+        QSV_SYM(Send, "ncclSend");
+        QSV_SYM(Recv, "ncclRecv");
+        QSV_SYM(GroupStart, "ncclGroupStart");
+        QSV_SYM(GroupEnd, "ncclGroupEnd");
+        QSV_SYM(AllReduce, "ncclAllReduce");
+        QSV_SYM(GetErrorString, "ncclGetErrorString");
+#undef QSV_SYM
+        return true;
+    }
+};
+
+inline Nccl &nccl() { static Nccl n; return n; }
+
+struct Comm {
+    ncclComm_t comm = nullptr;
+    void *bounce = nullptr;      // (peers) x chunk bytes, double buffered
+    size_t bounce_bytes = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_xfer[2] = {nullptr, nullptr};
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr};
+};
+
+}  // namespace qsvx
+
+static inline void qsv_comm_teardown(qsv_handle *h) {
+    auto *c = (qsvx::Comm *)h->comm;
+    if (!c) return;
+    if (c->comm) qsvx::nccl().CommDestroy(c->comm);
+    if (c->bounce) cudaFree(c->bounce);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    for (auto &e : c->ev_xfer) if (e) cudaEventDestroy(e);
+    for (auto &e : c->ev_copy) if (e) cudaEventDestroy(e);
+    delete c;
+    h->comm = nullptr;
+}
+
+#define QSVX_FAIL(h, code, ...)                      \
+    do {                                             \
+        char buf_[512];                              \
+        snprintf(buf_, sizeof(buf_), __VA_ARGS__);   \
+        (h)->err = buf_;                             \
+        return (code);                               \
+    } while (0)
+
+#define QSVX_NCCL(h, expr)                                                                  \
+    do {                                                                                    \
+        int r_ = (expr);                                                                    \
+        if (r_ != 0) QSVX_FAIL(h, QSV_ECOMM, "%s failed: %s", #expr, qsvx::nccl().GetErrorString(r_)); \
+    } while (0)
+
+#define QSVX_CUDA(h, expr)                                                                  \
+    do {                                                                                    \
+        cudaError_t e_ = (expr);                                                            \
+        if (e_ != cudaSuccess) QSVX_FAIL(h, QSV_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); \
+    } while (0)
+
+extern "C" int qsv_comm_unique_id(void *id128) {
+    if (!id128) return QSV_EINVAL;
+    if (!qsvx::nccl().load()) return QSV_ECOMM;
+    qsvx::ncclUniqueId id;
+    if (qsvx::nccl().GetUniqueId(&id) != 0) return QSV_ECOMM;
+    memcpy(id128, &id, 128);
+    return QSV_OK;
+}
+
+extern "C" int qsv_comm_init(qsv_handle *h, const void *id128) {
+    if (!h || !id128) return QSV_EINVAL;
+    if (!qsvx::nccl().load()) QSVX_FAIL(h, QSV_ECOMM, "NCCL unavailable: %s", qsvx::nccl().why.c_str());
+    if (h->comm) qsv_comm_teardown(h);
+    QSVX_CUDA(h, cudaSetDevice(h->device));
+    auto *c = new qsvx::Comm();
+    qsvx::ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    int r = qsvx::nccl().CommInitRank(&c->comm, h->world, id, h->rank);
+    if (r != 0) { delete c; QSVX_FAIL(h, QSV_ECOMM, "ncclCommInitRank: %s", qsvx::nccl().GetErrorString(r)); }
+    cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    for (auto &e : c->ev_xfer) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    for (auto &e : c->ev_copy) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    h->comm = c;
+    return QSV_OK;
+}
+
+// Swap rank bits global_bits[i] (physical positions >= n_local) with the TOP n_swap local bits:
+// local_bits[i] must be n_local - n_swap + i.  In place, chunked, collective over the group.
+extern "C" int qsv_swap_global_local(qsv_handle *h, int n_swap, const int *global_bits, const int *local_bits) {
+    if (!h) return QSV_EINVAL;
+    if (n_swap == 0) return QSV_OK;
+    int g = h->n_qubits - h->n_local;
+    if (n_swap < 0 || n_swap > g || !global_bits || !local_bits) QSVX_FAIL(h, QSV_EINVAL, "swap: n_swap=%d with %d rank bits", n_swap, g);
+    for (int i = 0; i < n_swap; ++i) {
+        if (global_bits[i] < h->n_local || global_bits[i] >= h->n_qubits) QSVX_FAIL(h, QSV_EINVAL, "swap: global bit %d is not a rank bit", global_bits[i]);
+        if (local_bits[i] != h->n_local - n_swap + i) QSVX_FAIL(h, QSV_EINVAL, "swap: local bits must be the top %d local positions in order", n_swap);
+        for (int j = 0; j < i; ++j) if (global_bits[i] == global_bits[j]) QSVX_FAIL(h, QSV_EINVAL, "swap: repeated global bit");
+    }
+    auto *c = (qsvx::Comm *)h->comm;
+    if (!c) QSVX_FAIL(h, QSV_ECOMM, "swap: qsv_comm_init was not called");
+    QSVX_CUDA(h, cudaSetDevice(h->device));
+    auto &N = qsvx::nccl();
+
+    const int peers = 1 << n_swap;
+    int me = 0;                                    // my value of the swapped rank bits
+    for (int i = 0; i < n_swap; ++i) me |= ((h->rank >> (global_bits[i] - h->n_local)) & 1) << i;
+    auto peer_rank = [&](int d) {
+        int r = h->rank;
+        for (int i = 0; i < n_swap; ++i) {
+            const int rb = global_bits[i] - h->n_local;
+            r = (r & ~(1 << rb)) | (((d >> i) & 1) << rb);
+        }
+        return r;
+    };
+    const size_t block_bytes = (h->n_amps >> n_swap) * h->amp_bytes;
+    size_t chunk = std::min(block_bytes, (size_t)256 << 20);
+    const size_t need = 2 * (size_t)(peers - 1) * chunk;
+    if (c->bounce_bytes < need) {
+        if (c->bounce) cudaFree(c->bounce);
+        c->bounce = nullptr; c->bounce_bytes = 0;
+        QSVX_CUDA(h, cudaMalloc(&c->bounce, need));
+        c->bounce_bytes = need;
+    }
+    char *state = (char *)h->d_state;
+    const size_t n_chunks = (block_bytes + chunk - 1) / chunk;
+    // main stream: NCCL group of chunk k; copy stream: bounce -> vacated slots of chunk k.
+    // Half (k&1) of the bounce buffer is reused by chunk k+2, which waits for copy k.
+    for (size_t k = 0; k < n_chunks; ++k) {
+        const size_t off = k * chunk;
+        const size_t len = std::min(chunk, block_bytes - off);
+        char *bb = (char *)c->bounce + (k & 1) * (size_t)(peers - 1) * chunk;
+        if (k >= 2) QSVX_CUDA(h, cudaStreamWaitEvent(h->stream, c->ev_copy[k & 1], 0));
+        QSVX_NCCL(h, N.GroupStart());
+        int slot = 0;
+        for (int d = 0; d < peers; ++d) {
+            if (d == me) continue;
+            const int pr = peer_rank(d);
+            QSVX_NCCL(h, N.Send(state + (size_t)d * block_bytes + off, len, qsvx::ncclChar, pr, c->comm, h->stream));
+            QSVX_NCCL(h, N.Recv(bb + (size_t)slot * chunk, len, qsvx::ncclChar, pr, c->comm, h->stream));
+            ++slot;
+        }
+        QSVX_NCCL(h, N.GroupEnd());
+        QSVX_CUDA(h, cudaEventRecord(c->ev_xfer[k & 1], h->stream));
+        QSVX_CUDA(h, cudaStreamWaitEvent(c->copy_stream, c->ev_xfer[k & 1], 0));
+        slot = 0;
+        for (int d = 0; d < peers; ++d) {
+            if (d == me) continue;
+            QSVX_CUDA(h, cudaMemcpyAsync(state + (size_t)d * block_bytes + off, bb + (size_t)slot * chunk, len, cudaMemcpyDeviceToDevice, c->copy_stream));
+            ++slot;
+        }
+        QSVX_CUDA(h, cudaEventRecord(c->ev_copy[k & 1], c->copy_stream));
+    }
+    QSVX_CUDA(h, cudaStreamWaitEvent(h->stream, c->ev_copy[0], 0));
+    if (n_chunks > 1) QSVX_CUDA(h, cudaStreamWaitEvent(h->stream, c->ev_copy[1], 0));
+    return QSV_OK;
+}
+
+// All-reduce (sum) of one double across the shards: norm / sampling plumbing.
+extern "C" int qsv_allreduce_sum(qsv_handle *h, double *value) {
+    if (!h || !value) return QSV_EINVAL;
+    if (h->world == 1) return QSV_OK;
+    auto *c = (qsvx::Comm *)h->comm;
+    if (!c) QSVX_FAIL(h, QSV_ECOMM, "allreduce: qsv_comm_init was not called");
+    QSVX_CUDA(h, cudaSetDevice(h->device));
+    double *d = h->d_partials + h->n_partials - 1;
+    QSVX_CUDA(h, cudaMemcpyAsync(d, value, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    QSVX_NCCL(h, qsvx::nccl().AllReduce(d, d, 1, /*ncclDouble*/ 8, /*ncclSum*/ 0, c->comm, h->stream));
+    QSVX_CUDA(h, cudaMemcpyAsync(value, d, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    QSVX_CUDA(h, cudaStreamSynchronize(h->stream));
+    return QSV_OK;
+}
+
+extern "C" int qsv_sample(qsv_handle *h, uint64_t, int, const double *, uint64_t *) {
+    if (!h) return QSV_EINVAL;
+    QSVX_FAIL(h, QSV_EINVAL, "qsv_sample: not built yet");
+}

@@ -1,0 +1,544 @@
+// qsv.cu — C ABI (include/qsv.h) over the sm_100a kernels.  No torch, no CPU path:
+// every entry point either launches CUDA work on the handle's stream or fails with a code.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "common.cuh"
+#include "gate_kernels.cuh"
+#include "pass_kernel.cuh"
+#include "exchange.cuh"
+
+static thread_local std::string g_create_error;
+
+#define QSV_FAIL(h, code, ...)                                  \
+    do {                                                        \
+        char buf_[512];                                         \
+        snprintf(buf_, sizeof(buf_), __VA_ARGS__);              \
+        if (h) (h)->err = buf_; else g_create_error = buf_;     \
+        return (code);                                          \
+    } while (0)
+
+#define QSV_CUDA(h, expr)                                                              \
+    do {                                                                               \
+        cudaError_t e_ = (expr);                                                       \
+        if (e_ != cudaSuccess)                                                         \
+            QSV_FAIL(h, QSV_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(e_));    \
+    } while (0)
+
+#define QSV_CHECK_H(h) do { if (!(h)) return QSV_EINVAL; } while (0)
+
+static inline int grid_for(uint64_t items, int threads, int max_blocks = 148 * 16) {
+    uint64_t b = (items + threads - 1) / threads;
+    if (b < 1) b = 1;
+    if (b > (uint64_t)max_blocks) b = max_blocks;
+    return (int)b;
+}
+
+namespace {
+struct ScopedTimer {
+    qsv_handle *h; int kind, pass_index; cudaEvent_t a = nullptr, b = nullptr;
+    ScopedTimer(qsv_handle *h_, int kind_, int pi = -1) : h(h_), kind(kind_), pass_index(pi) {
+        if (h->timing) {
+            cudaEventCreate(&a); cudaEventCreate(&b);
+            cudaEventRecord(a, h->stream);
+        }
+    }
+    ~ScopedTimer() {
+        if (h->timing) {
+            cudaEventRecord(b, h->stream);
+            h->timed.push_back({a, b, kind, pass_index});
+        }
+    }
+};
+template <typename R> Mat2<R> to_mat2(const double *U) {
+    Mat2<R> m;
+    for (int i = 0; i < 4; ++i) { m.m[i].x = (R)U[2 * i]; m.m[i].y = (R)U[2 * i + 1]; }
+    return m;
+}
+template <typename R> Mat4<R> to_mat4(const double *U) {
+    Mat4<R> m;
+    for (int i = 0; i < 16; ++i) { m.m[i].x = (R)U[2 * i]; m.m[i].y = (R)U[2 * i + 1]; }
+    return m;
+}
+}  // namespace
+
+extern "C" {
+
+int qsv_abi_version(void) { return QSV_ABI_VERSION; }
+
+int qsv_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char *qsv_last_error(const qsv_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int qsv_create(qsv_handle **out, int n_qubits, int dtype, int device, int rank, int world) {
+    qsv_handle *none = nullptr;
+    if (!out) return QSV_EINVAL;
+    *out = nullptr;
+    if (n_qubits < 1 || n_qubits > 62) QSV_FAIL(none, QSV_EINVAL, "n_qubits=%d out of range", n_qubits);
+    if (dtype != QSV_C64 && dtype != QSV_C128) QSV_FAIL(none, QSV_EINVAL, "bad dtype %d", dtype);
+    if (world < 1 || (world & (world - 1))) QSV_FAIL(none, QSV_EINVAL, "world=%d must be a power of two", world);
+    if (rank < 0 || rank >= world) QSV_FAIL(none, QSV_EINVAL, "rank=%d outside world=%d", rank, world);
+    int g = 0;
+    while ((1 << g) < world) ++g;
+    if (g >= n_qubits) QSV_FAIL(none, QSV_EINVAL, "world=%d too large for %d qubits", world, n_qubits);
+    int ndev = qsv_device_count();
+    if (ndev == 0) QSV_FAIL(none, QSV_ECUDA, "no CUDA device visible: libqsv has no CPU path");
+    if (device < 0 || device >= ndev) QSV_FAIL(none, QSV_EINVAL, "device=%d not in [0,%d)", device, ndev);
+
+    qsv_handle *h = new (std::nothrow) qsv_handle();
+    if (!h) return QSV_ENOMEM;
+    h->n_qubits = n_qubits; h->n_local = n_qubits - g; h->dtype = dtype; h->device = device;
+    h->rank = rank; h->world = world;
+    h->n_amps = (size_t)1 << h->n_local;
+    h->amp_bytes = dtype == QSV_C128 ? 16 : 8;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_state, h->n_amps * h->amp_bytes);
+    if (e == cudaSuccess) { h->n_partials = kNormBlocks + 8; e = cudaMalloc(&h->d_partials, h->n_partials * sizeof(double)); }
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_pass_scratch, sizeof(qsv_pass));
+    if (e != cudaSuccess) {
+        g_create_error = std::string("qsv_create: ") + cudaGetErrorString(e);
+        int code = (e == cudaErrorMemoryAllocation) ? QSV_ENOMEM : QSV_ECUDA;
+        cudaGetLastError();
+        if (h->d_state) cudaFree(h->d_state);
+        if (h->d_partials) cudaFree(h->d_partials);
+        if (h->stream) cudaStreamDestroy(h->stream);
+        delete h;
+        return code;
+    }
+    *out = h;
+    return QSV_OK;
+}
+
+int qsv_destroy(qsv_handle *h) {
+    QSV_CHECK_H(h);
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    qsv_comm_teardown(h);
+    for (auto &t : h->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+    if (h->t0) { cudaEventDestroy(h->t0); cudaEventDestroy(h->t1); }
+    cudaFree(h->d_state); cudaFree(h->d_partials); cudaFree(h->d_pass_scratch);
+    if (h->d_ops_scratch) cudaFree(h->d_ops_scratch);
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return QSV_OK;
+}
+
+int qsv_sync(qsv_handle *h) {
+    QSV_CHECK_H(h);
+    QSV_CUDA(h, cudaSetDevice(h->device));
+    QSV_CUDA(h, cudaStreamSynchronize(h->stream));
+    return QSV_OK;
+}
+
+int qsv_device_ptr(qsv_handle *h, void **ptr, size_t *n_amps_local, void **stream) {
+    QSV_CHECK_H(h);
+    if (ptr) *ptr = h->d_state;
+    if (n_amps_local) *n_amps_local = h->n_amps;
+    if (stream) *stream = (void *)h->stream;
+    return QSV_OK;
+}
+
+// ------------------------------------------------------------------ state I/O ----
+int qsv_init_basis(qsv_handle *h, uint64_t index) {
+    QSV_CHECK_H(h);
+    if (h->n_qubits < 64 && (index >> h->n_qubits)) QSV_FAIL(h, QSV_EINVAL, "basis index out of range");
+    QSV_CUDA(h, cudaSetDevice(h->device));
+    QSV_CUDA(h, cudaMemsetAsync(h->d_state, 0, h->n_amps * h->amp_bytes, h->stream));
+    if ((index >> h->n_local) == (uint64_t)h->rank) {
+        const uint64_t li = index & (h->n_amps - 1);
+        if (h->dtype == QSV_C128) k_set_amp<double><<<1, 1, 0, h->stream>>>((double2 *)h->d_state, li, 1.0, 0.0);
+        else k_set_amp<float><<<1, 1, 0, h->stream>>>((float2 *)h->d_state, li, 1.0f, 0.0f);
+        QSV_CUDA(h, cudaGetLastError());
+    }
+    return QSV_OK;
+}
+
+int qsv_init_zero(qsv_handle *h) { return qsv_init_basis(h, 0); }
+
+static int copy_range(qsv_handle *h, void *host, size_t off, size_t n, bool to_device, bool sync) {
+    QSV_CHECK_H(h);
+    if (!host && n) QSV_FAIL(h, QSV_EINVAL, "null host buffer");
+    if (off > h->n_amps || n > h->n_amps - off) QSV_FAIL(h, QSV_EINVAL, "range [%zu,+%zu) outside shard of %zu amps", off, n, h->n_amps);
+    QSV_CUDA(h, cudaSetDevice(h->device));
+    char *dev = (char *)h->d_state + off * h->amp_bytes;
+    if (to_device) QSV_CUDA(h, cudaMemcpyAsync(dev, host, n * h->amp_bytes, cudaMemcpyHostToDevice, h->stream));
+    else QSV_CUDA(h, cudaMemcpyAsync(host, dev, n * h->amp_bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (sync) QSV_CUDA(h, cudaStreamSynchronize(h->stream));
+    return QSV_OK;
+}
+int qsv_upload(qsv_handle *h, const void *host, size_t off, size_t n) { return copy_range(h, (void *)host, off, n, true, true); }
+int qsv_download(qsv_handle *h, void *host, size_t off, size_t n) { return copy_range(h, host, off, n, false, true); }
+int qsv_upload_async(qsv_handle *h, const void *host, size_t off, size_t n) { return copy_range(h, (void *)host, off, n, true, false); }
+int qsv_download_async(qsv_handle *h, void *host, size_t off, size_t n) { return copy_range(h, host, off, n, false, false); }
+
+int qsv_host_alloc(void **ptr, size_t bytes) {
+    if (!ptr) return QSV_EINVAL;
+    cudaError_t e = cudaHostAlloc(ptr, bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); cudaGetLastError(); return QSV_ENOMEM; }
+    return QSV_OK;
+}
+int qsv_host_free(void *ptr) { return cudaFreeHost(ptr) == cudaSuccess ? QSV_OK : QSV_ECUDA; }
+
+// ---------------------------------------------------------- per-gate operators ----
+static int check_local(qsv_handle *h, int q, const char *what) {
+    if (q < 0 || q >= h->n_qubits) QSV_FAIL(h, QSV_EINVAL, "%s: qubit %d out of range [0,%d)", what, q, h->n_qubits);
+    if (q >= h->n_local)
+        QSV_FAIL(h, QSV_ENONLOCAL, "%s: qubit %d >= n_local=%d: non-local gate requires a remap step", what, q, h->n_local);
+    return QSV_OK;
+}
+
+int qsv_apply_1q(qsv_handle *h, int q, const double U[8]) {
+    QSV_CHECK_H(h);
+    if (!U) QSV_FAIL(h, QSV_EINVAL, "null matrix");
+    int rc = check_local(h, q, "apply_1q");
+    if (rc) return rc;
+    QSV_CUDA(h, cudaSetDevice(h->device));
+    const uint64_t pairs = h->n_amps >> 1;
+    ScopedTimer t(h, 1);
+    if (h->dtype == QSV_C128)
+        k_apply_1q<double, 2><<<grid_for(pairs, kGateThreads * 2), kGateThreads, 0, h->stream>>>((double2 *)h->d_state, pairs, q, to_mat2<double>(U));
+    else
+        k_apply_1q<float, 2><<<grid_for(pairs, kGateThreads * 2), kGateThreads, 0, h->stream>>>((float2 *)h->d_state, pairs, q, to_mat2<float>(U));
+    QSV_CUDA(h, cudaGetLastError());
+    return QSV_OK;
+}
+
+int qsv_apply_ctrl_1q(qsv_handle *h, int ctrl, int tgt, const double U[8]) {
+    QSV_CHECK_H(h);
+    if (!U) QSV_FAIL(h, QSV_EINVAL, "null matrix");
+    if (ctrl == tgt) QSV_FAIL(h, QSV_EINVAL, "ctrl == tgt");
+    if (ctrl < 0 || ctrl >= h->n_qubits) QSV_FAIL(h, QSV_EINVAL, "apply_ctrl_1q: control %d out of range", ctrl);
+    int rc = check_local(h, tgt, "apply_ctrl_1q");
+    if (rc) return rc;
+    if (ctrl >= h->n_local) {           // control is a rank bit: whole shard or nothing
+        if ((h->rank >> (ctrl - h->n_local)) & 1) return qsv_apply_1q(h, tgt, U);
+        return QSV_OK;
+    }
+    QSV_CUDA(h, cudaSetDevice(h->device));
+    const uint64_t quads = h->n_amps >> 2;
+    ScopedTimer t(h, 2);
+    if (h->dtype == QSV_C128)
+        k_apply_ctrl_1q<double><<<grid_for(quads, kGateThreads), kGateThreads, 0, h->stream>>>((double2 *)h->d_state, quads, ctrl, tgt, to_mat2<double>(U));
+    else
+        k_apply_ctrl_1q<float><<<grid_for(quads, kGateThreads), kGateThreads, 0, h->stream>>>((float2 *)h->d_state, quads, ctrl, tgt, to_mat2<float>(U));
+    QSV_CUDA(h, cudaGetLastError());
+    return QSV_OK;
+}
+
+int qsv_apply_2q(qsv_handle *h, int qa, int qb, const double U[32]) {
+    QSV_CHECK_H(h);
+    if (!U) QSV_FAIL(h, QSV_EINVAL, "null matrix");
+    if (qa == qb) QSV_FAIL(h, QSV_EINVAL, "apply_2q: qa == qb");
+    int rc = check_local(h, qa, "apply_2q");
+    if (rc) return rc;
+    rc = check_local(h, qb, "apply_2q");
+    if (rc) return rc;
+    QSV_CUDA(h, cudaSetDevice(h->device));
+    const uint64_t quads = h->n_amps >> 2;
+    ScopedTimer t(h, 3);
+    if (h->dtype == QSV_C128)
+        k_apply_2q<double><<<grid_for(quads, kGateThreads), kGateThreads, 0, h->stream>>>((double2 *)h->d_state, quads, qa, qb, to_mat4<double>(U));
+    else
+        k_apply_2q<float><<<grid_for(quads, kGateThreads), kGateThreads, 0, h->stream>>>((float2 *)h->d_state, quads, qa, qb, to_mat4<float>(U));
+    QSV_CUDA(h, cudaGetLastError());
+    return QSV_OK;
+}
+
+}  // extern "C"
+template <typename R>
+static int launch_diag(qsv_handle *h, int nq, const int *qs, const double *phases) {
+    DiagArgs<R> a;
+    memset(&a, 0, sizeof(a));
+    a.nq = nq;
+    for (int i = 0; i < nq; ++i) a.qs[i] = qs[i];
+    for (int i = 0; i < (1 << nq); ++i) { a.phase[i].x = (R)phases[2 * i]; a.phase[i].y = (R)phases[2 * i + 1]; }
+    // args travel through the ops scratch buffer (stream ordered)
+    if (h->ops_scratch_cap < sizeof(a)) {
+        if (h->d_ops_scratch) cudaFree(h->d_ops_scratch);
+        h->ops_scratch_cap = 1 << 20;
+        QSV_CUDA(h, cudaMalloc((void **)&h->d_ops_scratch, h->ops_scratch_cap));
+    }
+    QSV_CUDA(h, cudaMemcpyAsync(h->d_ops_scratch, &a, sizeof(a), cudaMemcpyHostToDevice, h->stream));
+    QSV_CUDA(h, cudaStreamSynchronize(h->stream));   // `a` is a stack object
+    ScopedTimer t(h, 4);
+    k_apply_diag<R><<<grid_for(h->n_amps, kGateThreads), kGateThreads, 0, h->stream>>>(
+        (typename CxT<R>::V *)h->d_state, h->n_amps, (uint64_t)h->rank << h->n_local,
+        (const DiagArgs<R> *)h->d_ops_scratch);
+    QSV_CUDA(h, cudaGetLastError());
+    return QSV_OK;
+}
+
+extern "C" {
+int qsv_apply_diag(qsv_handle *h, int nq, const int *qs, const double *phases) {
+    QSV_CHECK_H(h);
+    if (nq < 1 || nq > 6 || !qs || !phases) QSV_FAIL(h, QSV_EINVAL, "apply_diag: need 1..6 qubits");
+    for (int i = 0; i < nq; ++i) {
+        if (qs[i] < 0 || qs[i] >= h->n_qubits) QSV_FAIL(h, QSV_EINVAL, "apply_diag: qubit %d out of range", qs[i]);
+        for (int j = 0; j < i; ++j) if (qs[i] == qs[j]) QSV_FAIL(h, QSV_EINVAL, "apply_diag: repeated qubit %d", qs[i]);
+    }
+    QSV_CUDA(h, cudaSetDevice(h->device));
+    return h->dtype == QSV_C128 ? launch_diag<double>(h, nq, qs, phases) : launch_diag<float>(h, nq, qs, phases);
+}
+
+}  // extern "C"
+template <typename R, int K>
+static int launch_kq(qsv_handle *h, const int *meta_dev, const void *U_dev) {
+    using V = typename CxT<R>::V;
+    const uint64_t groups = h->n_amps >> K;
+    const size_t smem = sizeof(V) << (2 * K);
+    QSV_CUDA(h, cudaFuncSetAttribute(k_apply_kq<R, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ScopedTimer t(h, 5);
+    k_apply_kq<R, K><<<grid_for(groups, 128), 128, smem, h->stream>>>((V *)h->d_state, groups, meta_dev, (const V *)U_dev);
+    QSV_CUDA(h, cudaGetLastError());
+    return QSV_OK;
+}
+
+extern "C" {
+int qsv_apply_kq(qsv_handle *h, int k, const int *qs, const double *U) {
+    QSV_CHECK_H(h);
+    if (k < 1 || k > 5 || !qs || !U) QSV_FAIL(h, QSV_EINVAL, "apply_kq: need 1 <= k <= 5");
+    if (k > h->n_local) QSV_FAIL(h, QSV_EINVAL, "apply_kq: k=%d > n_local=%d", k, h->n_local);
+    for (int i = 0; i < k; ++i) {
+        int rc = check_local(h, qs[i], "apply_kq");
+        if (rc) return rc;
+        for (int j = 0; j < i; ++j) if (qs[i] == qs[j]) QSV_FAIL(h, QSV_EINVAL, "apply_kq: repeated qubit %d", qs[i]);
+    }
+    QSV_CUDA(h, cudaSetDevice(h->device));
+    // meta: sorted qubits + the sub-space row bit each one drives (qs[0] = MSB)
+    int meta[10];
+    int order[5];
+    for (int i = 0; i < k; ++i) order[i] = i;
+    std::sort(order, order + k, [&](int a, int b) { return qs[a] < qs[b]; });
+    for (int j = 0; j < k; ++j) { meta[j] = qs[order[j]]; meta[k + j] = k - 1 - order[j]; }
+    const int D = 1 << k;
+    const size_t mat_elems = (size_t)D * D;
+    const size_t need = 64 + mat_elems * 16;
+    if (h->ops_scratch_cap < need) {
+        if (h->d_ops_scratch) cudaFree(h->d_ops_scratch);
+        h->ops_scratch_cap = 1 << 20;
+        QSV_CUDA(h, cudaMalloc((void **)&h->d_ops_scratch, h->ops_scratch_cap));
+    }
+    char *scratch = (char *)h->d_ops_scratch;
+    std::vector<char> stage(need);
+    memcpy(stage.data(), meta, sizeof(int) * 2 * k);
+    if (h->dtype == QSV_C128) memcpy(stage.data() + 64, U, mat_elems * 16);
+    else { float *f = (float *)(stage.data() + 64); for (size_t i = 0; i < mat_elems * 2; ++i) f[i] = (float)U[i]; }
+    QSV_CUDA(h, cudaMemcpyAsync(scratch, stage.data(), need, cudaMemcpyHostToDevice, h->stream));
+    QSV_CUDA(h, cudaStreamSynchronize(h->stream));
+    const int *meta_dev = (const int *)scratch;
+    const void *U_dev = scratch + 64;
+#define KQ_CASE(K_) case K_: return h->dtype == QSV_C128 ? launch_kq<double, K_>(h, meta_dev, U_dev) : launch_kq<float, K_>(h, meta_dev, U_dev)
+    switch (k) { KQ_CASE(1); KQ_CASE(2); KQ_CASE(3); KQ_CASE(4); KQ_CASE(5); }
+#undef KQ_CASE
+    return QSV_EINVAL;
+}
+
+// --------------------------------------------------------------- fused passes ----
+static int validate_pass(qsv_handle *h, const qsv_pass *p, const qsv_op *ops) {
+    const int T = p->n_tile;
+    const int maxT = h->dtype == QSV_C128 ? 12 : 13;
+    if (T < QSV_REG_BITS || T > maxT || T > h->n_local)
+        QSV_FAIL(h, QSV_EINVAL, "pass: n_tile=%d outside [%d, min(%d, n_local=%d)]", T, QSV_REG_BITS, maxT, h->n_local);
+    uint64_t tile_mask = 0, store_mask = 0;
+    for (int i = 0; i < T; ++i) {
+        const int b = p->load_bits[i], sb = p->store_bits[i];
+        if (b < 0 || b >= h->n_local || (i && b <= p->load_bits[i - 1]))
+            QSV_FAIL(h, QSV_EINVAL, "pass: load_bits must be ascending local bits (pos %d = %d)", i, b);
+        if (sb < 0 || sb >= h->n_local || ((store_mask >> sb) & 1)) QSV_FAIL(h, QSV_EINVAL, "pass: bad store_bits[%d]=%d", i, sb);
+        tile_mask |= 1ull << b; store_mask |= 1ull << sb;
+    }
+    if (tile_mask != store_mask) QSV_FAIL(h, QSV_EINVAL, "pass: store_bits is not a permutation of load_bits");
+    if (p->n_rounds < 1 || p->n_rounds > QSV_MAX_ROUNDS) QSV_FAIL(h, QSV_EINVAL, "pass: n_rounds=%d", p->n_rounds);
+    if (p->n_ops < 0) QSV_FAIL(h, QSV_EINVAL, "pass: n_ops < 0");
+    for (int r = 0; r < p->n_rounds; ++r) {
+        const qsv_round &rd = p->rounds[r];
+        uint32_t seen = 0, regm = 0;
+        for (int b = 0; b < QSV_REG_BITS; ++b) {
+            if (rd.reg_pos[b] >= T || ((seen >> rd.reg_pos[b]) & 1)) QSV_FAIL(h, QSV_EINVAL, "pass: round %d bad reg_pos", r);
+            seen |= 1u << rd.reg_pos[b];
+        }
+        regm = seen;
+        for (int i = 0; i < T - QSV_REG_BITS; ++i) {
+            if (rd.thr_pos[i] >= T || ((seen >> rd.thr_pos[i]) & 1)) QSV_FAIL(h, QSV_EINVAL, "pass: round %d bad thr_pos", r);
+            seen |= 1u << rd.thr_pos[i];
+        }
+        if (rd.op_begin < 0 || rd.op_end < rd.op_begin || rd.op_end > p->n_ops) QSV_FAIL(h, QSV_EINVAL, "pass: round %d op slice", r);
+        for (int o = rd.op_begin; o < rd.op_end; ++o) {
+            const qsv_op &op = ops[o];
+            if (op.kind < 0 || op.kind > QSV_OP_IPHASE) QSV_FAIL(h, QSV_EINVAL, "pass: op %d bad kind %d", o, op.kind);
+            const bool has_target = op.kind == QSV_OP_MAT || op.kind == QSV_OP_REAL || op.kind == QSV_OP_XPERM || op.kind == QSV_OP_HAD;
+            if (has_target && (op.target < 0 || op.target >= QSV_REG_BITS)) QSV_FAIL(h, QSV_EINVAL, "pass: op %d target", o);
+            if (op.reg_ctrl >> QSV_REG_BITS) QSV_FAIL(h, QSV_EINVAL, "pass: op %d reg_ctrl", o);
+            if (has_target && ((op.reg_ctrl >> op.target) & 1)) QSV_FAIL(h, QSV_EINVAL, "pass: op %d controls its own target", o);
+            if ((op.tile_ctrl >> T) || (op.tile_ctrl & regm)) QSV_FAIL(h, QSV_EINVAL, "pass: op %d tile_ctrl names a register position", o);
+            if (op.glob_ctrl & tile_mask) QSV_FAIL(h, QSV_EINVAL, "pass: op %d glob_ctrl names a tile bit", o);
+            if (h->n_qubits < 64 && (op.glob_ctrl >> h->n_qubits)) QSV_FAIL(h, QSV_EINVAL, "pass: op %d glob_ctrl out of range", o);
+        }
+    }
+    return QSV_OK;
+}
+
+static int launch_pass(qsv_handle *h, const qsv_pass *host_pass, const qsv_pass *dev_pass, const qsv_op *dev_ops, int pass_index) {
+    const int T = host_pass->n_tile;
+    const unsigned blocks = (unsigned)(h->n_amps >> T);
+    const unsigned threads = 1u << (T - QSV_REG_BITS);
+    const size_t smem = host_pass->n_rounds > 1 ? (h->amp_bytes << T) : 0;
+    const uint64_t rank_bits = (uint64_t)h->rank << h->n_local;
+    ScopedTimer t(h, 10, pass_index);
+    if (h->dtype == QSV_C128) {
+        QSV_CUDA(h, cudaFuncSetAttribute(k_pass<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        k_pass<double><<<blocks, threads, smem, h->stream>>>((double2 *)h->d_state, dev_pass, dev_ops, rank_bits);
+    } else {
+        QSV_CUDA(h, cudaFuncSetAttribute(k_pass<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        k_pass<float><<<blocks, threads, smem, h->stream>>>((float2 *)h->d_state, dev_pass, dev_ops, rank_bits);
+    }
+    QSV_CUDA(h, cudaGetLastError());
+    return QSV_OK;
+}
+
+int qsv_apply_pass(qsv_handle *h, const qsv_pass *pass, const qsv_op *ops) {
+    QSV_CHECK_H(h);
+    if (!pass || (pass->n_ops > 0 && !ops)) QSV_FAIL(h, QSV_EINVAL, "apply_pass: null argument");
+    int rc = validate_pass(h, pass, ops);
+    if (rc) return rc;
+    QSV_CUDA(h, cudaSetDevice(h->device));
+    const size_t need = sizeof(qsv_op) * (size_t)std::max(pass->n_ops, 1);
+    if (h->ops_scratch_cap < need) {
+        QSV_CUDA(h, cudaStreamSynchronize(h->stream));
+        if (h->d_ops_scratch) cudaFree(h->d_ops_scratch);
+        h->ops_scratch_cap = std::max(need, (size_t)1 << 20);
+        QSV_CUDA(h, cudaMalloc((void **)&h->d_ops_scratch, h->ops_scratch_cap));
+    }
+    // the previous one-shot pass may still be reading the scratch: stream order protects it,
+    // but the host buffers must outlive the copy -> synchronous staging copy (pageable memory).
+    QSV_CUDA(h, cudaMemcpyAsync(h->d_pass_scratch, pass, sizeof(qsv_pass), cudaMemcpyHostToDevice, h->stream));
+    if (pass->n_ops) QSV_CUDA(h, cudaMemcpyAsync(h->d_ops_scratch, ops, sizeof(qsv_op) * pass->n_ops, cudaMemcpyHostToDevice, h->stream));
+    return launch_pass(h, pass, h->d_pass_scratch, h->d_ops_scratch, -1);
+}
+
+int qsv_program_create(qsv_handle *h, const qsv_pass *passes, int n_passes, const qsv_op *ops, qsv_program **out) {
+    QSV_CHECK_H(h);
+    if (!out || n_passes < 0 || (n_passes && !passes)) QSV_FAIL(h, QSV_EINVAL, "program_create: bad arguments");
+    *out = nullptr;
+    QSV_CUDA(h, cudaSetDevice(h->device));
+    qsv_program *p = new (std::nothrow) qsv_program();
+    if (!p) return QSV_ENOMEM;
+    int total_ops = 0;
+    for (int i = 0; i < n_passes; ++i) {
+        int rc = validate_pass(h, &passes[i], ops ? ops + total_ops : nullptr);
+        if (rc) { delete p; return rc; }
+        p->passes.push_back(passes[i]);
+        p->op_offset.push_back(total_ops);
+        total_ops += passes[i].n_ops;
+    }
+    cudaError_t e = cudaSuccess;
+    if (n_passes) e = cudaMalloc((void **)&p->d_passes, sizeof(qsv_pass) * n_passes);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_ops, sizeof(qsv_op) * std::max(total_ops, 1));
+    if (e == cudaSuccess && n_passes) e = cudaMemcpy(p->d_passes, passes, sizeof(qsv_pass) * n_passes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && total_ops) e = cudaMemcpy(p->d_ops, ops, sizeof(qsv_op) * total_ops, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        h->err = std::string("program_create: ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        if (p->d_passes) cudaFree(p->d_passes);
+        if (p->d_ops) cudaFree(p->d_ops);
+        delete p;
+        return QSV_ECUDA;
+    }
+    *out = p;
+    return QSV_OK;
+}
+
+int qsv_program_run(qsv_handle *h, qsv_program *p) {
+    QSV_CHECK_H(h);
+    if (!p) QSV_FAIL(h, QSV_EINVAL, "program_run: null program");
+    QSV_CUDA(h, cudaSetDevice(h->device));
+    for (size_t i = 0; i < p->passes.size(); ++i) {
+        int rc = launch_pass(h, &p->passes[i], p->d_passes + i, p->d_ops + p->op_offset[i], (int)i);
+        if (rc) return rc;
+    }
+    return QSV_OK;
+}
+
+int qsv_program_destroy(qsv_handle *h, qsv_program *p) {
+    QSV_CHECK_H(h);
+    if (!p) return QSV_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    if (p->graph) cudaGraphExecDestroy(p->graph);
+    cudaFree(p->d_passes); cudaFree(p->d_ops);
+    delete p;
+    return QSV_OK;
+}
+
+// ----------------------------------------------------------------- reductions ----
+int qsv_norm2(qsv_handle *h, double *out) {
+    QSV_CHECK_H(h);
+    if (!out) QSV_FAIL(h, QSV_EINVAL, "norm2: null out");
+    QSV_CUDA(h, cudaSetDevice(h->device));
+    if (h->dtype == QSV_C128) k_norm2_partial<double><<<kNormBlocks, 256, 0, h->stream>>>((const double2 *)h->d_state, h->n_amps, h->d_partials);
+    else k_norm2_partial<float><<<kNormBlocks, 256, 0, h->stream>>>((const float2 *)h->d_state, h->n_amps, h->d_partials);
+    k_sum_partials<<<1, 256, 0, h->stream>>>(h->d_partials, kNormBlocks, h->d_partials + kNormBlocks);
+    QSV_CUDA(h, cudaGetLastError());
+    QSV_CUDA(h, cudaMemcpyAsync(out, h->d_partials + kNormBlocks, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    QSV_CUDA(h, cudaStreamSynchronize(h->stream));
+    return QSV_OK;
+}
+
+// --------------------------------------------------------------------- timing ----
+int qsv_timing_enable(qsv_handle *h, int on) {
+    QSV_CHECK_H(h);
+    h->timing = on != 0;
+    if (!on) {
+        for (auto &t : h->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+        h->timed.clear();
+    }
+    return QSV_OK;
+}
+
+int qsv_get_timings(qsv_handle *h, qsv_timing *out, int max, int *n_out) {
+    QSV_CHECK_H(h);
+    QSV_CUDA(h, cudaSetDevice(h->device));
+    QSV_CUDA(h, cudaStreamSynchronize(h->stream));
+    int n = 0;
+    for (auto &t : h->timed) {
+        if (out && n < max) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, t.a, t.b);
+            out[n].ms = ms; out[n].kind = t.kind; out[n].pass_index = t.pass_index;
+        }
+        ++n;
+        cudaEventDestroy(t.a); cudaEventDestroy(t.b);
+    }
+    h->timed.clear();
+    if (n_out) *n_out = n;
+    return QSV_OK;
+}
+
+int qsv_timer_start(qsv_handle *h) {
+    QSV_CHECK_H(h);
+    QSV_CUDA(h, cudaSetDevice(h->device));
+    if (!h->t0) { QSV_CUDA(h, cudaEventCreate(&h->t0)); QSV_CUDA(h, cudaEventCreate(&h->t1)); }
+    QSV_CUDA(h, cudaEventRecord(h->t0, h->stream));
+    return QSV_OK;
+}
+
+int qsv_timer_stop(qsv_handle *h, float *elapsed_ms) {
+    QSV_CHECK_H(h);
+    if (!h->t0 || !elapsed_ms) QSV_FAIL(h, QSV_EINVAL, "timer_stop without timer_start");
+    QSV_CUDA(h, cudaSetDevice(h->device));
+    QSV_CUDA(h, cudaEventRecord(h->t1, h->stream));
+    QSV_CUDA(h, cudaEventSynchronize(h->t1));
+    QSV_CUDA(h, cudaEventElapsedTime(elapsed_ms, h->t0, h->t1));
+    return QSV_OK;
+}
+
+}  // extern "C"

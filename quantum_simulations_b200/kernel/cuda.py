@@ -1,0 +1,249 @@
+"""kernel="cuda": the GPU operator face of the runner.
+
+Two faces, both over the C ABI in include/qsv.h (ctypes, no torch):
+
+* ``apply_1q(chunk, qubit, U)`` / ``apply_2q(chunk, qa, qb, U)`` — drop-in for the pair of
+  callables the reference runner threads down as ``a1, a2``
+  (wenbo_engine/runner/single_node.py:103-106; kernel/cpu_scalar.py:21-47): in place on a
+  host ndarray, ``NotImplementedError("... non-local ...")`` for a qubit >= log2(len(chunk)).
+  They round-trip the chunk over PCIe, so they are for parity tests and small chunks.
+* ``DeviceState`` — the state (or one shard of it) resident in HBM; this is what
+  ``runner.single_node.run(kernel="cuda")`` drives.
+
+There is no CPU fallback: without libqsv.so or without a CUDA device every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from quantum_simulations_b200 import _lib as L
+from quantum_simulations_b200.circuit.passes import PassStep, Dense2QStep, Program, lower_op, Dense2Q
+
+_DTYPES = {"complex64": L.QSV_C64, "complex128": L.QSV_C128}
+
+
+def _mat(U, dim: int):
+    u = np.ascontiguousarray(U, dtype=np.complex128)
+    if u.shape != (dim, dim):
+        raise ValueError(f"expected a {dim}x{dim} matrix, got {u.shape}")
+    return u, u.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class DeviceState:
+    """2^n_local amplitudes of an n-qubit state in HBM (shard `rank` of `world`)."""
+
+    def __init__(self, n_qubits: int, dtype="complex128", device: int = 0, rank: int = 0, world: int = 1):
+        self.lib = L.load()
+        self.dtype = np.dtype(dtype)
+        if self.dtype.name not in _DTYPES:
+            raise ValueError(f"unsupported dtype {dtype}")
+        self.n_qubits, self.rank, self.world, self.device = n_qubits, rank, world, device
+        self.n_local = n_qubits - int(math.log2(world))
+        self.n_amps = 1 << self.n_local
+        self._h = C.c_void_p()
+        rc = self.lib.qsv_create(C.byref(self._h), n_qubits, _DTYPES[self.dtype.name], device, rank, world)
+        if rc:
+            msg = self.lib.qsv_last_error(None)
+            raise L.QsvError(rc, msg.decode() if msg else "?")
+        self._programs: list = []
+
+    # ---- lifecycle ----
+    def close(self) -> None:
+        if getattr(self, "_h", None) and self._h.value:
+            for p in self._programs:
+                self.lib.qsv_program_destroy(self._h, p)
+            self._programs.clear()
+            self.lib.qsv_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc: int) -> None:
+        if rc:
+            msg = self.lib.qsv_last_error(self._h)
+            text = msg.decode(errors="replace") if msg else "?"
+            if rc == L.QSV_ENONLOCAL:
+                raise NotImplementedError(text)
+            raise L.QsvError(rc, text)
+
+    def sync(self) -> None:
+        self._ck(self.lib.qsv_sync(self._h))
+
+    # ---- state I/O ----
+    def init_zero(self) -> None:
+        self._ck(self.lib.qsv_init_zero(self._h))
+
+    def init_basis(self, index: int) -> None:
+        self._ck(self.lib.qsv_init_basis(self._h, index))
+
+    def upload(self, host: np.ndarray, offset: int = 0) -> None:
+        a = np.ascontiguousarray(host, dtype=self.dtype)
+        self._ck(self.lib.qsv_upload(self._h, a.ctypes.data, offset, a.size))
+
+    def download(self, out: np.ndarray | None = None, offset: int = 0, count: int | None = None) -> np.ndarray:
+        count = self.n_amps - offset if count is None else count
+        if out is None:
+            out = np.empty(count, dtype=self.dtype)
+        if out.dtype != self.dtype or not out.flags.c_contiguous or out.size < count:
+            raise ValueError("download buffer must be a contiguous array of the state's dtype")
+        self._ck(self.lib.qsv_download(self._h, out.ctypes.data, offset, count))
+        return out
+
+    def device_ptr(self) -> tuple[int, int, int]:
+        p, n, s = C.c_void_p(), C.c_size_t(), C.c_void_p()
+        self._ck(self.lib.qsv_device_ptr(self._h, C.byref(p), C.byref(n), C.byref(s)))
+        return p.value, n.value, s.value or 0
+
+    # ---- per-gate operators ----
+    def apply_1q(self, q: int, U) -> None:
+        _, p = _mat(U, 2)
+        self._ck(self.lib.qsv_apply_1q(self._h, q, p))
+
+    def apply_2q(self, qa: int, qb: int, U) -> None:
+        _, p = _mat(U, 4)
+        self._ck(self.lib.qsv_apply_2q(self._h, qa, qb, p))
+
+    def apply_ctrl_1q(self, ctrl: int, tgt: int, U) -> None:
+        _, p = _mat(U, 2)
+        self._ck(self.lib.qsv_apply_ctrl_1q(self._h, ctrl, tgt, p))
+
+    def apply_diag(self, qubits, phases) -> None:
+        qs = (C.c_int * len(qubits))(*qubits)
+        ph = np.ascontiguousarray(phases, dtype=np.complex128)
+        if ph.size != 1 << len(qubits):
+            raise ValueError("need 2^nq phases")
+        self._ck(self.lib.qsv_apply_diag(self._h, len(qubits), qs, ph.ctypes.data_as(C.POINTER(C.c_double))))
+
+    def apply_kq(self, qubits, U) -> None:
+        k = len(qubits)
+        qs = (C.c_int * k)(*qubits)
+        _, p = _mat(U, 1 << k)
+        self._ck(self.lib.qsv_apply_kq(self._h, k, qs, p))
+
+    def apply_op(self, qubits, U) -> None:
+        """One step-IR op through the per-gate kernels, picking the specialised kernel from
+        the matrix structure (diagonal / controlled / dense)."""
+        qubits = list(qubits)
+        if len(qubits) == 1:
+            u = np.asarray(U)
+            if u[0, 1] == 0 and u[1, 0] == 0:
+                return self.apply_diag(qubits, np.diag(u))
+            return self.apply_1q(qubits[0], U)
+        u = np.asarray(U, dtype=np.complex128)
+        if not np.any(u - np.diag(np.diag(u))):
+            return self.apply_diag(qubits, np.diag(u))
+        low = lower_op(qubits, u)
+        if len(low) == 1 and not isinstance(low[0], (tuple, Dense2Q)) and low[0].target is not None \
+                and len(low[0].ctrls) == 1:
+            (c,), t = low[0].ctrls, low[0].target
+            sub = u[2:, 2:] if c == qubits[0] else u[np.ix_([1, 3], [1, 3])]
+            return self.apply_ctrl_1q(c, t, sub)
+        return self.apply_2q(qubits[0], qubits[1], u)
+
+    # ---- fused passes ----
+    def apply_pass(self, step: PassStep) -> None:
+        self._ck(self.lib.qsv_apply_pass(self._h, C.byref(step.desc), step.ops))
+
+    def run_program(self, prog: Program) -> None:
+        """Execute a compiled program (passes + stand-alone dense 2q kernels) in order."""
+        if prog.n_local != self.n_local or prog.dtype != self.dtype.name:
+            raise ValueError("program was compiled for a different shard shape / dtype")
+        for step in prog.steps:
+            if isinstance(step, PassStep):
+                self.apply_pass(step)
+            elif isinstance(step, Dense2QStep):
+                self.apply_2q(step.qa_pos, step.qb_pos, step.U)
+            else:
+                raise TypeError(type(step))
+
+    def upload_program(self, prog: Program):
+        """Device-resident copy of an all-pass program for replay (qsv_program_*)."""
+        steps = prog.steps
+        if not all(isinstance(s, PassStep) for s in steps):
+            raise ValueError("only all-pass programs can be uploaded")
+        n = len(steps)
+        passes = (L.QsvPass * max(n, 1))(*[s.desc for s in steps])
+        total = sum(s.n_micro_ops for s in steps)
+        ops = (L.QsvOp * max(total, 1))()
+        k = 0
+        for s in steps:
+            for j in range(s.n_micro_ops):
+                ops[k] = s.ops[j]
+                k += 1
+        out = C.c_void_p()
+        self._ck(self.lib.qsv_program_create(self._h, passes, n, ops, C.byref(out)))
+        self._programs.append(out)
+        return out
+
+    def replay(self, handle) -> None:
+        self._ck(self.lib.qsv_program_run(self._h, handle))
+
+    # ---- reductions / timing ----
+    def norm2(self) -> float:
+        out = C.c_double()
+        self._ck(self.lib.qsv_norm2(self._h, C.byref(out)))
+        return out.value
+
+    def timing(self, on: bool) -> None:
+        self._ck(self.lib.qsv_timing_enable(self._h, int(on)))
+
+    def timer_start(self) -> None:
+        self._ck(self.lib.qsv_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        self._ck(self.lib.qsv_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    def take_timings(self, cap: int = 65536) -> list[tuple[float, int, int]]:
+        buf = (L.QsvTiming * cap)()
+        n = C.c_int()
+        self._ck(self.lib.qsv_get_timings(self._h, buf, cap, C.byref(n)))
+        return [(buf[i].ms, buf[i].kind, buf[i].pass_index) for i in range(min(n.value, cap))]
+
+
+# ------------------------------------------------------------ a1 / a2 drop-in callables
+def check_local(qubit: int, chunk_len: int) -> None:
+    k = int(math.log2(chunk_len))
+    if qubit >= k:
+        raise NotImplementedError(
+            f"qubit {qubit} >= log2(chunk_size)={k}: non-local gate requires layout/collect step")
+
+
+def _on_device(chunk: np.ndarray, fn) -> None:
+    if chunk.dtype not in (np.complex64, np.complex128) or chunk.ndim != 1:
+        raise ValueError("chunk must be a 1-D complex64/complex128 array")
+    n = int(math.log2(len(chunk)))
+    if 1 << n != len(chunk):
+        raise ValueError("chunk length must be a power of two")
+    with DeviceState(n, chunk.dtype) as st:
+        st.upload(chunk)
+        fn(st)
+        if chunk.flags.c_contiguous:
+            st.download(chunk)
+        else:
+            chunk[:] = st.download()
+
+
+def apply_1q(chunk: np.ndarray, qubit: int, U: np.ndarray) -> None:
+    check_local(qubit, len(chunk))
+    _on_device(chunk, lambda st: st.apply_1q(qubit, U))
+
+
+def apply_2q(chunk: np.ndarray, qa: int, qb: int, U: np.ndarray) -> None:
+    check_local(qa, len(chunk))
+    check_local(qb, len(chunk))
+    _on_device(chunk, lambda st: st.apply_2q(qa, qb, U))

@@ -1,0 +1,42 @@
+"""GPU counterpart of the reference's in-memory simulator
+(wenbo_engine/kernel/ref_dense.py:44-57): ``simulate(circuit_dict) -> ndarray``.
+
+Same contract — validate, start from |0...0>, apply every gate, return the final state as a
+host ndarray in logical qubit order — but the gates run as fused on-chip passes on the B200
+(circuit/passes.py + csrc/pass_kernel.cuh).  This is the call bench.py times end to end.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from quantum_simulations_b200.circuit.io import validate_circuit_dict
+from quantum_simulations_b200.circuit.passes import PassCompiler, Program, REG_BITS
+from quantum_simulations_b200.kernel import gates as gmod
+
+
+def circuit_ops(cd: dict) -> list:
+    """Normalised circuit -> step-IR op list [(qubits, U)] in program order."""
+    return [(g["qubits"], gmod.gate_matrix(g["gate"], g["params"])) for g in cd["gates"]]
+
+
+def compile_circuit(circuit_dict: dict, dtype="complex128", **compiler_kw) -> Program:
+    cd = validate_circuit_dict(circuit_dict)
+    return PassCompiler(cd["number_of_qubits"], dtype=np.dtype(dtype).name, **compiler_kw).compile(circuit_ops(cd))
+
+
+def simulate(circuit_dict: dict, dtype="complex128", device: int = 0, out: np.ndarray | None = None,
+             fused: bool = True, **compiler_kw) -> np.ndarray:
+    """Run the circuit on the GPU and return the final state vector (host, `dtype`)."""
+    from quantum_simulations_b200.kernel.cuda import DeviceState
+
+    cd = validate_circuit_dict(circuit_dict)
+    n = cd["number_of_qubits"]
+    ops = circuit_ops(cd)
+    with DeviceState(n, dtype, device) as st:
+        st.init_zero()
+        if fused and n >= REG_BITS:
+            st.run_program(PassCompiler(n, dtype=st.dtype.name, **compiler_kw).compile(ops))
+        else:
+            for qs, U in ops:
+                st.apply_op(qs, U)
+        return st.download(out)

@@ -1,0 +1,88 @@
+"""NumPy emulation of the qsv_pass semantics (include/qsv.h) — TEST INFRASTRUCTURE.
+
+Lets the pass compiler be verified on CPU: a compiled Program is executed here on a NumPy
+state and compared with the oracle.  It mirrors what pass_kernel.cuh does per tile, including
+the descriptor validation rules of qsv.cu (so an invalid plan fails here too)."""
+from __future__ import annotations
+
+import numpy as np
+
+from quantum_simulations_b200 import _lib as L
+from quantum_simulations_b200.circuit.passes import PassStep, Dense2QStep, Program
+from oracle import ref_dense as O
+
+R = L.QSV_REG_BITS
+
+
+def _insert_zero(x, p):
+    low = x & ((1 << p) - 1)
+    return ((x >> p) << (p + 1)) | low
+
+
+def run_pass(psi: np.ndarray, desc: L.QsvPass, ops, n_local: int, rank: int = 0) -> None:
+    t = desc.n_tile
+    load = [desc.load_bits[i] for i in range(t)]
+    store = [desc.store_bits[i] for i in range(t)]
+    assert load == sorted(load) and len(set(load)) == t and all(0 <= b < n_local for b in load)
+    assert sorted(store) == load, "store_bits must permute load_bits"
+    assert 1 <= desc.n_rounds <= L.QSV_MAX_ROUNDS
+    x = np.arange(1 << t, dtype=np.int64)
+    off_l = np.zeros_like(x)
+    off_s = np.zeros_like(x)
+    for i in range(t):
+        off_l |= ((x >> i) & 1) << load[i]
+        off_s |= ((x >> i) & 1) << store[i]
+    base = np.arange(len(psi) >> t, dtype=np.int64)
+    for p in load:
+        base = _insert_zero(base, p)
+    glob = (rank << n_local) | base
+    tile_mask = sum(1 << b for b in load)
+    work = psi[base[:, None] + off_l[None, :]]
+    for r in range(desc.n_rounds):
+        rd = desc.rounds[r]
+        regs = [rd.reg_pos[b] for b in range(R)]
+        thr = [rd.thr_pos[i] for i in range(t - R)]
+        assert sorted(regs + thr) == list(range(t)), f"round {r}: reg/thr positions do not partition the tile"
+        assert 0 <= rd.op_begin <= rd.op_end <= desc.n_ops
+        regmask = sum(1 << i for i in regs)
+        for o in range(rd.op_begin, rd.op_end):
+            op = ops[o]
+            assert not (op.tile_ctrl & regmask) and not (op.tile_ctrl >> t)
+            assert not (op.glob_ctrl & tile_mask)
+            assert not (op.reg_ctrl >> R)
+            rows = (glob & op.glob_ctrl) == op.glob_ctrl
+            need = op.tile_ctrl | sum(1 << regs[b] for b in range(R) if (op.reg_ctrl >> b) & 1)
+            cols = (x & need) == need
+            m = [op.m[k] for k in range(8)]
+            if op.kind in (L.OP_MAT, L.OP_REAL):
+                assert 0 <= op.target < R and not ((op.reg_ctrl >> op.target) & 1)
+                tb = 1 << regs[op.target]
+                x0 = x[cols & ((x & tb) == 0)]
+                a = work[np.ix_(rows, x0)]
+                b = work[np.ix_(rows, x0 | tb)]
+                if op.kind == L.OP_MAT:
+                    u = [complex(m[0], m[1]), complex(m[2], m[3]), complex(m[4], m[5]), complex(m[6], m[7])]
+                else:
+                    u = [m[0], m[2], m[4], m[6]]
+                work[np.ix_(rows, x0)] = u[0] * a + u[1] * b
+                work[np.ix_(rows, x0 | tb)] = u[2] * a + u[3] * b
+            elif op.kind == L.OP_PHASE:
+                xs = x[cols]
+                work[np.ix_(rows, xs)] = work[np.ix_(rows, xs)] * complex(m[0], m[1])
+            elif op.kind == L.OP_SIGN:
+                xs = x[cols]
+                work[np.ix_(rows, xs)] = -work[np.ix_(rows, xs)]
+            else:
+                raise AssertionError(f"emulator: unsupported op kind {op.kind}")
+    psi[base[:, None] + off_s[None, :]] = work
+
+
+def run_program(prog: Program, psi: np.ndarray, rank: int = 0) -> np.ndarray:
+    for step in prog.steps:
+        if isinstance(step, PassStep):
+            run_pass(psi, step.desc, step.ops, prog.n_local, rank)
+        elif isinstance(step, Dense2QStep):
+            O.apply_2q(psi, step.qa_pos, step.qb_pos, step.U)
+        else:
+            raise AssertionError(type(step))
+    return psi

@@ -1,0 +1,73 @@
+"""CPU-side checks of the drop-in boundary: libqsv.so loads, exports every symbol that
+include/qsv.h declares, mirrors the header's constants/struct sizes, and refuses to run
+without a GPU (no CPU fallback).  No compute is launched here."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import pytest
+
+from quantum_simulations_b200 import _lib as L
+
+ROOT = Path(__file__).resolve().parent.parent
+HEADER = (ROOT / "include" / "qsv.h").read_text()
+
+
+def declared_functions():
+    return sorted(set(re.findall(r"^\s*(?:const\s+char\s*\*|int)\s*\*?\s*(qsv_\w+)\s*\(", HEADER, re.M)))
+
+
+def test_header_declares_the_expected_surface():
+    names = declared_functions()
+    for must in ("qsv_create", "qsv_apply_1q", "qsv_apply_2q", "qsv_apply_diag", "qsv_apply_ctrl_1q",
+                 "qsv_apply_kq", "qsv_apply_pass", "qsv_program_run", "qsv_upload", "qsv_download",
+                 "qsv_norm2", "qsv_sample", "qsv_swap_global_local", "qsv_comm_init"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol():
+    lib = L.load()
+    for name in declared_functions():
+        assert hasattr(lib, name), f"libqsv.so lacks {name}"
+        assert name in L.SIGNATURES, f"ctypes binding lacks {name}"
+    assert sorted(L.SIGNATURES) == declared_functions()
+
+
+def test_constants_match_header():
+    def const(name):
+        return int(re.search(rf"#define\s+{name}\s+(-?\d+)", HEADER).group(1))
+    assert L.load().qsv_abi_version() == const("QSV_ABI_VERSION")
+    assert (L.QSV_C64, L.QSV_C128) == (const("QSV_C64"), const("QSV_C128"))
+    assert L.QSV_MAX_TILE_BITS == const("QSV_MAX_TILE_BITS")
+    assert L.QSV_REG_BITS == const("QSV_REG_BITS") and L.QSV_MAX_ROUNDS == const("QSV_MAX_ROUNDS")
+    for k in ("MAT", "REAL", "PHASE", "SIGN", "XPERM", "HAD", "IPHASE"):
+        assert getattr(L, f"OP_{k}") == const(f"QSV_OP_{k}")
+    for k in ("EINVAL", "ENONLOCAL", "ECUDA", "ENOMEM", "ECOMM", "EIO"):
+        assert getattr(L, f"QSV_{k}") == const(f"QSV_{k}")
+
+
+def test_struct_layouts():
+    assert C.sizeof(L.QsvOp) == 4 + 4 + 4 + 4 + 8 + 64
+    assert C.sizeof(L.QsvRound) == 4 + 14 + 2 + 8          # uint8[4], uint8[14], pad, 2 x int32
+    assert C.sizeof(L.QsvPass) == 4 + 14 * 4 * 2 + 4 + 16 * C.sizeof(L.QsvRound) + 4
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    lib = L.load()
+    if lib.qsv_device_count() > 0:
+        pytest.skip("a GPU is visible")
+    from quantum_simulations_b200.kernel.cuda import DeviceState
+    with pytest.raises(L.QsvError, match="no CUDA device"):
+        DeviceState(4)
+    from quantum_simulations_b200.kernel.cuda_dense import simulate
+    from quantum_simulations_b200 import workloads as W
+    with pytest.raises(L.QsvError):
+        simulate(W.bell_2q())
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: no file of the package may import it."""
+    pkg = ROOT / "quantum_simulations_b200"
+    for py in pkg.rglob("*.py"):
+        text = py.read_text()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), py

@@ -1,0 +1,292 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle and the reference's
+golden vectors.  Tolerances are the north star's: max|Δamp| <= 1e-12 (complex128),
+<= 1e-5 (complex64).  Nothing here reads /root/reference."""
+import tempfile
+
+import numpy as np
+import pytest
+
+from oracle import ref_dense as O
+from oracle import c_oracle as CO
+from quantum_simulations_b200 import workloads as W
+from quantum_simulations_b200.circuit.io import validate_circuit_dict
+from quantum_simulations_b200.kernel import gates as G
+from tests._specs import STATE_SPECS, RUNNER_SPECS, circuit_from_spec
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"complex128": 1e-12, "complex64": 1e-5}
+
+
+def _cuda():
+    from quantum_simulations_b200.kernel import cuda
+    return cuda
+
+
+def _rand_state(n, seed, dtype="complex128"):
+    rng = np.random.default_rng(seed)
+    v = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
+    v /= np.linalg.norm(v)
+    return v.astype(dtype)
+
+
+def _rand_unitary(dim, seed):
+    rng = np.random.default_rng(seed)
+    q, r = np.linalg.qr(rng.standard_normal((dim, dim)) + 1j * rng.standard_normal((dim, dim)))
+    return q * (np.diag(r) / np.abs(np.diag(r)))
+
+
+# ------------------------------------------------------------------ per-gate kernels
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+@pytest.mark.parametrize("n", [1, 2, 5, 9, 14])
+def test_apply_1q_every_qubit(n, dtype):
+    cuda = _cuda()
+    psi = _rand_state(n, n, dtype)
+    want = psi.astype(np.complex128)
+    with cuda.DeviceState(n, dtype) as st:
+        st.upload(psi)
+        for q in range(n):
+            U = _rand_unitary(2, 10 * n + q)
+            st.apply_1q(q, U)
+            O.apply_1q(want, q, U)
+        got = st.download()
+    assert got.dtype == np.dtype(dtype)
+    assert np.abs(got - want).max() <= TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+def test_apply_2q_all_pairs(dtype):
+    cuda = _cuda()
+    n = 7
+    psi = _rand_state(n, 3, dtype)
+    want = psi.astype(np.complex128)
+    with cuda.DeviceState(n, dtype) as st:
+        st.upload(psi)
+        for qa in range(n):
+            for qb in range(n):
+                if qa != qb:
+                    U = _rand_unitary(4, 100 * qa + qb)
+                    st.apply_2q(qa, qb, U)
+                    O.apply_2q(want, qa, qb, U)
+        got = st.download()
+    assert np.abs(got - want).max() <= TOL[dtype] * 4
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+def test_diag_ctrl_kq(dtype):
+    cuda = _cuda()
+    n = 9
+    psi = _rand_state(n, 4, dtype)
+    want = psi.astype(np.complex128)
+    rng = np.random.default_rng(8)
+    with cuda.DeviceState(n, dtype) as st:
+        st.upload(psi)
+        # diagonal on 1..4 qubits
+        for qs in ([3], [0, 8], [5, 2, 7], [1, 4, 6, 0]):
+            ph = np.exp(1j * rng.uniform(0, 2 * np.pi, 1 << len(qs)))
+            st.apply_diag(qs, ph)
+            idx = np.arange(1 << n)
+            t = np.zeros_like(idx)
+            for q in qs:
+                t = (t << 1) | ((idx >> q) & 1)
+            want *= ph[t]
+        # controlled 1q
+        for c, t in ((0, 5), (8, 1), (3, 2)):
+            U = _rand_unitary(2, c * 10 + t)
+            st.apply_ctrl_1q(c, t, U)
+            cu = np.eye(4, dtype=complex); cu[2:, 2:] = U
+            O.apply_2q(want, c, t, cu)
+        # dense k-qubit
+        for qs in ([4], [6, 1], [0, 7, 3], [8, 2, 5, 1], [3, 0, 6, 8, 4]):
+            k = len(qs)
+            U = _rand_unitary(1 << k, 77 + k)
+            st.apply_kq(qs, U)
+            # reference semantics: row bit (k-1-i) <-> qs[i]
+            idx = np.arange(1 << n)
+            mask = sum(1 << q for q in qs)
+            base = idx[(idx & mask) == 0]
+            offs = [sum(((r >> (k - 1 - i)) & 1) << qs[i] for i in range(k)) for r in range(1 << k)]
+            v = np.stack([want[base | o] for o in offs])
+            out = U @ v
+            for r, o in enumerate(offs):
+                want[base | o] = out[r]
+        got = st.download()
+    assert np.abs(got - want).max() <= TOL[dtype] * 8
+
+
+def test_apply_op_dispatch_all_gates():
+    cuda = _cuda()
+    n = 6
+    cd = validate_circuit_dict(W.random_mixed(n, 200, 99))
+    with cuda.DeviceState(n) as st:
+        st.init_zero()
+        for g in cd["gates"]:
+            st.apply_op(g["qubits"], G.gate_matrix(g["gate"], g["params"]))
+        got = st.download()
+    assert np.abs(got - O.simulate(cd)).max() <= 1e-12
+
+
+def test_a1_a2_host_callables_and_nonlocal_raise():
+    cuda = _cuda()
+    chunk = _rand_state(6, 1)
+    want = chunk.copy()
+    U1, U2 = _rand_unitary(2, 1), _rand_unitary(4, 2)
+    cuda.apply_1q(chunk, 3, U1); O.apply_1q(want, 3, U1)
+    cuda.apply_2q(chunk, 5, 0, U2); O.apply_2q(want, 5, 0, U2)
+    assert np.abs(chunk - want).max() <= 1e-12
+    small = np.zeros(4, dtype=np.complex128); small[0] = 1
+    with pytest.raises(NotImplementedError, match="non-local"):
+        cuda.apply_1q(small, 2, G.H())
+    with pytest.raises(NotImplementedError, match="non-local"):
+        cuda.apply_2q(small, 0, 2, G.CNOT())
+
+
+def test_sharded_handle_semantics_on_one_gpu():
+    """4 shards of an 8-qubit state as 4 handles on one device: rank bits as controls /
+    diagonal qubits work without communication; mixing one raises QSV_ENONLOCAL."""
+    cuda = _cuda()
+    n, world = 8, 4
+    n_local = 6
+    full = _rand_state(n, 21)
+    want = full.copy()
+    ops = [([0], G.H()), ([7], G.Z()), ([7, 2], G.CNOT()), ([6, 7], G.CZ()), ([1, 6], G.CR(3))]
+    O.apply_ops(want, ops)
+    for rank in range(world):
+        with cuda.DeviceState(n, rank=rank, world=world) as st:
+            st.upload(full[rank << n_local:(rank + 1) << n_local])
+            for qs, U in ops:
+                st.apply_op(qs, U)
+            got = st.download()
+            with pytest.raises(NotImplementedError, match="non-local"):
+                st.apply_1q(7, G.H())
+        assert np.abs(got - want[rank << n_local:(rank + 1) << n_local]).max() <= 1e-12
+
+
+# ------------------------------------------------------------------ fused pass path
+@pytest.mark.parametrize("spec", STATE_SPECS)
+def test_golden_states_fused_and_unfused(golden, spec):
+    from quantum_simulations_b200.kernel.cuda_dense import simulate
+    want = golden[f"state/{spec}"]
+    cd = circuit_from_spec(spec)
+    for fused in (False, True):
+        got = simulate(cd, fused=fused)
+        assert np.abs(got - want).max() <= 1e-12, (spec, fused)
+    got64 = simulate(cd, dtype="complex64")
+    assert got64.dtype == np.complex64 and np.abs(got64 - want).max() <= 1e-5
+
+
+@pytest.mark.parametrize("n,t,a", [(10, 6, 2), (12, 8, 3), (14, 10, 4), (14, 12, 5), (16, 12, 5),
+                                   (16, 11, 3), (18, 12, 6)])
+def test_pass_kernel_tile_shapes(n, t, a):
+    from quantum_simulations_b200.kernel.cuda_dense import simulate
+    cd = W.random_mixed(n, 300, n * 7 + t)
+    want = CO.simulate_c(validate_circuit_dict(cd))
+    got = simulate(cd, tile_bits=t, low_bits=a)
+    assert np.abs(got - want).max() <= 1e-12
+
+
+@pytest.mark.parametrize("dtype,t", [("complex64", 13), ("complex64", 9), ("complex128", 12)])
+def test_random_1q_cz_depth20(dtype, t):
+    from quantum_simulations_b200.kernel.cuda_dense import simulate
+    n = 20
+    cd = W.random_1q_cz(n, 20, 1234)
+    want = CO.simulate_c(validate_circuit_dict(cd))
+    got = simulate(cd, dtype=dtype, tile_bits=t)
+    assert np.abs(got - want).max() <= TOL[dtype]
+
+
+def test_ghz20_config0_known_answer():
+    from quantum_simulations_b200.kernel.cuda_dense import simulate
+    got = simulate(W.ghz(20))
+    s2 = 1 / np.sqrt(2)
+    assert abs(got[0] - s2) < 1e-12 and abs(got[-1] - s2) < 1e-12
+    assert np.count_nonzero(np.abs(got) > 1e-12) == 2
+
+
+def test_program_replay_matches_one_shot():
+    cuda = _cuda()
+    from quantum_simulations_b200.kernel.cuda_dense import compile_circuit
+    cd = W.random_1q_cz(16, 10, 5)
+    prog = compile_circuit(cd)
+    with cuda.DeviceState(16) as st:
+        st.init_zero(); st.run_program(prog); a = st.download()
+        h = st.upload_program(prog)
+        st.init_zero(); st.replay(h); b = st.download()
+        st.init_zero(); st.replay(h); c = st.download()
+    assert np.array_equal(a, b) and np.array_equal(b, c)
+    assert np.abs(a - CO.simulate_c(validate_circuit_dict(cd))).max() <= 1e-12
+
+
+# ------------------------------------------------------- size-independent properties
+@pytest.mark.parametrize("n", [24, 27])
+def test_large_invariants(n):
+    """Sizes the NumPy oracle cannot reach cheaply: norm, QFT|0> uniform, GHZ, U U^dagger."""
+    cuda = _cuda()
+    from quantum_simulations_b200.kernel.cuda_dense import compile_circuit, circuit_ops
+    from quantum_simulations_b200.circuit.passes import PassCompiler
+    with cuda.DeviceState(n) as st:
+        # QFT of |0> is the uniform superposition
+        st.init_zero(); st.run_program(compile_circuit(W.qft(n)))
+        assert abs(st.norm2() - 1.0) < 1e-10
+        head = st.download(count=1 << 12)
+        assert np.abs(head - 2.0 ** (-n / 2)).max() < 1e-12
+        # GHZ
+        st.init_zero(); st.run_program(compile_circuit(W.ghz(n)))
+        assert abs(st.norm2() - 1.0) < 1e-12
+        assert abs(st.download(count=1)[0] - 1 / np.sqrt(2)) < 1e-12
+        assert abs(st.download(offset=(1 << n) - 1, count=1)[0] - 1 / np.sqrt(2)) < 1e-12
+        # random circuit followed by its inverse returns |0...0>
+        cd = validate_circuit_dict(W.random_1q_cz(n, 8, 77))
+        ops = circuit_ops(cd)
+        inv = [(qs, U.conj().T) for qs, U in reversed(ops)]
+        st.init_zero(); st.run_program(PassCompiler(n).compile(ops + inv))
+        assert abs(st.norm2() - 1.0) < 1e-10
+        assert abs(st.download(count=1)[0] - 1.0) < 1e-10
+
+
+def test_n26_matches_c_oracle_sampled():
+    from quantum_simulations_b200.kernel.cuda_dense import simulate
+    n = 26
+    cd = W.random_1q_cz(n, 20, 1234)
+    want = CO.simulate_c(validate_circuit_dict(cd))
+    got = simulate(cd)
+    assert np.abs(got - want).max() <= 1e-12
+
+
+# ----------------------------------------------------------------------- runner
+@pytest.mark.parametrize("spec,chunk_size,kw", RUNNER_SPECS)
+def test_runner_matches_reference_runner_golden(golden_runner, spec, chunk_size, kw):
+    from quantum_simulations_b200.runner.single_node import run, collect_state
+    key = f"runner/{spec}/cs{chunk_size}/" + ",".join(f"{k}={v}" for k, v in sorted(kw.items()))
+    want = golden_runner[key]                        # reference stores complex64: atol 1e-6
+    cd = circuit_from_spec(spec)
+    with tempfile.TemporaryDirectory() as td:
+        final = run(cd, td, chunk_size=chunk_size, **kw)
+        got = collect_state(final, apply_permutation=True, work_dir=td)
+    assert got.dtype == np.complex128
+    assert np.abs(got - want).max() <= 1e-6
+    assert np.abs(got - O.simulate(validate_circuit_dict(cd))).max() <= 1e-12
+
+
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+def test_runner_dtypes_and_manifest(dtype):
+    from quantum_simulations_b200.runner.single_node import run, collect_state
+    from quantum_simulations_b200.storage.manifest import read_manifest
+    cd = W.qft(10)
+    with tempfile.TemporaryDirectory() as td:
+        final = run(cd, td, chunk_size=256, use_fusion=True, dtype=dtype)
+        m = read_manifest(final)
+        assert (m.dtype, m.n_chunks, m.chunk_size) == (dtype, 4, 256)
+        got = collect_state(final)
+    assert np.abs(got - O.simulate(validate_circuit_dict(cd))).max() <= TOL[dtype]
+
+
+def test_runner_errors():
+    from quantum_simulations_b200.runner.single_node import run
+    with tempfile.TemporaryDirectory() as td:
+        with pytest.raises(ValueError, match="divisible by chunk_size"):
+            run(W.qft(4), td, chunk_size=3)
+        with pytest.raises(ValueError, match="kernel="):
+            run(W.qft(4), td, kernel="scalar")
+        with pytest.raises(ValueError, match="missing required keys"):
+            run({"gates": []}, td)

@@ -1,0 +1,124 @@
+"""The pass compiler against the oracle, through the NumPy pass emulator (no GPU needed)."""
+import numpy as np
+import pytest
+
+from oracle import ref_dense as O
+from quantum_simulations_b200.circuit.io import validate_circuit_dict
+from quantum_simulations_b200.circuit.passes import PassCompiler, lower_op, MicroOp, Dense2Q
+from quantum_simulations_b200.kernel import gates as G
+from quantum_simulations_b200 import workloads as W
+from quantum_simulations_b200 import _lib as L
+from tests.pass_emulator import run_program
+
+
+def ir_ops(cd):
+    cd = validate_circuit_dict(cd)
+    return [(g["qubits"], G.gate_matrix(g["gate"], g["params"])) for g in cd["gates"]]
+
+
+def check(cd, **kw):
+    n = cd["number_of_qubits"]
+    prog = PassCompiler(n, **kw).compile(ir_ops(cd))
+    psi = np.zeros(1 << n, dtype=np.complex128)
+    psi[0] = 1
+    run_program(prog, psi)
+    want = O.simulate(validate_circuit_dict(cd))
+    assert prog.final_pos == list(range(n))
+    assert np.abs(psi - want).max() <= 1e-12
+    return prog
+
+
+@pytest.mark.parametrize("n,t,a", [(6, 6, 5), (7, 5, 1), (8, 6, 2), (9, 7, 3), (10, 8, 3), (10, 12, 5), (12, 8, 4)])
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_random_mixed(n, t, a, seed):
+    check(W.random_mixed(n, 120, seed), tile_bits=t, low_bits=a)
+
+
+@pytest.mark.parametrize("n,t,a", [(8, 6, 2), (10, 7, 3), (12, 8, 3), (12, 12, 5)])
+def test_random_1q_cz(n, t, a):
+    check(W.random_1q_cz(n, 20, 1234), tile_bits=t, low_bits=a)
+
+
+@pytest.mark.parametrize("n", [5, 8, 11])
+def test_qft_and_ghz(n):
+    check(W.qft(n), tile_bits=min(n, 7), low_bits=2)
+    check(W.ghz(n), tile_bits=min(n, 6), low_bits=2)
+
+
+@pytest.mark.parametrize("max_rounds", [2, 3, 6])
+def test_round_budget(max_rounds):
+    prog = check(W.random_1q_cz(10, 12, 7), tile_bits=8, low_bits=3, max_rounds=max_rounds)
+    assert all(s.desc.n_rounds <= max_rounds + 2 for s in prog.passes)
+
+
+def test_reference_staging_bug_case_is_right_here():
+    """H(2) H(0) CZ(2,0) H(0) H(1) — the reference's heuristic stager
+    reorders H0·CZ·H0 into H0·H0·CZ.  Per-qubit program order must be kept."""
+    cd = {"number_of_qubits": 5, "gates": [
+        {"qubits": [2], "gate": "H"}, {"qubits": [0], "gate": "H"}, {"qubits": [2, 0], "gate": "CZ"},
+        {"qubits": [0], "gate": "H"}, {"qubits": [1], "gate": "H"}]}
+    check(cd, tile_bits=4, low_bits=0)
+
+
+def test_swap_is_a_rename_not_arithmetic():
+    cd = {"number_of_qubits": 6, "gates": [
+        {"qubits": [0], "gate": "H"}, {"qubits": [0, 5], "gate": "SWAP"}, {"qubits": [5], "gate": "T"},
+        {"qubits": [0], "gate": "X"}, {"qubits": [1, 4], "gate": "SWAP"}, {"qubits": [4, 0], "gate": "CNOT"}]}
+    prog = check(cd, tile_bits=5, low_bits=1)
+    assert all(s.n_micro_ops <= 4 for s in prog.passes)
+
+
+def test_dense_2q_runs_as_own_step():
+    rng = np.random.default_rng(5)
+    q, _ = np.linalg.qr(rng.standard_normal((4, 4)) + 1j * rng.standard_normal((4, 4)))
+    n = 7
+    ops = [([0], G.H()), ([3], G.H()), ([3, 1], q), ([1], G.T()), ([6, 3], G.CNOT())]
+    prog = PassCompiler(n, tile_bits=5, low_bits=1).compile(ops)
+    psi = np.zeros(1 << n, dtype=np.complex128); psi[0] = 1
+    run_program(prog, psi)
+    want = np.zeros(1 << n, dtype=np.complex128); want[0] = 1
+    O.apply_ops(want, ops)
+    assert prog.stats["dense2q_steps"] == 1
+    assert np.abs(psi - want).max() <= 1e-12
+
+
+def test_lowering_structures():
+    assert [o.kind for o in lower_op([3], G.H())] == [L.OP_REAL]
+    assert [o.kind for o in lower_op([3], G.Y())] == [L.OP_MAT]
+    assert [(o.kind, o.ctrls) for o in lower_op([3], G.Z())] == [(L.OP_SIGN, (3,))]
+    assert [(o.kind, o.ctrls) for o in lower_op([3], G.T())] == [(L.OP_PHASE, (3,))]
+    assert [(o.kind, o.ctrls) for o in lower_op([2, 5], G.CZ())] == [(L.OP_SIGN, (2, 5))]
+    assert [(o.kind, o.target, o.ctrls) for o in lower_op([2, 5], G.CNOT())] == [(L.OP_REAL, 5, (2,))]
+    assert [(o.kind, o.target, o.ctrls) for o in lower_op([2, 5], G.CY())] == [(L.OP_MAT, 5, (2,))]
+    assert lower_op([2, 5], G.SWAP()) == [("swap", 2, 5)]
+    assert lower_op([1], np.eye(2)) == []
+    # control on qubits[1]
+    cu = np.eye(4, dtype=complex); cu[np.ix_([1, 3], [1, 3])] = G.H()
+    assert [(o.kind, o.target, o.ctrls) for o in lower_op([2, 5], cu)] == [(L.OP_REAL, 2, (5,))]
+
+
+def test_rank_bit_controls_and_nonlocal_targets():
+    """n=8 state split over 4 shards (n_local=6): diagonal / control use of rank bits is free,
+    mixing a rank bit raises like the reference's local kernels do (cpu_scalar.py:13-18)."""
+    n, n_local = 8, 6
+    ops = [([0], G.H()), ([7], G.Z()), ([7, 2], G.CNOT()), ([6, 7], G.CZ()), ([1, 6], G.CR(3))]
+    for rank in range(4):
+        full = np.zeros(1 << n, dtype=np.complex128)
+        rng = np.random.default_rng(rank)
+        full[:] = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
+        want = full.copy()
+        O.apply_ops(want, ops)
+        prog = PassCompiler(n, n_local, tile_bits=5, low_bits=1).compile(ops)
+        shard = full[rank << n_local:(rank + 1) << n_local].copy()
+        run_program(prog, shard, rank=rank)
+        assert np.abs(shard - want[rank << n_local:(rank + 1) << n_local]).max() <= 1e-12
+    with pytest.raises(NotImplementedError, match="non-local"):
+        PassCompiler(n, n_local, tile_bits=5, low_bits=1).compile([([7], G.H())])
+
+
+def test_headline_plan_sizes():
+    """Planning the BASELINE.json circuits is cheap and collapses layers into few passes."""
+    prog = PassCompiler(28).compile(ir_ops(W.qft(28)))
+    assert prog.stats["passes"] <= 6          # 55 levels, 406 gates
+    prog = PassCompiler(30).compile(ir_ops(W.random_1q_cz(30, 20, 1234)))
+    assert prog.stats["passes"] <= 16         # 20 levels, 445 gates
