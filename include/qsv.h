@@ -115,23 +115,33 @@ int qsv_apply_kq(qsv_handle *h, int k, const int *qs, const double *U);
 #define QSV_REG_BITS       4
 #define QSV_MAX_ROUNDS    16
 
-/* op kinds */
-#define QSV_OP_MAT    0  /* general complex 2x2 on register bit `target`                 */
-#define QSV_OP_REAL   1  /* real 2x2 (m[0],m[2],m[4],m[6]) times scalar phase-free       */
-#define QSV_OP_PHASE  2  /* amp *= (m[0] + i m[1]) where all control bits are 1          */
-#define QSV_OP_SIGN   3  /* amp = -amp where all control bits are 1 (CZ, Z)              */
-#define QSV_OP_XPERM  4  /* swap the pair (X), no flops                                  */
-#define QSV_OP_HAD    5  /* (a+b, a-b) * m[0]                                            */
-#define QSV_OP_IPHASE 6  /* amp *= i^m_int where control bits are 1 (S, S^dagger)        */
+/* op kinds.  Every op is an IN-PLACE update of register-resident amplitudes (each arithmetic
+ * statement overwrites one of its own operands), which is what lets the kernel interpret a gate
+ * list without shuffling its 64 data registers.  The pass compiler lowers any 1-qubit unitary
+ * to these primitives (U = e^{ia} diag(1,e^{ip}) Ry diag(1,e^{il}), ZYZ).
+ * An op with a TARGET mixes the pairs (a, b) = (target bit 0, target bit 1); CONTROLS
+ * (reg_ctrl / tile_ctrl / glob_ctrl) restrict it to amplitudes whose named bits are all 1. */
+#define QSV_OP_HAD    0  /* (a, b) -> (a + b, a - b), UNNORMALISED (b <- a-b ; a <- 2a-b); the
+                            compiler emits the 1/sqrt2 factors as one SCALE per pass; no controls */
+#define QSV_OP_ROT    1  /* (a, b) -> (c a - s b, s a + c b), |theta| <= pi/2, as three shears
+                            a -= t b ; b += s a ; a -= t b with m[0] = t = tan(theta/2), m[1] = s */
+#define QSV_OP_XSWAP  2  /* X: (a, b) -> (b, a), no arithmetic                                */
+#define QSV_OP_YSWAP  3  /* Y: (a, b) -> (-i b, i a), no arithmetic                           */
+#define QSV_OP_PHASE  4  /* no target: amp *= e^{i phi}, |phi| <= pi/2, where all controls are 1;
+                            m[0] = tan(phi/2), m[1] = sin(phi), m[2] = cos(phi), m[3] = sin(phi) */
+#define QSV_OP_SIGN   5  /* no target: amp = -amp where all controls are 1 (Z, CZ)            */
+#define QSV_OP_SCALE  6  /* no target, no controls: amp *= m[0] (real)                        */
+#define QSV_OP_KINDS  7
 
 typedef struct {
-    int32_t  kind;         /* QSV_OP_*                                                   */
-    int32_t  target;       /* register-slot index 0..QSV_REG_BITS-1 (non-diagonal kinds) */
-    uint32_t reg_ctrl;     /* controls among register slots (bit b = slot b)             */
+    uint8_t  kind;         /* QSV_OP_*                                                   */
+    uint8_t  target;       /* register-slot index 0..QSV_REG_BITS-1 (kinds with a target) */
+    uint8_t  reg_ctrl;     /* controls among register slots (bit b = slot b)             */
+    uint8_t  flags;        /* dispatch code filled in by the library (callers pass 0)    */
     uint32_t tile_ctrl;    /* controls among thread-fixed tile positions (bit i = pos i) */
     uint64_t glob_ctrl;    /* controls among physical bits outside the tile (rank bits ok)*/
-    double   m[8];         /* coefficients, meaning depends on kind                      */
-} qsv_op;
+    double   m[4];         /* coefficients, meaning depends on kind                      */
+} qsv_op;                  /* 48 bytes, 16-byte aligned records                          */
 
 typedef struct {
     uint8_t  reg_pos[QSV_REG_BITS];        /* tile positions held in registers, ascending */

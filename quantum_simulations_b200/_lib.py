@@ -14,12 +14,13 @@ LIB_PATH = _CSRC / "libqsv.so"
 QSV_C64, QSV_C128 = 0, 1
 QSV_OK, QSV_EINVAL, QSV_ENONLOCAL, QSV_ECUDA, QSV_ENOMEM, QSV_ECOMM, QSV_EIO = 0, -1, -2, -3, -4, -5, -6
 QSV_MAX_TILE_BITS, QSV_REG_BITS, QSV_MAX_ROUNDS = 14, 4, 16
-OP_MAT, OP_REAL, OP_PHASE, OP_SIGN, OP_XPERM, OP_HAD, OP_IPHASE = range(7)
+OP_HAD, OP_ROT, OP_XSWAP, OP_YSWAP, OP_PHASE, OP_SIGN, OP_SCALE = range(7)
+OP_WITH_TARGET = (OP_HAD, OP_ROT, OP_XSWAP, OP_YSWAP)
 
 
 class QsvOp(C.Structure):
-    _fields_ = [("kind", C.c_int32), ("target", C.c_int32), ("reg_ctrl", C.c_uint32),
-                ("tile_ctrl", C.c_uint32), ("glob_ctrl", C.c_uint64), ("m", C.c_double * 8)]
+    _fields_ = [("kind", C.c_uint8), ("target", C.c_uint8), ("reg_ctrl", C.c_uint8), ("flags", C.c_uint8),
+                ("tile_ctrl", C.c_uint32), ("glob_ctrl", C.c_uint64), ("m", C.c_double * 4)]
 
 
 class QsvRound(C.Structure):

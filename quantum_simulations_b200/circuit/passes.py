@@ -33,6 +33,7 @@ import numpy as np
 from quantum_simulations_b200 import _lib as L
 
 REG_BITS = L.QSV_REG_BITS
+RING_TILE_BITS = 11
 _ONE = 1.0 + 0.0j
 _Z8 = (0.0,) * 8
 
@@ -43,7 +44,7 @@ class MicroOp:
     kind: int
     target: int | None                 # content that is mixed (None: purely diagonal)
     ctrls: tuple[int, ...]             # contents that must be 1 for the op to act
-    m: tuple[float, ...] = _Z8         # coefficients (see qsv.h)
+    m: tuple[float, ...] = (0.0,) * 4  # coefficients (see qsv.h)
     src: int = -1                      # IR op index it came from
     seq: int = -1                      # position in the lowered stream (stable order key)
 
@@ -57,31 +58,101 @@ class Dense2Q:
     src: int = -1
 
 
-def _flat(u) -> tuple[float, ...]:
-    out: list[float] = []
-    for z in np.asarray(u, dtype=np.complex128).ravel():
-        out += [float(z.real), float(z.imag)]
-    return tuple(out)
+@dataclass
+class Dense1Q:
+    """1-qubit op that is not unitary (cannot be written with the in-place primitives)."""
+    q: int
+    U: np.ndarray
+    ctrl: int | None = None
+    src: int = -1
+
+
+_Z4 = (0.0,) * 4
+_H_EXACT = np.array([[1, 1], [1, -1]], dtype=np.complex128) * (1.0 / np.sqrt(2.0))
+_X_EXACT = np.array([[0, 1], [1, 0]], dtype=np.complex128)
+_Y_EXACT = np.array([[0, -1j], [1j, 0]], dtype=np.complex128)
+INV_SQRT2 = 1.0 / np.sqrt(2.0)
+_UNITARY_TOL = 1e-13
+
+
+_SNAP = 4e-16      # phases within a couple of ulp of 1, -1, i, -i are snapped to them
 
 
 def _phase(d: complex, ctrls: tuple[int, ...], src: int) -> list[MicroOp]:
+    """amp *= d (|d| = 1) where all ctrls are 1 -> optional SIGN + PHASE with |phi| <= pi/2."""
+    d = complex(d)
+    if abs(d.imag) <= _SNAP:
+        d = complex(1.0 if d.real > 0 else -1.0, 0.0)
+    elif abs(d.real) <= _SNAP:
+        d = complex(0.0, 1.0 if d.imag > 0 else -1.0)
     if d == _ONE:
         return []
-    if d == -_ONE and ctrls:
-        return [MicroOp(L.OP_SIGN, None, ctrls, _Z8, src)]
-    return [MicroOp(L.OP_PHASE, None, ctrls, (float(d.real), float(d.imag)) + (0.0,) * 6, src)]
+    out: list[MicroOp] = []
+    if d.real < 0:                      # e^{i phi} = -e^{i (phi -+ pi)}
+        out.append(MicroOp(L.OP_SIGN, None, ctrls, _Z4, src))
+        d = -d
+        if d == _ONE:
+            return out
+    c, sn = d.real, d.imag              # c >= 0 : phi in [-pi/2, pi/2]
+    norm = np.hypot(c, sn)
+    c, sn = c / norm, sn / norm
+    t = sn / (1.0 + c)                  # tan(phi/2), |t| <= 1
+    out.append(MicroOp(L.OP_PHASE, None, ctrls, (float(t), float(sn), float(c), float(sn)), src))
+    return out
 
 
-def lower_1q(u, q: int, ctrls: tuple[int, ...] = (), src: int = -1) -> list[MicroOp]:
-    """2x2 `u` on content q, active where all `ctrls` are 1."""
+def _rot(c: float, sn: float, q: int, ctrls: tuple[int, ...], src: int) -> list[MicroOp]:
+    """(a, b) -> (c a - sn b, sn a + c b) with c >= 0 (|theta| <= pi/2)."""
+    if sn == 0.0:
+        return []
+    t = sn / (1.0 + c)
+    return [MicroOp(L.OP_ROT, q, ctrls, (float(t), float(sn), float(c), 0.0), src)]
+
+
+def lower_1q(u, q: int, ctrls: tuple[int, ...] = (), src: int = -1) -> list:
+    """2x2 unitary `u` on content q, active where all `ctrls` are 1, as in-place primitives."""
     u = np.asarray(u, dtype=np.complex128)
     if u[0, 1] == 0 and u[1, 0] == 0:                       # diagonal
         d0, d1 = complex(u[0, 0]), complex(u[1, 1])
+        if abs(abs(d0) - 1) > _UNITARY_TOL or abs(abs(d1) - 1) > _UNITARY_TOL:
+            return [Dense1Q(q, u, ctrls[0] if ctrls else None, src)] if len(ctrls) <= 1 else _not_lowerable()
         rel = d1 if d0 == _ONE else d1 / d0
         return _phase(d0, ctrls, src) + _phase(rel, ctrls + (q,), src)
-    if not np.any(u.imag):
-        return [MicroOp(L.OP_REAL, q, ctrls, _flat(u), src)]
-    return [MicroOp(L.OP_MAT, q, ctrls, _flat(u), src)]
+    if np.array_equal(u, _X_EXACT):
+        return [MicroOp(L.OP_XSWAP, q, ctrls, _Z4, src)]
+    if np.array_equal(u, _Y_EXACT):
+        return [MicroOp(L.OP_YSWAP, q, ctrls, _Z4, src)]
+    if not ctrls and np.array_equal(u, _H_EXACT):
+        # unnormalised butterfly; the 1/sqrt2 becomes part of the pass's single SCALE op
+        return [MicroOp(L.OP_HAD, q, (), _Z4, src),
+                MicroOp(L.OP_SCALE, None, (), (INV_SQRT2, 0.0, 0.0, 0.0), src)]
+    if np.abs(u.conj().T @ u - np.eye(2)).max() > _UNITARY_TOL:
+        if len(ctrls) <= 1:
+            return [Dense1Q(q, u, ctrls[0] if ctrls else None, src)]
+        return _not_lowerable()
+    if u[0, 0] == 0 and u[1, 1] == 0:                       # anti-diagonal: X then a diagonal
+        return [MicroOp(L.OP_XSWAP, q, ctrls, _Z4, src)] + lower_1q(
+            np.array([[u[0, 1], 0], [0, u[1, 0]]]), q, ctrls, src)
+    # ZYZ: u = e^{ia} diag(1, e^{ip}) [[c, -S], [S, c]] diag(1, e^{il}),  c = |u00| > 0, S real
+    a = u[0, 0] / abs(u[0, 0])                              # e^{ia}
+    c = float(abs(u[0, 0]))
+    w10 = u[1, 0] / a                                       # = e^{ip} S
+    w01 = -u[0, 1] / a                                      # = e^{il} S
+    S = float(abs(w10))
+    ep = w10 / S
+    if ep.real < 0:                                         # keep |p| <= pi/2 by signing S
+        ep, S = -ep, -S
+    el = w01 / S
+    norm = np.hypot(c, S)
+    ops = _phase(complex(el), ctrls + (q,), src)
+    ops += _rot(c / norm, S / norm, q, ctrls, src)
+    ops += _phase(complex(ep), ctrls + (q,), src)
+    ops += _phase(complex(a), ctrls, src)
+    return ops
+
+
+def _not_lowerable():
+    raise NotImplementedError("non-unitary multi-controlled block cannot be lowered to pass ops")
 
 
 _SWAP = np.eye(4)[[0, 2, 1, 3]]
@@ -89,8 +160,8 @@ _I2, _O2 = np.eye(2), np.zeros((2, 2))
 
 
 def lower_op(qubits, U, src: int = -1) -> list:
-    """One step-IR op -> micro-ops | ('swap', a, b) | Dense2Q.  Structure is detected on exact
-    zeros/ones, which gate constructors and products of structured matrices preserve."""
+    """One step-IR op -> micro-ops | ('swap', a, b) | Dense1Q | Dense2Q.  Structure is detected
+    on exact zeros/ones, which gate constructors and products of structured matrices preserve."""
     U = np.asarray(U, dtype=np.complex128)
     if len(qubits) == 1:
         return lower_1q(U, qubits[0], (), src)
@@ -101,6 +172,8 @@ def lower_op(qubits, U, src: int = -1) -> list:
         return [("swap", qa, qb)]
     if not np.any(U - np.diag(np.diag(U))):
         d = [complex(x) for x in np.diag(U)]                 # index = 2*bit(qa) + bit(qb)
+        if max(abs(abs(x) - 1) for x in d) > _UNITARY_TOL:
+            return [Dense2Q(qa, qb, U, src)]
         s = d[0]
         pb = d[1] if s == _ONE else d[1] / s
         pa = d[2] if s == _ONE else d[2] / s
@@ -108,10 +181,12 @@ def lower_op(qubits, U, src: int = -1) -> list:
         return (_phase(s, (), src) + _phase(pb, (qb,), src) + _phase(pa, (qa,), src)
                 + _phase(pab, (qa, qb), src))
     if np.array_equal(U[:2, :2], _I2) and np.array_equal(U[:2, 2:], _O2) and np.array_equal(U[2:, :2], _O2):
-        return lower_1q(U[2:, 2:], qb, (qa,), src)           # control = qubits[0]
+        low = lower_1q(U[2:, 2:], qb, (qa,), src)            # control = qubits[0]
+        return [Dense2Q(qa, qb, U, src)] if any(isinstance(x, Dense1Q) for x in low) else low
     ev, od = [0, 2], [1, 3]
     if np.array_equal(U[np.ix_(ev, ev)], _I2) and not np.any(U[np.ix_(ev, od)]) and not np.any(U[np.ix_(od, ev)]):
-        return lower_1q(U[np.ix_(od, od)], qa, (qb,), src)   # control = qubits[1]
+        low = lower_1q(U[np.ix_(od, od)], qa, (qb,), src)    # control = qubits[1]
+        return [Dense2Q(qa, qb, U, src)] if any(isinstance(x, Dense1Q) for x in low) else low
     return [Dense2Q(qa, qb, U, src)]
 
 
@@ -129,6 +204,13 @@ class PassStep:
 class Dense2QStep:
     qa_pos: int
     qb_pos: int
+    U: np.ndarray
+    src_ops: set
+
+
+@dataclass
+class Dense1QStep:
+    q_pos: int
     U: np.ndarray
     src_ops: set
 
@@ -176,15 +258,21 @@ class PassCompiler:
 
     def __init__(self, n_qubits: int, n_local: int | None = None, dtype: str = "complex128",
                  tile_bits: int | None = None, low_bits: int | None = None,
-                 max_rounds: int = 6, restore_layout: bool = True, lookahead: int = 4096):
+                 max_rounds: int = 6, restore_layout: bool = True, lookahead: int = 4096,
+                 ring: bool | None = None, max_ops: int = 380):
         self.n = n_qubits
         self.n_local = n_qubits if n_local is None else n_local
         self.dtype = np.dtype(dtype).name
         if self.dtype not in ("complex64", "complex128"):
             raise ValueError(f"unsupported dtype {dtype}")
         max_t = 12 if self.dtype == "complex128" else 13
+        # default tile: 2^11 complex128 (32 KB) = what the persistent ring kernel stages
+        default_t = RING_TILE_BITS if self.dtype == "complex128" else max_t
         self.W = 3 if self.dtype == "complex128" else 4      # log2(128 B / sizeof(amp))
-        self.t = min(tile_bits or max_t, max_t, self.n_local)
+        self.t = min(tile_bits or default_t, max_t, self.n_local)
+        # the ring kernel (pass_ring.cuh) fills shared memory through cp.async in the swizzled
+        # layout, so its FIRST round may hold any tile position in registers
+        self.ring = (self.dtype == "complex128" and self.t == RING_TILE_BITS) if ring is None else ring
         if self.t < REG_BITS:
             raise ValueError(f"pass kernel needs n_local >= {REG_BITS} (got {self.n_local})")
         a = 5 if low_bits is None else low_bits
@@ -193,6 +281,7 @@ class PassCompiler:
         self.max_rounds = max(2, min(max_rounds, L.QSV_MAX_ROUNDS - 2))
         self.restore_layout = restore_layout
         self.lookahead = lookahead
+        self.max_ops = max_ops          # ops of one pass live in shared memory (kRingMaxOps = 400)
 
     # ---- public -----------------------------------------------------------------------
     def compile(self, ir_ops, init_pos=None) -> Program:
@@ -205,7 +294,7 @@ class PassCompiler:
                 if isinstance(item, tuple):         # swap: rename, no data movement
                     qa, qb = list(qs)
                     alias[qa], alias[qb] = alias[qb], alias[qa]
-                elif isinstance(item, Dense2Q):
+                elif isinstance(item, (Dense2Q, Dense1Q)):
                     segments.append(item)
                     segments.append([])
                 else:
@@ -217,9 +306,14 @@ class PassCompiler:
         for q in range(n):
             home[alias[q]] = q if init_pos is None else init_pos[q]
         prog = Program(n, self.n_local, self.dtype)
-        live = [s for s in segments if isinstance(s, Dense2Q) or s]
+        live = [s for s in segments if isinstance(s, (Dense2Q, Dense1Q)) or s]
         for k, seg in enumerate(live):
-            if isinstance(seg, Dense2Q):
+            if isinstance(seg, Dense1Q):
+                if pos[seg.q] >= self.n_local:
+                    raise NotImplementedError(
+                        f"non-local gate: content {seg.q} sits on rank bit {pos[seg.q]}")
+                prog.steps.append(Dense1QStep(pos[seg.q], seg.U, {seg.src}))
+            elif isinstance(seg, Dense2Q):
                 for c in (seg.qa, seg.qb):
                     if pos[c] >= self.n_local:
                         raise NotImplementedError(
@@ -232,7 +326,8 @@ class PassCompiler:
         prog.final_pos = [pos[alias[q]] for q in range(n)]
         ps = prog.passes
         prog.stats = {
-            "passes": len(ps), "dense2q_steps": len(prog.steps) - len(ps),
+            "passes": len(ps), "dense2q_steps": sum(isinstance(x, Dense2QStep) for x in prog.steps),
+            "dense1q_steps": sum(isinstance(x, Dense1QStep) for x in prog.steps),
             "micro_ops": sum(s.n_micro_ops for s in ps),
             "rounds": sum(s.desc.n_rounds for s in ps),
             "max_rounds_in_pass": max((s.desc.n_rounds for s in ps), default=0),
@@ -313,7 +408,8 @@ class PassCompiler:
         with rounds = [(reg_contents, ops)]; ops beyond max_rounds are deferred to a later pass."""
         pend = list(chosen)
         rounds = []
-        while pend and len(rounds) < self.max_rounds:
+        total = 0
+        while pend and len(rounds) < self.max_rounds and total < self.max_ops:
             regs: list = []
             while len(regs) < REG_BITS:
                 _, missing = _scan(pend, set(regs))
@@ -321,8 +417,10 @@ class PassCompiler:
                     break
                 regs.append(pend[missing[0]].target)
             run, _ = _scan(pend, set(regs))
+            run = run[: self.max_ops - total]          # a prefix is still dependency-closed
             if not run:
                 break
+            total += len(run)
             rs = set(run)
             rounds.append((regs, [pend[i] for i in run]))
             pend = [op for i, op in enumerate(pend) if i not in rs]
@@ -351,8 +449,8 @@ class PassCompiler:
                     regs.append(i)
             plan.append((regs, rops))
         if not plan:
-            plan.append((self._idle_regs(lo_load | lo_store), []))
-        if set(plan[0][0]) & lo_load:
+            plan.append((self._idle_regs(lo_store if self.ring else lo_load | lo_store), []))
+        if set(plan[0][0]) & lo_load and not self.ring:
             plan.insert(0, (self._idle_regs(lo_load), []))
         if set(plan[-1][0]) & lo_store:
             plan.append((self._idle_regs(lo_store), []))
@@ -362,7 +460,7 @@ class PassCompiler:
             free = [i for i in range(t) if i not in plan[0][0]]
             by_load = sorted(free, key=lambda i: load_bits[i])[:W]
             by_store = sorted(free, key=lambda i: store[i])[:W]
-            if by_load != by_store:
+            if by_load != by_store and not self.ring:
                 plan.append((self._idle_regs(lo_store), []))
         if len(plan) > L.QSV_MAX_ROUNDS:
             raise RuntimeError("too many rounds in one pass")
@@ -375,6 +473,8 @@ class PassCompiler:
         desc.n_rounds = len(plan)
         flat: list = []
         srcs: set = set()
+        g_scale = 1.0                 # product of SCALE micro-ops (1/sqrt2 per Hadamard)
+        g_phase = _ONE                # product of uncontrolled PHASE / SIGN micro-ops
         for r, (regs, rops) in enumerate(plan):
             rd = desc.rounds[r]
             slot_of = {}
@@ -382,18 +482,37 @@ class PassCompiler:
                 rd.reg_pos[b] = i
                 slot_of[content[i]] = b
             free = [i for i in range(t) if i not in regs]
-            if r == 0:
-                thr = sorted(free, key=lambda i: load_bits[i])
-            elif r == len(plan) - 1:
+            if r == len(plan) - 1:
                 thr = sorted(free, key=lambda i: store[i])
+            elif r == 0 and not self.ring:
+                thr = sorted(free, key=lambda i: load_bits[i])
             else:
                 thr = self._bank_friendly(free)
             for k, i in enumerate(thr):
                 rd.thr_pos[k] = i
             rd.op_begin = len(flat)
             for op in rops:
-                flat.append(self._encode(op, slot_of, idx_of, pos))
                 srcs.add(op.src)
+                if op.kind == L.OP_SCALE:                    # global scalars are not executed
+                    g_scale *= op.m[0]                       # where they occur: they commute
+                    continue                                 # with everything
+                if not op.ctrls and op.kind == L.OP_SIGN:
+                    g_phase = -g_phase
+                    continue
+                if not op.ctrls and op.kind == L.OP_PHASE:
+                    g_phase *= complex(op.m[2], op.m[3])
+                    continue
+                flat.append(self._encode(op, slot_of, idx_of, pos))
+            if r == len(plan) - 1:
+                if g_phase != _ONE:
+                    g_phase /= abs(g_phase)
+                    for gop in _phase(complex(g_phase), (), -1):
+                        flat.append(self._encode(gop, slot_of, idx_of, pos))
+                if g_scale != 1.0:
+                    sc = L.QsvOp()
+                    sc.kind = L.OP_SCALE
+                    sc.m[0] = g_scale
+                    flat.append(sc)
             rd.op_end = len(flat)
         desc.n_ops = len(flat)
         arr = (L.QsvOp * max(len(flat), 1))(*flat)
@@ -488,7 +607,7 @@ class PassCompiler:
             else:
                 glob |= 1 << pos[c]
         o.reg_ctrl, o.tile_ctrl, o.glob_ctrl = reg_ctrl, tile_ctrl, glob
-        for k in range(8):
+        for k in range(4):
             o.m[k] = op.m[k]
         return o
 

@@ -51,6 +51,8 @@ struct qsv_program {
 
 struct qsv_handle {
     int n_qubits = 0, n_local = 0, dtype = QSV_C128, device = 0, rank = 0, world = 1;
+    int sm_count = 148;
+    bool force_simple_pass = false;   // tests: run every pass on the one-CTA-per-tile kernel
     size_t n_amps = 0;            // local amplitudes
     size_t amp_bytes = 16;
     void *d_state = nullptr;

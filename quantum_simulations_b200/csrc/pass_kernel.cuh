@@ -22,81 +22,10 @@
 // HBM traffic is exactly 2 * sizeof(amp) * 2^n per pass, whatever the number of gates.
 #pragma once
 #include "common.cuh"
-
-constexpr int kRegBits = QSV_REG_BITS;          // 4
-constexpr int kRegAmps = 1 << kRegBits;         // 16 amplitudes per thread
-
-// GF(2)-linear swizzle of a tile index: fold every W-bit group above the lowest into the
-// lowest W bits (W = log2(128 B / sizeof(amp)): 3 for complex128, 4 for complex64).
-template <int W> __host__ __device__ __forceinline__ uint32_t tile_swizzle(uint32_t x) {
-    constexpr uint32_t M = (1u << W) - 1u;
-    uint32_t f = x;
-#pragma unroll
-    for (int s = W; s < 16; s += W) f ^= (x >> s) & M;
-    return f;
-}
-
-template <typename V> __device__ __forceinline__ V cx_neg(V a) { a.x = -a.x; a.y = -a.y; return a; }
-
-// ---- op bodies: everything is unrolled over the 16 register slots ----------------------
-// general complex 2x2 on register slot TB
-template <typename V, int TB>
-__device__ __forceinline__ void op_mat(V (&v)[kRegAmps], const V u00, const V u01, const V u10,
-                                       const V u11, const uint32_t rc) {
-#pragma unroll
-    for (int j = 0; j < kRegAmps; ++j) {
-        if (j & (1 << TB)) continue;
-        if ((j & rc) != rc) continue;              // rc is warp-uniform: no divergence
-        const V a = v[j], b = v[j | (1 << TB)];
-        v[j] = cx_fma(u01, b, cx_mul(u00, a));
-        v[j | (1 << TB)] = cx_fma(u11, b, cx_mul(u10, a));
-    }
-}
-
-// real 2x2 on register slot TB: half the flops of op_mat
-template <typename V, typename R, int TB>
-__device__ __forceinline__ void op_real(V (&v)[kRegAmps], const R m00, const R m01, const R m10,
-                                        const R m11, const uint32_t rc) {
-#pragma unroll
-    for (int j = 0; j < kRegAmps; ++j) {
-        if (j & (1 << TB)) continue;
-        if ((j & rc) != rc) continue;
-        const V a = v[j], b = v[j | (1 << TB)];
-        v[j].x = fma(m01, b.x, m00 * a.x);
-        v[j].y = fma(m01, b.y, m00 * a.y);
-        v[j | (1 << TB)].x = fma(m11, b.x, m10 * a.x);
-        v[j | (1 << TB)].y = fma(m11, b.y, m10 * a.y);
-    }
-}
-
-template <typename V>
-__device__ __forceinline__ void op_phase(V (&v)[kRegAmps], const V ph, const uint32_t rc) {
-#pragma unroll
-    for (int j = 0; j < kRegAmps; ++j) {
-        if ((j & rc) != rc) continue;
-        v[j] = cx_mul(ph, v[j]);
-    }
-}
-
-template <typename V>
-__device__ __forceinline__ void op_sign(V (&v)[kRegAmps], const uint32_t rc) {
-#pragma unroll
-    for (int j = 0; j < kRegAmps; ++j) {
-        if ((j & rc) != rc) continue;
-        v[j] = cx_neg(v[j]);
-    }
-}
-
-#define QSV_DISPATCH_TB(CALL)                                   \
-    switch (tb) {                                               \
-        case 0: { constexpr int TB = 0; CALL; } break;          \
-        case 1: { constexpr int TB = 1; CALL; } break;          \
-        case 2: { constexpr int TB = 2; CALL; } break;          \
-        default: { constexpr int TB = 3; CALL; } break;         \
-    }
+#include "pass_ops.cuh"
 
 template <typename R>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(sizeof(R) == 8 ? 256 : 512, sizeof(R) == 8 ? 2 : 1)
 k_pass(typename CxT<R>::V *__restrict__ state, const qsv_pass *__restrict__ pass_ptr,
        const qsv_op *__restrict__ ops, const uint64_t rank_bits) {
     using V = typename CxT<R>::V;
@@ -162,26 +91,7 @@ k_pass(typename CxT<R>::V *__restrict__ state, const qsv_pass *__restrict__ pass
             const qsv_op &op = ops[o];
             if ((glob & op.glob_ctrl) != op.glob_ctrl) continue;        // CTA-uniform
             if ((xb & op.tile_ctrl) != op.tile_ctrl) continue;          // per thread
-            const uint32_t rc = op.reg_ctrl;
-            const int tb = op.target;
-            switch (op.kind) {
-                case QSV_OP_MAT: {
-                    const V u00 = cx_make<V>((R)op.m[0], (R)op.m[1]), u01 = cx_make<V>((R)op.m[2], (R)op.m[3]);
-                    const V u10 = cx_make<V>((R)op.m[4], (R)op.m[5]), u11 = cx_make<V>((R)op.m[6], (R)op.m[7]);
-                    QSV_DISPATCH_TB((op_mat<V, TB>(v, u00, u01, u10, u11, rc)));
-                } break;
-                case QSV_OP_REAL: {
-                    const R m00 = (R)op.m[0], m01 = (R)op.m[2], m10 = (R)op.m[4], m11 = (R)op.m[6];
-                    QSV_DISPATCH_TB((op_real<V, R, TB>(v, m00, m01, m10, m11, rc)));
-                } break;
-                case QSV_OP_PHASE:
-                    op_phase<V>(v, cx_make<V>((R)op.m[0], (R)op.m[1]), rc);
-                    break;
-                case QSV_OP_SIGN:
-                    op_sign<V>(v, rc);
-                    break;
-                default: break;
-            }
+            apply_reg_op<V, R>(v, op.kind, op.target, op.reg_ctrl, op.m);
         }
 
         if (r == n_rounds - 1) {

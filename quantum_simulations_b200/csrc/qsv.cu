@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "gate_kernels.cuh"
 #include "pass_kernel.cuh"
+#include "pass_ring.cuh"
 #include "exchange.cuh"
 
 static thread_local std::string g_create_error;
@@ -100,6 +101,7 @@ int qsv_create(qsv_handle **out, int n_qubits, int dtype, int device, int rank, 
     h->n_amps = (size_t)1 << h->n_local;
     h->amp_bytes = dtype == QSV_C128 ? 16 : 8;
     cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&h->d_state, h->n_amps * h->amp_bytes);
     if (e == cudaSuccess) { h->n_partials = kNormBlocks + 8; e = cudaMalloc(&h->d_partials, h->n_partials * sizeof(double)); }
@@ -374,11 +376,14 @@ static int validate_pass(qsv_handle *h, const qsv_pass *p, const qsv_op *ops) {
         if (rd.op_begin < 0 || rd.op_end < rd.op_begin || rd.op_end > p->n_ops) QSV_FAIL(h, QSV_EINVAL, "pass: round %d op slice", r);
         for (int o = rd.op_begin; o < rd.op_end; ++o) {
             const qsv_op &op = ops[o];
-            if (op.kind < 0 || op.kind > QSV_OP_IPHASE) QSV_FAIL(h, QSV_EINVAL, "pass: op %d bad kind %d", o, op.kind);
-            const bool has_target = op.kind == QSV_OP_MAT || op.kind == QSV_OP_REAL || op.kind == QSV_OP_XPERM || op.kind == QSV_OP_HAD;
-            if (has_target && (op.target < 0 || op.target >= QSV_REG_BITS)) QSV_FAIL(h, QSV_EINVAL, "pass: op %d target", o);
-            if (op.reg_ctrl >> QSV_REG_BITS) QSV_FAIL(h, QSV_EINVAL, "pass: op %d reg_ctrl", o);
-            if (has_target && ((op.reg_ctrl >> op.target) & 1)) QSV_FAIL(h, QSV_EINVAL, "pass: op %d controls its own target", o);
+            if (op.kind >= QSV_OP_KINDS) QSV_FAIL(h, QSV_EINVAL, "pass: op %d bad kind %d", o, (int)op.kind);
+            const bool has_target = op.kind == QSV_OP_HAD || op.kind == QSV_OP_ROT || op.kind == QSV_OP_XSWAP ||
+                                    op.kind == QSV_OP_YSWAP;
+            if (has_target && op.target >= QSV_REG_BITS) QSV_FAIL(h, QSV_EINVAL, "pass: op %d target", o);
+            const bool any_ctrl = op.reg_ctrl || op.tile_ctrl || op.glob_ctrl;
+            if ((op.kind == QSV_OP_HAD || op.kind == QSV_OP_SCALE) && any_ctrl) QSV_FAIL(h, QSV_EINVAL, "pass: op %d: HAD/SCALE cannot be controlled", o);
+            if ((op.kind == QSV_OP_ROT || op.kind == QSV_OP_PHASE) && (!(op.m[0] >= -1.0000001 && op.m[0] <= 1.0000001)))
+                QSV_FAIL(h, QSV_EINVAL, "pass: op %d: |tan(angle/2)| must be <= 1 (split larger angles)", o);
             if ((op.tile_ctrl >> T) || (op.tile_ctrl & regm)) QSV_FAIL(h, QSV_EINVAL, "pass: op %d tile_ctrl names a register position", o);
             if (op.glob_ctrl & tile_mask) QSV_FAIL(h, QSV_EINVAL, "pass: op %d glob_ctrl names a tile bit", o);
             if (h->n_qubits < 64 && (op.glob_ctrl >> h->n_qubits)) QSV_FAIL(h, QSV_EINVAL, "pass: op %d glob_ctrl out of range", o);
@@ -389,11 +394,21 @@ static int validate_pass(qsv_handle *h, const qsv_pass *p, const qsv_op *ops) {
 
 static int launch_pass(qsv_handle *h, const qsv_pass *host_pass, const qsv_pass *dev_pass, const qsv_op *dev_ops, int pass_index) {
     const int T = host_pass->n_tile;
+    const uint64_t rank_bits = (uint64_t)h->rank << h->n_local;
+    ScopedTimer t(h, 10, pass_index);
+    if (h->dtype == QSV_C128 && T == kRingT && host_pass->n_ops <= kRingMaxOps && !h->force_simple_pass) {
+        // persistent ring kernel: one CTA per SM, tiles streamed through shared memory
+        const uint32_t n_tiles = (uint32_t)(h->n_amps >> T);
+        const unsigned grid = n_tiles < (uint32_t)h->sm_count ? n_tiles : (unsigned)h->sm_count;
+        const size_t smem = sizeof(RingSmem);
+        QSV_CUDA(h, cudaFuncSetAttribute(k_pass_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_pass_ring<<<grid, kRingThreads, smem, h->stream>>>((double2 *)h->d_state, dev_pass, dev_ops, rank_bits, n_tiles);
+        QSV_CUDA(h, cudaGetLastError());
+        return QSV_OK;
+    }
     const unsigned blocks = (unsigned)(h->n_amps >> T);
     const unsigned threads = 1u << (T - QSV_REG_BITS);
     const size_t smem = host_pass->n_rounds > 1 ? (h->amp_bytes << T) : 0;
-    const uint64_t rank_bits = (uint64_t)h->rank << h->n_local;
-    ScopedTimer t(h, 10, pass_index);
     if (h->dtype == QSV_C128) {
         QSV_CUDA(h, cudaFuncSetAttribute(k_pass<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
         k_pass<double><<<blocks, threads, smem, h->stream>>>((double2 *)h->d_state, dev_pass, dev_ops, rank_bits);

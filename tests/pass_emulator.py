@@ -8,7 +8,7 @@ from __future__ import annotations
 import numpy as np
 
 from quantum_simulations_b200 import _lib as L
-from quantum_simulations_b200.circuit.passes import PassStep, Dense2QStep, Program
+from quantum_simulations_b200.circuit.passes import PassStep, Dense2QStep, Dense1QStep, Program
 from oracle import ref_dense as O
 
 R = L.QSV_REG_BITS
@@ -53,25 +53,47 @@ def run_pass(psi: np.ndarray, desc: L.QsvPass, ops, n_local: int, rank: int = 0)
             rows = (glob & op.glob_ctrl) == op.glob_ctrl
             need = op.tile_ctrl | sum(1 << regs[b] for b in range(R) if (op.reg_ctrl >> b) & 1)
             cols = (x & need) == need
-            m = [op.m[k] for k in range(8)]
-            if op.kind in (L.OP_MAT, L.OP_REAL):
+            m = [op.m[k] for k in range(4)]
+            ctrl_any = bool(op.reg_ctrl or op.tile_ctrl or op.glob_ctrl)
+            if op.kind in L.OP_WITH_TARGET:
                 assert 0 <= op.target < R and not ((op.reg_ctrl >> op.target) & 1)
                 tb = 1 << regs[op.target]
                 x0 = x[cols & ((x & tb) == 0)]
                 a = work[np.ix_(rows, x0)]
                 b = work[np.ix_(rows, x0 | tb)]
-                if op.kind == L.OP_MAT:
-                    u = [complex(m[0], m[1]), complex(m[2], m[3]), complex(m[4], m[5]), complex(m[6], m[7])]
-                else:
-                    u = [m[0], m[2], m[4], m[6]]
-                work[np.ix_(rows, x0)] = u[0] * a + u[1] * b
-                work[np.ix_(rows, x0 | tb)] = u[2] * a + u[3] * b
+                if op.kind == L.OP_HAD:
+                    assert not ctrl_any, "HAD cannot be controlled"
+                    nb = a - b                     # the kernel's two in-place steps
+                    na = 2.0 * a - nb
+                elif op.kind == L.OP_ROT:
+                    t_, s_ = m[0], m[1]
+                    assert abs(t_) <= 1 + 1e-12 and abs(s_) <= 1 + 1e-12
+                    na = a - t_ * b
+                    nb = b + s_ * na
+                    na = na - t_ * nb
+                elif op.kind == L.OP_XSWAP:
+                    na, nb = b, a
+                else:                               # YSWAP: (a, b) -> (-i b, i a)
+                    na, nb = -1j * b, 1j * a
+                work[np.ix_(rows, x0)] = na
+                work[np.ix_(rows, x0 | tb)] = nb
             elif op.kind == L.OP_PHASE:
+                t_, s_ = m[0], m[1]
+                assert abs(t_) <= 1 + 1e-12 and abs(m[2] ** 2 + m[3] ** 2 - 1) < 1e-12 and m[2] >= 0
+                assert abs(s_ - m[3]) < 1e-15 and abs(t_ - m[3] / (1 + m[2])) < 1e-14
                 xs = x[cols]
-                work[np.ix_(rows, xs)] = work[np.ix_(rows, xs)] * complex(m[0], m[1])
+                w = work[np.ix_(rows, xs)]
+                re, im = w.real.copy(), w.imag.copy()
+                re = re - t_ * im                   # rotation of (re, im) by three shears
+                im = im + s_ * re
+                re = re - t_ * im
+                work[np.ix_(rows, xs)] = re + 1j * im
             elif op.kind == L.OP_SIGN:
                 xs = x[cols]
                 work[np.ix_(rows, xs)] = -work[np.ix_(rows, xs)]
+            elif op.kind == L.OP_SCALE:
+                assert not ctrl_any
+                work *= m[0]
             else:
                 raise AssertionError(f"emulator: unsupported op kind {op.kind}")
     psi[base[:, None] + off_s[None, :]] = work
@@ -83,6 +105,8 @@ def run_program(prog: Program, psi: np.ndarray, rank: int = 0) -> np.ndarray:
             run_pass(psi, step.desc, step.ops, prog.n_local, rank)
         elif isinstance(step, Dense2QStep):
             O.apply_2q(psi, step.qa_pos, step.qb_pos, step.U)
+        elif isinstance(step, Dense1QStep):
+            O.apply_1q(psi, step.q_pos, step.U)
         else:
             raise AssertionError(type(step))
     return psi

@@ -40,14 +40,14 @@ def test_constants_match_header():
     assert (L.QSV_C64, L.QSV_C128) == (const("QSV_C64"), const("QSV_C128"))
     assert L.QSV_MAX_TILE_BITS == const("QSV_MAX_TILE_BITS")
     assert L.QSV_REG_BITS == const("QSV_REG_BITS") and L.QSV_MAX_ROUNDS == const("QSV_MAX_ROUNDS")
-    for k in ("MAT", "REAL", "PHASE", "SIGN", "XPERM", "HAD", "IPHASE"):
+    for k in ("HAD", "ROT", "XSWAP", "YSWAP", "PHASE", "SIGN", "SCALE"):
         assert getattr(L, f"OP_{k}") == const(f"QSV_OP_{k}")
     for k in ("EINVAL", "ENONLOCAL", "ECUDA", "ENOMEM", "ECOMM", "EIO"):
         assert getattr(L, f"QSV_{k}") == const(f"QSV_{k}")
 
 
 def test_struct_layouts():
-    assert C.sizeof(L.QsvOp) == 4 + 4 + 4 + 4 + 8 + 64
+    assert C.sizeof(L.QsvOp) == 4 + 4 + 8 + 32
     assert C.sizeof(L.QsvRound) == 4 + 14 + 2 + 8          # uint8[4], uint8[14], pad, 2 x int32
     assert C.sizeof(L.QsvPass) == 4 + 14 * 4 * 2 + 4 + 16 * C.sizeof(L.QsvRound) + 4
 

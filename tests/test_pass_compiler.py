@@ -65,7 +65,7 @@ def test_swap_is_a_rename_not_arithmetic():
         {"qubits": [0], "gate": "H"}, {"qubits": [0, 5], "gate": "SWAP"}, {"qubits": [5], "gate": "T"},
         {"qubits": [0], "gate": "X"}, {"qubits": [1, 4], "gate": "SWAP"}, {"qubits": [4, 0], "gate": "CNOT"}]}
     prog = check(cd, tile_bits=5, low_bits=1)
-    assert all(s.n_micro_ops <= 4 for s in prog.passes)
+    assert all(s.n_micro_ops <= 5 for s in prog.passes)   # 4 gates + 1 SCALE
 
 
 def test_dense_2q_runs_as_own_step():
@@ -83,18 +83,60 @@ def test_dense_2q_runs_as_own_step():
 
 
 def test_lowering_structures():
-    assert [o.kind for o in lower_op([3], G.H())] == [L.OP_REAL]
-    assert [o.kind for o in lower_op([3], G.Y())] == [L.OP_MAT]
+    kinds = lambda ops: [o.kind for o in ops]
+    assert kinds(lower_op([3], G.H())) == [L.OP_HAD, L.OP_SCALE]
+    assert kinds(lower_op([3], G.Y())) == [L.OP_YSWAP]
+    assert kinds(lower_op([3], G.X())) == [L.OP_XSWAP]
+    assert kinds(lower_op([3], G.RY(0.3))) == [L.OP_ROT]
+    assert kinds(lower_op([3], G.RY(4.0))) == [L.OP_ROT, L.OP_SIGN]        # cos < 0: global -1
     assert [(o.kind, o.ctrls) for o in lower_op([3], G.Z())] == [(L.OP_SIGN, (3,))]
     assert [(o.kind, o.ctrls) for o in lower_op([3], G.T())] == [(L.OP_PHASE, (3,))]
+    assert [(o.kind, o.ctrls) for o in lower_op([3], G.S())] == [(L.OP_PHASE, (3,))]
     assert [(o.kind, o.ctrls) for o in lower_op([2, 5], G.CZ())] == [(L.OP_SIGN, (2, 5))]
-    assert [(o.kind, o.target, o.ctrls) for o in lower_op([2, 5], G.CNOT())] == [(L.OP_REAL, 5, (2,))]
-    assert [(o.kind, o.target, o.ctrls) for o in lower_op([2, 5], G.CY())] == [(L.OP_MAT, 5, (2,))]
+    assert [(o.kind, o.target, o.ctrls) for o in lower_op([2, 5], G.CNOT())] == [(L.OP_XSWAP, 5, (2,))]
+    assert [(o.kind, o.target, o.ctrls) for o in lower_op([2, 5], G.CY())] == [(L.OP_YSWAP, 5, (2,))]
     assert lower_op([2, 5], G.SWAP()) == [("swap", 2, 5)]
     assert lower_op([1], np.eye(2)) == []
-    # control on qubits[1]
+    # a general unitary becomes phase . rotation . phase (. global phase)
+    assert set(kinds(lower_op([3], G.T() @ G.H()))) <= {L.OP_PHASE, L.OP_ROT, L.OP_SIGN}
+    # control on qubits[1]; controlled-H is a controlled sign + rotation
     cu = np.eye(4, dtype=complex); cu[np.ix_([1, 3], [1, 3])] = G.H()
-    assert [(o.kind, o.target, o.ctrls) for o in lower_op([2, 5], cu)] == [(L.OP_REAL, 2, (5,))]
+    low = lower_op([2, 5], cu)
+    assert all(5 in o.ctrls for o in low) and L.OP_ROT in kinds(low)
+    # every PHASE / ROT coefficient stays in the stable range |t| <= 1
+    for seed in range(20):
+        rng = np.random.default_rng(seed)
+        q, r = np.linalg.qr(rng.standard_normal((2, 2)) + 1j * rng.standard_normal((2, 2)))
+        for o in lower_op([0], q):
+            if o.kind in (L.OP_PHASE, L.OP_ROT):
+                assert abs(o.m[0]) <= 1 + 1e-12
+    # non-unitary blocks cannot be lowered: they run through the dense per-gate kernels
+    from quantum_simulations_b200.circuit.passes import Dense1Q
+    assert isinstance(lower_op([0], np.array([[1, 2], [3, 4]]))[0], Dense1Q)
+    assert isinstance(lower_op([0, 1], np.diag([1, 2, 1, 1]))[0], Dense2Q)
+
+
+def test_arbitrary_unitaries_and_non_unitary_fallback():
+    rng = np.random.default_rng(3)
+    n = 7
+    ops = []
+    for k in range(40):
+        q, r = np.linalg.qr(rng.standard_normal((2, 2)) + 1j * rng.standard_normal((2, 2)))
+        tq = int(rng.integers(n))
+        if k % 3 == 0:
+            c = int((tq + 1 + rng.integers(n - 1)) % n)
+            cu = np.eye(4, dtype=complex); cu[2:, 2:] = q
+            ops.append(([c, tq], cu))
+        else:
+            ops.append(([tq], q))
+    ops.insert(10, ([2], np.array([[1, 0.5], [0.25, 1]], dtype=complex)))      # non-unitary
+    prog = PassCompiler(n, tile_bits=5, low_bits=1).compile(ops)
+    psi = np.zeros(1 << n, dtype=np.complex128); psi[0] = 1
+    run_program(prog, psi)
+    want = np.zeros(1 << n, dtype=np.complex128); want[0] = 1
+    O.apply_ops(want, ops)
+    assert prog.stats["dense1q_steps"] == 1
+    assert np.abs(psi - want).max() <= 1e-12
 
 
 def test_rank_bit_controls_and_nonlocal_targets():

@@ -26,7 +26,7 @@ OUT = ROOT / "gpurun_out"
 OUT.mkdir(exist_ok=True)
 
 
-def make_pass(n, t, a, rounds=1, ops_per_round=0, kind=L.OP_MAT, high="top", W=3):
+def make_pass(n, t, a, rounds=1, ops_per_round=0, kind=L.OP_ROT, high="top", W=3):
     """Identity-layout pass: tile = low a positions + (t-a) high positions."""
     if high == "top":
         hi = list(range(n - (t - a), n))
@@ -77,19 +77,26 @@ def make_pass(n, t, a, rounds=1, ops_per_round=0, kind=L.OP_MAT, high="top", W=3
         rd.op_begin = len(ops)
         for g in range(ops_per_round):
             o = L.QsvOp()
-            o.kind = kind
+            fold = isinstance(kind, str)
+            kind_ = {"PHASE_FOLD": L.OP_PHASE, "SIGN_FOLD": L.OP_SIGN}.get(kind, kind)
+            o.kind = kind_
             o.target = g % 4
-            u = G.RY(0.3 + g) @ G.T() @ G.H() if kind == L.OP_MAT else G.RY(0.3 + g)
-            flat = []
-            for z in u.ravel():
-                flat += [z.real, z.imag]
-            if kind == L.OP_PHASE:
-                flat = [np.cos(0.1 * g + .3), np.sin(0.1 * g + .3)] + [0] * 6
-                o.tile_ctrl = 0
-                o.reg_ctrl = 1 << (g % 4)
-            if kind == L.OP_SIGN:
-                o.reg_ctrl = 1 << (g % 4)
-            for k_ in range(8):
+            th = 0.3 + 0.07 * g
+            if kind_ == L.OP_ROT:
+                flat = [np.tan(th / 2), np.sin(th), np.cos(th), 0.0]
+            elif kind_ == L.OP_PHASE:
+                flat = [np.tan(th / 2), np.sin(th), np.cos(th), np.sin(th)]
+            elif kind_ == L.OP_SCALE:
+                flat = [1.0000001, 0, 0, 0]
+            else:
+                flat = [0.0] * 4
+            if kind_ in (L.OP_PHASE, L.OP_SIGN):
+                if fold:    # controls on two thread-fixed tile positions
+                    free_pos = [i for i in range(t) if i not in regs]
+                    o.tile_ctrl = (1 << free_pos[g % len(free_pos)]) | (1 << free_pos[(g + 3) % len(free_pos)])
+                else:
+                    o.reg_ctrl = 1 << (g % 4)
+            for k_ in range(4):
                 o.m[k_] = float(flat[k_])
             ops.append(o)
         rd.op_end = len(ops)
@@ -125,8 +132,8 @@ def main():
     with DeviceState(n, dtype) as st:
         st.init_zero()
         # 1. identity pass: t x a
-        for t in (tmax - 3, tmax - 2, tmax - 1, tmax):
-            for a in (2, 3, 4, 5, 6, 7, 8):
+        for t in (tmax - 1, tmax):
+            for a in (2, 3, 4, 5, 6, 7):
                 if a > t - 4:
                     continue
                 for high in ("top", "spread"):
@@ -134,15 +141,18 @@ def main():
                     emit(exp="identity", n=n, dtype=dtype, t=t, a=a, high=high, ms=med, ms_min=best, gbs=gb / med * 1e3)
         # 2. rounds
         for t in (tmax - 1, tmax):
-            for R in (1, 2, 3, 4, 5, 6, 8, 10):
+            for R in (1, 2, 3, 4, 5, 6, 8):
                 med, best = time_pass(st, make_pass(n, t, 5, R, 0, W=W))
                 emit(exp="rounds", n=n, dtype=dtype, t=t, a=5, rounds=R, ms=med, ms_min=best, gbs=gb / med * 1e3)
         # 3. arithmetic in a single round and spread over 3 rounds
-        for kind, nm in ((L.OP_MAT, "MAT"), (L.OP_REAL, "REAL"), (L.OP_PHASE, "PHASE"), (L.OP_SIGN, "SIGN")):
+        tops = tmax - 1 if ab == 16 else tmax
+        for kind, nm in ((L.OP_ROT, "ROT"), (L.OP_HAD, "HAD"), (L.OP_XSWAP, "XSWAP"),
+                         (L.OP_YSWAP, "YSWAP"), (L.OP_PHASE, "PHASE"), (L.OP_SIGN, "SIGN"),
+                         ("PHASE_FOLD", "PHASE_FOLD"), ("SIGN_FOLD", "SIGN_FOLD")):
             for R in (1, 3):
-                for g in (1, 2, 4, 8, 12, 16, 24):
-                    med, best = time_pass(st, make_pass(n, tmax, 5, R, g, kind=kind, W=W))
-                    emit(exp="ops", n=n, dtype=dtype, t=tmax, a=5, rounds=R, kind=nm, ops_per_round=g,
+                for g in (2, 8, 16, 32):
+                    med, best = time_pass(st, make_pass(n, tops, 5, R, g, kind=kind, W=W))
+                    emit(exp="ops", n=n, dtype=dtype, t=tops, a=5, rounds=R, kind=nm, ops_per_round=g,
                          total_ops=g * R, ms=med, ms_min=best, gbs=gb / med * 1e3)
         # 4. per-gate kernels
         st.timing(True)
