@@ -157,6 +157,11 @@ typedef struct {
     int32_t   n_rounds;
     qsv_round rounds[QSV_MAX_ROUNDS];
     int32_t   n_ops;
+    int32_t   reserved;
+    uint64_t  store_flip;                      /* physical tile bits XOR-ed into every store address:
+                                                  pending X gates are never executed on data — the
+                                                  compiler carries them as a Pauli frame and the last
+                                                  pass that holds the qubit flips its index bit here */
 } qsv_pass;
 
 /* One-shot: run one pass now. */

@@ -31,7 +31,8 @@ class QsvRound(C.Structure):
 class QsvPass(C.Structure):
     _fields_ = [("n_tile", C.c_int32), ("load_bits", C.c_int32 * QSV_MAX_TILE_BITS),
                 ("store_bits", C.c_int32 * QSV_MAX_TILE_BITS), ("n_rounds", C.c_int32),
-                ("rounds", QsvRound * QSV_MAX_ROUNDS), ("n_ops", C.c_int32)]
+                ("rounds", QsvRound * QSV_MAX_ROUNDS), ("n_ops", C.c_int32), ("reserved", C.c_int32),
+                ("store_flip", C.c_uint64)]
 
 
 class QsvTiming(C.Structure):

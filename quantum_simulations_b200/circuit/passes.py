@@ -26,7 +26,7 @@ rounds always execute a dependency-closed set, so per-qubit program order is pre
 from __future__ import annotations
 
 import ctypes as C
-from dataclasses import dataclass, field
+from dataclasses import dataclass, field, replace
 
 import numpy as np
 
@@ -190,6 +190,76 @@ def lower_op(qubits, U, src: int = -1) -> list:
     return [Dense2Q(qa, qb, U, src)]
 
 
+# ------------------------------------------------------------------- Pauli-X frame
+def _inverse(op: MicroOp) -> MicroOp:
+    if op.kind == L.OP_PHASE:
+        t, s, c, s2 = op.m
+        return replace(op, m=(-t, -s, c, -s2))
+    if op.kind == L.OP_ROT:
+        t, s, c, z = op.m
+        return replace(op, m=(-t, -s, c, z))
+    return op                                   # SIGN, XSWAP, YSWAP are involutions
+
+
+def _conj_x(U: np.ndarray, which: tuple[bool, ...]) -> np.ndarray:
+    """(X^f (x) ...) U (X^f (x) ...) for a dense block; which[i] = flip qubit i (MSB first)."""
+    k = len(which)
+    mask = sum(1 << (k - 1 - i) for i, f in enumerate(which) if f)
+    idx = [r ^ mask for r in range(1 << k)]
+    return np.asarray(U)[np.ix_(idx, idx)]
+
+
+def frame_transform(item, xf: list) -> list:
+    """Rewrite one lowered item for a state stored with some index bits flipped.
+
+    xf[c] = 1 means the stored state is X_c |true state>.  X (and the X part of Y) gates are
+    never executed: they toggle xf and every later op is conjugated instead —
+      control on a flipped content :  C_c(O) -> O(without c) . C_c(O^-1)
+      rotation on a flipped target :  X R(theta) X = R(-theta)
+      Hadamard on a flipped target :  H X = Z H  (the flip is absorbed)
+      Y = i X Z; X Y X = -Y
+    The flips still pending at the end are applied by the final passes as an XOR on the store
+    address (qsv_pass.store_flip) — no arithmetic, no data movement."""
+    if isinstance(item, Dense2Q):
+        fa, fb = bool(xf[item.qa]), bool(xf[item.qb])
+        return [replace(item, U=_conj_x(item.U, (fa, fb)))] if (fa or fb) else [item]
+    if isinstance(item, Dense1Q):
+        return [replace(item, U=_conj_x(item.U, (True,)))] if xf[item.q] else [item]
+    op: MicroOp = item
+    for c in op.ctrls:
+        if xf[c]:
+            rest = tuple(x for x in op.ctrls if x != c)
+            out = frame_transform(replace(op, ctrls=rest), xf)
+            xf[c] = 0                                   # treat c as a plain control for the inverse
+            try:
+                out += frame_transform(_inverse(op), xf)
+            finally:
+                xf[c] = 1
+            return out
+    t = op.target
+    if t is None:
+        return [op]
+    if op.kind == L.OP_HAD:
+        if xf[t]:
+            xf[t] = 0
+            return [op, MicroOp(L.OP_SIGN, None, (t,), _Z4, op.src)]
+        return [op]
+    if op.kind == L.OP_ROT:
+        return [_inverse(op)] if xf[t] else [op]
+    if op.kind == L.OP_XSWAP:
+        if not op.ctrls:
+            xf[t] ^= 1
+            return []
+        return [op]
+    if op.kind == L.OP_YSWAP:
+        if not op.ctrls:                                # Y = i X Z (Z first); X Y X = -Y
+            g = -1j if xf[t] else 1j
+            xf[t] ^= 1
+            return [MicroOp(L.OP_SIGN, None, (t,), _Z4, op.src)] + _phase(g, (), op.src)
+        return ([MicroOp(L.OP_SIGN, None, op.ctrls, _Z4, op.src)] if xf[t] else []) + [op]
+    return [op]
+
+
 # ------------------------------------------------------------------------ compiled form
 @dataclass
 class PassStep:
@@ -222,6 +292,7 @@ class Program:
     dtype: str
     steps: list = field(default_factory=list)
     final_pos: list = field(default_factory=list)   # final_pos[q] = position of IR qubit q
+    final_flips: list = field(default_factory=list) # final_flips[q] = 1: qubit q is still stored flipped
     stats: dict = field(default_factory=dict)
 
     @property
@@ -259,7 +330,8 @@ class PassCompiler:
     def __init__(self, n_qubits: int, n_local: int | None = None, dtype: str = "complex128",
                  tile_bits: int | None = None, low_bits: int | None = None,
                  max_rounds: int = 6, restore_layout: bool = True, lookahead: int = 4096,
-                 ring: bool | None = None, max_ops: int = 380):
+                 ring: bool | None = None, max_ops: int = 380, x_frame: bool = True,
+                 merge_diagonals: bool = True):
         self.n = n_qubits
         self.n_local = n_qubits if n_local is None else n_local
         self.dtype = np.dtype(dtype).name
@@ -282,25 +354,56 @@ class PassCompiler:
         self.restore_layout = restore_layout
         self.lookahead = lookahead
         self.max_ops = max_ops          # ops of one pass live in shared memory (kRingMaxOps = 400)
+        self.x_frame = x_frame
+        self.merge_diagonals = merge_diagonals
 
     # ---- public -----------------------------------------------------------------------
-    def compile(self, ir_ops, init_pos=None) -> Program:
+    def compile(self, ir_ops, init_pos=None, init_flips=None) -> Program:
         n = self.n
         alias = list(range(n))                      # IR qubit -> content
+        xf = list(init_flips) if init_flips is not None else [0] * n   # Pauli-X frame per content
         segments: list = [[]]
         seq = 0
+        # Diagonal micro-ops commute with each other and with everything that only INSPECTS
+        # their contents, so they are pooled per control set (phases multiply, signs cancel)
+        # and only emitted right before an op that MIXES one of their contents.
+        pool: dict = {}
+
+        def emit(item) -> None:
+            nonlocal seq
+            if isinstance(item, (Dense2Q, Dense1Q)):
+                segments.append(item)
+                segments.append([])
+            else:
+                item.seq = seq
+                seq += 1
+                segments[-1].append(item)
+
+        def flush(touching=None, src=-1) -> None:
+            for key in [k for k in pool if touching is None or (k & touching)]:
+                for op in _phase(pool.pop(key), tuple(sorted(key)), src):
+                    emit(op)
+
         for i, (qs, U) in enumerate(ir_ops):
-            for item in lower_op([alias[q] for q in qs], U, i):
-                if isinstance(item, tuple):         # swap: rename, no data movement
+            for low in lower_op([alias[q] for q in qs], U, i):
+                if isinstance(low, tuple):          # swap: rename, no data movement
                     qa, qb = list(qs)
                     alias[qa], alias[qb] = alias[qb], alias[qa]
-                elif isinstance(item, (Dense2Q, Dense1Q)):
-                    segments.append(item)
-                    segments.append([])
-                else:
-                    item.seq = seq
-                    seq += 1
-                    segments[-1].append(item)
+                    continue
+                for item in (frame_transform(low, xf) if self.x_frame else [low]):
+                    if isinstance(item, Dense2Q):
+                        flush({item.qa, item.qb}, item.src)
+                    elif isinstance(item, Dense1Q):
+                        flush({item.q}, item.src)
+                    elif item.target is None and item.kind in (L.OP_PHASE, L.OP_SIGN) and self.merge_diagonals:
+                        key = frozenset(item.ctrls)
+                        val = -1.0 + 0j if item.kind == L.OP_SIGN else complex(item.m[2], item.m[3])
+                        pool[key] = pool.get(key, _ONE) * val
+                        continue
+                    elif item.target is not None:
+                        flush({item.target}, item.src)
+                    emit(item)
+        flush()
         pos = list(init_pos) if init_pos is not None else list(range(n))
         home = [0] * n                              # home[content] = position it must end at
         for q in range(n):
@@ -320,10 +423,11 @@ class PassCompiler:
                             f"non-local gate: content {c} sits on rank bit {pos[c]}")
                 prog.steps.append(Dense2QStep(pos[seg.qa], pos[seg.qb], seg.U, {seg.src}))
             else:
-                self._plan_segment(seg, pos, home, prog, last_segment=(k == len(live) - 1))
+                self._plan_segment(seg, pos, home, prog, xf, last_segment=(k == len(live) - 1))
         if self.restore_layout:
-            self._restore(prog, pos, home)
+            self._restore(prog, pos, home, xf)
         prog.final_pos = [pos[alias[q]] for q in range(n)]
+        prog.final_flips = [xf[alias[q]] for q in range(n)]
         ps = prog.passes
         prog.stats = {
             "passes": len(ps), "dense2q_steps": sum(isinstance(x, Dense2QStep) for x in prog.steps),
@@ -336,7 +440,7 @@ class PassCompiler:
         return prog
 
     # ---- pass planning ----------------------------------------------------------------
-    def _plan_segment(self, ops, pos, home, prog, last_segment):
+    def _plan_segment(self, ops, pos, home, prog, xf, last_segment):
         remaining = list(ops)
         while remaining:
             tile = self._choose_tile(remaining, pos, forced=self._low_contents(pos))
@@ -359,7 +463,7 @@ class PassCompiler:
             if remaining and self.a:
                 wish = self._choose_tile(remaining, pos, forced=[], pool=set(tile))
                 park = [c for c in wish if c in set(tile)][: self.a]
-            prog.steps.append(self._emit_pass(tile, rounds, pos, home, park, final))
+            prog.steps.append(self._emit_pass(tile, rounds, pos, home, park, final, xf if final else None))
 
     def _low_contents(self, pos):
         at = {p: c for c, p in enumerate(pos)}
@@ -427,7 +531,7 @@ class PassCompiler:
         return rounds, pend
 
     # ---- pass emission ----------------------------------------------------------------
-    def _emit_pass(self, tile, rounds, pos, home, park, final) -> PassStep:
+    def _emit_pass(self, tile, rounds, pos, home, park, final, xf=None) -> PassStep:
         t, W = self.t, min(self.W, self.t - REG_BITS)
         load_bits = sorted(pos[c] for c in tile)
         at = {p: c for c, p in enumerate(pos)}
@@ -516,6 +620,13 @@ class PassCompiler:
             rd.op_end = len(flat)
         desc.n_ops = len(flat)
         arr = (L.QsvOp * max(len(flat), 1))(*flat)
+        flip = 0
+        if xf is not None:                                # materialise pending X gates for free
+            for i in range(t):
+                if xf[content[i]]:
+                    flip |= 1 << store[i]
+                    xf[content[i]] = 0
+        desc.store_flip = flip
         for i in range(t):                                # commit the relabelling
             pos[content[i]] = store[i]
         return PassStep(desc, arr, len(flat), srcs, list(tile))
@@ -612,12 +723,15 @@ class PassCompiler:
         return o
 
     # ---- layout restoration -----------------------------------------------------------
-    def _restore(self, prog, pos, home) -> None:
+    def _restore(self, prog, pos, home, xf) -> None:
         """Relabel-only passes until every local content is at its home position."""
         n_loc = self.n_local
         for _ in range(8 * self.n + 8):
             bad = [c for c in range(self.n) if pos[c] < n_loc and pos[c] != home[c]]
-            if not bad:
+            flipped = [c for c in range(self.n) if xf[c]]
+            if any(pos[c] >= n_loc for c in flipped):
+                raise NotImplementedError("a pending X sits on a rank bit")
+            if not bad and not flipped:
                 return
             if any(home[c] >= n_loc for c in bad):
                 raise NotImplementedError("layout restoration across rank bits needs a global swap")
@@ -635,6 +749,9 @@ class PassCompiler:
                 cycles.append(cyc)
             cycles.sort(key=lambda cyc: (not any(p < self.a for p in cyc), len(cyc)))
             chosen = set(range(self.a))
+            for c in flipped:                              # pending flips need their bit in a tile
+                if len(chosen) < self.t:
+                    chosen.add(pos[c])
             for cyc in cycles:
                 fresh = [p for p in cyc if p not in chosen]
                 room = self.t - len(chosen)
@@ -652,7 +769,7 @@ class PassCompiler:
                     break
                 chosen.add(p)
             tile = [at[p] for p in sorted(chosen)]
-            prog.steps.append(self._emit_pass(tile, [], pos, home, [], True))
+            prog.steps.append(self._emit_pass(tile, [], pos, home, [], True, xf))
         raise RuntimeError("layout restoration did not converge")
 
 

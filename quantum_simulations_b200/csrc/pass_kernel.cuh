@@ -107,7 +107,7 @@ k_pass(typename CxT<R>::V *__restrict__ state, const qsv_pass *__restrict__ pass
                 uint64_t a = gb;
 #pragma unroll
                 for (int b = 0; b < kRegBits; ++b) if (j & (1 << b)) a |= gr[b];
-                state[a] = v[j];
+                state[a ^ P.store_flip] = v[j];
             }
         } else {
             const uint32_t sb = tile_swizzle<W>(xb);

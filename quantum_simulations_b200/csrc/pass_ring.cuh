@@ -12,9 +12,7 @@
 //     always belongs to group b % 3, so each group double-buffers privately;
 //   * producers stream tiles HBM -> shared with cp.async (LDGSTS, 16 B per lane, no register
 //     staging), writing directly in the XOR-swizzled layout, and publish a tile through an
-//     mbarrier (cp.async.mbarrier.arrive.noinc); they also bulk-prefetch the tiles three
-//     steps ahead into L2 (cp.async.bulk.prefetch.L2), which deepens the HBM queue without
-//     spending shared memory;
+//     mbarrier (cp.async.mbarrier.arrive.noinc);
 //   * a group pulls its tile into registers (16 amplitudes per thread), runs the pass's
 //     rounds (gates in registers; in-place exchange through its buffer between rounds, one
 //     named barrier per exchange), releases the buffer to the producers after the last
@@ -36,7 +34,7 @@ constexpr int kRingGroupThreads = kRingTileAmps / kRegAmps;   // 128
 constexpr int kRingProducers = 128;                // 4 producer warps = one warpgroup
 constexpr int kRingThreads = kRingGroups * kRingGroupThreads + kRingProducers;   // 512
 constexpr int kRingMaxOps = 400;                   // ops of one pass kept in shared memory
-constexpr int kRingPrefetchAhead = 3;              // tiles prefetched into L2 beyond the ring
+constexpr int kRingPrefetchAhead = 0;              // >0: bulk-prefetch tiles beyond the ring into L2 (measured: hurts, TMA issue rate)
 
 struct RingSmem {
     double2 buf[kRingBufs][kRingTileAmps];         // 196608 B
@@ -160,7 +158,7 @@ k_pass_ring(double2 *__restrict__ state, const qsv_pass *__restrict__ pass_ptr,
             const uint32_t use = s / kRingBufs;
             // deepen the HBM queue: pull a tile that is still outside the ring into L2
             const uint64_t ahead = (uint64_t)tile + (uint64_t)gridDim.x * (kRingBufs - kRingGroups + kRingPrefetchAhead);
-            if (ahead < n_tiles) {
+            if (kRingPrefetchAhead > 0 && ahead < n_tiles) {
                 const uint64_t abase = ring_tile_base(P, (uint32_t)ahead);
                 for (uint32_t r = pt; r < n_runs; r += kRingProducers) {
                     uint64_t o = 0;
@@ -289,7 +287,7 @@ k_pass_ring(double2 *__restrict__ state, const qsv_pass *__restrict__ pass_ptr,
                     uint64_t a = gb;
 #pragma unroll
                     for (int q = 0; q < kRegBits; ++q) if (j & (1 << q)) a |= gr[q];
-                    state[a] = v[j];
+                    state[a ^ P.store_flip] = v[j];
                 }
             } else {
                 // registers -> the same shared slots, then the group re-partitions the tile

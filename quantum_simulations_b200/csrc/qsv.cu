@@ -359,6 +359,7 @@ static int validate_pass(qsv_handle *h, const qsv_pass *p, const qsv_op *ops) {
         tile_mask |= 1ull << b; store_mask |= 1ull << sb;
     }
     if (tile_mask != store_mask) QSV_FAIL(h, QSV_EINVAL, "pass: store_bits is not a permutation of load_bits");
+    if (p->store_flip & ~tile_mask) QSV_FAIL(h, QSV_EINVAL, "pass: store_flip names a bit outside the tile");
     if (p->n_rounds < 1 || p->n_rounds > QSV_MAX_ROUNDS) QSV_FAIL(h, QSV_EINVAL, "pass: n_rounds=%d", p->n_rounds);
     if (p->n_ops < 0) QSV_FAIL(h, QSV_EINVAL, "pass: n_ops < 0");
     for (int r = 0; r < p->n_rounds; ++r) {

@@ -96,7 +96,8 @@ def run_pass(psi: np.ndarray, desc: L.QsvPass, ops, n_local: int, rank: int = 0)
                 work *= m[0]
             else:
                 raise AssertionError(f"emulator: unsupported op kind {op.kind}")
-    psi[base[:, None] + off_s[None, :]] = work
+    assert not (desc.store_flip & ~tile_mask)
+    psi[base[:, None] + (off_s ^ int(desc.store_flip))[None, :]] = work
 
 
 def run_program(prog: Program, psi: np.ndarray, rank: int = 0) -> np.ndarray:

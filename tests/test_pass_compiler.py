@@ -164,3 +164,22 @@ def test_headline_plan_sizes():
     assert prog.stats["passes"] <= 6          # 55 levels, 406 gates
     prog = PassCompiler(30).compile(ir_ops(W.random_1q_cz(30, 20, 1234)))
     assert prog.stats["passes"] <= 16         # 20 levels, 445 gates
+
+
+def test_x_and_y_gates_never_touch_data():
+    """The Pauli-X frame: uncontrolled X / Y gates become address flips of the final pass."""
+    cd = W.random_1q_cz(12, 20, 1234)
+    prog = check(cd, tile_bits=8, low_bits=3)
+    kinds = [s.ops[i].kind for s in prog.passes for i in range(s.n_micro_ops)]
+    assert L.OP_XSWAP not in kinds and L.OP_YSWAP not in kinds
+    assert any(s.desc.store_flip for s in prog.passes)
+    assert prog.final_flips == [0] * 12
+    # controlled X survives as a real op (GHZ), with the frame applied to its control
+    cd = {"number_of_qubits": 6, "gates": [
+        {"qubits": [0], "gate": "X"}, {"qubits": [0, 1], "gate": "CNOT"}, {"qubits": [1], "gate": "Y"},
+        {"qubits": [1, 2], "gate": "CY"}, {"qubits": [2], "gate": "H"}, {"qubits": [2, 3], "gate": "CZ"},
+        {"qubits": [0, 3], "gate": "CR", "params": {"k": 3}}, {"qubits": [3], "gate": "RY", "params": {"theta": 0.7}},
+        {"qubits": [3], "gate": "X"}, {"qubits": [3], "gate": "RY", "params": {"theta": 1.9}},
+        {"qubits": [3, 4], "gate": "CU", "params": {"U": [[0.6, -0.8], [0.8, 0.6]], "exponent": 1}}]}
+    check(cd, tile_bits=4, low_bits=0)
+    check(cd, tile_bits=6, low_bits=2, x_frame=False)

@@ -81,7 +81,7 @@ def make_pass(n, t, a, rounds=1, ops_per_round=0, kind=L.OP_ROT, high="top", W=3
             kind_ = {"PHASE_FOLD": L.OP_PHASE, "SIGN_FOLD": L.OP_SIGN}.get(kind, kind)
             o.kind = kind_
             o.target = g % 4
-            th = 0.3 + 0.07 * g
+            th = 0.3 + 0.07 * (g % 16)
             if kind_ == L.OP_ROT:
                 flat = [np.tan(th / 2), np.sin(th), np.cos(th), 0.0]
             elif kind_ == L.OP_PHASE:
