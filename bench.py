@@ -192,8 +192,9 @@ def bench_single(args) -> None:
     cd, info = workload(n)
     amp_bytes = np.dtype(dtype).itemsize
     t0 = time.perf_counter()
-    prog = PassCompiler(n, dtype=dtype, tile_bits=args.tile_bits, low_bits=args.low_bits,
-                        max_rounds=args.max_rounds).compile(circuit_ops(cd))
+    ckw = dict(tile_bits=args.tile_bits, low_bits=args.low_bits, max_rounds=args.max_rounds,
+               defer_diagonals=args.defer_diagonals, fold_tables=not args.no_fold_tables)
+    prog = PassCompiler(n, dtype=dtype, **ckw).compile(circuit_ops(cd))
     compile_s = time.perf_counter() - t0
     n_pass = len(prog.passes)
     updates_per_step = len(cd["gates"]) * (1 << n)
@@ -230,13 +231,11 @@ def bench_single(args) -> None:
     if not args.no_e2e:
         host = PinnedBuffer((1 << n) * amp_bytes)
         out = host.array(dtype, 1 << n)
-        simulate(cd, dtype=dtype, device=args.device, out=out, tile_bits=args.tile_bits,
-                 low_bits=args.low_bits, max_rounds=args.max_rounds)       # warm-up
+        simulate(cd, dtype=dtype, device=args.device, out=out, **ckw)       # warm-up
         reps = max(1, min(args.steps, 3))
         t0 = time.perf_counter()
         for _ in range(reps):
-            simulate(cd, dtype=dtype, device=args.device, out=out, tile_bits=args.tile_bits,
-                     low_bits=args.low_bits, max_rounds=args.max_rounds)
+            simulate(cd, dtype=dtype, device=args.device, out=out, **ckw)
         e2e_s = (time.perf_counter() - t0) / reps
         import ctypes
         from quantum_simulations_b200 import _lib as L
@@ -254,6 +253,9 @@ def bench_single(args) -> None:
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
         "config": {**info, "passes_per_step": n_pass, "rounds_per_step": prog.stats["rounds"],
+                   "ops_per_step": prog.stats["micro_ops"], "per_pass_ms": [round(x, 3) for x in pass_ms[-n_pass:]],
+                   "per_pass_ops": [s_.n_micro_ops for s_ in prog.passes],
+                   "per_pass_rounds": [s_.desc.n_rounds for s_ in prog.passes],
                    "tile_bits": prog.stats["tile_bits"], "low_bits": prog.stats["low_bits"],
                    "l2_hygiene": f"state {(1 << n) * amp_bytes / 2**30:.0f} GiB >> 126 MB L2: every pass streams from HBM",
                    "host_compile_s": compile_s},
@@ -285,6 +287,8 @@ def main() -> None:
     ap.add_argument("--tile-bits", type=int, default=None)
     ap.add_argument("--low-bits", type=int, default=None)
     ap.add_argument("--max-rounds", type=int, default=6)
+    ap.add_argument("--defer-diagonals", action="store_true")
+    ap.add_argument("--no-fold-tables", action="store_true")
     ap.add_argument("--cpu-qubits", type=int, default=20)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

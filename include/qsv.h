@@ -147,6 +147,12 @@ typedef struct {
     uint8_t  reg_pos[QSV_REG_BITS];        /* tile positions held in registers, ascending */
     uint8_t  thr_pos[QSV_MAX_TILE_BITS];   /* tile position of each thread-index bit      */
     int32_t  op_begin, op_end;             /* slice of the pass's op array                */
+    int32_t  fold_off;                     /* -1, or first entry of this round's FOLD TABLE in the
+                                              pass's table array: 2^(n_tile-4) unit complex numbers
+                                              (re, im), entry k = product of all diagonal ops of the
+                                              round whose controls are thread-fixed tile bits, for
+                                              the thread with index k.  One multiply per thread
+                                              replaces the whole CZ / CR layer of the round.      */
 } qsv_round;
 
 typedef struct {
@@ -157,18 +163,19 @@ typedef struct {
     int32_t   n_rounds;
     qsv_round rounds[QSV_MAX_ROUNDS];
     int32_t   n_ops;
-    int32_t   reserved;
+    int32_t   n_fold;                          /* complex entries in this pass's fold-table array */
     uint64_t  store_flip;                      /* physical tile bits XOR-ed into every store address:
                                                   pending X gates are never executed on data — the
                                                   compiler carries them as a Pauli frame and the last
                                                   pass that holds the qubit flips its index bit here */
 } qsv_pass;
 
-/* One-shot: run one pass now. */
-int qsv_apply_pass(qsv_handle *h, const qsv_pass *pass, const qsv_op *ops);
-/* Compiled circuit: upload all passes once, replay with one call (CUDA-graph replay). */
+/* One-shot: run one pass now.  `tables` (may be NULL) holds pass->n_fold complex entries. */
+int qsv_apply_pass(qsv_handle *h, const qsv_pass *pass, const qsv_op *ops, const double *tables);
+/* Compiled circuit: upload all passes once, replay with one call. */
 int qsv_program_create(qsv_handle *h, const qsv_pass *passes, int n_passes,
-                       const qsv_op *ops /* concatenated */, qsv_program **out);
+                       const qsv_op *ops /* concatenated */, const double *tables /* concatenated */,
+                       qsv_program **out);
 int qsv_program_run(qsv_handle *h, qsv_program *p);
 int qsv_program_destroy(qsv_handle *h, qsv_program *p);
 

@@ -6,10 +6,11 @@ product path raises — it never routes through NumPy or the oracle.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 _CSRC = Path(__file__).resolve().parent / "csrc"
-LIB_PATH = _CSRC / "libqsv.so"
+LIB_PATH = _CSRC / os.environ.get("QSV_LIB_NAME", "libqsv.so")   # env override: A/B builds in experiments
 
 QSV_C64, QSV_C128 = 0, 1
 QSV_OK, QSV_EINVAL, QSV_ENONLOCAL, QSV_ECUDA, QSV_ENOMEM, QSV_ECOMM, QSV_EIO = 0, -1, -2, -3, -4, -5, -6
@@ -25,13 +26,13 @@ class QsvOp(C.Structure):
 
 class QsvRound(C.Structure):
     _fields_ = [("reg_pos", C.c_uint8 * QSV_REG_BITS), ("thr_pos", C.c_uint8 * QSV_MAX_TILE_BITS),
-                ("op_begin", C.c_int32), ("op_end", C.c_int32)]
+                ("op_begin", C.c_int32), ("op_end", C.c_int32), ("fold_off", C.c_int32)]
 
 
 class QsvPass(C.Structure):
     _fields_ = [("n_tile", C.c_int32), ("load_bits", C.c_int32 * QSV_MAX_TILE_BITS),
                 ("store_bits", C.c_int32 * QSV_MAX_TILE_BITS), ("n_rounds", C.c_int32),
-                ("rounds", QsvRound * QSV_MAX_ROUNDS), ("n_ops", C.c_int32), ("reserved", C.c_int32),
+                ("rounds", QsvRound * QSV_MAX_ROUNDS), ("n_ops", C.c_int32), ("n_fold", C.c_int32),
                 ("store_flip", C.c_uint64)]
 
 
@@ -72,8 +73,8 @@ SIGNATURES = {
     "qsv_apply_diag": (C.c_int, [_H, C.c_int, _ip, _dp]),
     "qsv_apply_ctrl_1q": (C.c_int, [_H, C.c_int, C.c_int, _dp]),
     "qsv_apply_kq": (C.c_int, [_H, C.c_int, _ip, _dp]),
-    "qsv_apply_pass": (C.c_int, [_H, C.POINTER(QsvPass), C.POINTER(QsvOp)]),
-    "qsv_program_create": (C.c_int, [_H, C.POINTER(QsvPass), C.c_int, C.POINTER(QsvOp), C.POINTER(_P)]),
+    "qsv_apply_pass": (C.c_int, [_H, C.POINTER(QsvPass), C.POINTER(QsvOp), _dp]),
+    "qsv_program_create": (C.c_int, [_H, C.POINTER(QsvPass), C.c_int, C.POINTER(QsvOp), _dp, C.POINTER(_P)]),
     "qsv_program_run": (C.c_int, [_H, _P]),
     "qsv_program_destroy": (C.c_int, [_H, _P]),
     "qsv_norm2": (C.c_int, [_H, _dp]),

@@ -268,6 +268,8 @@ class PassStep:
     n_micro_ops: int
     src_ops: set
     tile_contents: list
+    tables: np.ndarray | None = None  # complex128 fold tables (desc.n_fold entries)
+    n_folded: int = 0                 # diagonal micro-ops absorbed into the tables
 
 
 @dataclass
@@ -331,7 +333,8 @@ class PassCompiler:
                  tile_bits: int | None = None, low_bits: int | None = None,
                  max_rounds: int = 6, restore_layout: bool = True, lookahead: int = 4096,
                  ring: bool | None = None, max_ops: int = 380, x_frame: bool = True,
-                 merge_diagonals: bool = True):
+                 merge_diagonals: bool = True, fold_tables: bool = True,
+                 defer_diagonals: bool = False):
         self.n = n_qubits
         self.n_local = n_qubits if n_local is None else n_local
         self.dtype = np.dtype(dtype).name
@@ -347,7 +350,9 @@ class PassCompiler:
         self.ring = (self.dtype == "complex128" and self.t == RING_TILE_BITS) if ring is None else ring
         if self.t < REG_BITS:
             raise ValueError(f"pass kernel needs n_local >= {REG_BITS} (got {self.n_local})")
-        a = 5 if low_bits is None else low_bits
+        # 3 contiguous low positions (128 B runs) already stream at full rate when the other tile
+        # bits are spread out (profiles/r01 sweep); fewer forced positions = fewer passes
+        a = 3 if low_bits is None else low_bits
         # when the tile does not cover the whole shard, leave room for >= 4 free tile slots
         self.a = self.t if self.t >= self.n_local else max(0, min(a, self.t - REG_BITS))
         self.max_rounds = max(2, min(max_rounds, L.QSV_MAX_ROUNDS - 2))
@@ -356,6 +361,8 @@ class PassCompiler:
         self.max_ops = max_ops          # ops of one pass live in shared memory (kRingMaxOps = 400)
         self.x_frame = x_frame
         self.merge_diagonals = merge_diagonals
+        self.fold_tables = fold_tables
+        self.defer_diagonals = defer_diagonals
 
     # ---- public -----------------------------------------------------------------------
     def compile(self, ir_ops, init_pos=None, init_flips=None) -> Program:
@@ -410,13 +417,32 @@ class PassCompiler:
             home[alias[q]] = q if init_pos is None else init_pos[q]
         prog = Program(n, self.n_local, self.dtype)
         live = [s for s in segments if isinstance(s, (Dense2Q, Dense1Q)) or s]
+        # uses[c] = micro-ops not yet scheduled that touch content c.  A content with no
+        # remaining use can go home / be un-flipped by whichever pass holds it last.
+        self._uses = [0] * n
+        self._xf, self._home = xf, home
+        for seg in live:
+            if isinstance(seg, Dense2Q):
+                self._uses[seg.qa] += 1
+                self._uses[seg.qb] += 1
+            elif isinstance(seg, Dense1Q):
+                self._uses[seg.q] += 1
+            else:
+                for op in seg:
+                    for c in op.ctrls + ((op.target,) if op.target is not None else ()):
+                        self._uses[c] += 1
         for k, seg in enumerate(live):
             if isinstance(seg, Dense1Q):
                 if pos[seg.q] >= self.n_local:
                     raise NotImplementedError(
                         f"non-local gate: content {seg.q} sits on rank bit {pos[seg.q]}")
+                if xf[seg.q]:
+                    raise AssertionError("frame_transform leaves no flip on a dense block")
+                self._uses[seg.q] -= 1
                 prog.steps.append(Dense1QStep(pos[seg.q], seg.U, {seg.src}))
             elif isinstance(seg, Dense2Q):
+                self._uses[seg.qa] -= 1
+                self._uses[seg.qb] -= 1
                 for c in (seg.qa, seg.qb):
                     if pos[c] >= self.n_local:
                         raise NotImplementedError(
@@ -432,7 +458,7 @@ class PassCompiler:
         prog.stats = {
             "passes": len(ps), "dense2q_steps": sum(isinstance(x, Dense2QStep) for x in prog.steps),
             "dense1q_steps": sum(isinstance(x, Dense1QStep) for x in prog.steps),
-            "micro_ops": sum(s.n_micro_ops for s in ps),
+            "micro_ops": sum(s.n_micro_ops for s in ps), "folded_ops": sum(s.n_folded for s in ps),
             "rounds": sum(s.desc.n_rounds for s in ps),
             "max_rounds_in_pass": max((s.desc.n_rounds for s in ps), default=0),
             "tile_bits": self.t, "low_bits": self.a,
@@ -457,13 +483,17 @@ class PassCompiler:
             chosen = [remaining[i] for i in run]
             rounds, deferred = self._plan_rounds(chosen, tile)
             done = {id(op) for r in rounds for op in r[1]}
+            for r in rounds:
+                for op in r[1]:
+                    for c in op.ctrls + ((op.target,) if op.target is not None else ()):
+                        self._uses[c] -= 1
             remaining = [op for op in remaining if id(op) not in done]
             final = not remaining and last_segment and self.restore_layout
             park = []
             if remaining and self.a:
                 wish = self._choose_tile(remaining, pos, forced=[], pool=set(tile))
                 park = [c for c in wish if c in set(tile)][: self.a]
-            prog.steps.append(self._emit_pass(tile, rounds, pos, home, park, final, xf if final else None))
+            prog.steps.append(self._emit_pass(tile, rounds, pos, home, park, final, xf))
 
     def _low_contents(self, pos):
         at = {p: c for c, p in enumerate(pos)}
@@ -497,9 +527,16 @@ class PassCompiler:
             in_tile.add(pick)
         if pool is not None:
             return tile
-        # pad with idle local contents (highest positions first)
+        # pad with idle local contents: first those that still need a free fix-up (pending X
+        # flip or displaced from home) and have no remaining use, then highest positions
         if len(tile) < self.t:
-            for c in sorted((c for c in range(self.n) if pos[c] < self.n_local), key=lambda c: -pos[c]):
+            xf, home, uses = self._xf, self._home, self._uses
+
+            def pad_key(c):
+                needs_fix = (xf[c] or pos[c] != home[c]) and uses[c] == 0 and self.restore_layout
+                return (0 if needs_fix else 1, -pos[c])
+
+            for c in sorted((c for c in range(self.n) if pos[c] < self.n_local), key=pad_key):
                 if c not in in_tile:
                     tile.append(c)
                     in_tile.add(c)
@@ -522,6 +559,23 @@ class PassCompiler:
                 regs.append(pend[missing[0]].target)
             run, _ = _scan(pend, set(regs))
             run = run[: self.max_ops - total]          # a prefix is still dependency-closed
+            if self.fold_tables and self.defer_diagonals and len(rounds) + 1 < self.max_rounds:
+                # A diagonal op with a control in this round's registers costs a register op;
+                # if nothing later in this round needs it done, let it wait for a round where
+                # all its controls are thread-fixed: there it folds into the round's table.
+                regset = set(regs)
+                mixed_later: set = set()
+                keep = []
+                for i in reversed(run):
+                    op = pend[i]
+                    if (op.target is None and op.ctrls and (regset & set(op.ctrls))
+                            and not (mixed_later & set(op.ctrls))):
+                        continue                        # deferred
+                    if op.target is not None:
+                        mixed_later.add(op.target)
+                    keep.append(i)
+                if any(pend[i].target is not None for i in keep):
+                    run = keep[::-1]
             if not run:
                 break
             total += len(run)
@@ -537,7 +591,8 @@ class PassCompiler:
         at = {p: c for c, p in enumerate(pos)}
         content = [at[p] for p in load_bits]              # content at tile index i
         idx_of = {c: i for i, c in enumerate(content)}
-        store = self._choose_store(content, load_bits, home, park, final)   # per tile index
+        finished = {c for c in content if self._uses[c] == 0} if self.restore_layout else set()
+        store = self._choose_store(content, load_bits, home, park, final, finished)   # per tile index
 
         lo_load = {i for i in range(t) if load_bits[i] < W}
         lo_store = {i for i in range(t) if store[i] < W}
@@ -577,6 +632,8 @@ class PassCompiler:
         desc.n_rounds = len(plan)
         flat: list = []
         srcs: set = set()
+        tables: list = []
+        n_folded = 0
         g_scale = 1.0                 # product of SCALE micro-ops (1/sqrt2 per Hadamard)
         g_phase = _ONE                # product of uncontrolled PHASE / SIGN micro-ops
         for r, (regs, rops) in enumerate(plan):
@@ -595,6 +652,8 @@ class PassCompiler:
             for k, i in enumerate(thr):
                 rd.thr_pos[k] = i
             rd.op_begin = len(flat)
+            rd.fold_off = -1
+            fold = None                                      # per-thread phase of this round
             for op in rops:
                 srcs.add(op.src)
                 if op.kind == L.OP_SCALE:                    # global scalars are not executed
@@ -606,7 +665,25 @@ class PassCompiler:
                 if not op.ctrls and op.kind == L.OP_PHASE:
                     g_phase *= complex(op.m[2], op.m[3])
                     continue
-                flat.append(self._encode(op, slot_of, idx_of, pos))
+                o = self._encode(op, slot_of, idx_of, pos)
+                if self.fold_tables and o.kind in (L.OP_PHASE, L.OP_SIGN) and not o.reg_ctrl and not o.glob_ctrl:
+                    # controls are thread-fixed tile bits only: commutes with every register op of
+                    # the round -> multiply into the round's per-thread table instead of an op
+                    if fold is None:
+                        fold = np.ones(1 << (t - REG_BITS), dtype=np.complex128)
+                        tix = np.arange(1 << (t - REG_BITS))
+                        xb_of = np.zeros_like(tix)
+                        for k, i in enumerate(thr):
+                            xb_of |= ((tix >> k) & 1) << i
+                    hit = (xb_of & o.tile_ctrl) == o.tile_ctrl
+                    fold[hit] *= -1.0 if o.kind == L.OP_SIGN else complex(o.m[2], o.m[3])
+                    n_folded += 1
+                    continue
+                flat.append(o)
+            if fold is not None:
+                fold /= np.abs(fold)
+                rd.fold_off = sum(len(x) for x in tables)
+                tables.append(fold)
             if r == len(plan) - 1:
                 if g_phase != _ONE:
                     g_phase /= abs(g_phase)
@@ -619,17 +696,19 @@ class PassCompiler:
                     flat.append(sc)
             rd.op_end = len(flat)
         desc.n_ops = len(flat)
+        tab = np.ascontiguousarray(np.concatenate(tables)) if tables else None
+        desc.n_fold = 0 if tab is None else len(tab)
         arr = (L.QsvOp * max(len(flat), 1))(*flat)
         flip = 0
-        if xf is not None:                                # materialise pending X gates for free
-            for i in range(t):
-                if xf[content[i]]:
+        if xf is not None:                                # materialise pending X gates for free:
+            for i in range(t):                            # safe once nothing later looks at the bit
+                if xf[content[i]] and (final or content[i] in finished):
                     flip |= 1 << store[i]
                     xf[content[i]] = 0
         desc.store_flip = flip
         for i in range(t):                                # commit the relabelling
             pos[content[i]] = store[i]
-        return PassStep(desc, arr, len(flat), srcs, list(tile))
+        return PassStep(desc, arr, len(flat), srcs, list(tile), tab, n_folded)
 
     def _idle_regs(self, avoid) -> list:
         regs = [i for i in range(self.t - 1, -1, -1) if i not in avoid][:REG_BITS]
@@ -652,7 +731,7 @@ class PassCompiler:
                 break
         return head + [i for i in free if i not in head]
 
-    def _choose_store(self, content, load_bits, home, park, final) -> list:
+    def _choose_store(self, content, load_bits, home, park, final, finished=frozenset()) -> list:
         """New position of the content at every tile index (a permutation of load_bits)."""
         import itertools
         t = len(content)
@@ -683,7 +762,7 @@ class PassCompiler:
         vacate = [p for p in low if occ[p] not in parked][: len(movers)]
         movers = movers[: len(vacate)]
         if not movers:
-            return [new[c] for c in content]
+            return [self._send_home(new, content, home, finished, parked)[c] for c in content]
 
         def assign(order):
             out = dict(cur)
@@ -702,7 +781,23 @@ class PassCompiler:
             sc = score(asg)
             if sc > best_s:
                 best, best_s = asg, sc
-        return [best[c] for c in content]
+        return [self._send_home(best, content, home, finished, parked)[c] for c in content]
+
+    def _send_home(self, asg: dict, content, home, finished, parked) -> dict:
+        """Finished contents (no remaining use) swap into their home slot when that slot is in
+        the tile and its current assignee is not parked there for the next pass."""
+        by_slot = {p: c for c, p in asg.items()}
+        for c in content:
+            if c not in finished or asg[c] == home[c] or home[c] not in by_slot:
+                continue
+            other = by_slot[home[c]]
+            if other in parked or (other in finished and asg[other] == home[other]):
+                continue
+            if c in parked:
+                continue
+            asg[c], asg[other] = asg[other], asg[c]
+            by_slot[asg[c]], by_slot[asg[other]] = c, other
+        return asg
 
     def _encode(self, op: MicroOp, slot_of, idx_of, pos) -> L.QsvOp:
         o = L.QsvOp()

@@ -44,6 +44,8 @@ __host__ __device__ __forceinline__ uint64_t insert_zero_bit(uint64_t x, int pos
 struct qsv_program {
     std::vector<qsv_pass> passes;
     std::vector<int>      op_offset;     // first op of each pass in d_ops
+    std::vector<int>      fold_offset;   // first fold-table entry of each pass in d_tables
+    double2 *d_tables = nullptr;
     qsv_op  *d_ops   = nullptr;          // device copy of all ops
     qsv_pass *d_passes = nullptr;        // device copy of pass descriptors
     cudaGraphExec_t graph = nullptr;

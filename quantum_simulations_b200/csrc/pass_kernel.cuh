@@ -27,7 +27,7 @@
 template <typename R>
 __global__ void __launch_bounds__(sizeof(R) == 8 ? 256 : 512, sizeof(R) == 8 ? 2 : 1)
 k_pass(typename CxT<R>::V *__restrict__ state, const qsv_pass *__restrict__ pass_ptr,
-       const qsv_op *__restrict__ ops, const uint64_t rank_bits) {
+       const qsv_op *__restrict__ ops, const double2 *__restrict__ tables, const uint64_t rank_bits) {
     using V = typename CxT<R>::V;
     constexpr int W = (sizeof(V) == 16) ? 3 : 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -87,6 +87,14 @@ k_pass(typename CxT<R>::V *__restrict__ state, const qsv_pass *__restrict__ pass
         }
 
         // ---- the round's gates, all in registers ----
+        if (rd.fold_off >= 0) {                         // fold table: one phase per thread
+            const double2 f = tables[rd.fold_off + tid];
+            R pr = (R)f.x, pi = (R)f.y;
+            const bool neg = pr < (R)0;
+            if (neg) { pr = -pr; pi = -pi; }
+            op_phase_mask<V, R>(v, pi / ((R)1 + pr), pi, 0u);
+            if (neg) op_sign_mask<V>(v, 0u);
+        }
         for (int o = rd.op_begin; o < rd.op_end; ++o) {
             const qsv_op &op = ops[o];
             if ((glob & op.glob_ctrl) != op.glob_ctrl) continue;        // CTA-uniform

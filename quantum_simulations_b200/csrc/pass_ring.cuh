@@ -28,7 +28,13 @@
 
 constexpr int kRingT = 11;                         // tile bits
 constexpr int kRingTileAmps = 1 << kRingT;         // 2048 amplitudes = 32 KB
-constexpr int kRingGroups = 3;
+#ifndef QSV_RING_GROUPS
+#define QSV_RING_GROUPS 3
+#endif
+#ifndef QSV_RING_CONSUMER_REGS
+#define QSV_RING_CONSUMER_REGS 152
+#endif
+constexpr int kRingGroups = QSV_RING_GROUPS;
 constexpr int kRingBufs = 6;
 constexpr int kRingGroupThreads = kRingTileAmps / kRegAmps;   // 128
 constexpr int kRingProducers = 128;                // 4 producer warps = one warpgroup
@@ -102,7 +108,8 @@ __device__ __forceinline__ uint64_t ring_tile_base(const qsv_pass &P, uint32_t t
 
 __global__ void __launch_bounds__(kRingThreads, 1)
 k_pass_ring(double2 *__restrict__ state, const qsv_pass *__restrict__ pass_ptr,
-            const qsv_op *__restrict__ ops_ptr, const uint64_t rank_bits, const uint32_t n_tiles) {
+            const qsv_op *__restrict__ ops_ptr, const double2 *__restrict__ tables,
+            const uint64_t rank_bits, const uint32_t n_tiles) {
     using V = double2;
     using R = double;
     constexpr int W = 3, T = kRingT;
@@ -177,7 +184,7 @@ k_pass_ring(double2 *__restrict__ state, const qsv_pass *__restrict__ pass_ptr,
     }
 
     // =========================== consumer groups ===========================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(QSV_RING_CONSUMER_REGS));
     const int grp = tid / kRingGroupThreads;
     const uint32_t gt = tid % kRingGroupThreads;
     const int n_rounds = P.n_rounds;
@@ -204,6 +211,11 @@ k_pass_ring(double2 *__restrict__ state, const qsv_pass *__restrict__ pass_ptr,
             uint32_t sr[kRegBits];
 #pragma unroll
             for (int q = 0; q < kRegBits; ++q) sr[q] = tile_swizzle<W>(1u << rd.reg_pos[q]);
+            // this thread's entry of the round's fold table (issued early: L2 latency hides
+            // behind the shared-memory reads)
+            const int fold_off = rd.fold_off;
+            double2 fold = make_double2(1.0, 0.0);
+            if (fold_off >= 0) fold = __ldg(&tables[fold_off + gt]);
 
             // shared tile -> registers
 #pragma unroll
@@ -217,22 +229,29 @@ k_pass_ring(double2 *__restrict__ state, const qsv_pass *__restrict__ pass_ptr,
             if (last) mbar_arrive(&S.empty[b]);    // buffer no longer needed: back to the producers
 
             // ---- the round's gates, in registers ----
-            R pr = 1.0, pi = 0.0;                 // folded per-thread phase (unit modulus)
-            bool dirty = false;
+            R pr = fold.x, pi = fold.y;           // folded per-thread phase (unit modulus)
+            bool dirty = fold_off >= 0;
             const int o_end = rd.op_end;
             int o = rd.op_begin;
             uint4 nxt = make_uint4(0, 0, 0, 0);
-            if (o < o_end) nxt = *reinterpret_cast<const uint4 *>(&S.ops[o]);
+            double2 nxt_c = make_double2(0.0, 0.0);
+            if (o < o_end) {
+                nxt = *reinterpret_cast<const uint4 *>(&S.ops[o]);
+                nxt_c = *reinterpret_cast<const double2 *>(S.ops[o].m);
+            }
             for (; o < o_end; ++o) {
                 const uint4 hd = nxt;                                      // header of op o
-                const double2 c = *reinterpret_cast<const double2 *>(S.ops[o].m);   // m[0], m[1]
-                if (o + 1 < o_end) nxt = *reinterpret_cast<const uint4 *>(&S.ops[o + 1]);   // prefetch
+                const double2 c = nxt_c;                                   // m[0], m[1]
+                if (o + 1 < o_end) {                                       // prefetch op o+1
+                    nxt = *reinterpret_cast<const uint4 *>(&S.ops[o + 1]);
+                    nxt_c = *reinterpret_cast<const double2 *>(S.ops[o + 1].m);
+                }
                 if (hd.y | hd.z | hd.w) {
                     const uint64_t gc = ((uint64_t)hd.w << 32) | hd.z;
                     if ((glob & gc) != gc) continue;                       // group-uniform
                     if ((xb & hd.y) != hd.y) continue;                     // per thread
                 }
-                switch (hd.x >> 24) {
+                switch ((hd.x >> 24) & 31) {
 #define RING_CASE4(BASE, CALL)                                              \
                     case BASE + 0: { constexpr int TB = 0; CALL; } break;   \
                     case BASE + 1: { constexpr int TB = 1; CALL; } break;   \
@@ -252,9 +271,10 @@ k_pass_ring(double2 *__restrict__ state, const qsv_pass *__restrict__ pass_ptr,
                         pi = pr * e.y + pi * e.x; pr = nr; dirty = true;
                     } break;
                     case RC_SCALE: op_scale<V, R>(v, c.x); break;
-                    default:
+                    case RC_GENERIC:
                         apply_reg_op<V, R>(v, hd.x & 0xff, (hd.x >> 8) & 0xff, (hd.x >> 16) & 0xff, S.ops[o].m);
                         break;
+                    default: __builtin_unreachable();
                 }
             }
             // apply the folded phase P in place; sign-bit flips only if every P of the warp is real

@@ -361,7 +361,7 @@ static int validate_pass(qsv_handle *h, const qsv_pass *p, const qsv_op *ops) {
     if (tile_mask != store_mask) QSV_FAIL(h, QSV_EINVAL, "pass: store_bits is not a permutation of load_bits");
     if (p->store_flip & ~tile_mask) QSV_FAIL(h, QSV_EINVAL, "pass: store_flip names a bit outside the tile");
     if (p->n_rounds < 1 || p->n_rounds > QSV_MAX_ROUNDS) QSV_FAIL(h, QSV_EINVAL, "pass: n_rounds=%d", p->n_rounds);
-    if (p->n_ops < 0) QSV_FAIL(h, QSV_EINVAL, "pass: n_ops < 0");
+    if (p->n_ops < 0 || p->n_fold < 0) QSV_FAIL(h, QSV_EINVAL, "pass: n_ops / n_fold < 0");
     for (int r = 0; r < p->n_rounds; ++r) {
         const qsv_round &rd = p->rounds[r];
         uint32_t seen = 0, regm = 0;
@@ -375,6 +375,8 @@ static int validate_pass(qsv_handle *h, const qsv_pass *p, const qsv_op *ops) {
             seen |= 1u << rd.thr_pos[i];
         }
         if (rd.op_begin < 0 || rd.op_end < rd.op_begin || rd.op_end > p->n_ops) QSV_FAIL(h, QSV_EINVAL, "pass: round %d op slice", r);
+        if (rd.fold_off < -1 || (rd.fold_off >= 0 && rd.fold_off + (1 << (T - QSV_REG_BITS)) > p->n_fold))
+            QSV_FAIL(h, QSV_EINVAL, "pass: round %d fold table outside the pass's %d entries", r, p->n_fold);
         for (int o = rd.op_begin; o < rd.op_end; ++o) {
             const qsv_op &op = ops[o];
             if (op.kind >= QSV_OP_KINDS) QSV_FAIL(h, QSV_EINVAL, "pass: op %d bad kind %d", o, (int)op.kind);
@@ -393,7 +395,8 @@ static int validate_pass(qsv_handle *h, const qsv_pass *p, const qsv_op *ops) {
     return QSV_OK;
 }
 
-static int launch_pass(qsv_handle *h, const qsv_pass *host_pass, const qsv_pass *dev_pass, const qsv_op *dev_ops, int pass_index) {
+static int launch_pass(qsv_handle *h, const qsv_pass *host_pass, const qsv_pass *dev_pass, const qsv_op *dev_ops,
+                       const double2 *dev_tables, int pass_index) {
     const int T = host_pass->n_tile;
     const uint64_t rank_bits = (uint64_t)h->rank << h->n_local;
     ScopedTimer t(h, 10, pass_index);
@@ -403,7 +406,7 @@ static int launch_pass(qsv_handle *h, const qsv_pass *host_pass, const qsv_pass 
         const unsigned grid = n_tiles < (uint32_t)h->sm_count ? n_tiles : (unsigned)h->sm_count;
         const size_t smem = sizeof(RingSmem);
         QSV_CUDA(h, cudaFuncSetAttribute(k_pass_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_pass_ring<<<grid, kRingThreads, smem, h->stream>>>((double2 *)h->d_state, dev_pass, dev_ops, rank_bits, n_tiles);
+        k_pass_ring<<<grid, kRingThreads, smem, h->stream>>>((double2 *)h->d_state, dev_pass, dev_ops, dev_tables, rank_bits, n_tiles);
         QSV_CUDA(h, cudaGetLastError());
         return QSV_OK;
     }
@@ -412,53 +415,63 @@ static int launch_pass(qsv_handle *h, const qsv_pass *host_pass, const qsv_pass 
     const size_t smem = host_pass->n_rounds > 1 ? (h->amp_bytes << T) : 0;
     if (h->dtype == QSV_C128) {
         QSV_CUDA(h, cudaFuncSetAttribute(k_pass<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-        k_pass<double><<<blocks, threads, smem, h->stream>>>((double2 *)h->d_state, dev_pass, dev_ops, rank_bits);
+        k_pass<double><<<blocks, threads, smem, h->stream>>>((double2 *)h->d_state, dev_pass, dev_ops, dev_tables, rank_bits);
     } else {
         QSV_CUDA(h, cudaFuncSetAttribute(k_pass<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-        k_pass<float><<<blocks, threads, smem, h->stream>>>((float2 *)h->d_state, dev_pass, dev_ops, rank_bits);
+        k_pass<float><<<blocks, threads, smem, h->stream>>>((float2 *)h->d_state, dev_pass, dev_ops, dev_tables, rank_bits);
     }
     QSV_CUDA(h, cudaGetLastError());
     return QSV_OK;
 }
 
-int qsv_apply_pass(qsv_handle *h, const qsv_pass *pass, const qsv_op *ops) {
+int qsv_apply_pass(qsv_handle *h, const qsv_pass *pass, const qsv_op *ops, const double *tables) {
     QSV_CHECK_H(h);
-    if (!pass || (pass->n_ops > 0 && !ops)) QSV_FAIL(h, QSV_EINVAL, "apply_pass: null argument");
+    if (!pass || (pass->n_ops > 0 && !ops) || (pass->n_fold > 0 && !tables)) QSV_FAIL(h, QSV_EINVAL, "apply_pass: null argument");
     int rc = validate_pass(h, pass, ops);
     if (rc) return rc;
     QSV_CUDA(h, cudaSetDevice(h->device));
-    const size_t need = sizeof(qsv_op) * (size_t)std::max(pass->n_ops, 1);
+    const size_t ops_bytes = sizeof(qsv_op) * (size_t)std::max(pass->n_ops, 1);
+    const size_t tab_off = (ops_bytes + 255) & ~(size_t)255;
+    const size_t need = tab_off + sizeof(double2) * (size_t)std::max(pass->n_fold, 1);
     if (h->ops_scratch_cap < need) {
         QSV_CUDA(h, cudaStreamSynchronize(h->stream));
         if (h->d_ops_scratch) cudaFree(h->d_ops_scratch);
         h->ops_scratch_cap = std::max(need, (size_t)1 << 20);
         QSV_CUDA(h, cudaMalloc((void **)&h->d_ops_scratch, h->ops_scratch_cap));
     }
-    // the previous one-shot pass may still be reading the scratch: stream order protects it,
-    // but the host buffers must outlive the copy -> synchronous staging copy (pageable memory).
+    // stream order protects the scratch against the previous one-shot pass; the host buffers
+    // are pageable, so cudaMemcpyAsync stages them before returning.
+    char *scratch = (char *)h->d_ops_scratch;
     QSV_CUDA(h, cudaMemcpyAsync(h->d_pass_scratch, pass, sizeof(qsv_pass), cudaMemcpyHostToDevice, h->stream));
-    if (pass->n_ops) QSV_CUDA(h, cudaMemcpyAsync(h->d_ops_scratch, ops, sizeof(qsv_op) * pass->n_ops, cudaMemcpyHostToDevice, h->stream));
-    return launch_pass(h, pass, h->d_pass_scratch, h->d_ops_scratch, -1);
+    if (pass->n_ops) QSV_CUDA(h, cudaMemcpyAsync(scratch, ops, sizeof(qsv_op) * pass->n_ops, cudaMemcpyHostToDevice, h->stream));
+    if (pass->n_fold) QSV_CUDA(h, cudaMemcpyAsync(scratch + tab_off, tables, sizeof(double2) * pass->n_fold, cudaMemcpyHostToDevice, h->stream));
+    return launch_pass(h, pass, h->d_pass_scratch, (const qsv_op *)scratch, (const double2 *)(scratch + tab_off), -1);
 }
 
-int qsv_program_create(qsv_handle *h, const qsv_pass *passes, int n_passes, const qsv_op *ops, qsv_program **out) {
+int qsv_program_create(qsv_handle *h, const qsv_pass *passes, int n_passes, const qsv_op *ops, const double *tables,
+                       qsv_program **out) {
     QSV_CHECK_H(h);
     if (!out || n_passes < 0 || (n_passes && !passes)) QSV_FAIL(h, QSV_EINVAL, "program_create: bad arguments");
     *out = nullptr;
     QSV_CUDA(h, cudaSetDevice(h->device));
     qsv_program *p = new (std::nothrow) qsv_program();
     if (!p) return QSV_ENOMEM;
-    int total_ops = 0;
+    int total_ops = 0, total_fold = 0;
     for (int i = 0; i < n_passes; ++i) {
         int rc = validate_pass(h, &passes[i], ops ? ops + total_ops : nullptr);
         if (rc) { delete p; return rc; }
         p->passes.push_back(passes[i]);
         p->op_offset.push_back(total_ops);
+        p->fold_offset.push_back(total_fold);
         total_ops += passes[i].n_ops;
+        total_fold += passes[i].n_fold;
     }
+    if (total_fold > 0 && !tables) { delete p; QSV_FAIL(h, QSV_EINVAL, "program_create: fold tables missing"); }
     cudaError_t e = cudaSuccess;
     if (n_passes) e = cudaMalloc((void **)&p->d_passes, sizeof(qsv_pass) * n_passes);
     if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_ops, sizeof(qsv_op) * std::max(total_ops, 1));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_tables, sizeof(double2) * std::max(total_fold, 1));
+    if (e == cudaSuccess && total_fold) e = cudaMemcpy(p->d_tables, tables, sizeof(double2) * total_fold, cudaMemcpyHostToDevice);
     if (e == cudaSuccess && n_passes) e = cudaMemcpy(p->d_passes, passes, sizeof(qsv_pass) * n_passes, cudaMemcpyHostToDevice);
     if (e == cudaSuccess && total_ops) e = cudaMemcpy(p->d_ops, ops, sizeof(qsv_op) * total_ops, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
@@ -466,6 +479,7 @@ int qsv_program_create(qsv_handle *h, const qsv_pass *passes, int n_passes, cons
         cudaGetLastError();
         if (p->d_passes) cudaFree(p->d_passes);
         if (p->d_ops) cudaFree(p->d_ops);
+        if (p->d_tables) cudaFree(p->d_tables);
         delete p;
         return QSV_ECUDA;
     }
@@ -478,7 +492,8 @@ int qsv_program_run(qsv_handle *h, qsv_program *p) {
     if (!p) QSV_FAIL(h, QSV_EINVAL, "program_run: null program");
     QSV_CUDA(h, cudaSetDevice(h->device));
     for (size_t i = 0; i < p->passes.size(); ++i) {
-        int rc = launch_pass(h, &p->passes[i], p->d_passes + i, p->d_ops + p->op_offset[i], (int)i);
+        int rc = launch_pass(h, &p->passes[i], p->d_passes + i, p->d_ops + p->op_offset[i],
+                             p->d_tables + p->fold_offset[i], (int)i);
         if (rc) return rc;
     }
     return QSV_OK;
@@ -490,7 +505,7 @@ int qsv_program_destroy(qsv_handle *h, qsv_program *p) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     if (p->graph) cudaGraphExecDestroy(p->graph);
-    cudaFree(p->d_passes); cudaFree(p->d_ops);
+    cudaFree(p->d_passes); cudaFree(p->d_ops); cudaFree(p->d_tables);
     delete p;
     return QSV_OK;
 }

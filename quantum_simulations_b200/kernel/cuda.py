@@ -155,7 +155,8 @@ class DeviceState:
 
     # ---- fused passes ----
     def apply_pass(self, step: PassStep) -> None:
-        self._ck(self.lib.qsv_apply_pass(self._h, C.byref(step.desc), step.ops))
+        tab = None if step.tables is None else step.tables.ctypes.data_as(C.POINTER(C.c_double))
+        self._ck(self.lib.qsv_apply_pass(self._h, C.byref(step.desc), step.ops, tab))
 
     def run_program(self, prog: Program) -> None:
         """Execute a compiled program (passes + stand-alone dense 2q kernels) in order."""
@@ -183,8 +184,11 @@ class DeviceState:
             for j in range(s.n_micro_ops):
                 ops[k] = s.ops[j]
                 k += 1
+        tabs = [s.tables for s in steps if s.tables is not None]
+        tab = np.ascontiguousarray(np.concatenate(tabs)) if tabs else None
+        tab_p = None if tab is None else tab.ctypes.data_as(C.POINTER(C.c_double))
         out = C.c_void_p()
-        self._ck(self.lib.qsv_program_create(self._h, passes, n, ops, C.byref(out)))
+        self._ck(self.lib.qsv_program_create(self._h, passes, n, ops, tab_p, C.byref(out)))
         self._programs.append(out)
         return out
 

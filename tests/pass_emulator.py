@@ -19,7 +19,7 @@ def _insert_zero(x, p):
     return ((x >> p) << (p + 1)) | low
 
 
-def run_pass(psi: np.ndarray, desc: L.QsvPass, ops, n_local: int, rank: int = 0) -> None:
+def run_pass(psi: np.ndarray, desc: L.QsvPass, ops, n_local: int, rank: int = 0, tables=None) -> None:
     t = desc.n_tile
     load = [desc.load_bits[i] for i in range(t)]
     store = [desc.store_bits[i] for i in range(t)]
@@ -45,6 +45,16 @@ def run_pass(psi: np.ndarray, desc: L.QsvPass, ops, n_local: int, rank: int = 0)
         assert sorted(regs + thr) == list(range(t)), f"round {r}: reg/thr positions do not partition the tile"
         assert 0 <= rd.op_begin <= rd.op_end <= desc.n_ops
         regmask = sum(1 << i for i in regs)
+        assert rd.fold_off >= -1
+        if rd.fold_off >= 0:
+            nthr = 1 << (t - R)
+            assert tables is not None and rd.fold_off + nthr <= desc.n_fold == len(tables)
+            tab = tables[rd.fold_off:rd.fold_off + nthr]
+            assert np.abs(np.abs(tab) - 1).max() < 1e-12
+            tix = np.zeros(1 << t, dtype=np.int64)       # thread index that owns tile index x
+            for k, i in enumerate(thr):
+                tix |= ((x >> i) & 1) << k
+            work *= tab[tix][None, :]
         for o in range(rd.op_begin, rd.op_end):
             op = ops[o]
             assert not (op.tile_ctrl & regmask) and not (op.tile_ctrl >> t)
@@ -103,7 +113,7 @@ def run_pass(psi: np.ndarray, desc: L.QsvPass, ops, n_local: int, rank: int = 0)
 def run_program(prog: Program, psi: np.ndarray, rank: int = 0) -> np.ndarray:
     for step in prog.steps:
         if isinstance(step, PassStep):
-            run_pass(psi, step.desc, step.ops, prog.n_local, rank)
+            run_pass(psi, step.desc, step.ops, prog.n_local, rank, step.tables)
         elif isinstance(step, Dense2QStep):
             O.apply_2q(psi, step.qa_pos, step.qb_pos, step.U)
         elif isinstance(step, Dense1QStep):

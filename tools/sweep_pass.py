@@ -75,6 +75,7 @@ def make_pass(n, t, a, rounds=1, ops_per_round=0, kind=L.OP_ROT, high="top", W=3
         for k_, i in enumerate(free):
             rd.thr_pos[k_] = i
         rd.op_begin = len(ops)
+        rd.fold_off = -1
         for g in range(ops_per_round):
             o = L.QsvOp()
             fold = isinstance(kind, str)
