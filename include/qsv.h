@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define QSV_ABI_VERSION 1
+#define QSV_ABI_VERSION 2
 
 /* dtypes (wenbo_engine/storage/block_store.py:11 fixes complex64; the oracle is complex128) */
 #define QSV_C64  0
@@ -124,7 +124,8 @@ int qsv_apply_kq(qsv_handle *h, int k, const int *qs, const double *U);
 #define QSV_OP_HAD    0  /* (a, b) -> (a + b, a - b), UNNORMALISED (b <- a-b ; a <- 2a-b); the
                             compiler emits the 1/sqrt2 factors as one SCALE per pass; no controls */
 #define QSV_OP_ROT    1  /* (a, b) -> (c a - s b, s a + c b), |theta| <= pi/2, as three shears
-                            a -= t b ; b += s a ; a -= t b with m[0] = t = tan(theta/2), m[1] = s */
+                            a -= t b ; b += s a ; a -= t b with m[0] = t = tan(theta/2), m[1] = s
+                            (m[2], m[3] belong to the PREPHASE pre-op, see QSV_OPF_*)             */
 #define QSV_OP_XSWAP  2  /* X: (a, b) -> (b, a), no arithmetic                                */
 #define QSV_OP_YSWAP  3  /* Y: (a, b) -> (-i b, i a), no arithmetic                           */
 #define QSV_OP_PHASE  4  /* no target: amp *= e^{i phi}, |phi| <= pi/2, where all controls are 1;
@@ -133,11 +134,22 @@ int qsv_apply_kq(qsv_handle *h, int k, const int *qs, const double *U);
 #define QSV_OP_SCALE  6  /* no target, no controls: amp *= m[0] (real)                        */
 #define QSV_OP_KINDS  7
 
+/* PRE-OPS of an UNCONTROLLED HAD / ROT (qsv_op.flags).  Diagonal gates that sit right before a
+ * mixing gate on its target are folded into it by the compiler, so they cost no dispatch:
+ * before (a, b) is mixed, the b half (target bit = 1) is multiplied by
+ *     (-1)^( parity(tile_index & tile_ctrl) ^ parity(global_index & glob_ctrl) ^ PRENEG )   and then by
+ *     e^{i phi},  m[2] = tan(phi/2), m[3] = sin(phi), |phi| <= pi/2                          (PREPHASE).
+ * With any of these flags set reg_ctrl must be 0 and tile_ctrl / glob_ctrl are PARITY masks (the
+ * partners of the CZ gates pending on the target), not AND-controls. */
+#define QSV_OPF_PRESIGN   1  /* tile_ctrl / glob_ctrl are parity masks of a pre-sign              */
+#define QSV_OPF_PRENEG    2  /* b = -b (a pending Z on the target)                                */
+#define QSV_OPF_PREPHASE  4  /* b *= e^{i phi} with m[2], m[3]                                     */
+
 typedef struct {
     uint8_t  kind;         /* QSV_OP_*                                                   */
     uint8_t  target;       /* register-slot index 0..QSV_REG_BITS-1 (kinds with a target) */
     uint8_t  reg_ctrl;     /* controls among register slots (bit b = slot b)             */
-    uint8_t  flags;        /* dispatch code filled in by the library (callers pass 0)    */
+    uint8_t  flags;        /* QSV_OPF_* pre-ops (HAD / ROT without controls only), else 0 */
     uint32_t tile_ctrl;    /* controls among thread-fixed tile positions (bit i = pos i) */
     uint64_t glob_ctrl;    /* controls among physical bits outside the tile (rank bits ok)*/
     double   m[4];         /* coefficients, meaning depends on kind                      */
@@ -178,6 +190,18 @@ int qsv_program_create(qsv_handle *h, const qsv_pass *passes, int n_passes,
                        qsv_program **out);
 int qsv_program_run(qsv_handle *h, qsv_program *p);
 int qsv_program_destroy(qsv_handle *h, qsv_program *p);
+/* qsv_program_create SPECIALISES each complex128 pass at run time (NVRTC, sm_100a): the same ring
+ * kernel with the pass's bit positions and op sequence as straight-line code and the coefficients
+ * in the kernel-parameter bank; cubins are cached by pass STRUCTURE (in memory and under
+ * <libqsv dir>/jit_cache, env QSV_JIT_CACHE=<dir>|0).  QSV_JIT=0 or QSV_OPT_JIT=0 keeps the
+ * interpreting kernels; so does a missing libnvrtc (qsv_last_error says why). */
+#define QSV_OPT_JIT          1   /* 1 (default) / 0                                        */
+#define QSV_OPT_SIMPLE_PASS  2   /* 1: run passes on the one-CTA-per-tile kernel (tests)    */
+int qsv_set_option(qsv_handle *h, int option, long long value);
+int qsv_jit_stats(int *compiled, int *disk_hits, int *mem_hits, int *failed, double *compile_seconds);
+/* Generate + NVRTC-compile the specialised kernel of one pass WITHOUT a device (build check /
+ * cache warm-up; nvrtc cross-compiles sm_100a on a CPU-only host).  log receives the error text. */
+int qsv_jit_build_pass(const qsv_pass *pass, const qsv_op *ops, size_t *cubin_bytes, char *log, size_t log_cap);
 
 /* --------------------------------------------------------------- reductions ---- */
 int qsv_norm2(qsv_handle *h, double *out);   /* sum |amp|^2 of the LOCAL shard */

@@ -17,6 +17,8 @@ QSV_OK, QSV_EINVAL, QSV_ENONLOCAL, QSV_ECUDA, QSV_ENOMEM, QSV_ECOMM, QSV_EIO = 0
 QSV_MAX_TILE_BITS, QSV_REG_BITS, QSV_MAX_ROUNDS = 14, 4, 16
 OP_HAD, OP_ROT, OP_XSWAP, OP_YSWAP, OP_PHASE, OP_SIGN, OP_SCALE = range(7)
 OP_WITH_TARGET = (OP_HAD, OP_ROT, OP_XSWAP, OP_YSWAP)
+OPF_PRESIGN, OPF_PRENEG, OPF_PREPHASE = 1, 2, 4
+OPT_JIT, OPT_SIMPLE_PASS = 1, 2
 
 
 class QsvOp(C.Structure):
@@ -77,6 +79,9 @@ SIGNATURES = {
     "qsv_program_create": (C.c_int, [_H, C.POINTER(QsvPass), C.c_int, C.POINTER(QsvOp), _dp, C.POINTER(_P)]),
     "qsv_program_run": (C.c_int, [_H, _P]),
     "qsv_program_destroy": (C.c_int, [_H, _P]),
+    "qsv_set_option": (C.c_int, [_H, C.c_int, C.c_longlong]),
+    "qsv_jit_stats": (C.c_int, [_ip, _ip, _ip, _ip, _dp]),
+    "qsv_jit_build_pass": (C.c_int, [C.POINTER(QsvPass), C.POINTER(QsvOp), C.POINTER(C.c_size_t), C.c_char_p, C.c_size_t]),
     "qsv_norm2": (C.c_int, [_H, _dp]),
     "qsv_sample": (C.c_int, [_H, C.c_uint64, C.c_int, _dp, C.POINTER(C.c_uint64)]),
     "qsv_comm_unique_id": (C.c_int, [C.c_void_p]),

@@ -47,6 +47,15 @@ class MicroOp:
     m: tuple[float, ...] = (0.0,) * 4  # coefficients (see qsv.h)
     src: int = -1                      # IR op index it came from
     seq: int = -1                      # position in the lowered stream (stable order key)
+    # pre-ops folded into an uncontrolled HAD / ROT (qsv.h QSV_OPF_*): diagonal action on the b half
+    pre_neg: bool = False              # pending Z on the target
+    pre_par: frozenset = frozenset()   # partners of the CZ gates pending on the target (parity)
+    pre_phase: complex = 1.0 + 0.0j    # pending diag(1, e^{i phi}) on the target
+
+    @property
+    def looks(self) -> tuple:
+        """Contents the op inspects without mixing them (controls + pre-sign partners)."""
+        return self.ctrls + tuple(self.pre_par) if self.pre_par else self.ctrls
 
 
 @dataclass
@@ -190,6 +199,43 @@ def lower_op(qubits, U, src: int = -1) -> list:
     return [Dense2Q(qa, qb, U, src)]
 
 
+def absorb_diagonals(rops: list, regset: set) -> tuple[list, int]:
+    """Fold the diagonal micro-ops of one round into the mixing op that follows them.
+
+    A diagonal op D commutes with everything up to the first later op that MIXES one of its
+    contents.  If that op M is an uncontrolled HAD / ROT on target t and D is
+        SIGN{t}        (a Z on the target)                      -> M.pre_neg
+        SIGN{t, p}     (a CZ; p not register-resident)          -> M.pre_par ^= {p}
+        PHASE{t}       (diag(1, e^{i phi}) on the target)       -> M.pre_phase *= e^{i phi}
+    then D is executed by M's record (no dispatch, no divergence: the sign is a per-thread
+    xor mask, the phase three more shears on the b half).  Returns (ops, n_absorbed)."""
+    out = list(rops)
+    n_abs = 0
+    for i, d in enumerate(rops):
+        if d.target is not None or d.kind not in (L.OP_SIGN, L.OP_PHASE) or not d.ctrls:
+            continue
+        cs = set(d.ctrls)
+        j = next((k for k in range(i + 1, len(rops)) if rops[k].target in cs), None)
+        if j is None:
+            continue
+        m = out[j]
+        if m.kind not in (L.OP_HAD, L.OP_ROT) or m.ctrls:
+            continue
+        t = m.target
+        if d.kind == L.OP_SIGN and cs == {t}:
+            m = replace(m, pre_neg=not m.pre_neg)
+        elif d.kind == L.OP_SIGN and len(cs) == 2 and not ((cs - {t}) & regset):
+            m = replace(m, pre_par=m.pre_par ^ frozenset(cs - {t}))
+        elif d.kind == L.OP_PHASE and cs == {t}:
+            m = replace(m, pre_phase=m.pre_phase * complex(d.m[2], d.m[3]))
+        else:
+            continue
+        out[j] = m
+        out[i] = None
+        n_abs += 1
+    return [o for o in out if o is not None], n_abs
+
+
 # ------------------------------------------------------------------- Pauli-X frame
 def _inverse(op: MicroOp) -> MicroOp:
     if op.kind == L.OP_PHASE:
@@ -270,6 +316,7 @@ class PassStep:
     tile_contents: list
     tables: np.ndarray | None = None  # complex128 fold tables (desc.n_fold entries)
     n_folded: int = 0                 # diagonal micro-ops absorbed into the tables
+    n_absorbed: int = 0               # diagonal micro-ops riding as pre-ops of a HAD / ROT
 
 
 @dataclass
@@ -314,7 +361,7 @@ def _scan(ops, mixable, lookahead: int | None = None):
         if lookahead is not None and i >= lookahead:
             break
         t = op.target
-        free = (t is None or (t not in bt and t not in bc)) and not any(c in bt for c in op.ctrls)
+        free = (t is None or (t not in bt and t not in bc)) and not any(c in bt for c in op.looks)
         if free and (t is None or t in mixable):
             run.append(i)
             continue
@@ -322,7 +369,7 @@ def _scan(ops, mixable, lookahead: int | None = None):
             missing.append(i)
         if t is not None:
             bt.add(t)
-        bc.update(op.ctrls)
+        bc.update(op.looks)
     return run, missing
 
 
@@ -334,7 +381,7 @@ class PassCompiler:
                  max_rounds: int = 6, restore_layout: bool = True, lookahead: int = 4096,
                  ring: bool | None = None, max_ops: int = 380, x_frame: bool = True,
                  merge_diagonals: bool = True, fold_tables: bool = True,
-                 defer_diagonals: bool = False):
+                 defer_diagonals: bool = False, absorb: bool = True):
         self.n = n_qubits
         self.n_local = n_qubits if n_local is None else n_local
         self.dtype = np.dtype(dtype).name
@@ -363,6 +410,7 @@ class PassCompiler:
         self.merge_diagonals = merge_diagonals
         self.fold_tables = fold_tables
         self.defer_diagonals = defer_diagonals
+        self.absorb = absorb
 
     # ---- public -----------------------------------------------------------------------
     def compile(self, ir_ops, init_pos=None, init_flips=None) -> Program:
@@ -408,6 +456,8 @@ class PassCompiler:
                         pool[key] = pool.get(key, _ONE) * val
                         continue
                     elif item.target is not None:
+                        if self.absorb and item.kind in (L.OP_HAD, L.OP_ROT) and not item.ctrls:
+                            item = self._absorb_pool(pool, item)
                         flush({item.target}, item.src)
                     emit(item)
         flush()
@@ -429,7 +479,7 @@ class PassCompiler:
                 self._uses[seg.q] += 1
             else:
                 for op in seg:
-                    for c in op.ctrls + ((op.target,) if op.target is not None else ()):
+                    for c in op.looks + ((op.target,) if op.target is not None else ()):
                         self._uses[c] += 1
         for k, seg in enumerate(live):
             if isinstance(seg, Dense1Q):
@@ -459,11 +509,32 @@ class PassCompiler:
             "passes": len(ps), "dense2q_steps": sum(isinstance(x, Dense2QStep) for x in prog.steps),
             "dense1q_steps": sum(isinstance(x, Dense1QStep) for x in prog.steps),
             "micro_ops": sum(s.n_micro_ops for s in ps), "folded_ops": sum(s.n_folded for s in ps),
+            "absorbed_ops": sum(s.n_absorbed for s in ps),
             "rounds": sum(s.desc.n_rounds for s in ps),
             "max_rounds_in_pass": max((s.desc.n_rounds for s in ps), default=0),
             "tile_bits": self.t, "low_bits": self.a,
         }
         return prog
+
+    @staticmethod
+    def _absorb_pool(pool: dict, m: MicroOp) -> MicroOp:
+        """Pending diagonals on m's target that an uncontrolled HAD / ROT can carry as pre-ops:
+        the 1-qubit phase {t} and every pure CZ sign {t, p}.  They leave the pool, so they are
+        scheduled WITH the mixing op instead of whenever their contents happen to be on chip."""
+        t = m.target
+        neg, par, ph = m.pre_neg, set(m.pre_par), m.pre_phase
+        for key in [k for k in pool if t in k]:
+            val = pool[key]
+            if len(key) == 1:
+                ph *= val
+            elif len(key) == 2 and val == -_ONE:
+                par ^= set(key - {t})
+            elif val == _ONE:
+                pass
+            else:
+                continue
+            del pool[key]
+        return replace(m, pre_neg=neg, pre_par=frozenset(par), pre_phase=ph)
 
     # ---- pass planning ----------------------------------------------------------------
     def _plan_segment(self, ops, pos, home, prog, xf, last_segment):
@@ -485,7 +556,7 @@ class PassCompiler:
             done = {id(op) for r in rounds for op in r[1]}
             for r in rounds:
                 for op in r[1]:
-                    for c in op.ctrls + ((op.target,) if op.target is not None else ()):
+                    for c in op.looks + ((op.target,) if op.target is not None else ()):
                         self._uses[c] -= 1
             remaining = [op for op in remaining if id(op) not in done]
             final = not remaining and last_segment and self.restore_layout
@@ -634,6 +705,7 @@ class PassCompiler:
         srcs: set = set()
         tables: list = []
         n_folded = 0
+        n_absorbed = 0
         g_scale = 1.0                 # product of SCALE micro-ops (1/sqrt2 per Hadamard)
         g_phase = _ONE                # product of uncontrolled PHASE / SIGN micro-ops
         for r, (regs, rops) in enumerate(plan):
@@ -654,6 +726,18 @@ class PassCompiler:
             rd.op_begin = len(flat)
             rd.fold_off = -1
             fold = None                                      # per-thread phase of this round
+            if self.absorb:
+                regset = {content[i] for i in regs}
+                split = []
+                for op in rops:                              # a pre-sign partner that sits in a register
+                    inreg = op.pre_par & regset              # slot of this round runs as its own CZ op
+                    if inreg:
+                        split += [MicroOp(L.OP_SIGN, None, (op.target, c), _Z4, op.src) for c in sorted(inreg)]
+                        op = replace(op, pre_par=op.pre_par - inreg)
+                    n_absorbed += len(op.pre_par) + int(op.pre_neg) + int(op.pre_phase != _ONE)
+                    split.append(op)
+                rops, na = absorb_diagonals(split, regset)
+                n_absorbed += na
             for op in rops:
                 srcs.add(op.src)
                 if op.kind == L.OP_SCALE:                    # global scalars are not executed
@@ -708,7 +792,7 @@ class PassCompiler:
         desc.store_flip = flip
         for i in range(t):                                # commit the relabelling
             pos[content[i]] = store[i]
-        return PassStep(desc, arr, len(flat), srcs, list(tile), tab, n_folded)
+        return PassStep(desc, arr, len(flat), srcs, list(tile), tab, n_folded, n_absorbed)
 
     def _idle_regs(self, avoid) -> list:
         regs = [i for i in range(self.t - 1, -1, -1) if i not in avoid][:REG_BITS]
@@ -815,6 +899,31 @@ class PassCompiler:
         o.reg_ctrl, o.tile_ctrl, o.glob_ctrl = reg_ctrl, tile_ctrl, glob
         for k in range(4):
             o.m[k] = op.m[k]
+        if op.kind in (L.OP_HAD, L.OP_ROT):
+            o.m[2] = o.m[3] = 0.0
+            flags, neg = 0, bool(op.pre_neg)
+            ph = complex(op.pre_phase)
+            if ph != _ONE:
+                ph /= abs(ph)
+                if abs(ph.imag) <= _SNAP:
+                    ph = complex(1.0 if ph.real > 0 else -1.0, 0.0)
+                if ph.real < 0:                     # keep |phi| <= pi/2: e^{i phi} = -e^{i (phi -+ pi)}
+                    ph, neg = -ph, not neg
+                if ph != _ONE:
+                    flags |= L.OPF_PREPHASE
+                    o.m[2], o.m[3] = ph.imag / (1.0 + ph.real), ph.imag
+            if neg:
+                flags |= L.OPF_PRENEG
+            if op.pre_par:
+                assert not op.ctrls
+                flags |= L.OPF_PRESIGN
+                for c in op.pre_par:
+                    assert c not in slot_of
+                    if c in idx_of:
+                        o.tile_ctrl |= 1 << idx_of[c]
+                    else:
+                        o.glob_ctrl |= 1 << pos[c]
+            o.flags = flags
         return o
 
     # ---- layout restoration -----------------------------------------------------------

@@ -49,12 +49,16 @@ struct qsv_program {
     qsv_op  *d_ops   = nullptr;          // device copy of all ops
     qsv_pass *d_passes = nullptr;        // device copy of pass descriptors
     cudaGraphExec_t graph = nullptr;
+    // run-time specialised kernels (jit.cuh): one per pass, null = interpret the pass
+    std::vector<cudaKernel_t> jit;
+    std::vector<std::vector<double>> jit_coefs;
 };
 
 struct qsv_handle {
     int n_qubits = 0, n_local = 0, dtype = QSV_C128, device = 0, rank = 0, world = 1;
     int sm_count = 148;
     bool force_simple_pass = false;   // tests: run every pass on the one-CTA-per-tile kernel
+    bool jit = true;                  // specialise the passes of a program at qsv_program_create
     size_t n_amps = 0;            // local amplitudes
     size_t amp_bytes = 16;
     void *d_state = nullptr;

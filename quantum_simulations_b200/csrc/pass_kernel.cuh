@@ -97,6 +97,12 @@ k_pass(typename CxT<R>::V *__restrict__ state, const qsv_pass *__restrict__ pass
         }
         for (int o = rd.op_begin; o < rd.op_end; ++o) {
             const qsv_op &op = ops[o];
+            if (op.flags) {     // HAD / ROT with pre-ops: the control fields are parity masks
+                const int sm = (int)(((uint32_t)__popc(xb & op.tile_ctrl) + (uint32_t)__popcll(glob & op.glob_ctrl) +
+                                      ((uint32_t)op.flags >> 1)) << 31);
+                apply_reg_op<V, R>(v, op.kind, op.target, 0u, op.m, op.flags, sm);
+                continue;
+            }
             if ((glob & op.glob_ctrl) != op.glob_ctrl) continue;        // CTA-uniform
             if ((xb & op.tile_ctrl) != op.tile_ctrl) continue;          // per thread
             apply_reg_op<V, R>(v, op.kind, op.target, op.reg_ctrl, op.m);

@@ -16,7 +16,9 @@
 //   SCALE  re *= s ; im *= s                                2 / amplitude
 // FP64 (B200: 64 lanes/SM, 34 TFLOP/s measured) is the scarce resource next to HBM.
 #pragma once
+#ifndef QSV_JIT          // the NVRTC build (jit_prelude.cuh) supplies the few names needed instead
 #include "common.cuh"
+#endif
 
 constexpr int kRegBits = QSV_REG_BITS;          // 4
 constexpr int kRegAmps = 1 << kRegBits;         // 16 amplitudes per thread
@@ -25,6 +27,9 @@ __device__ __forceinline__ double flip_sign(double x) {
     return __hiloint2double(__double2hiint(x) ^ (int)0x80000000, __double2loint(x));
 }
 __device__ __forceinline__ float flip_sign(float x) { return __int_as_float(__float_as_int(x) ^ (int)0x80000000); }
+// x with its sign bit xor-ed by m (m = 0 or 0x80000000)
+__device__ __forceinline__ double xor_sign(double x, int m) { return __hiloint2double(__double2hiint(x) ^ m, __double2loint(x)); }
+__device__ __forceinline__ float xor_sign(float x, int m) { return __int_as_float(__float_as_int(x) ^ m); }
 
 // swap two scalars in place with three xors per 32-bit word (no temporaries => no shuffles)
 __device__ __forceinline__ void xor_swap(double &a, double &b) {
@@ -43,6 +48,29 @@ __device__ __forceinline__ void xor_swap(float &a, float &b) {
 #define QSV_PAIR_LOOP(TB, CHECK, rc)                                   \
     _Pragma("unroll") for (int j = 0; j < kRegAmps; ++j)               \
         if (!(j & (1 << TB)) && (!(CHECK) || (j & (rc)) == (rc)))
+
+// PRE-OPS of a mixing op (qsv.h QSV_OPF_*): diagonal work on the b half (target bit = 1) that the
+// compiler folded into the HAD / ROT that follows it, so it costs no dispatch of its own:
+//   sign   b.hi ^= sm      sm = 0 or 0x80000000 per THREAD (parity of the partner bits of the CZ / Z
+//                          gates pending on the target) — 2 LOP3 per b on the integer pipe
+//   phase  b *= e^{i phi}  three shears per b (the diag(1, e^{il}) factor of the ZYZ form)
+template <typename V, typename R, int TB>
+__device__ __forceinline__ void op_pre(V (&v)[kRegAmps], const uint32_t fl, const int sm, const R tp, const R sp) {
+    if (fl & (QSV_OPF_PRESIGN | QSV_OPF_PRENEG)) {
+#pragma unroll
+        for (int j = 0; j < kRegAmps; ++j) if (j & (1 << TB)) {
+            v[j].x = xor_sign(v[j].x, sm); v[j].y = xor_sign(v[j].y, sm);
+        }
+    }
+    if (fl & QSV_OPF_PREPHASE) {
+#pragma unroll
+        for (int j = 0; j < kRegAmps; ++j) if (j & (1 << TB)) {
+            v[j].x = fma(-tp, v[j].y, v[j].x);
+            v[j].y = fma(sp, v[j].x, v[j].y);
+            v[j].x = fma(-tp, v[j].y, v[j].x);
+        }
+    }
+}
 
 template <typename V, int TB>
 __device__ __forceinline__ void op_had(V (&v)[kRegAmps]) {
@@ -102,6 +130,13 @@ __device__ __forceinline__ void op_sign_slot(V (&v)[kRegAmps]) {
     for (int j = 0; j < kRegAmps; ++j) if (j & (1 << TB)) { v[j].x = flip_sign(v[j].x); v[j].y = flip_sign(v[j].y); }
 }
 
+// SIGN controlled by exactly TWO register slots (a CZ between two register-resident qubits)
+template <typename V, int A, int B>
+__device__ __forceinline__ void op_sign_slot2(V (&v)[kRegAmps]) {
+#pragma unroll
+    for (int j = 0; j < kRegAmps; ++j) if ((j & (1 << A)) && (j & (1 << B))) { v[j].x = flip_sign(v[j].x); v[j].y = flip_sign(v[j].y); }
+}
+
 // diagonal ops with an arbitrary register-slot control mask (rc == 0: all 16 amplitudes)
 template <typename V, typename R>
 __device__ __forceinline__ void op_phase_mask(V (&v)[kRegAmps], const R t, const R s, const uint32_t rc) {
@@ -130,13 +165,16 @@ __device__ __forceinline__ void op_scale(V (&v)[kRegAmps], const R s) {
 
 // Straightforward interpreter of one op (used by the one-CTA-per-tile kernel and as the rare
 // path of the ring kernel).  Thread-fixed controls were already checked by the caller.
+// `fl` / `sm`: pre-op flags of a mixing op and this thread's pre-sign mask (see op_pre).
 template <typename V, typename R>
 __device__ __forceinline__ void apply_reg_op(V (&v)[kRegAmps], const int kind, const int tb,
-                                             const uint32_t rc, const double *__restrict__ m) {
+                                             const uint32_t rc, const double *__restrict__ m,
+                                             const uint32_t fl = 0u, const int sm = 0) {
     switch (kind) {
-        case QSV_OP_HAD: QSV_DISPATCH_TB(tb, (op_had<V, TB>(v))); break;
-        case QSV_OP_ROT: { const R t = (R)m[0], s = (R)m[1];
-                           QSV_DISPATCH_TB(tb, (op_rot<V, R, TB, true>(v, t, s, rc))); } break;
+        case QSV_OP_HAD: { const R tp = (R)m[2], sp = (R)m[3];
+                           QSV_DISPATCH_TB(tb, (op_pre<V, R, TB>(v, fl, sm, tp, sp), op_had<V, TB>(v))); } break;
+        case QSV_OP_ROT: { const R t = (R)m[0], s = (R)m[1], tp = (R)m[2], sp = (R)m[3];
+                           QSV_DISPATCH_TB(tb, (op_pre<V, R, TB>(v, fl, sm, tp, sp), op_rot<V, R, TB, true>(v, t, s, rc))); } break;
         case QSV_OP_XSWAP: QSV_DISPATCH_TB(tb, (op_xswap<V, TB, true>(v, rc))); break;
         case QSV_OP_YSWAP: QSV_DISPATCH_TB(tb, (op_yswap<V, TB, true>(v, rc))); break;
         case QSV_OP_PHASE: op_phase_mask<V, R>(v, (R)m[0], (R)m[1], rc); break;

@@ -52,20 +52,27 @@ struct RingSmem {
     unsigned long long empty[kRingBufs];
 };
 
-// dense dispatch codes (stored in qsv_op.flags while the ops are staged in shared memory)
-enum : int { RC_HAD = 0, RC_ROT = 4, RC_XSWAP = 8, RC_YSWAP = 12, RC_PHASE1 = 16, RC_SIGN1 = 20,
-             RC_FOLD_SIGN = 24, RC_FOLD_PHASE = 25, RC_SCALE = 26, RC_GENERIC = 27 };
+// dense dispatch codes (kept in bits 2..7 of qsv_op.target while the ops are staged in shared memory)
+enum : int { RC_HAD = 0, RC_ROT = 4, RC_MIX_END = 8, RC_PHASE1 = 8, RC_SIGN1 = 12, RC_SIGN2 = 16,
+             RC_FOLD_SIGN = 22, RC_FOLD_PHASE = 23, RC_SCALE = 24, RC_XSWAP = 25, RC_YSWAP = 29, RC_GENERIC = 33 };
 
-__device__ __forceinline__ int ring_dispatch_code(int kind, int tb, uint32_t rc) {
+__device__ __forceinline__ int ring_dispatch_code(int kind, int tb, uint32_t rc, uint32_t fl, bool other_ctrl) {
     const bool one = rc != 0 && (rc & (rc - 1)) == 0;
     const int slot = 31 - __clz((int)(rc | 1));
     switch (kind) {
         case QSV_OP_HAD: return RC_HAD + tb;
-        case QSV_OP_ROT: return rc ? RC_GENERIC : RC_ROT + tb;
+        case QSV_OP_ROT: return (rc || (!fl && other_ctrl)) ? RC_GENERIC : RC_ROT + tb;
         case QSV_OP_XSWAP: return rc ? RC_GENERIC : RC_XSWAP + tb;
         case QSV_OP_YSWAP: return rc ? RC_GENERIC : RC_YSWAP + tb;
         case QSV_OP_PHASE: return rc == 0 ? RC_FOLD_PHASE : (one ? RC_PHASE1 + slot : RC_GENERIC);
-        case QSV_OP_SIGN: return rc == 0 ? RC_FOLD_SIGN : (one ? RC_SIGN1 + slot : RC_GENERIC);
+        case QSV_OP_SIGN:
+            if (rc == 0) return RC_FOLD_SIGN;
+            if (one) return RC_SIGN1 + slot;
+            if (__popc(rc) == 2) {                       // pair (lo, hi) -> 0..5
+                const int lo = __ffs((int)rc) - 1, hi = slot;
+                return RC_SIGN2 + (lo == 0 ? hi - 1 : (lo == 1 ? hi + 1 : 5));
+            }
+            return RC_GENERIC;
         case QSV_OP_SCALE: return RC_SCALE;
         default: return RC_GENERIC;
     }
@@ -127,8 +134,11 @@ k_pass_ring(double2 *__restrict__ state, const qsv_pass *__restrict__ pass_ptr,
         uint4 *sd = reinterpret_cast<uint4 *>(S.ops);
         for (int i = tid; i < n_ops * (int)(sizeof(qsv_op) / 16); i += kRingThreads) sd[i] = so[i];
         __syncthreads();
-        for (int i = tid; i < n_ops; i += kRingThreads)
-            S.ops[i].flags = (uint8_t)ring_dispatch_code(S.ops[i].kind, S.ops[i].target, S.ops[i].reg_ctrl);
+        for (int i = tid; i < n_ops; i += kRingThreads) {
+            const qsv_op &q = S.ops[i];
+            const int code = ring_dispatch_code(q.kind, q.target, q.reg_ctrl, q.flags, q.tile_ctrl != 0 || q.glob_ctrl != 0);
+            S.ops[i].target = (uint8_t)(q.target | (code << 2));
+        }
         if (tid < 16) {
             unsigned long long o = 0;
             for (int i = 0; i < 4; ++i) if (tid & (1 << i)) o |= 1ull << S.pass.load_bits[7 + i];
@@ -246,24 +256,47 @@ k_pass_ring(double2 *__restrict__ state, const qsv_pass *__restrict__ pass_ptr,
                     nxt = *reinterpret_cast<const uint4 *>(&S.ops[o + 1]);
                     nxt_c = *reinterpret_cast<const double2 *>(S.ops[o + 1].m);
                 }
-                if (hd.y | hd.z | hd.w) {
-                    const uint64_t gc = ((uint64_t)hd.w << 32) | hd.z;
-                    if ((glob & gc) != gc) continue;                       // group-uniform
-                    if ((xb & hd.y) != hd.y) continue;                     // per thread
-                }
-                switch ((hd.x >> 24) & 31) {
+                const uint32_t code = (hd.x >> 10) & 63u;
+                if (code < RC_MIX_END) {
+                    // HAD / ROT without controls: the bulk of the FP64 work.  Pre-ops (pending Z / CZ
+                    // signs and the ZYZ pre-phase on the target) ride along in the same record.
+                    const uint32_t fl = hd.x >> 24;
+                    int sm = 0;
+                    double2 pc = make_double2(0.0, 0.0);
+                    if (fl) {
+                        const uint64_t gc = ((uint64_t)hd.w << 32) | hd.z;
+                        sm = (int)(((uint32_t)__popc(xb & hd.y) + (uint32_t)__popcll(glob & gc) + (fl >> 1)) << 31);
+                        pc = *reinterpret_cast<const double2 *>(S.ops[o].m + 2);
+                    }
+                    switch (code) {
 #define RING_CASE4(BASE, CALL)                                              \
                     case BASE + 0: { constexpr int TB = 0; CALL; } break;   \
                     case BASE + 1: { constexpr int TB = 1; CALL; } break;   \
                     case BASE + 2: { constexpr int TB = 2; CALL; } break;   \
                     case BASE + 3: { constexpr int TB = 3; CALL; } break;
-                    RING_CASE4(RC_HAD, (op_had<V, TB>(v)))
-                    RING_CASE4(RC_ROT, (op_rot<V, R, TB, false>(v, c.x, c.y, 0u)))
-                    RING_CASE4(RC_XSWAP, (op_xswap<V, TB, false>(v, 0u)))
-                    RING_CASE4(RC_YSWAP, (op_yswap<V, TB, false>(v, 0u)))
+                        RING_CASE4(RC_HAD, (op_pre<V, R, TB>(v, fl, sm, pc.x, pc.y), op_had<V, TB>(v)))
+                        RING_CASE4(RC_ROT, (op_pre<V, R, TB>(v, fl, sm, pc.x, pc.y), op_rot<V, R, TB, false>(v, c.x, c.y, 0u)))
+                        default: __builtin_unreachable();
+                    }
+                    continue;
+                }
+                if (hd.y | hd.z | hd.w) {
+                    const uint64_t gc = ((uint64_t)hd.w << 32) | hd.z;
+                    if ((glob & gc) != gc) continue;                       // group-uniform
+                    if ((xb & hd.y) != hd.y) continue;                     // per thread
+                }
+                switch (code) {
                     RING_CASE4(RC_PHASE1, (op_phase_slot<V, R, TB>(v, c.x, c.y)))
                     RING_CASE4(RC_SIGN1, (op_sign_slot<V, TB>(v)))
+                    RING_CASE4(RC_XSWAP, (op_xswap<V, TB, false>(v, 0u)))
+                    RING_CASE4(RC_YSWAP, (op_yswap<V, TB, false>(v, 0u)))
 #undef RING_CASE4
+                    case RC_SIGN2 + 0: op_sign_slot2<V, 0, 1>(v); break;
+                    case RC_SIGN2 + 1: op_sign_slot2<V, 0, 2>(v); break;
+                    case RC_SIGN2 + 2: op_sign_slot2<V, 0, 3>(v); break;
+                    case RC_SIGN2 + 3: op_sign_slot2<V, 1, 2>(v); break;
+                    case RC_SIGN2 + 4: op_sign_slot2<V, 1, 3>(v); break;
+                    case RC_SIGN2 + 5: op_sign_slot2<V, 2, 3>(v); break;
                     case RC_FOLD_SIGN: pr = flip_sign(pr); pi = flip_sign(pi); dirty = true; break;
                     case RC_FOLD_PHASE: {
                         const double2 e = *reinterpret_cast<const double2 *>(S.ops[o].m + 2);   // cos, sin
@@ -272,7 +305,7 @@ k_pass_ring(double2 *__restrict__ state, const qsv_pass *__restrict__ pass_ptr,
                     } break;
                     case RC_SCALE: op_scale<V, R>(v, c.x); break;
                     case RC_GENERIC:
-                        apply_reg_op<V, R>(v, hd.x & 0xff, (hd.x >> 8) & 0xff, (hd.x >> 16) & 0xff, S.ops[o].m);
+                        apply_reg_op<V, R>(v, hd.x & 0xff, (hd.x >> 8) & 3, (hd.x >> 16) & 0xff, S.ops[o].m);
                         break;
                     default: __builtin_unreachable();
                 }

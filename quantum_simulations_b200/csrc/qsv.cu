@@ -12,6 +12,7 @@
 #include "pass_kernel.cuh"
 #include "pass_ring.cuh"
 #include "exchange.cuh"
+#include "jit.cuh"
 
 static thread_local std::string g_create_error;
 
@@ -384,7 +385,16 @@ static int validate_pass(qsv_handle *h, const qsv_pass *p, const qsv_op *ops) {
                                     op.kind == QSV_OP_YSWAP;
             if (has_target && op.target >= QSV_REG_BITS) QSV_FAIL(h, QSV_EINVAL, "pass: op %d target", o);
             const bool any_ctrl = op.reg_ctrl || op.tile_ctrl || op.glob_ctrl;
-            if ((op.kind == QSV_OP_HAD || op.kind == QSV_OP_SCALE) && any_ctrl) QSV_FAIL(h, QSV_EINVAL, "pass: op %d: HAD/SCALE cannot be controlled", o);
+            if (op.flags & ~(QSV_OPF_PRESIGN | QSV_OPF_PRENEG | QSV_OPF_PREPHASE)) QSV_FAIL(h, QSV_EINVAL, "pass: op %d: unknown flags", o);
+            if (op.flags) {
+                if (op.kind != QSV_OP_HAD && op.kind != QSV_OP_ROT) QSV_FAIL(h, QSV_EINVAL, "pass: op %d: pre-ops need HAD or ROT", o);
+                if (op.reg_ctrl) QSV_FAIL(h, QSV_EINVAL, "pass: op %d: pre-ops exclude register controls", o);
+                if (!(op.flags & QSV_OPF_PRESIGN) && (op.tile_ctrl || op.glob_ctrl))
+                    QSV_FAIL(h, QSV_EINVAL, "pass: op %d: parity masks without QSV_OPF_PRESIGN", o);
+                if ((op.flags & QSV_OPF_PREPHASE) && !(op.m[2] >= -1.0000001 && op.m[2] <= 1.0000001))
+                    QSV_FAIL(h, QSV_EINVAL, "pass: op %d: pre-phase |tan(phi/2)| must be <= 1", o);
+            } else if ((op.kind == QSV_OP_HAD || op.kind == QSV_OP_SCALE) && any_ctrl)
+                QSV_FAIL(h, QSV_EINVAL, "pass: op %d: HAD/SCALE cannot be controlled", o);
             if ((op.kind == QSV_OP_ROT || op.kind == QSV_OP_PHASE) && (!(op.m[0] >= -1.0000001 && op.m[0] <= 1.0000001)))
                 QSV_FAIL(h, QSV_EINVAL, "pass: op %d: |tan(angle/2)| must be <= 1 (split larger angles)", o);
             if ((op.tile_ctrl >> T) || (op.tile_ctrl & regm)) QSV_FAIL(h, QSV_EINVAL, "pass: op %d tile_ctrl names a register position", o);
@@ -483,7 +493,35 @@ int qsv_program_create(qsv_handle *h, const qsv_pass *passes, int n_passes, cons
         delete p;
         return QSV_ECUDA;
     }
+    // specialise every eligible pass (complex128 ring tiles); the rest is interpreted
+    p->jit.assign(n_passes, nullptr);
+    p->jit_coefs.assign(n_passes, {});
+    if (h->jit && qsvjit::enabled() && h->dtype == QSV_C128 && !h->force_simple_pass) {
+        std::vector<std::string> srcs(n_passes);
+        for (int i = 0; i < n_passes; ++i)
+            if (!qsvjit::generate(passes[i], ops ? ops + p->op_offset[i] : nullptr, srcs[i], p->jit_coefs[i])) srcs[i].clear();
+        std::vector<qsvjit::Kernel> ks;
+        std::string err;
+        qsvjit::resolve(h->device, srcs, ks, err);
+        for (int i = 0; i < n_passes; ++i) p->jit[i] = ks[i].fn;
+        if (!err.empty()) h->err = "jit (falling back to the interpreting kernel): " + err;
+    }
     *out = p;
+    return QSV_OK;
+}
+
+static int launch_pass_jit(qsv_handle *h, qsv_program *p, int i) {
+    const uint32_t n_tiles = (uint32_t)(h->n_amps >> qsvjit::kT);
+    const unsigned grid = n_tiles < (uint32_t)h->sm_count ? n_tiles : (unsigned)h->sm_count;
+    void *state = h->d_state;
+    const double2 *tables = p->d_tables + p->fold_offset[i];
+    unsigned long long rank_bits = (unsigned long long)h->rank << h->n_local;
+    unsigned nt = n_tiles;
+    static const double zero = 0.0;
+    void *args[] = {&state, &tables, &rank_bits, &nt,
+                    p->jit_coefs[i].empty() ? (void *)&zero : (void *)p->jit_coefs[i].data()};
+    ScopedTimer t(h, 10, i);
+    QSV_CUDA(h, cudaLaunchKernel((const void *)p->jit[i], dim3(grid), dim3(512), args, sizeof(double2) * 6 * 2048 + 128, h->stream));
     return QSV_OK;
 }
 
@@ -492,10 +530,44 @@ int qsv_program_run(qsv_handle *h, qsv_program *p) {
     if (!p) QSV_FAIL(h, QSV_EINVAL, "program_run: null program");
     QSV_CUDA(h, cudaSetDevice(h->device));
     for (size_t i = 0; i < p->passes.size(); ++i) {
-        int rc = launch_pass(h, &p->passes[i], p->d_passes + i, p->d_ops + p->op_offset[i],
-                             p->d_tables + p->fold_offset[i], (int)i);
+        int rc = p->jit[i] ? launch_pass_jit(h, p, (int)i)
+                           : launch_pass(h, &p->passes[i], p->d_passes + i, p->d_ops + p->op_offset[i],
+                                         p->d_tables + p->fold_offset[i], (int)i);
         if (rc) return rc;
     }
+    return QSV_OK;
+}
+
+int qsv_set_option(qsv_handle *h, int option, long long value) {
+    QSV_CHECK_H(h);
+    switch (option) {
+        case QSV_OPT_JIT: h->jit = value != 0; return QSV_OK;
+        case QSV_OPT_SIMPLE_PASS: h->force_simple_pass = value != 0; return QSV_OK;
+        default: QSV_FAIL(h, QSV_EINVAL, "set_option: unknown option %d", option);
+    }
+}
+
+int qsv_jit_build_pass(const qsv_pass *pass, const qsv_op *ops, size_t *cubin_bytes, char *log, size_t log_cap) {
+    if (!pass || (pass->n_ops > 0 && !ops)) return QSV_EINVAL;
+    std::string src, msg;
+    std::vector<double> coefs;
+    std::vector<char> cubin;
+    int rc = QSV_OK;
+    if (!qsvjit::generate(*pass, ops, src, coefs)) { msg = "pass is not eligible for specialisation"; rc = QSV_EINVAL; }
+    else if (!qsvjit::nvrtc().load()) { msg = "NVRTC unavailable: " + qsvjit::nvrtc().why; rc = QSV_EIO; }
+    else if (!qsvjit::compile(src, cubin, msg)) rc = QSV_ECUDA;
+    if (cubin_bytes) *cubin_bytes = cubin.size();
+    if (log && log_cap) { snprintf(log, log_cap, "%s", msg.c_str()); }
+    return rc;
+}
+
+int qsv_jit_stats(int *compiled, int *disk_hits, int *mem_hits, int *failed, double *compile_seconds) {
+    const qsvjit::Stats &s = qsvjit::stats();
+    if (compiled) *compiled = s.compiled;
+    if (disk_hits) *disk_hits = s.disk_hits;
+    if (mem_hits) *mem_hits = s.mem_hits;
+    if (failed) *failed = s.failed;
+    if (compile_seconds) *compile_seconds = s.compile_s;
     return QSV_OK;
 }
 

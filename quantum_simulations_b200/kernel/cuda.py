@@ -20,7 +20,7 @@ import math
 import numpy as np
 
 from quantum_simulations_b200 import _lib as L
-from quantum_simulations_b200.circuit.passes import PassStep, Dense2QStep, Program, lower_op, Dense2Q
+from quantum_simulations_b200.circuit.passes import PassStep, Dense1QStep, Dense2QStep, Program, lower_op, Dense2Q
 
 _DTYPES = {"complex64": L.QSV_C64, "complex128": L.QSV_C128}
 
@@ -158,15 +158,42 @@ class DeviceState:
         tab = None if step.tables is None else step.tables.ctypes.data_as(C.POINTER(C.c_double))
         self._ck(self.lib.qsv_apply_pass(self._h, C.byref(step.desc), step.ops, tab))
 
-    def run_program(self, prog: Program) -> None:
-        """Execute a compiled program (passes + stand-alone dense 2q kernels) in order."""
+    def set_option(self, option: int, value: int) -> None:
+        self._ck(self.lib.qsv_set_option(self._h, option, value))
+
+    def run_program(self, prog: Program, jit: bool | None = None) -> None:
+        """Execute a compiled program (passes + stand-alone dense 2q kernels) in order.
+
+        jit=None/True: maximal runs of passes go through qsv_program_create, which specialises
+        them at run time (csrc/jit.cuh); jit=False: every pass is interpreted (one-shot
+        qsv_apply_pass)."""
         if prog.n_local != self.n_local or prog.dtype != self.dtype.name:
             raise ValueError("program was compiled for a different shard shape / dtype")
+        if jit is None or jit:
+            run: list = []
+            for step in list(prog.steps) + [None]:
+                if isinstance(step, PassStep):
+                    run.append(step)
+                    continue
+                if run:
+                    h = self.upload_steps(run)
+                    self.replay(h)
+                    self.release_program(h)
+                    run = []
+                if isinstance(step, Dense2QStep):
+                    self.apply_2q(step.qa_pos, step.qb_pos, step.U)
+                elif isinstance(step, Dense1QStep):
+                    self.apply_1q(step.q_pos, step.U)
+                elif step is not None:
+                    raise TypeError(type(step))
+            return
         for step in prog.steps:
             if isinstance(step, PassStep):
                 self.apply_pass(step)
             elif isinstance(step, Dense2QStep):
                 self.apply_2q(step.qa_pos, step.qb_pos, step.U)
+            elif isinstance(step, Dense1QStep):
+                self.apply_1q(step.q_pos, step.U)
             else:
                 raise TypeError(type(step))
 
@@ -175,6 +202,13 @@ class DeviceState:
         steps = prog.steps
         if not all(isinstance(s, PassStep) for s in steps):
             raise ValueError("only all-pass programs can be uploaded")
+        return self.upload_steps(steps)
+
+    def release_program(self, handle) -> None:
+        self._ck(self.lib.qsv_program_destroy(self._h, handle))
+        self._programs = [p for p in self._programs if p.value != handle.value]
+
+    def upload_steps(self, steps):
         n = len(steps)
         passes = (L.QsvPass * max(n, 1))(*[s.desc for s in steps])
         total = sum(s.n_micro_ops for s in steps)

@@ -25,7 +25,7 @@ def compile_circuit(circuit_dict: dict, dtype="complex128", **compiler_kw) -> Pr
 
 
 def simulate(circuit_dict: dict, dtype="complex128", device: int = 0, out: np.ndarray | None = None,
-             fused: bool = True, **compiler_kw) -> np.ndarray:
+             fused: bool = True, jit: bool | None = None, **compiler_kw) -> np.ndarray:
     """Run the circuit on the GPU and return the final state vector (host, `dtype`)."""
     from quantum_simulations_b200.kernel.cuda import DeviceState
 
@@ -35,7 +35,7 @@ def simulate(circuit_dict: dict, dtype="complex128", device: int = 0, out: np.nd
     with DeviceState(n, dtype, device) as st:
         st.init_zero()
         if fused and n >= REG_BITS:
-            st.run_program(PassCompiler(n, dtype=st.dtype.name, **compiler_kw).compile(ops))
+            st.run_program(PassCompiler(n, dtype=st.dtype.name, **compiler_kw).compile(ops), jit=jit)
         else:
             for qs, U in ops:
                 st.apply_op(qs, U)

@@ -65,6 +65,30 @@ def run_pass(psi: np.ndarray, desc: L.QsvPass, ops, n_local: int, rank: int = 0,
             cols = (x & need) == need
             m = [op.m[k] for k in range(4)]
             ctrl_any = bool(op.reg_ctrl or op.tile_ctrl or op.glob_ctrl)
+            if op.flags:
+                # HAD / ROT with pre-ops: the control fields are parity masks of a sign on the b half
+                assert op.kind in (L.OP_HAD, L.OP_ROT) and not op.reg_ctrl
+                assert not (op.flags & ~(L.OPF_PRESIGN | L.OPF_PRENEG | L.OPF_PREPHASE))
+                assert (op.flags & L.OPF_PRESIGN) or not (op.tile_ctrl or op.glob_ctrl)
+                tb = 1 << regs[op.target]
+                x1 = x[(x & tb) != 0]
+                par_c = np.array([bin(int(v) & op.tile_ctrl).count("1") for v in x1])
+                par_r = np.array([bin(int(g) & op.glob_ctrl).count("1") for g in glob])
+                neg = 1 if op.flags & L.OPF_PRENEG else 0
+                sgn = 1.0 - 2.0 * ((par_r[:, None] + par_c[None, :] + neg) & 1)
+                w = work[:, x1] * sgn
+                if op.flags & L.OPF_PREPHASE:
+                    t_, s_ = m[2], m[3]
+                    assert abs(t_) <= 1 + 1e-12 and abs(s_) <= 1 + 1e-12
+                    re, im = w.real.copy(), w.imag.copy()
+                    re = re - t_ * im
+                    im = im + s_ * re
+                    re = re - t_ * im
+                    w = re + 1j * im
+                work[:, x1] = w
+                rows = np.ones(len(glob), dtype=bool)
+                cols = np.ones(1 << t, dtype=bool)
+                ctrl_any = False
             if op.kind in L.OP_WITH_TARGET:
                 assert 0 <= op.target < R and not ((op.reg_ctrl >> op.target) & 1)
                 tb = 1 << regs[op.target]
