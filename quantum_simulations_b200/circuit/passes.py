@@ -335,6 +335,14 @@ class Dense1QStep:
 
 
 @dataclass
+class SwapStep:
+    """Global<->local qubit swap (qsv_swap_global_local): rank bit global_bits[i] <-> local bit
+    local_bits[i] = n_local - len + i.  One all-to-all among groups of 2^len ranks."""
+    global_bits: list
+    local_bits: list
+
+
+@dataclass
 class Program:
     n_qubits: int
     n_local: int
@@ -381,7 +389,7 @@ class PassCompiler:
                  max_rounds: int = 6, restore_layout: bool = True, lookahead: int = 4096,
                  ring: bool | None = None, max_ops: int = 380, x_frame: bool = True,
                  merge_diagonals: bool = True, fold_tables: bool = True,
-                 defer_diagonals: bool = False, absorb: bool = True):
+                 defer_diagonals: bool = False, absorb: bool = True, allow_swaps: bool = True):
         self.n = n_qubits
         self.n_local = n_qubits if n_local is None else n_local
         self.dtype = np.dtype(dtype).name
@@ -411,9 +419,12 @@ class PassCompiler:
         self.fold_tables = fold_tables
         self.defer_diagonals = defer_diagonals
         self.absorb = absorb
+        self.allow_swaps = allow_swaps and self.n_local < self.n
 
     # ---- public -----------------------------------------------------------------------
-    def compile(self, ir_ops, init_pos=None, init_flips=None) -> Program:
+    def compile(self, ir_ops, init_pos=None, init_flips=None, home_pos=None) -> Program:
+        """init_pos[q]: physical position of IR qubit q before the first op (default q);
+        home_pos[q]: position it must have after the last one (default: init_pos[q])."""
         n = self.n
         alias = list(range(n))                      # IR qubit -> content
         xf = list(init_flips) if init_flips is not None else [0] * n   # Pauli-X frame per content
@@ -464,7 +475,7 @@ class PassCompiler:
         pos = list(init_pos) if init_pos is not None else list(range(n))
         home = [0] * n                              # home[content] = position it must end at
         for q in range(n):
-            home[alias[q]] = q if init_pos is None else init_pos[q]
+            home[alias[q]] = home_pos[q] if home_pos is not None else (q if init_pos is None else init_pos[q])
         prog = Program(n, self.n_local, self.dtype)
         live = [s for s in segments if isinstance(s, (Dense2Q, Dense1Q)) or s]
         # uses[c] = micro-ops not yet scheduled that touch content c.  A content with no
@@ -511,6 +522,8 @@ class PassCompiler:
             "micro_ops": sum(s.n_micro_ops for s in ps), "folded_ops": sum(s.n_folded for s in ps),
             "absorbed_ops": sum(s.n_absorbed for s in ps),
             "rounds": sum(s.desc.n_rounds for s in ps),
+            "swaps": sum(isinstance(x, SwapStep) for x in prog.steps),
+            "swap_bits": sum(len(x.global_bits) for x in prog.steps if isinstance(x, SwapStep)),
             "max_rounds_in_pass": max((s.desc.n_rounds for s in ps), default=0),
             "tile_bits": self.t, "low_bits": self.a,
         }
@@ -544,12 +557,14 @@ class PassCompiler:
             run, _ = _scan(remaining, set(tile), self.lookahead)
             if not run:
                 _, missing = _scan(remaining, set(tile), self.lookahead)
-                for i in missing:
-                    c = remaining[i].target
-                    if pos[c] >= self.n_local:
-                        raise NotImplementedError(
-                            f"non-local gate: content {c} sits on rank bit {pos[c]} and must be "
-                            "mixed; swap it with a local bit first")
+                stuck = [remaining[i].target for i in missing if pos[remaining[i].target] >= self.n_local]
+                if stuck and self.allow_swaps:
+                    self._swap_in(remaining, pos, home, prog, xf)
+                    continue
+                for c in stuck:
+                    raise NotImplementedError(
+                        f"non-local gate: content {c} sits on rank bit {pos[c]} and must be "
+                        "mixed; swap it with a local bit first")
                 raise RuntimeError("planner made no progress")
             chosen = [remaining[i] for i in run]
             rounds, deferred = self._plan_rounds(chosen, tile)
@@ -656,14 +671,17 @@ class PassCompiler:
         return rounds, pend
 
     # ---- pass emission ----------------------------------------------------------------
-    def _emit_pass(self, tile, rounds, pos, home, park, final, xf=None) -> PassStep:
+    def _emit_pass(self, tile, rounds, pos, home, park, final, xf=None, explicit_store=None) -> PassStep:
         t, W = self.t, min(self.W, self.t - REG_BITS)
         load_bits = sorted(pos[c] for c in tile)
         at = {p: c for c, p in enumerate(pos)}
         content = [at[p] for p in load_bits]              # content at tile index i
         idx_of = {c: i for i, c in enumerate(content)}
         finished = {c for c in content if self._uses[c] == 0} if self.restore_layout else set()
-        store = self._choose_store(content, load_bits, home, park, final, finished)   # per tile index
+        if explicit_store is not None:
+            store = [explicit_store[c] for c in content]
+        else:
+            store = self._choose_store(content, load_bits, home, park, final, finished)   # per tile index
 
         lo_load = {i for i in range(t) if load_bits[i] < W}
         lo_store = {i for i in range(t) if store[i] < W}
@@ -926,10 +944,116 @@ class PassCompiler:
             o.flags = flags
         return o
 
+    # ---- global <-> local swaps ---------------------------------------------------------
+    def _relabel_to(self, prog, pos, home, xf, want: dict, touch=()) -> None:
+        """Relabel-only passes that move content c to local position want[c] (the displaced
+        contents take the vacated slots).  Flips of finished contents are materialised; contents
+        in `touch` are put through a pass even if they are already in place."""
+        todo = {c: p for c, p in want.items() if pos[c] != p or c in touch}
+        while todo:
+            at = {p: c for c, p in enumerate(pos)}
+            chosen = set(range(self.a))
+            batch = {}
+            for c, p in todo.items():
+                extra = {pos[c], p} - chosen
+                if len(chosen) + len(extra) > self.t:
+                    continue
+                chosen |= extra
+                batch[c] = p
+            if not batch:
+                raise RuntimeError("relabel: tile too small")
+            for p in range(self.n_local - 1, -1, -1):
+                if len(chosen) >= self.t:
+                    break
+                chosen.add(p)
+            tile = [at[p] for p in sorted(chosen)]
+            # explicit store: movers go to their slots; the evicted take the movers' old slots
+            new = {c: pos[c] for c in tile}
+            for c, p in batch.items():
+                d = next(x for x in tile if new[x] == p)
+                new[d], new[c] = new[c], p
+            prog.steps.append(self._emit_pass(tile, [], pos, home, [], False, xf, explicit_store=new))
+            todo = {c: p for c, p in todo.items() if c not in batch}
+
+    def _do_swap(self, prog, pos, home, xf, incoming: list, outgoing: list, materialise=False) -> None:
+        """incoming[i] (on a rank bit) <-> outgoing[i] (local): park the outgoing contents on the
+        top local positions, then one all-to-all."""
+        s_ = len(incoming)
+        assert s_ == len(outgoing) and s_ > 0
+        top = [self.n_local - s_ + i for i in range(s_)]
+        touch = {c for c in outgoing if xf[c]} if materialise else ()
+        self._relabel_to(prog, pos, home, xf, {c: top[i] for i, c in enumerate(outgoing)}, touch)
+        gbits = [pos[c] for c in incoming]
+        prog.steps.append(SwapStep(gbits, top))
+        for i in range(s_):
+            pos[incoming[i]], pos[outgoing[i]] = top[i], gbits[i]
+
+    def _swap_in(self, remaining, pos, home, prog, xf) -> None:
+        """The stage is exhausted: bring every rank-bit content that still has to be MIXED into the
+        shard, sending out the local contents that need it least (finished first, then those
+        whose next use as a target is furthest away; a content whose home is a rank bit is
+        preferred so that the final restoration may need no swap)."""
+        first_target: dict = {}
+        for i, op in enumerate(remaining):
+            if op.target is not None and op.target not in first_target:
+                first_target[op.target] = i
+        incoming = sorted((c for c in first_target if pos[c] >= self.n_local), key=lambda c: first_target[c])
+        if not incoming:
+            raise RuntimeError("swap requested but no rank-bit content needs mixing")
+        inf = len(remaining) + 1
+
+        def key(c):
+            return (-first_target.get(c, inf), 0 if home[c] >= self.n_local else 1, -pos[c])
+
+        locals_ = sorted((c for c in range(self.n) if pos[c] < self.n_local), key=key)
+        chosen = locals_[: len(incoming)]
+        # send a content whose home is one of the vacated rank bits exactly there
+        outgoing = [None] * len(incoming)
+        for i, cin in enumerate(incoming):
+            hit = next((c for c in chosen if home[c] == pos[cin]), None)
+            if hit is not None:
+                outgoing[i] = hit
+                chosen.remove(hit)
+        for i in range(len(incoming)):
+            if outgoing[i] is None:
+                outgoing[i] = chosen.pop(0)
+        # a flip pending on an unfinished outgoing content simply stays in the frame (xf)
+        self._do_swap(prog, pos, home, xf, incoming, outgoing)
+
+    def _restore_global(self, prog, pos, home, xf) -> None:
+        """After the last op: contents whose home is a rank bit go back out, the exiles on rank
+        bits come home.  A pending X on a rank bit is brought into the shard first (it can
+        only be materialised as a store-address flip)."""
+        n_loc = self.n_local
+        flipped_glob = [c for c in range(self.n) if pos[c] >= n_loc and xf[c] and home[c] == pos[c]]
+        if flipped_glob:
+            locals_ = sorted((c for c in range(self.n) if pos[c] < n_loc), key=lambda c: -pos[c])
+            self._do_swap(prog, pos, home, xf, flipped_glob, locals_[: len(flipped_glob)])
+        for _ in range(4):
+            out = [c for c in range(self.n) if pos[c] < n_loc and home[c] >= n_loc]
+            inc = [c for c in range(self.n) if pos[c] >= n_loc and home[c] != pos[c]]
+            if not out and not inc:
+                return
+            # every rank bit that is someone's unmet home, or holds a displaced content, takes part;
+            # the content whose home it is goes there if it is local, else a filler that comes
+            # back in the next iteration (a rank-bit -> rank-bit move needs two swaps)
+            at = {p: c for c, p in enumerate(pos)}
+            bits = sorted({home[c] for c in out} | {pos[c] for c in inc})
+            incoming = [at[b] for b in bits]
+            out_by_home = {home[c]: c for c in out}
+            fillers = [c for c in sorted(range(self.n), key=lambda c: -pos[c])
+                       if pos[c] < n_loc and home[c] < n_loc]
+            outgoing = [out_by_home[b] if b in out_by_home else fillers.pop(0) for b in bits]
+            # all ops are done (uses == 0): the relabel pass materialises the flips of what leaves
+            self._do_swap(prog, pos, home, xf, incoming, outgoing, materialise=True)
+        raise RuntimeError("rank-bit restoration did not converge")
+
     # ---- layout restoration -----------------------------------------------------------
     def _restore(self, prog, pos, home, xf) -> None:
         """Relabel-only passes until every local content is at its home position."""
         n_loc = self.n_local
+        if n_loc < self.n and self.allow_swaps:
+            self._restore_global(prog, pos, home, xf)
         for _ in range(8 * self.n + 8):
             bad = [c for c in range(self.n) if pos[c] < n_loc and pos[c] != home[c]]
             flipped = [c for c in range(self.n) if xf[c]]

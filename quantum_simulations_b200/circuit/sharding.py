@@ -1,0 +1,91 @@
+"""Stage planning for a state sharded over G = 2^g devices by its top g physical index bits.
+
+This is the role of the reference's ``atlas_stages`` (wenbo_engine/circuit/staging.py:587-634)
+and of HiSVSIM's part files (hisvsim_repo/svsim-mpi.hpp:123-173): group gates into stages that
+only MIX local qubits and connect the stages with qubit swaps.  The mechanics live in the pass
+compiler (circuit/passes.py: ``PassCompiler(n, n_local)`` inserts ``SwapStep``s whenever the
+remaining gates need a rank-bit qubit mixed, and restores the layout at the end); this module
+chooses the one free parameter that decides how many swaps that takes:
+
+    |0...0> is invariant under qubit relabelling, so when a run starts from the zero state the
+    INITIAL placement of logical qubits on physical bits is free.  Starting with g "cheap"
+    qubits on the rank bits and the logical top qubits local lets the planner finish the top
+    qubits in the first stage and end with them on their home rank bits: one all-to-all per
+    circuit instead of two (swap in + swap back).
+
+Cost model (seconds, per device), used only to rank candidate placements:
+    pass   2 * sizeof(amp) * 2^n_local / HBM_BW   (+ a term per FP64 op, small)
+    swap   (1 - 2^-s) * sizeof(amp) * 2^n_local / NVLINK_BW  (+ one relabel pass, already counted)
+"""
+from __future__ import annotations
+
+from quantum_simulations_b200.circuit.passes import PassCompiler, PassStep, Program, SwapStep
+
+HBM_BW = 5.8e12          # achieved by a pass kernel, B/s (profiles/r01)
+NVLINK_BW = 0.55e12      # achieved by the chunked in-place exchange, B/s per direction
+
+
+def estimate_seconds(prog: Program) -> float:
+    amp = 16 if prog.dtype == "complex128" else 8
+    shard = amp * (1 << prog.n_local)
+    t = 0.0
+    for s in prog.steps:
+        if isinstance(s, PassStep):
+            t += 2 * shard / HBM_BW * (1.0 + 0.012 * s.n_micro_ops)
+        elif isinstance(s, SwapStep):
+            t += (1.0 - 0.5 ** len(s.global_bits)) * shard / NVLINK_BW
+    return t
+
+
+def candidate_placements(n: int, g: int) -> list[list[int]]:
+    """init_pos candidates: which g logical qubits start on the rank bits [n-g, n)."""
+    ident = list(range(n))
+    out = [ident]
+    if g == 0:
+        return out
+
+    def place(global_qubits):
+        # the chosen qubits take the rank bits; the logical top qubits take their local slots
+        pos = list(range(n))
+        tops = [q for q in range(n - g, n) if q not in global_qubits]
+        vac = [q for q in global_qubits if q < n - g]
+        for q, t in zip(vac, tops):
+            pos[q], pos[t] = pos[t], pos[q]
+        return pos
+
+    out.append(place(list(range(g))))                               # bottom qubits global first
+    mid = (n - g) // 2
+    out.append(place(list(range(mid - g // 2, mid - g // 2 + g))))  # middle qubits
+    step = max(1, (n - g) // (g + 1))
+    out.append(place([min(n - g - 1, step * (i + 1)) for i in range(g)]))   # spread out
+    uniq = []
+    for p in out:
+        if p not in uniq:
+            uniq.append(p)
+    return uniq
+
+
+def plan(ir_ops, n_qubits: int, n_local: int, dtype: str = "complex128", zero_init: bool = True,
+         **compiler_kw) -> Program:
+    """Compile `ir_ops` for shards of 2^n_local amplitudes.  With zero_init the initial
+    placement is chosen among a few candidates by the cost model; the final layout is always
+    the identity (logical qubit q on physical bit q)."""
+    comp = PassCompiler(n_qubits, n_local, dtype, **compiler_kw)
+    g = n_qubits - n_local
+    ident = list(range(n_qubits))
+    if g == 0 or not zero_init:
+        return comp.compile(ir_ops)
+    best, best_t = None, None
+    for init in candidate_placements(n_qubits, g):
+        try:
+            prog = comp.compile(ir_ops, init_pos=init, home_pos=ident)
+        except (NotImplementedError, RuntimeError):
+            continue
+        t = estimate_seconds(prog)
+        if best is None or t < best_t:
+            best, best_t = prog, t
+            best.stats["init_pos"] = init
+    if best is None:
+        return comp.compile(ir_ops)
+    best.stats["estimated_s"] = best_t
+    return best

@@ -169,6 +169,11 @@ extern "C" int qsv_swap_global_local(qsv_handle *h, int n_swap, const int *globa
     }
     char *state = (char *)h->d_state;
     const size_t n_chunks = (block_bytes + chunk - 1) / chunk;
+    cudaEvent_t t_a = nullptr, t_b = nullptr;
+    if (h->timing) {
+        cudaEventCreate(&t_a); cudaEventCreate(&t_b);
+        cudaEventRecord(t_a, h->stream);
+    }
     // main stream: NCCL group of chunk k; copy stream: bounce -> vacated slots of chunk k.
     // Half (k&1) of the bounce buffer is reused by chunk k+2, which waits for copy k.
     for (size_t k = 0; k < n_chunks; ++k) {
@@ -198,6 +203,10 @@ extern "C" int qsv_swap_global_local(qsv_handle *h, int n_swap, const int *globa
     }
     QSVX_CUDA(h, cudaStreamWaitEvent(h->stream, c->ev_copy[0], 0));
     if (n_chunks > 1) QSVX_CUDA(h, cudaStreamWaitEvent(h->stream, c->ev_copy[1], 0));
+    if (h->timing) {
+        cudaEventRecord(t_b, h->stream);
+        h->timed.push_back({t_a, t_b, 20 + n_swap, -1});      // kind 20+s: swap of s bits
+    }
     return QSV_OK;
 }
 

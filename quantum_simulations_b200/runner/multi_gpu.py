@@ -1,0 +1,158 @@
+"""One process per GPU: execute a sharded program (circuit/sharding.py) on this rank's shard.
+
+The reference's multi-chunk runner walks chunk files and, for a gate on a "non-local" qubit,
+loads the 2 or 4 chunks of a group together (wenbo_engine/runner/single_node.py:219-321).
+Here every rank keeps its 2^n_local amplitudes in HBM for the whole run; stages only mix local
+qubits (zero communication, rank bits enter as constants) and are connected by
+``SwapStep``s = one NCCL all-to-all of the swapped blocks over NVLink (csrc/exchange.cuh).
+
+``torch.distributed`` is used for PLUMBING only (rendezvous: broadcast of the NCCL unique id,
+barriers, max-reduction of timings); no tensor of the state ever passes through it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+
+import numpy as np
+
+from quantum_simulations_b200 import _lib as L
+from quantum_simulations_b200.circuit import sharding
+from quantum_simulations_b200.circuit.io import validate_circuit_dict
+from quantum_simulations_b200.circuit.passes import PassStep, Program, SwapStep
+
+
+def execute(prog: Program, backend) -> None:
+    """Run `prog` on one shard.  `backend` provides run_passes(list[PassStep]) and
+    swap(global_bits, local_bits); consecutive passes are handed over together so that the
+    CUDA backend can specialise and replay them as one program."""
+    run: list = []
+    for step in list(prog.steps) + [None]:
+        if isinstance(step, PassStep):
+            run.append(step)
+            continue
+        if run:
+            backend.run_passes(run)
+            run = []
+        if isinstance(step, SwapStep):
+            backend.swap(list(step.global_bits), list(step.local_bits))
+        elif step is not None:
+            raise TypeError(f"sharded programs hold passes and swaps only, got {type(step).__name__}")
+
+
+class CudaShard:
+    """backend of `execute` over libqsv: a DeviceState for (rank, world) with an NCCL communicator."""
+
+    def __init__(self, n_qubits: int, rank: int, world: int, dtype="complex128", device: int | None = None,
+                 unique_id: bytes | None = None):
+        from quantum_simulations_b200.kernel.cuda import DeviceState
+        self.state = DeviceState(n_qubits, dtype, rank if device is None else device, rank, world)
+        self.rank, self.world = rank, world
+        self._uploaded: dict = {}
+        if world > 1:
+            if unique_id is None or len(unique_id) != 128:
+                raise ValueError("world > 1 needs the 128-byte NCCL unique id of rank 0 (nccl_unique_id())")
+            buf = C.create_string_buffer(unique_id, 128)
+            self.state._ck(self.state.lib.qsv_comm_init(self.state._h, buf))
+
+    def prepare(self, prog: Program) -> None:
+        """Upload (and specialise) every run of passes once; execute() then only replays."""
+        run: list = []
+        for step in list(prog.steps) + [None]:
+            if isinstance(step, PassStep):
+                run.append(step)
+            elif run:
+                self._uploaded[id(run[0])] = self.state.upload_steps(run)
+                run = []
+
+    def run_passes(self, steps) -> None:
+        h = self._uploaded.get(id(steps[0]))
+        if h is None:
+            h = self.state.upload_steps(steps)
+            self.state.replay(h)
+            self.state.release_program(h)
+        else:
+            self.state.replay(h)
+
+    def swap(self, global_bits, local_bits) -> None:
+        s = len(global_bits)
+        g = (C.c_int * s)(*global_bits)
+        l = (C.c_int * s)(*local_bits)
+        self.state._ck(self.state.lib.qsv_swap_global_local(self.state._h, s, g, l))
+
+    def close(self) -> None:
+        self.state.close()
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    rc = L.load().qsv_comm_unique_id(buf)
+    if rc:
+        raise L.QsvError(rc, "ncclGetUniqueId failed (is libnccl.so.2 loadable?)")
+    return buf.raw
+
+
+# ------------------------------------------------------------------ torch.distributed plumbing
+def dist_env() -> tuple[int, int, int]:
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")),
+            int(os.environ.get("WORLD_SIZE", "1")))
+
+
+def init_plumbing():
+    """gloo process group over MASTER_ADDR/MASTER_PORT (set by torchrun); returns torch.distributed."""
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29531")
+        dist.init_process_group(backend="gloo")
+    return dist
+
+
+def share_unique_id(dist, rank: int) -> bytes:
+    box = [nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    return box[0]
+
+
+class ShardedSimulator:
+    """Public multi-GPU surface (run under torchrun, one process per GPU).  The constructor does
+    the one-time work (rendezvous, NCCL communicator, shard allocation); ``simulate`` runs one
+    circuit from |0...0> and returns THIS rank's shard in host memory."""
+
+    def __init__(self, n_qubits: int, dtype="complex128"):
+        self.rank, self.local_rank, self.world = dist_env()
+        self.n = n_qubits
+        self.g = int(math.log2(self.world))
+        if 1 << self.g != self.world:
+            raise ValueError("world size must be a power of two")
+        self.dtype = np.dtype(dtype)
+        self.dist = init_plumbing() if self.world > 1 else None
+        uid = share_unique_id(self.dist, self.rank) if self.world > 1 else None
+        self.shard = CudaShard(n_qubits, self.rank, self.world, dtype, self.local_rank, uid)
+
+    def plan(self, circuit_dict: dict, **compiler_kw) -> Program:
+        from quantum_simulations_b200.kernel.cuda_dense import circuit_ops
+        cd = validate_circuit_dict(circuit_dict)
+        if cd["number_of_qubits"] != self.n:
+            raise ValueError("circuit size differs from the simulator's")
+        return sharding.plan(circuit_ops(cd), self.n, self.n - self.g, self.dtype.name, **compiler_kw)
+
+    def simulate(self, circuit_dict: dict, out: np.ndarray | None = None, **compiler_kw) -> np.ndarray:
+        prog = self.plan(circuit_dict, **compiler_kw)
+        self.shard.state.init_zero()
+        execute(prog, self.shard)
+        return self.shard.state.download(out)
+
+    def close(self) -> None:
+        self.shard.close()
+
+
+def simulate_sharded(circuit_dict: dict, dtype="complex128", out: np.ndarray | None = None, **compiler_kw):
+    """One-shot form of ShardedSimulator."""
+    cd = validate_circuit_dict(circuit_dict)
+    sim = ShardedSimulator(cd["number_of_qubits"], dtype)
+    try:
+        return sim.simulate(cd, out, **compiler_kw)
+    finally:
+        sim.close()

@@ -1,0 +1,86 @@
+"""Worker of tests/test_multi_process_gloo.py: one PROCESS per shard, gloo for the exchange.
+
+Runs the product-side multi-GPU logic (sharding.plan + runner.multi_gpu.execute) with the NumPy
+pass emulator standing in for libqsv (there is no GPU here); the SwapStep is a real
+all-to-all between processes with the same block arithmetic as csrc/exchange.cuh."""
+from __future__ import annotations
+
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+
+class EmuShard:
+    def __init__(self, n, rank, world, dist):
+        import math
+        self.n, self.rank, self.world, self.dist = n, rank, world, dist
+        self.n_local = n - int(math.log2(world))
+        self.psi = np.zeros(1 << self.n_local, dtype=np.complex128)
+        if rank == 0:
+            self.psi[0] = 1.0
+        self.swaps = 0
+
+    def run_passes(self, steps):
+        from tests.pass_emulator import run_pass
+        for s in steps:
+            run_pass(self.psi, s.desc, s.ops, self.n_local, self.rank, s.tables)
+
+    def swap(self, global_bits, local_bits):
+        import torch
+        s = len(global_bits)
+        assert list(local_bits) == [self.n_local - s + i for i in range(s)]
+        me = 0
+        for i, gb in enumerate(global_bits):
+            me |= ((self.rank >> (gb - self.n_local)) & 1) << i
+        blocks = self.psi.reshape(1 << s, -1)
+        reqs, recv = [], {}
+        for d in range(1 << s):
+            if d == me:
+                continue
+            peer = self.rank
+            for i, gb in enumerate(global_bits):
+                rb = gb - self.n_local
+                peer = (peer & ~(1 << rb)) | (((d >> i) & 1) << rb)
+            out = torch.from_numpy(np.ascontiguousarray(blocks[d]).view(np.float64).copy())
+            recv[d] = torch.empty_like(out)
+            reqs.append(self.dist.isend(out, dst=peer))
+            reqs.append(self.dist.irecv(recv[d], src=peer))
+        for r in reqs:
+            r.wait()
+        for d, t in recv.items():
+            blocks[d] = t.numpy().view(np.complex128)
+        self.swaps += 1
+
+
+def main():
+    import torch.distributed as dist
+    from quantum_simulations_b200 import workloads as W
+    from quantum_simulations_b200.circuit import sharding
+    from quantum_simulations_b200.circuit.io import validate_circuit_dict
+    from quantum_simulations_b200.kernel.cuda_dense import circuit_ops
+    from quantum_simulations_b200.runner.multi_gpu import execute, dist_env, init_plumbing
+
+    rank, _, world = dist_env()
+    dist = init_plumbing()
+    out_dir = Path(sys.argv[1])
+    n = int(sys.argv[2])
+    for name, cd in (("random_1q_cz", W.random_1q_cz(n, 12, 99)), ("qft", W.qft(n)), ("random_mixed", W.random_mixed(n, 100, 4))):
+        cd = validate_circuit_dict(cd)
+        g = world.bit_length() - 1
+        prog = sharding.plan(circuit_ops(cd), n, n - g, tile_bits=6, low_bits=2)
+        shard = EmuShard(n, rank, world, dist)
+        execute(prog, shard)
+        np.save(out_dir / f"{name}_rank{rank}.npy", shard.psi)
+        if rank == 0:
+            (out_dir / f"{name}_swaps.txt").write_text(str(shard.swaps))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,45 @@
+"""Worker of tests/test_multi_gpu.py (run under torchrun on a multi-GPU box): real libqsv
+shards + NCCL swaps, gathered over gloo on rank 0 and compared with the C oracle."""
+from __future__ import annotations
+
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+
+def main():
+    import torch
+    from oracle import c_oracle as CO
+    from quantum_simulations_b200 import workloads as W
+    from quantum_simulations_b200.circuit.io import validate_circuit_dict
+    from quantum_simulations_b200.runner.multi_gpu import ShardedSimulator
+
+    n = int(sys.argv[1])
+    sim = ShardedSimulator(n)
+    dist, rank, world = sim.dist, sim.rank, sim.world
+    worst = 0.0
+    for name, cd in (("random_1q_cz", W.random_1q_cz(n, 20, 1234)), ("qft", W.qft(n)), ("ghz", W.ghz(n)),
+                     ("random_mixed", W.random_mixed(n, 300, 8))):
+        cd = validate_circuit_dict(cd)
+        shard = sim.simulate(cd)
+        parts = [torch.empty(shard.size * 2, dtype=torch.float64) for _ in range(world)] if rank == 0 else None
+        dist.gather(torch.from_numpy(shard.view(np.float64).copy()), parts, dst=0)
+        if rank == 0:
+            got = np.concatenate([p.numpy().view(np.complex128) for p in parts])
+            want = CO.simulate_c(cd)
+            err = float(np.abs(got - want).max())
+            print(f"{name}: n={n} world={world} max|d|={err:.3e}", flush=True)
+            worst = max(worst, err)
+    sim.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0 and worst > 1e-12:
+        raise SystemExit(f"multi-GPU parity failed: {worst}")
+
+
+if __name__ == "__main__":
+    main()

@@ -8,7 +8,7 @@ from __future__ import annotations
 import numpy as np
 
 from quantum_simulations_b200 import _lib as L
-from quantum_simulations_b200.circuit.passes import PassStep, Dense2QStep, Dense1QStep, Program
+from quantum_simulations_b200.circuit.passes import PassStep, Dense2QStep, Dense1QStep, Program, SwapStep
 from oracle import ref_dense as O
 
 R = L.QSV_REG_BITS
@@ -142,6 +142,32 @@ def run_program(prog: Program, psi: np.ndarray, rank: int = 0) -> np.ndarray:
             O.apply_2q(psi, step.qa_pos, step.qb_pos, step.U)
         elif isinstance(step, Dense1QStep):
             O.apply_1q(psi, step.q_pos, step.U)
+        else:
+            raise AssertionError(type(step))
+    return psi
+
+
+def swap_bits_full(psi: np.ndarray, n: int, global_bits, local_bits) -> np.ndarray:
+    """SwapStep on the FULL 2^n vector (rank bits = top index bits): exchange index bits."""
+    t = psi.reshape((2,) * n)                       # axis k <-> index bit n-1-k
+    for g, l in zip(global_bits, local_bits):
+        t = np.swapaxes(t, n - 1 - g, n - 1 - l)
+    return np.ascontiguousarray(t).reshape(-1)
+
+
+def run_program_sharded(prog: Program, psi: np.ndarray) -> np.ndarray:
+    """Execute a program compiled for n_local < n on all 2^(n - n_local) shards of `psi`."""
+    n, n_loc = prog.n_qubits, prog.n_local
+    world = 1 << (n - n_loc)
+    for step in prog.steps:
+        if isinstance(step, PassStep):
+            shards = psi.reshape(world, 1 << n_loc)
+            for r in range(world):
+                run_pass(shards[r], step.desc, step.ops, n_loc, r, step.tables)
+        elif isinstance(step, SwapStep):
+            assert all(g >= n_loc for g in step.global_bits)
+            assert list(step.local_bits) == [n_loc - len(step.local_bits) + i for i in range(len(step.local_bits))]
+            psi = swap_bits_full(psi, n, step.global_bits, step.local_bits)
         else:
             raise AssertionError(type(step))
     return psi

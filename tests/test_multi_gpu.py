@@ -1,0 +1,25 @@
+"""Real multi-GPU parity (needs >= 2 GPUs on the box; skipped otherwise)."""
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _gpus() -> int:
+    from quantum_simulations_b200 import _lib as L
+    return L.load().qsv_device_count()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_gpus_match_oracle(world):
+    if _gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(29700 + world),
+           str(ROOT / "tests" / "multi_gpu_worker.py"), "20"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]

@@ -155,7 +155,9 @@ def test_rank_bit_controls_and_nonlocal_targets():
         run_program(prog, shard, rank=rank)
         assert np.abs(shard - want[rank << n_local:(rank + 1) << n_local]).max() <= 1e-12
     with pytest.raises(NotImplementedError, match="non-local"):
-        PassCompiler(n, n_local, tile_bits=5, low_bits=1).compile([([7], G.H())])
+        PassCompiler(n, n_local, tile_bits=5, low_bits=1, allow_swaps=False).compile([([7], G.H())])
+    prog = PassCompiler(n, n_local, tile_bits=5, low_bits=1).compile([([7], G.H())])   # default: swap it in
+    assert prog.stats["swaps"] == 2
 
 
 def test_headline_plan_sizes():
