@@ -375,7 +375,8 @@ def bench_multi(args) -> None:
                          "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
                          "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_pass_ms,
                          "launches_timed": len(pass_ms), "share_of_step": sum(pass_ms) / total_ms},
-            "nvlink": {"swaps": nv, "share_of_step": sum(ms for ms, _ in swap_ms) / total_ms if swap_ms else 0.0,
+            "nvlink": {"path": "peer-memory kernel (CUDA IPC, loads/stores over NVLink)" if sim.peer_swap
+                       else f"chunked ncclSend/ncclRecv ({sim.shard.peer_error or 'QSV_SWAP=nccl'})", "swaps": nv, "share_of_step": sum(ms for ms, _ in swap_ms) / total_ms if swap_ms else 0.0,
                        "peak_gbs_per_direction": 900.0},
             "gpu_launches": len(per_launch) + 2 * args.steps,
             "clocks": clk,

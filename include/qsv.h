@@ -197,6 +197,7 @@ int qsv_program_destroy(qsv_handle *h, qsv_program *p);
  * interpreting kernels; so does a missing libnvrtc (qsv_last_error says why). */
 #define QSV_OPT_JIT          1   /* 1 (default) / 0                                        */
 #define QSV_OPT_SIMPLE_PASS  2   /* 1: run passes on the one-CTA-per-tile kernel (tests)    */
+#define QSV_OPT_PEER_SWAP    3   /* 1 (default): swaps go through mapped peer memory when available */
 int qsv_set_option(qsv_handle *h, int option, long long value);
 int qsv_jit_stats(int *compiled, int *disk_hits, int *mem_hits, int *failed, double *compile_seconds);
 /* Generate + NVRTC-compile the specialised kernel of one pass WITHOUT a device (build check /
@@ -216,6 +217,13 @@ int qsv_sample(qsv_handle *h, uint64_t seed_unused, int shots, const double *sor
 int qsv_comm_unique_id(void *id128);                       /* ncclGetUniqueId, 128 bytes   */
 int qsv_comm_init(qsv_handle *h, const void *id128);       /* ncclCommInitRank(world,rank) */
 int qsv_swap_global_local(qsv_handle *h, int n_swap, const int *global_bits, const int *local_bits);
+/* Peer-memory path of the swap (one box, one process per GPU): every rank exports its shard with
+ * CUDA IPC (64-byte handle), the host plumbing all-gathers the handles, qsv_comm_set_peers maps them.
+ * The swap is then ONE kernel that exchanges the block pairs in place with loads/stores through
+ * NVLink (no bounce buffer, no NCCL data path; NCCL only provides the two stream-ordered barriers).
+ * Without it (or QSV_OPT_PEER_SWAP=0) the chunked ncclSend/ncclRecv exchange is used. */
+int qsv_comm_ipc_handle(qsv_handle *h, void *out64);
+int qsv_comm_set_peers(qsv_handle *h, const void *handles /* world x 64 bytes */);
 /* Sum one double across all shards (norm, sampling offsets). world==1: no-op. */
 int qsv_allreduce_sum(qsv_handle *h, double *value);
 

@@ -18,7 +18,7 @@ QSV_MAX_TILE_BITS, QSV_REG_BITS, QSV_MAX_ROUNDS = 14, 4, 16
 OP_HAD, OP_ROT, OP_XSWAP, OP_YSWAP, OP_PHASE, OP_SIGN, OP_SCALE = range(7)
 OP_WITH_TARGET = (OP_HAD, OP_ROT, OP_XSWAP, OP_YSWAP)
 OPF_PRESIGN, OPF_PRENEG, OPF_PREPHASE = 1, 2, 4
-OPT_JIT, OPT_SIMPLE_PASS = 1, 2
+OPT_JIT, OPT_SIMPLE_PASS, OPT_PEER_SWAP = 1, 2, 3
 
 
 class QsvOp(C.Structure):
@@ -87,6 +87,8 @@ SIGNATURES = {
     "qsv_comm_unique_id": (C.c_int, [C.c_void_p]),
     "qsv_comm_init": (C.c_int, [_H, C.c_void_p]),
     "qsv_swap_global_local": (C.c_int, [_H, C.c_int, _ip, _ip]),
+    "qsv_comm_ipc_handle": (C.c_int, [_H, C.c_void_p]),
+    "qsv_comm_set_peers": (C.c_int, [_H, C.c_void_p]),
     "qsv_allreduce_sum": (C.c_int, [_H, _dp]),
     "qsv_timing_enable": (C.c_int, [_H, C.c_int]),
     "qsv_get_timings": (C.c_int, [_H, C.POINTER(QsvTiming), C.c_int, _ip]),

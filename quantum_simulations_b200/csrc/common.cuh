@@ -72,6 +72,8 @@ struct qsv_handle {
     struct TimedLaunch { cudaEvent_t a, b; int kind, pass_index; };
     std::vector<TimedLaunch> timed;
     cudaEvent_t t0 = nullptr, t1 = nullptr;   // qsv_timer_*
+    cudaEvent_t swap_t0 = nullptr, swap_t1 = nullptr;
+    bool use_peer_swap = true;        // swap through mapped peer memory when qsv_comm_set_peers succeeded
     // comm (NCCL) — opaque here, owned by exchange.cuh
     void *comm = nullptr;
     std::string err;

@@ -63,6 +63,9 @@ inline Nccl &nccl() { static Nccl n; return n; }
 
 struct Comm {
     ncclComm_t comm = nullptr;
+    // peer-memory path: the other shards of the box mapped into this process (CUDA IPC)
+    std::vector<void *> peer;    // peer[r] = rank r's shard, nullptr if not mapped
+    bool peers_ready = false;
     void *bounce = nullptr;      // (peers) x chunk bytes, double buffered
     size_t bounce_bytes = 0;
     cudaStream_t copy_stream = nullptr;
@@ -75,6 +78,7 @@ struct Comm {
 static inline void qsv_comm_teardown(qsv_handle *h) {
     auto *c = (qsvx::Comm *)h->comm;
     if (!c) return;
+    for (size_t r = 0; r < c->peer.size(); ++r) if (c->peer[r] && (int)r != h->rank) cudaIpcCloseMemHandle(c->peer[r]);
     if (c->comm) qsvx::nccl().CommDestroy(c->comm);
     if (c->bounce) cudaFree(c->bounce);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -104,6 +108,17 @@ static inline void qsv_comm_teardown(qsv_handle *h) {
         if (e_ != cudaSuccess) QSVX_FAIL(h, QSV_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); \
     } while (0)
 
+static inline void qsvx_timer_begin(qsv_handle *h) {
+    if (!h->timing) return;
+    cudaEventCreate(&h->swap_t0); cudaEventCreate(&h->swap_t1);
+    cudaEventRecord(h->swap_t0, h->stream);
+}
+static inline void qsvx_timer_end(qsv_handle *h, int kind) {
+    if (!h->timing) return;
+    cudaEventRecord(h->swap_t1, h->stream);
+    h->timed.push_back({h->swap_t0, h->swap_t1, kind, -1});
+}
+
 extern "C" int qsv_comm_unique_id(void *id128) {
     if (!id128) return QSV_EINVAL;
     if (!qsvx::nccl().load()) return QSV_ECOMM;
@@ -127,6 +142,83 @@ extern "C" int qsv_comm_init(qsv_handle *h, const void *id128) {
     for (auto &e : c->ev_xfer) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     for (auto &e : c->ev_copy) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     h->comm = c;
+    return QSV_OK;
+}
+
+// ---- peer-memory exchange -------------------------------------------------------------
+// The block pair (rank a: block b) <-> (rank b: block a) is swapped IN PLACE by plain loads and
+// stores through NVLink: rank a owns the first half of the pair's elements, rank b the second
+// half (a < b in swapped-bit order), so every element is touched by exactly one thread of one
+// GPU: no bounce buffer, no extra HBM pass, both NVLink directions carry one block each.
+struct PeerTable { void *ptr[8]; };
+
+template <typename V, int U>
+__global__ void __launch_bounds__(512)
+k_swap_peer(V *__restrict__ mine, PeerTable peers, const int n_peers, const int me, const uint64_t block_amps) {
+    const uint64_t half = block_amps >> 1;
+    const uint64_t total = (uint64_t)(n_peers - 1) * half;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t e0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e0 < total; e0 += stride * U) {
+        V x[U], y[U];
+        V *pl[U], *pr[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t e = e0 + (uint64_t)u * stride;
+            const uint64_t ee = e < total ? e : e0;
+            int k = (int)(ee / half);                       // 0 .. n_peers-2  -> peer index skipping me
+            const uint64_t i = ee - (uint64_t)k * half;
+            const int d = k < me ? k : k + 1;
+            const uint64_t off = (me < d ? 0 : half) + i;   // my half of the pair
+            pl[u] = mine + (uint64_t)d * block_amps + off;
+            pr[u] = (V *)peers.ptr[d] + (uint64_t)me * block_amps + off;
+            y[u] = *pr[u];
+            x[u] = *pl[u];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (e0 + (uint64_t)u * stride < total) { *pl[u] = y[u]; *pr[u] = x[u]; }
+        }
+    }
+}
+
+extern "C" int qsv_comm_ipc_handle(qsv_handle *h, void *out64) {
+    if (!h || !out64) return QSV_EINVAL;
+    QSVX_CUDA(h, cudaSetDevice(h->device));
+    cudaIpcMemHandle_t mh;
+    static_assert(sizeof(mh) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    QSVX_CUDA(h, cudaIpcGetMemHandle(&mh, h->d_state));
+    memcpy(out64, &mh, 64);
+    return QSV_OK;
+}
+
+// handles: world x 64 bytes (entry r = qsv_comm_ipc_handle of rank r).  Maps every other shard.
+extern "C" int qsv_comm_set_peers(qsv_handle *h, const void *handles) {
+    if (!h || !handles) return QSV_EINVAL;
+    auto *c = (qsvx::Comm *)h->comm;
+    if (!c) QSVX_FAIL(h, QSV_ECOMM, "set_peers: qsv_comm_init was not called");
+    if (h->world > 8) QSVX_FAIL(h, QSV_EINVAL, "set_peers: the peer path serves one box (world <= 8)");
+    QSVX_CUDA(h, cudaSetDevice(h->device));
+    c->peer.assign(h->world, nullptr);
+    c->peers_ready = false;
+    for (int r = 0; r < h->world; ++r) {
+        if (r == h->rank) { c->peer[r] = h->d_state; continue; }
+        cudaIpcMemHandle_t mh;
+        memcpy(&mh, (const char *)handles + 64 * r, 64);
+        cudaError_t e = cudaIpcOpenMemHandle(&c->peer[r], mh, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            c->peer[r] = nullptr;
+            QSVX_FAIL(h, QSV_ECOMM, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+        }
+    }
+    c->peers_ready = true;
+    return QSV_OK;
+}
+
+static int swap_barrier(qsv_handle *h, qsvx::Comm *c) {
+    // stream-ordered barrier across the box: a 1-element all-reduce
+    double *d = h->d_partials + h->n_partials - 2;
+    QSVX_NCCL(h, qsvx::nccl().AllReduce(d, d, 1, /*ncclDouble*/ 8, /*ncclSum*/ 0, c->comm, h->stream));
     return QSV_OK;
 }
 
@@ -159,6 +251,22 @@ extern "C" int qsv_swap_global_local(qsv_handle *h, int n_swap, const int *globa
         return r;
     };
     const size_t block_bytes = (h->n_amps >> n_swap) * h->amp_bytes;
+    if (c->peers_ready && h->use_peer_swap) {
+        qsvx_timer_begin(h);
+        PeerTable pt;
+        for (int d = 0; d < 8; ++d) pt.ptr[d] = d < peers ? c->peer[peer_rank(d)] : nullptr;
+        int rc = swap_barrier(h, c);                 // every peer has finished its previous pass
+        if (rc) return rc;
+        const uint64_t block_amps = h->n_amps >> n_swap;
+        const int grid = h->sm_count * 4;
+        if (h->dtype == QSV_C128) k_swap_peer<double2, 4><<<grid, 512, 0, h->stream>>>((double2 *)h->d_state, pt, peers, me, block_amps);
+        else k_swap_peer<float2, 8><<<grid, 512, 0, h->stream>>>((float2 *)h->d_state, pt, peers, me, block_amps);
+        QSVX_CUDA(h, cudaGetLastError());
+        rc = swap_barrier(h, c);                     // nobody reads its shard before all exchanges landed
+        if (rc) return rc;
+        qsvx_timer_end(h, 20 + n_swap);
+        return QSV_OK;
+    }
     size_t chunk = std::min(block_bytes, (size_t)256 << 20);
     const size_t need = 2 * (size_t)(peers - 1) * chunk;
     if (c->bounce_bytes < need) {
@@ -169,11 +277,7 @@ extern "C" int qsv_swap_global_local(qsv_handle *h, int n_swap, const int *globa
     }
     char *state = (char *)h->d_state;
     const size_t n_chunks = (block_bytes + chunk - 1) / chunk;
-    cudaEvent_t t_a = nullptr, t_b = nullptr;
-    if (h->timing) {
-        cudaEventCreate(&t_a); cudaEventCreate(&t_b);
-        cudaEventRecord(t_a, h->stream);
-    }
+    qsvx_timer_begin(h);
     // main stream: NCCL group of chunk k; copy stream: bounce -> vacated slots of chunk k.
     // Half (k&1) of the bounce buffer is reused by chunk k+2, which waits for copy k.
     for (size_t k = 0; k < n_chunks; ++k) {
@@ -203,10 +307,7 @@ extern "C" int qsv_swap_global_local(qsv_handle *h, int n_swap, const int *globa
     }
     QSVX_CUDA(h, cudaStreamWaitEvent(h->stream, c->ev_copy[0], 0));
     if (n_chunks > 1) QSVX_CUDA(h, cudaStreamWaitEvent(h->stream, c->ev_copy[1], 0));
-    if (h->timing) {
-        cudaEventRecord(t_b, h->stream);
-        h->timed.push_back({t_a, t_b, 20 + n_swap, -1});      // kind 20+s: swap of s bits
-    }
+    qsvx_timer_end(h, 20 + n_swap);                           // kind 20+s: swap of s bits
     return QSV_OK;
 }
 

@@ -543,6 +543,7 @@ int qsv_set_option(qsv_handle *h, int option, long long value) {
     switch (option) {
         case QSV_OPT_JIT: h->jit = value != 0; return QSV_OK;
         case QSV_OPT_SIMPLE_PASS: h->force_simple_pass = value != 0; return QSV_OK;
+        case QSV_OPT_PEER_SWAP: h->use_peer_swap = value != 0; return QSV_OK;
         default: QSV_FAIL(h, QSV_EINVAL, "set_option: unknown option %d", option);
     }
 }

@@ -50,11 +50,37 @@ class CudaShard:
         self.state = DeviceState(n_qubits, dtype, rank if device is None else device, rank, world)
         self.rank, self.world = rank, world
         self._uploaded: dict = {}
+        self.peer_swap, self.peer_error = False, None
         if world > 1:
             if unique_id is None or len(unique_id) != 128:
                 raise ValueError("world > 1 needs the 128-byte NCCL unique id of rank 0 (nccl_unique_id())")
             buf = C.create_string_buffer(unique_id, 128)
             self.state._ck(self.state.lib.qsv_comm_init(self.state._h, buf))
+
+    def map_peers(self, dist) -> bool:
+        """Exchange CUDA IPC handles of the shards (plumbing: an all-gather of 64 bytes per rank) so
+        that swaps run as one peer-memory kernel over NVLink.  Returns False (NCCL send/recv swaps
+        stay in use) if the box does not allow IPC mappings; QSV_SWAP=nccl skips the attempt."""
+        self.peer_error = None
+        if self.world == 1 or os.environ.get("QSV_SWAP", "peer") == "nccl":
+            return False
+        lib, h = self.state.lib, self.state._h
+        mine = C.create_string_buffer(64)
+        ok = lib.qsv_comm_ipc_handle(h, mine) == 0
+        box = [None] * self.world
+        dist.all_gather_object(box, mine.raw if ok else None)
+        if any(b is None for b in box):
+            self.peer_error = "cudaIpcGetMemHandle failed on some rank"
+            mapped = False
+        else:
+            mapped = lib.qsv_comm_set_peers(h, C.create_string_buffer(b"".join(box), 64 * self.world)) == 0
+            if not mapped:
+                self.peer_error = (lib.qsv_last_error(h) or b"?").decode(errors="replace")
+        flags = [None] * self.world
+        dist.all_gather_object(flags, bool(mapped))
+        self.peer_swap = all(flags)
+        lib.qsv_set_option(h, L.OPT_PEER_SWAP, int(self.peer_swap))     # all ranks must take the same path
+        return self.peer_swap
 
     def prepare(self, prog: Program) -> None:
         """Upload (and specialise) every run of passes once; execute() then only replays."""
@@ -130,6 +156,7 @@ class ShardedSimulator:
         self.dist = init_plumbing() if self.world > 1 else None
         uid = share_unique_id(self.dist, self.rank) if self.world > 1 else None
         self.shard = CudaShard(n_qubits, self.rank, self.world, dtype, self.local_rank, uid)
+        self.peer_swap = self.shard.map_peers(self.dist) if self.world > 1 else False
 
     def plan(self, circuit_dict: dict, **compiler_kw) -> Program:
         from quantum_simulations_b200.kernel.cuda_dense import circuit_ops
