@@ -895,6 +895,8 @@ class PassCompiler:
             other = by_slot[home[c]]
             if other in parked or (other in finished and asg[other] == home[other]):
                 continue
+            if home[other] >= self.n_local and asg[other] >= self.n_local - (self.n - self.n_local):
+                continue          # `other` waits on a top slot for the swap that takes it home
             if c in parked:
                 continue
             asg[c], asg[other] = asg[other], asg[c]
@@ -981,7 +983,19 @@ class PassCompiler:
         s_ = len(incoming)
         assert s_ == len(outgoing) and s_ > 0
         top = [self.n_local - s_ + i for i in range(s_)]
-        touch = {c for c in outgoing if xf[c]} if materialise else ()
+        # any pairing of rank bits with top slots is one all-to-all: keep outgoing contents that
+        # already sit on a top slot where they are (saves the relabel pass)
+        pairs = list(zip(incoming, outgoing))
+        order = [None] * s_
+        for pr in list(pairs):
+            if pos[pr[1]] in top and order[top.index(pos[pr[1]])] is None:
+                order[top.index(pos[pr[1]])] = pr
+                pairs.remove(pr)
+        for j in range(s_):
+            if order[j] is None:
+                order[j] = pairs.pop(0)
+        incoming, outgoing = [p_[0] for p_ in order], [p_[1] for p_ in order]
+        touch = {c for c in outgoing if xf[c] and self._uses[c] == 0} if materialise else ()
         self._relabel_to(prog, pos, home, xf, {c: top[i] for i, c in enumerate(outgoing)}, touch)
         gbits = [pos[c] for c in incoming]
         prog.steps.append(SwapStep(gbits, top))
@@ -1017,8 +1031,10 @@ class PassCompiler:
         for i in range(len(incoming)):
             if outgoing[i] is None:
                 outgoing[i] = chosen.pop(0)
-        # a flip pending on an unfinished outgoing content simply stays in the frame (xf)
-        self._do_swap(prog, pos, home, xf, incoming, outgoing)
+        # a flip pending on an UNFINISHED outgoing content simply stays in the frame (xf); a finished
+        # one is materialised by the relabel pass now (it could not be undone on a rank bit)
+        self._do_swap(prog, pos, home, xf, incoming, outgoing,
+                      materialise=any(xf[c] and self._uses[c] == 0 for c in outgoing))
 
     def _restore_global(self, prog, pos, home, xf) -> None:
         """After the last op: contents whose home is a rank bit go back out, the exiles on rank

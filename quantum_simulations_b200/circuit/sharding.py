@@ -45,12 +45,23 @@ def candidate_placements(n: int, g: int) -> list[list[int]]:
         return out
 
     def place(global_qubits):
-        # the chosen qubits take the rank bits; the logical top qubits take their local slots
+        # the chosen qubits take the rank bits; the logical top qubits wait on the TOP local
+        # positions (where a swap takes its outgoing qubits from, so no relabel pass is needed
+        # before it); the local qubits they displace take the slots the chosen qubits left
+        n_loc = n - g
         pos = list(range(n))
-        tops = [q for q in range(n - g, n) if q not in global_qubits]
-        vac = [q for q in global_qubits if q < n - g]
-        for q, t in zip(vac, tops):
-            pos[q], pos[t] = pos[t], pos[q]
+        chosen = [q for q in global_qubits if q < n_loc]
+        tops = list(range(n_loc, n))[: len(chosen)]                 # logical qubits whose home is a rank bit
+        for q, t in zip(chosen, tops):
+            pos[q] = t                                              # onto t's rank bit
+        wait = [n_loc - len(chosen) + i for i in range(len(chosen))]
+        displaced = [q for q in wait if q not in chosen]
+        for t, w in zip(tops, wait):
+            pos[t] = w
+        free = [q for q in chosen if q not in wait]                 # original slots now empty
+        for q, slot in zip(displaced, free):
+            pos[q] = slot
+        assert sorted(pos) == list(range(n)), pos
         return pos
 
     out.append(place(list(range(g))))                               # bottom qubits global first
