@@ -165,9 +165,11 @@ k_swap_peer(V *__restrict__ mine, PeerTable peers, const int n_peers, const int 
         for (int u = 0; u < U; ++u) {
             const uint64_t e = e0 + (uint64_t)u * stride;
             const uint64_t ee = e < total ? e : e0;
-            int k = (int)(ee / half);                       // 0 .. n_peers-2  -> peer index skipping me
+            const int k = (int)(ee / half);                 // phase 0 .. n_peers-2
             const uint64_t i = ee - (uint64_t)k * half;
-            const int d = k < me ? k : k + 1;
+            const int d = me ^ (k + 1);                     // phase k pairs me with me^(k+1): a perfect
+                                                            // matching of the group, so no GPU is the
+                                                            // target of two others at the same time
             const uint64_t off = (me < d ? 0 : half) + i;   // my half of the pair
             pl[u] = mine + (uint64_t)d * block_amps + off;
             pr[u] = (V *)peers.ptr[d] + (uint64_t)me * block_amps + off;
