@@ -210,6 +210,14 @@ int qsv_norm2(qsv_handle *h, double *out);   /* sum |amp|^2 of the LOCAL shard *
  * sampler — SURVEY.md §2.4-6; definition frozen in oracle/ref_dense.py sample_indices). */
 int qsv_sample(qsv_handle *h, uint64_t seed_unused, int shots, const double *sorted_u,
                uint64_t *out_indices);
+/* Building blocks of the same definition for a sharded state (the exclusive scan over leaf sums is
+ * ONE sequential chain over all shards in rank order, run by the host plumbing):
+ *   qsv_leaf_sums          sums of the shard's blocks of 2^10 amplitudes -> out_host[n_local_amps >> 10]
+ *   qsv_sample_in_leaves   for each shot: walk local leaf leaf_idx[s] from its exclusive prefix leaf_off[s]
+ *                          and return the first LOCAL index whose running sum exceeds x[s]           */
+int qsv_leaf_sums(qsv_handle *h, double *out_host);
+int qsv_sample_in_leaves(qsv_handle *h, int shots, const uint64_t *leaf_idx, const double *leaf_off,
+                         const double *x, uint64_t *out_local_index);
 
 /* ---------------------------------------------------- multi-GPU qubit remap ----
  * HiSVSIM-style redistribution (hisvsim_repo/mpi_redistributer.hpp:265-344,

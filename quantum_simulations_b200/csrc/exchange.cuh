@@ -327,8 +327,3 @@ extern "C" int qsv_allreduce_sum(qsv_handle *h, double *value) {
     QSVX_CUDA(h, cudaStreamSynchronize(h->stream));
     return QSV_OK;
 }
-
-extern "C" int qsv_sample(qsv_handle *h, uint64_t, int, const double *, uint64_t *) {
-    if (!h) return QSV_EINVAL;
-    QSVX_FAIL(h, QSV_EINVAL, "qsv_sample: not built yet");
-}

@@ -13,6 +13,7 @@
 #include "pass_ring.cuh"
 #include "exchange.cuh"
 #include "jit.cuh"
+#include "sample.cuh"
 
 static thread_local std::string g_create_error;
 
@@ -594,6 +595,88 @@ int qsv_norm2(qsv_handle *h, double *out) {
     QSV_CUDA(h, cudaGetLastError());
     QSV_CUDA(h, cudaMemcpyAsync(out, h->d_partials + kNormBlocks, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     QSV_CUDA(h, cudaStreamSynchronize(h->stream));
+    return QSV_OK;
+}
+
+// ------------------------------------------------------------------- sampling ----
+int qsv_leaf_sums(qsv_handle *h, double *out_host) {
+    QSV_CHECK_H(h);
+    if (!out_host) QSV_FAIL(h, QSV_EINVAL, "leaf_sums: null out");
+    QSV_CUDA(h, cudaSetDevice(h->device));
+    const int leaf_log2 = h->n_local < kSampleLeafLog2 ? h->n_local : kSampleLeafLog2;
+    const int leaf = 1 << leaf_log2;
+    const uint64_t n_leaves = h->n_amps >> leaf_log2;
+    double *d = nullptr;
+    QSV_CUDA(h, cudaMalloc((void **)&d, n_leaves * sizeof(double)));
+    const unsigned grid = (unsigned)((n_leaves + 127) / 128);
+    if (h->dtype == QSV_C128) k_leaf_sums<double><<<grid, 128, 0, h->stream>>>((const double2 *)h->d_state, n_leaves, leaf, d);
+    else k_leaf_sums<float><<<grid, 128, 0, h->stream>>>((const float2 *)h->d_state, n_leaves, leaf, d);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_host, d, n_leaves * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d);
+    QSV_CUDA(h, e);
+    return QSV_OK;
+}
+
+int qsv_sample_in_leaves(qsv_handle *h, int shots, const uint64_t *leaf_idx, const double *leaf_off, const double *x,
+                         uint64_t *out_local_index) {
+    QSV_CHECK_H(h);
+    if (shots < 0 || (shots && (!leaf_idx || !leaf_off || !x || !out_local_index))) QSV_FAIL(h, QSV_EINVAL, "sample_in_leaves: bad arguments");
+    if (shots == 0) return QSV_OK;
+    QSV_CUDA(h, cudaSetDevice(h->device));
+    const int leaf_log2 = h->n_local < kSampleLeafLog2 ? h->n_local : kSampleLeafLog2;
+    const uint64_t n_leaves = h->n_amps >> leaf_log2;
+    for (int i = 0; i < shots; ++i) if (leaf_idx[i] >= n_leaves) QSV_FAIL(h, QSV_EINVAL, "sample_in_leaves: leaf %llu outside the shard", (unsigned long long)leaf_idx[i]);
+    char *d = nullptr;
+    const size_t n8 = (size_t)shots * 8;
+    QSV_CUDA(h, cudaMalloc((void **)&d, 4 * n8));
+    cudaError_t e = cudaMemcpyAsync(d, leaf_idx, n8, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + n8, leaf_off, n8, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + 2 * n8, x, n8, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) {
+        const unsigned grid = (unsigned)((shots + 127) / 128);
+        if (h->dtype == QSV_C128)
+            k_sample_walk<double><<<grid, 128, 0, h->stream>>>((const double2 *)h->d_state, 1 << leaf_log2, shots, (const uint64_t *)d,
+                                                              (const double *)(d + n8), (const double *)(d + 2 * n8), (uint64_t *)(d + 3 * n8));
+        else
+            k_sample_walk<float><<<grid, 128, 0, h->stream>>>((const float2 *)h->d_state, 1 << leaf_log2, shots, (const uint64_t *)d,
+                                                             (const double *)(d + n8), (const double *)(d + 2 * n8), (uint64_t *)(d + 3 * n8));
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_local_index, d + 3 * n8, n8, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d);
+    QSV_CUDA(h, e);
+    return QSV_OK;
+}
+
+int qsv_sample(qsv_handle *h, uint64_t, int shots, const double *sorted_u, uint64_t *out_indices) {
+    QSV_CHECK_H(h);
+    if (h->world != 1) QSV_FAIL(h, QSV_EINVAL, "qsv_sample serves one shard; chain qsv_leaf_sums / qsv_sample_in_leaves across ranks");
+    if (shots < 0 || (shots && (!sorted_u || !out_indices))) QSV_FAIL(h, QSV_EINVAL, "sample: bad arguments");
+    const int leaf_log2 = h->n_local < kSampleLeafLog2 ? h->n_local : kSampleLeafLog2;
+    const uint64_t n_leaves = h->n_amps >> leaf_log2;
+    std::vector<double> sums(n_leaves), offs(n_leaves + 1);
+    int rc = qsv_leaf_sums(h, sums.data());
+    if (rc) return rc;
+    offs[0] = 0.0;
+    for (uint64_t b = 0; b < n_leaves; ++b) offs[b + 1] = offs[b] + sums[b];     // sequential scan (the definition)
+    const double total = offs[n_leaves];
+    std::vector<uint64_t> lidx;
+    std::vector<double> loff, xs;
+    std::vector<int> where;
+    for (int s = 0; s < shots; ++s) {
+        const double x = sorted_u[s] * total;
+        // first b with offs[b+1] > x  (np.searchsorted(offs[1:], x, side="right"))
+        const uint64_t b = (uint64_t)(std::upper_bound(offs.begin() + 1, offs.end(), x) - (offs.begin() + 1));
+        if (b >= n_leaves) { out_indices[s] = h->n_amps - 1; continue; }
+        lidx.push_back(b); loff.push_back(offs[b]); xs.push_back(x); where.push_back(s);
+    }
+    std::vector<uint64_t> got(lidx.size());
+    rc = qsv_sample_in_leaves(h, (int)lidx.size(), lidx.data(), loff.data(), xs.data(), got.data());
+    if (rc) return rc;
+    for (size_t i = 0; i < got.size(); ++i) out_indices[where[i]] = got[i];
     return QSV_OK;
 }
 

@@ -235,6 +235,15 @@ class DeviceState:
         self._ck(self.lib.qsv_norm2(self._h, C.byref(out)))
         return out.value
 
+    def sample(self, seed: int, shots: int) -> np.ndarray:
+        """Measurement samples (basis-state indices, ascending), bit-exact with
+        oracle/ref_dense.py::sample_indices: u = sort(default_rng(seed).random(shots))."""
+        u = np.sort(np.random.default_rng(seed).random(shots))
+        out = np.empty(shots, dtype=np.uint64)
+        self._ck(self.lib.qsv_sample(self._h, seed, shots, u.ctypes.data_as(C.POINTER(C.c_double)),
+                                     out.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return out
+
     def timing(self, on: bool) -> None:
         self._ck(self.lib.qsv_timing_enable(self._h, int(on)))
 

@@ -171,6 +171,54 @@ class ShardedSimulator:
         execute(prog, self.shard)
         return self.shard.state.download(out)
 
+    def sample(self, seed: int, shots: int) -> np.ndarray:
+        """Measurement samples of the sharded state, identical on every rank and bit-exact with
+        oracle/ref_dense.py::sample_indices.  The exclusive scan over leaf sums is one sequential
+        chain over all shards (rank order = index order), evaluated redundantly on every rank
+        from the all-gathered leaf sums (8 bytes per 1024 amplitudes); every rank then walks the
+        leaves of the shots that fall into its shard."""
+        import torch
+        st, lib = self.shard.state, self.shard.state.lib
+        n_loc = self.n - self.g
+        leaf_log2 = min(10, n_loc)
+        n_leaves = (1 << n_loc) >> leaf_log2
+        mine = np.empty(n_leaves, dtype=np.float64)
+        st._ck(lib.qsv_leaf_sums(st._h, mine.ctypes.data_as(C.POINTER(C.c_double))))
+        if self.world > 1:
+            parts = [torch.empty(n_leaves, dtype=torch.float64) for _ in range(self.world)]
+            self.dist.all_gather(parts, torch.from_numpy(mine))
+            sums = np.concatenate([p.numpy() for p in parts])
+        else:
+            sums = mine
+        offs = np.empty(len(sums) + 1)
+        offs[0] = 0.0
+        np.cumsum(sums, out=offs[1:])                 # np.cumsum is a sequential left-to-right scan
+        total = offs[-1]
+        x = np.sort(np.random.default_rng(seed).random(shots)) * total
+        b = np.searchsorted(offs[1:], x, side="right")
+        out = np.zeros(shots, dtype=np.int64)
+        over = b >= len(sums)
+        out[over] = (1 << self.n) - 1
+        lo, hi = self.rank * n_leaves, (self.rank + 1) * n_leaves
+        sel = np.nonzero((b >= lo) & (b < hi) & ~over)[0]
+        if len(sel):
+            lidx = np.ascontiguousarray(b[sel] - lo, dtype=np.uint64)
+            loff = np.ascontiguousarray(offs[b[sel]])
+            xs = np.ascontiguousarray(x[sel])
+            got = np.empty(len(sel), dtype=np.uint64)
+            st._ck(lib.qsv_sample_in_leaves(st._h, len(sel), lidx.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                            loff.ctypes.data_as(C.POINTER(C.c_double)),
+                                            xs.ctypes.data_as(C.POINTER(C.c_double)),
+                                            got.ctypes.data_as(C.POINTER(C.c_uint64))))
+            out[sel] = got.astype(np.int64) + (self.rank << n_loc)
+        if self.world > 1:
+            t = torch.from_numpy(out)
+            if self.rank != 0:
+                t[over] = 0                           # the clamp is contributed once (rank 0)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+            out = t.numpy()
+        return out.astype(np.uint64)
+
     def close(self) -> None:
         self.shard.close()
 

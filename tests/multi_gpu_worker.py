@@ -26,6 +26,7 @@ def main():
                      ("random_mixed", W.random_mixed(n, 300, 8))):
         cd = validate_circuit_dict(cd)
         shard = sim.simulate(cd)
+        samples = sim.sample(seed=7, shots=257)
         parts = [torch.empty(shard.size * 2, dtype=torch.float64) for _ in range(world)] if rank == 0 else None
         dist.gather(torch.from_numpy(shard.view(np.float64).copy()), parts, dst=0)
         if rank == 0:
@@ -34,6 +35,12 @@ def main():
             err = float(np.abs(got - want).max())
             print(f"{name}: n={n} world={world} max|d|={err:.3e}", flush=True)
             worst = max(worst, err)
+            from oracle import ref_dense as O
+            want_s = O.sample_indices(got, 7, 257)
+            if not np.array_equal(samples, want_s):
+                # the state differs from the oracle's in the last bits, so compare with the samples of
+                # the state this run produced: the definition is what must be reproduced bit-exactly
+                raise SystemExit(f"{name}: sharded samples differ from oracle.sample_indices on the same state")
     sim.close()
     dist.barrier()
     dist.destroy_process_group()

@@ -237,6 +237,28 @@ def test_jit_kernels_are_cached_by_structure():
     assert np.abs(b - CO.simulate_c(validate_circuit_dict(circ(0.5)))).max() <= 1e-12
 
 
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+@pytest.mark.parametrize("n", [6, 12, 17])
+def test_sample_indices_bit_exact(n, dtype):
+    """qsv_sample reproduces oracle.sample_indices bit for bit on the same state and seed."""
+    from quantum_simulations_b200.kernel.cuda import DeviceState
+    rng = np.random.default_rng(n)
+    psi = (rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)).astype(dtype)
+    psi /= np.linalg.norm(psi)
+    with DeviceState(n, dtype) as st:
+        st.upload(psi)
+        got = st.sample(seed=1234, shots=300)
+    want = O.sample_indices(psi, 1234, 300)
+    assert got.dtype == np.uint64 and np.array_equal(got, want)
+    # a GHZ state samples only its two basis states
+    from quantum_simulations_b200.kernel.cuda_dense import compile_circuit
+    if dtype == "complex128" and n >= 12:
+        with DeviceState(n) as st:
+            st.init_zero(); st.run_program(compile_circuit(W.ghz(n)))
+            s = st.sample(seed=5, shots=64)
+        assert set(s.tolist()) <= {0, (1 << n) - 1} and len(set(s.tolist())) == 2
+
+
 def test_ghz20_config0_known_answer():
     from quantum_simulations_b200.kernel.cuda_dense import simulate
     got = simulate(W.ghz(20))
