@@ -191,6 +191,16 @@ def reference_arm(args) -> None:
     print(json.dumps(line), flush=True)
 
 
+def jit_stats() -> dict:
+    import ctypes as C
+    from quantum_simulations_b200 import _lib as L
+    v = [C.c_int() for _ in range(4)]
+    sec = C.c_double()
+    L.load().qsv_jit_stats(*[C.byref(x) for x in v], C.byref(sec))
+    return {"kernels_compiled": v[0].value, "disk_cache_hits": v[1].value, "memory_cache_hits": v[2].value,
+            "failed": v[3].value, "nvrtc_seconds": round(sec.value, 3)}
+
+
 # ----------------------------------------------------------------------- GPU arm
 def bench_single(args) -> None:
     from quantum_simulations_b200.kernel.cuda import DeviceState
@@ -235,6 +245,11 @@ def bench_single(args) -> None:
     peak, peak_src = _peaks()
     achieved = alg_bytes / (avg_pass_ms * 1e-3) / 1e9
     pass_share = sum(pass_ms) / total_ms if total_ms else None
+    traffic, traffic_src = None, None
+    tf = ROOT / "profiles" / "r01" / "traffic_k_pass_jit_n30.json"
+    if tf.exists() and n == 30 and dtype == "complex128" and WORKLOAD == "random":
+        t_ = json.loads(tf.read_text())
+        traffic, traffic_src = t_["dram_bytes_per_launch"], t_["source"]
 
     # ---- end to end through the public API, result in pinned HOST memory ----
     e2e = None
@@ -271,11 +286,13 @@ def bench_single(args) -> None:
                    "host_compile_s": compile_s},
         "gate_layers_per_s": info["levels"] / (ms_per_step * 1e-3),
         "hbm_gbs_per_gate_layer": info["levels"] * alg_bytes / (ms_per_step * 1e-3) / 1e9,
-        "roofline": {"bound": "hbm", "kernel": f"k_pass<{'double' if dtype == 'complex128' else 'float'}>",
+        "roofline": {"bound": "hbm", "kernel": "k_pass_jit (run-time specialised ring kernel; k_pass_ring / k_pass interpret "
+                                                 "the passes NVRTC could not build)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "peak_source": peak_src, "traffic": None,
+                     "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_pass_ms,
                      "launches_timed": len(pass_ms), "share_of_step": pass_share},
+        "jit": jit_stats(),
         "gpu_launches": len(per_launch) + 2 * args.steps,        # + memset & set-amp of |0>
         "clocks": clk,
         "e2e": e2e,

@@ -190,7 +190,7 @@ int qsv_program_create(qsv_handle *h, const qsv_pass *passes, int n_passes,
                        qsv_program **out);
 int qsv_program_run(qsv_handle *h, qsv_program *p);
 int qsv_program_destroy(qsv_handle *h, qsv_program *p);
-/* qsv_program_create SPECIALISES each complex128 pass at run time (NVRTC, sm_100a): the same ring
+/* qsv_program_create SPECIALISES each 2^11-amplitude pass (complex128 and complex64) at run time (NVRTC, sm_100a): the same ring
  * kernel with the pass's bit positions and op sequence as straight-line code and the coefficients
  * in the kernel-parameter bank; cubins are cached by pass STRUCTURE (in memory and under
  * <libqsv dir>/jit_cache, env QSV_JIT_CACHE=<dir>|0).  QSV_JIT=0 or QSV_OPT_JIT=0 keeps the
@@ -202,7 +202,7 @@ int qsv_set_option(qsv_handle *h, int option, long long value);
 int qsv_jit_stats(int *compiled, int *disk_hits, int *mem_hits, int *failed, double *compile_seconds);
 /* Generate + NVRTC-compile the specialised kernel of one pass WITHOUT a device (build check /
  * cache warm-up; nvrtc cross-compiles sm_100a on a CPU-only host).  log receives the error text. */
-int qsv_jit_build_pass(const qsv_pass *pass, const qsv_op *ops, size_t *cubin_bytes, char *log, size_t log_cap);
+int qsv_jit_build_pass(const qsv_pass *pass, const qsv_op *ops, int dtype, size_t *cubin_bytes, char *log, size_t log_cap);
 
 /* --------------------------------------------------------------- reductions ---- */
 int qsv_norm2(qsv_handle *h, double *out);   /* sum |amp|^2 of the LOCAL shard */

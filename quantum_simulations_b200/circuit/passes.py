@@ -397,7 +397,7 @@ class PassCompiler:
             raise ValueError(f"unsupported dtype {dtype}")
         max_t = 12 if self.dtype == "complex128" else 13
         # default tile: 2^11 complex128 (32 KB) = what the persistent ring kernel stages
-        default_t = RING_TILE_BITS if self.dtype == "complex128" else max_t
+        default_t = RING_TILE_BITS        # both dtypes: the tile the ring / specialised kernels stage
         self.W = 3 if self.dtype == "complex128" else 4      # log2(128 B / sizeof(amp))
         self.t = min(tile_bits or default_t, max_t, self.n_local)
         # the ring kernel (pass_ring.cuh) fills shared memory through cp.async in the swizzled

@@ -52,6 +52,7 @@ struct qsv_program {
     // run-time specialised kernels (jit.cuh): one per pass, null = interpret the pass
     std::vector<cudaKernel_t> jit;
     std::vector<std::vector<double>> jit_coefs;
+    std::vector<std::vector<float>> jit_coefs_f;      // the same values for complex64 kernels
 };
 
 struct qsv_handle {

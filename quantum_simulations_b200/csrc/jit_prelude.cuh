@@ -24,12 +24,25 @@ __device__ __forceinline__ uint64_t insert_zero_bit(uint64_t x, int pos) {
 }
 #include "pass_ops.cuh"
 
-__device__ __forceinline__ uint32_t tile_swizzle3(uint32_t x) { return tile_swizzle<3>(x); }
+// element type of the pass: complex128 (default) or complex64 (-> #define JIT_F32 before the include)
+#ifdef JIT_F32
+typedef float2 JV;
+typedef float JR;
+#define JIT_NBUF 12          // 12 x 16 KB: four private buffers per consumer group
+// shared slot of tile index x: the 16-byte PAIR index is swizzled, the pair stays in order, so a
+// 16-byte cp.async still lands two consecutive amplitudes correctly
+__device__ __forceinline__ uint32_t jit_slot(uint32_t x) { return (tile_swizzle<3>(x >> 1) << 1) | (x & 1u); }
+#else
+typedef double2 JV;
+typedef double JR;
+#define JIT_NBUF 6           //  6 x 32 KB: two private buffers per consumer group
+__device__ __forceinline__ uint32_t jit_slot(uint32_t x) { return tile_swizzle<3>(x); }
+#endif
 
 struct JitRingSmem {
-    double2 buf[6][2048];
-    unsigned long long full[6];
-    unsigned long long empty[6];
+    JV buf[JIT_NBUF][2048];
+    unsigned long long full[JIT_NBUF];
+    unsigned long long empty[JIT_NBUF];
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -67,11 +80,11 @@ __device__ __forceinline__ void group_bar(int grp) {
 }
 
 // the round's fold-table entry (unit complex) applied to all 16 amplitudes
-__device__ __forceinline__ void apply_fold(double2 (&v)[16], const double2 f) {
-    double pr = f.x, pi = f.y;
-    const bool neg = pr < 0.0;
+__device__ __forceinline__ void apply_fold(JV (&v)[16], const double2 f) {
+    JR pr = (JR)f.x, pi = (JR)f.y;
+    const bool neg = pr < (JR)0;
     if (neg) { pr = -pr; pi = -pi; }
-    if (pi != 0.0) op_phase_mask<double2, double>(v, pi / (1.0 + pr), pi, 0u);
+    if (pi != (JR)0) op_phase_mask<JV, JR>(v, pi / ((JR)1 + pr), pi, 0u);
     const int mask = neg ? (int)0x80000000 : 0;
 #pragma unroll
     for (int j = 0; j < 16; ++j) { v[j].x = xor_sign(v[j].x, mask); v[j].y = xor_sign(v[j].y, mask); }
@@ -82,7 +95,7 @@ __device__ __forceinline__ void apply_fold(double2 (&v)[16], const double2 f) {
     JitRingSmem &S = *reinterpret_cast<JitRingSmem *>(smem_raw);                       \
     const int tid = threadIdx.x;                                                       \
     if (tid == 0) {                                                                    \
-        for (int b = 0; b < 6; ++b) { mbar_init(&S.full[b], 128); mbar_init(&S.empty[b], 128); } \
+        for (int b = 0; b < JIT_NBUF; ++b) { mbar_init(&S.full[b], 128); mbar_init(&S.empty[b], 128); } \
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");             \
     }                                                                                  \
     __syncthreads();

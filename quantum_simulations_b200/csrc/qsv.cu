@@ -497,10 +497,14 @@ int qsv_program_create(qsv_handle *h, const qsv_pass *passes, int n_passes, cons
     // specialise every eligible pass (complex128 ring tiles); the rest is interpreted
     p->jit.assign(n_passes, nullptr);
     p->jit_coefs.assign(n_passes, {});
-    if (h->jit && qsvjit::enabled() && h->dtype == QSV_C128 && !h->force_simple_pass) {
+    if (h->jit && qsvjit::enabled() && !h->force_simple_pass) {
+        const bool f32 = h->dtype == QSV_C64;
         std::vector<std::string> srcs(n_passes);
-        for (int i = 0; i < n_passes; ++i)
-            if (!qsvjit::generate(passes[i], ops ? ops + p->op_offset[i] : nullptr, srcs[i], p->jit_coefs[i])) srcs[i].clear();
+        p->jit_coefs_f.assign(n_passes, {});
+        for (int i = 0; i < n_passes; ++i) {
+            if (!qsvjit::generate(passes[i], ops ? ops + p->op_offset[i] : nullptr, srcs[i], p->jit_coefs[i], f32)) srcs[i].clear();
+            if (f32) p->jit_coefs_f[i].assign(p->jit_coefs[i].begin(), p->jit_coefs[i].end());
+        }
         std::vector<qsvjit::Kernel> ks;
         std::string err;
         qsvjit::resolve(h->device, srcs, ks, err);
@@ -519,10 +523,11 @@ static int launch_pass_jit(qsv_handle *h, qsv_program *p, int i) {
     unsigned long long rank_bits = (unsigned long long)h->rank << h->n_local;
     unsigned nt = n_tiles;
     static const double zero = 0.0;
-    void *args[] = {&state, &tables, &rank_bits, &nt,
-                    p->jit_coefs[i].empty() ? (void *)&zero : (void *)p->jit_coefs[i].data()};
+    void *coefs = p->jit_coefs[i].empty() ? (void *)&zero
+                : (h->dtype == QSV_C64 ? (void *)p->jit_coefs_f[i].data() : (void *)p->jit_coefs[i].data());
+    void *args[] = {&state, &tables, &rank_bits, &nt, coefs};
     ScopedTimer t(h, 10, i);
-    QSV_CUDA(h, cudaLaunchKernel((const void *)p->jit[i], dim3(grid), dim3(512), args, sizeof(double2) * 6 * 2048 + 128, h->stream));
+    QSV_CUDA(h, cudaLaunchKernel((const void *)p->jit[i], dim3(grid), dim3(512), args, qsvjit::kSmemBytes, h->stream));
     return QSV_OK;
 }
 
@@ -549,13 +554,13 @@ int qsv_set_option(qsv_handle *h, int option, long long value) {
     }
 }
 
-int qsv_jit_build_pass(const qsv_pass *pass, const qsv_op *ops, size_t *cubin_bytes, char *log, size_t log_cap) {
+int qsv_jit_build_pass(const qsv_pass *pass, const qsv_op *ops, int dtype, size_t *cubin_bytes, char *log, size_t log_cap) {
     if (!pass || (pass->n_ops > 0 && !ops)) return QSV_EINVAL;
     std::string src, msg;
     std::vector<double> coefs;
     std::vector<char> cubin;
     int rc = QSV_OK;
-    if (!qsvjit::generate(*pass, ops, src, coefs)) { msg = "pass is not eligible for specialisation"; rc = QSV_EINVAL; }
+    if (!qsvjit::generate(*pass, ops, src, coefs, dtype == QSV_C64)) { msg = "pass is not eligible for specialisation"; rc = QSV_EINVAL; }
     else if (!qsvjit::nvrtc().load()) { msg = "NVRTC unavailable: " + qsvjit::nvrtc().why; rc = QSV_EIO; }
     else if (!qsvjit::compile(src, cubin, msg)) rc = QSV_ECUDA;
     if (cubin_bytes) *cubin_bytes = cubin.size();

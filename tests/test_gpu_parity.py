@@ -195,9 +195,10 @@ def test_random_1q_cz_depth20(dtype, t):
     assert np.abs(got - want).max() <= TOL[dtype]
 
 
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
 @pytest.mark.parametrize("jit", [True, False])
 @pytest.mark.parametrize("workload", ["random_1q_cz", "random_mixed", "qft", "ghz"])
-def test_specialised_and_interpreted_passes_agree_with_oracle(workload, jit):
+def test_specialised_and_interpreted_passes_agree_with_oracle(workload, jit, dtype):
     """The run-time specialised kernels (csrc/jit.cuh) and the interpreting ring kernel run the
     same compiled passes; both must match the C oracle (default ring tiles: 2^11 amplitudes)."""
     from quantum_simulations_b200.kernel.cuda_dense import simulate
@@ -205,8 +206,8 @@ def test_specialised_and_interpreted_passes_agree_with_oracle(workload, jit):
     cd = {"random_1q_cz": lambda: W.random_1q_cz(n, 20, 1234), "random_mixed": lambda: W.random_mixed(n, 400, 5),
           "qft": lambda: W.qft(n), "ghz": lambda: W.ghz(n)}[workload]()
     want = CO.simulate_c(validate_circuit_dict(cd))
-    got = simulate(cd, jit=jit)
-    assert np.abs(got - want).max() <= 1e-12
+    got = simulate(cd, jit=jit, dtype=dtype)
+    assert got.dtype == np.dtype(dtype) and np.abs(got - want).max() <= TOL[dtype]
 
 
 def test_jit_kernels_are_cached_by_structure():

@@ -8,9 +8,9 @@ from quantum_simulations_b200 import _lib as L, workloads as W
 from quantum_simulations_b200.kernel.cuda_dense import compile_circuit
 
 
-def _build(step):
+def _build(step, dtype=L.QSV_C128):
     n, log = C.c_size_t(), C.create_string_buffer(1 << 14)
-    rc = L.load().qsv_jit_build_pass(C.byref(step.desc), step.ops, C.byref(n), log, len(log))
+    rc = L.load().qsv_jit_build_pass(C.byref(step.desc), step.ops, dtype, C.byref(n), log, len(log))
     return rc, n.value, log.value.decode(errors="replace")
 
 
@@ -22,6 +22,16 @@ def test_every_ring_pass_specialises(circuit):
     assert prog.passes
     for step in prog.passes[:3]:
         rc, size, log = _build(step)
+        if rc == L.QSV_EIO:
+            pytest.skip(f"NVRTC not installed: {log}")
+        assert rc == 0 and size > 10000, log
+
+
+def test_complex64_passes_specialise_too():
+    prog = compile_circuit(W.random_1q_cz(16, 20, 1234), dtype="complex64")
+    assert prog.stats["tile_bits"] == 11
+    for step in prog.passes[:2]:
+        rc, size, log = _build(step, L.QSV_C64)
         if rc == L.QSV_EIO:
             pytest.skip(f"NVRTC not installed: {log}")
         assert rc == 0 and size > 10000, log
