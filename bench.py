@@ -431,7 +431,7 @@ def main() -> None:
     ap.add_argument("--device", type=int, default=0)
     ap.add_argument("--tile-bits", type=int, default=None)
     ap.add_argument("--low-bits", type=int, default=None)
-    ap.add_argument("--max-rounds", type=int, default=6)
+    ap.add_argument("--max-rounds", type=int, default=3)
     ap.add_argument("--defer-diagonals", action="store_true")
     ap.add_argument("--no-fold-tables", action="store_true")
     ap.add_argument("--cpu-qubits", type=int, default=20)

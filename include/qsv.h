@@ -202,6 +202,8 @@ int qsv_set_option(qsv_handle *h, int option, long long value);
 int qsv_jit_stats(int *compiled, int *disk_hits, int *mem_hits, int *failed, double *compile_seconds);
 /* Generate + NVRTC-compile the specialised kernel of one pass WITHOUT a device (build check /
  * cache warm-up; nvrtc cross-compiles sm_100a on a CPU-only host).  log receives the error text. */
+/* The CUDA source qsv_program_create would hand to NVRTC for this pass (inspection / profiling). */
+int qsv_jit_source(const qsv_pass *pass, const qsv_op *ops, int dtype, char *out, size_t cap, size_t *needed);
 int qsv_jit_build_pass(const qsv_pass *pass, const qsv_op *ops, int dtype, size_t *cubin_bytes, char *log, size_t log_cap);
 
 /* --------------------------------------------------------------- reductions ---- */

@@ -81,6 +81,7 @@ SIGNATURES = {
     "qsv_program_destroy": (C.c_int, [_H, _P]),
     "qsv_set_option": (C.c_int, [_H, C.c_int, C.c_longlong]),
     "qsv_jit_stats": (C.c_int, [_ip, _ip, _ip, _ip, _dp]),
+    "qsv_jit_source": (C.c_int, [C.POINTER(QsvPass), C.POINTER(QsvOp), C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "qsv_jit_build_pass": (C.c_int, [C.POINTER(QsvPass), C.POINTER(QsvOp), C.c_int, C.POINTER(C.c_size_t), C.c_char_p, C.c_size_t]),
     "qsv_norm2": (C.c_int, [_H, _dp]),
     "qsv_sample": (C.c_int, [_H, C.c_uint64, C.c_int, _dp, C.POINTER(C.c_uint64)]),

@@ -386,7 +386,7 @@ class PassCompiler:
 
     def __init__(self, n_qubits: int, n_local: int | None = None, dtype: str = "complex128",
                  tile_bits: int | None = None, low_bits: int | None = None,
-                 max_rounds: int = 6, restore_layout: bool = True, lookahead: int = 4096,
+                 max_rounds: int = 3, restore_layout: bool = True, lookahead: int = 4096,
                  ring: bool | None = None, max_ops: int = 380, x_frame: bool = True,
                  merge_diagonals: bool = True, fold_tables: bool = True,
                  defer_diagonals: bool = False, absorb: bool = True, allow_swaps: bool = True):

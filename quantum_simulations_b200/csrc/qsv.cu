@@ -527,7 +527,7 @@ static int launch_pass_jit(qsv_handle *h, qsv_program *p, int i) {
                 : (h->dtype == QSV_C64 ? (void *)p->jit_coefs_f[i].data() : (void *)p->jit_coefs[i].data());
     void *args[] = {&state, &tables, &rank_bits, &nt, coefs};
     ScopedTimer t(h, 10, i);
-    QSV_CUDA(h, cudaLaunchKernel((const void *)p->jit[i], dim3(grid), dim3(512), args, qsvjit::kSmemBytes, h->stream));
+    QSV_CUDA(h, cudaLaunchKernel((const void *)p->jit[i], dim3(grid), dim3(128 * (qsvjit::groups() + 1)), args, qsvjit::kSmemBytes, h->stream));
     return QSV_OK;
 }
 
@@ -566,6 +566,16 @@ int qsv_jit_build_pass(const qsv_pass *pass, const qsv_op *ops, int dtype, size_
     if (cubin_bytes) *cubin_bytes = cubin.size();
     if (log && log_cap) { snprintf(log, log_cap, "%s", msg.c_str()); }
     return rc;
+}
+
+int qsv_jit_source(const qsv_pass *pass, const qsv_op *ops, int dtype, char *out, size_t cap, size_t *needed) {
+    if (!pass || (pass->n_ops > 0 && !ops)) return QSV_EINVAL;
+    std::string src;
+    std::vector<double> coefs;
+    if (!qsvjit::generate(*pass, ops, src, coefs, dtype == QSV_C64)) return QSV_EINVAL;
+    if (needed) *needed = src.size() + 1;
+    if (out && cap) snprintf(out, cap, "%s", src.c_str());
+    return QSV_OK;
 }
 
 int qsv_jit_stats(int *compiled, int *disk_hits, int *mem_hits, int *failed, double *compile_seconds) {
