@@ -328,8 +328,7 @@ def bench_multi(args) -> None:
     updates_per_step = len(cd["gates"]) * (1 << n)
 
     def step():
-        st.init_zero()
-        execute(prog, sim.shard)
+        sim.run(prog)
 
     for _ in range(args.warmup):
         step()

@@ -223,7 +223,9 @@ int qsv_sample_in_leaves(qsv_handle *h, int shots, const uint64_t *leaf_idx, con
 
 /* ---------------------------------------------------- multi-GPU qubit remap ----
  * HiSVSIM-style redistribution (hisvsim_repo/mpi_redistributer.hpp:265-344,
- * svsim-mpi.hpp:123-173): swap `n_swap` rank bits with local bits. */
+ * svsim-mpi.hpp:123-173): swap `n_swap` (<= 3) rank bits with local bits.  local_bits may be any
+ * distinct local positions on the peer-memory path; the ncclSend/ncclRecv path needs them to be the
+ * top n_swap local positions in order (contiguous blocks). */
 int qsv_comm_unique_id(void *id128);                       /* ncclGetUniqueId, 128 bytes   */
 int qsv_comm_init(qsv_handle *h, const void *id128);       /* ncclCommInitRank(world,rank) */
 int qsv_swap_global_local(qsv_handle *h, int n_swap, const int *global_bits, const int *local_bits);

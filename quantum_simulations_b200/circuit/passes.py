@@ -350,6 +350,7 @@ class Program:
     steps: list = field(default_factory=list)
     final_pos: list = field(default_factory=list)   # final_pos[q] = position of IR qubit q
     final_flips: list = field(default_factory=list) # final_flips[q] = 1: qubit q is still stored flipped
+    rank_flip_mask: int = 0                          # shard r holds logical shard r ^ rank_flip_mask
     stats: dict = field(default_factory=dict)
 
     @property
@@ -389,7 +390,8 @@ class PassCompiler:
                  max_rounds: int = 3, restore_layout: bool = True, lookahead: int = 4096,
                  ring: bool | None = None, max_ops: int = 380, x_frame: bool = True,
                  merge_diagonals: bool = True, fold_tables: bool = True,
-                 defer_diagonals: bool = False, absorb: bool = True, allow_swaps: bool = True):
+                 defer_diagonals: bool = False, absorb: bool = True, allow_swaps: bool = True,
+                 swap_anywhere: bool = False, rank_flips: bool = False):
         self.n = n_qubits
         self.n_local = n_qubits if n_local is None else n_local
         self.dtype = np.dtype(dtype).name
@@ -420,6 +422,13 @@ class PassCompiler:
         self.defer_diagonals = defer_diagonals
         self.absorb = absorb
         self.allow_swaps = allow_swaps and self.n_local < self.n
+        # True: a SwapStep may name any local positions >= 5 (peer-memory swap kernel); False: the
+        # outgoing qubits are first relabelled onto the top local positions (contiguous blocks)
+        self.swap_anywhere = swap_anywhere
+        # True: an X still pending on a rank bit at the end is NOT executed; it is reported in
+        # Program.rank_flip_mask and means "shard r holds logical shard r ^ mask" (a free renaming
+        # of the ranks by the runner).  False: such a qubit is swapped in and its flip materialised.
+        self.rank_flips = rank_flips
 
     # ---- public -----------------------------------------------------------------------
     def compile(self, ir_ops, init_pos=None, init_flips=None, home_pos=None) -> Program:
@@ -515,6 +524,8 @@ class PassCompiler:
             self._restore(prog, pos, home, xf)
         prog.final_pos = [pos[alias[q]] for q in range(n)]
         prog.final_flips = [xf[alias[q]] for q in range(n)]
+        prog.rank_flip_mask = sum(1 << (prog.final_pos[q] - self.n_local) for q in range(n)
+                                  if prog.final_flips[q] and prog.final_pos[q] >= self.n_local)
         ps = prog.passes
         prog.stats = {
             "passes": len(ps), "dense2q_steps": sum(isinstance(x, Dense2QStep) for x in prog.steps),
@@ -901,6 +912,17 @@ class PassCompiler:
                 continue
             asg[c], asg[other] = asg[other], asg[c]
             by_slot[asg[c]], by_slot[asg[other]] = c, other
+        # a finished content whose home is a RANK bit leaves with the next swap: lift it out of the
+        # low positions (a swap names local positions >= 5, else it needs a relabel pass first)
+        if self.n_local < self.n:
+            for c in content:
+                if c in finished and home[c] >= self.n_local and asg[c] < 5 and c not in parked:
+                    cand = [d for d in content if asg[d] >= 5 and d not in parked
+                            and not (home[d] >= self.n_local and d in finished)
+                            and not (d in finished and asg[d] == home[d])]
+                    if cand:
+                        d = max(cand, key=lambda x: asg[x])
+                        asg[c], asg[d] = asg[d], asg[c]
         return asg
 
     def _encode(self, op: MicroOp, slot_of, idx_of, pos) -> L.QsvOp:
@@ -983,6 +1005,13 @@ class PassCompiler:
         s_ = len(incoming)
         assert s_ == len(outgoing) and s_ > 0
         top = [self.n_local - s_ + i for i in range(s_)]
+        touch = {c for c in outgoing if xf[c] and self._uses[c] == 0} if materialise else set()
+        if self.swap_anywhere and not touch and all(pos[c] >= 5 for c in outgoing):
+            gbits, lbits = [pos[c] for c in incoming], [pos[c] for c in outgoing]
+            prog.steps.append(SwapStep(gbits, lbits))
+            for i in range(s_):
+                pos[incoming[i]], pos[outgoing[i]] = lbits[i], gbits[i]
+            return
         # any pairing of rank bits with top slots is one all-to-all: keep outgoing contents that
         # already sit on a top slot where they are (saves the relabel pass)
         pairs = list(zip(incoming, outgoing))
@@ -995,7 +1024,6 @@ class PassCompiler:
             if order[j] is None:
                 order[j] = pairs.pop(0)
         incoming, outgoing = [p_[0] for p_ in order], [p_[1] for p_ in order]
-        touch = {c for c in outgoing if xf[c] and self._uses[c] == 0} if materialise else ()
         self._relabel_to(prog, pos, home, xf, {c: top[i] for i, c in enumerate(outgoing)}, touch)
         gbits = [pos[c] for c in incoming]
         prog.steps.append(SwapStep(gbits, top))
@@ -1034,7 +1062,7 @@ class PassCompiler:
         # a flip pending on an UNFINISHED outgoing content simply stays in the frame (xf); a finished
         # one is materialised by the relabel pass now (it could not be undone on a rank bit)
         self._do_swap(prog, pos, home, xf, incoming, outgoing,
-                      materialise=any(xf[c] and self._uses[c] == 0 for c in outgoing))
+                      materialise=not self.rank_flips and any(xf[c] and self._uses[c] == 0 for c in outgoing))
 
     def _restore_global(self, prog, pos, home, xf) -> None:
         """After the last op: contents whose home is a rank bit go back out, the exiles on rank
@@ -1042,7 +1070,7 @@ class PassCompiler:
         only be materialised as a store-address flip)."""
         n_loc = self.n_local
         flipped_glob = [c for c in range(self.n) if pos[c] >= n_loc and xf[c] and home[c] == pos[c]]
-        if flipped_glob:
+        if flipped_glob and not self.rank_flips:
             locals_ = sorted((c for c in range(self.n) if pos[c] < n_loc), key=lambda c: -pos[c])
             self._do_swap(prog, pos, home, xf, flipped_glob, locals_[: len(flipped_glob)])
         for _ in range(4):
@@ -1061,7 +1089,7 @@ class PassCompiler:
                        if pos[c] < n_loc and home[c] < n_loc]
             outgoing = [out_by_home[b] if b in out_by_home else fillers.pop(0) for b in bits]
             # all ops are done (uses == 0): the relabel pass materialises the flips of what leaves
-            self._do_swap(prog, pos, home, xf, incoming, outgoing, materialise=True)
+            self._do_swap(prog, pos, home, xf, incoming, outgoing, materialise=not self.rank_flips)
         raise RuntimeError("rank-bit restoration did not converge")
 
     # ---- layout restoration -----------------------------------------------------------
@@ -1073,6 +1101,8 @@ class PassCompiler:
         for _ in range(8 * self.n + 8):
             bad = [c for c in range(self.n) if pos[c] < n_loc and pos[c] != home[c]]
             flipped = [c for c in range(self.n) if xf[c]]
+            if self.rank_flips:
+                flipped = [c for c in flipped if pos[c] < n_loc]      # rank-bit flips rename the shards
             if any(pos[c] >= n_loc for c in flipped):
                 raise NotImplementedError("a pending X sits on a rank bit")
             if not bad and not flipped:

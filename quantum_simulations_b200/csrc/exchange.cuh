@@ -151,10 +151,23 @@ extern "C" int qsv_comm_init(qsv_handle *h, const void *id128) {
 // half (a < b in swapped-bit order), so every element is touched by exactly one thread of one
 // GPU: no bounce buffer, no extra HBM pass, both NVLink directions carry one block each.
 struct PeerTable { void *ptr[8]; };
+// the swapped LOCAL bit positions: sorted[] ascending (for the zero-bit insertion), bit[i] = position
+// of the local bit that is exchanged with the i-th swapped rank bit
+struct SwapBits { int n; int sorted[3]; int bit[3]; };
+
+__device__ __forceinline__ uint64_t swap_addr(const SwapBits &sb, uint64_t off, int blk) {
+    uint64_t a = off;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) if (i < sb.n) a = insert_zero_bit(a, sb.sorted[i]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) if (i < sb.n) a |= (uint64_t)((blk >> i) & 1) << sb.bit[i];
+    return a;
+}
 
 template <typename V, int U>
 __global__ void __launch_bounds__(512)
-k_swap_peer(V *__restrict__ mine, PeerTable peers, const int n_peers, const int me, const uint64_t block_amps) {
+k_swap_peer(V *__restrict__ mine, PeerTable peers, const int n_peers, const int me, const uint64_t block_amps,
+            const SwapBits sb) {
     const uint64_t half = block_amps >> 1;
     const uint64_t total = (uint64_t)(n_peers - 1) * half;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -171,8 +184,8 @@ k_swap_peer(V *__restrict__ mine, PeerTable peers, const int n_peers, const int 
                                                             // matching of the group, so no GPU is the
                                                             // target of two others at the same time
             const uint64_t off = (me < d ? 0 : half) + i;   // my half of the pair
-            pl[u] = mine + (uint64_t)d * block_amps + off;
-            pr[u] = (V *)peers.ptr[d] + (uint64_t)me * block_amps + off;
+            pl[u] = mine + swap_addr(sb, off, d);                     // my "block d" (swapped local bits = d)
+            pr[u] = (V *)peers.ptr[d] + swap_addr(sb, off, me);       // peer d's "block me"
             y[u] = *pr[u];
             x[u] = *pl[u];
         }
@@ -224,8 +237,9 @@ static int swap_barrier(qsv_handle *h, qsvx::Comm *c) {
     return QSV_OK;
 }
 
-// Swap rank bits global_bits[i] (physical positions >= n_local) with the TOP n_swap local bits:
-// local_bits[i] must be n_local - n_swap + i.  In place, chunked, collective over the group.
+// Swap rank bits global_bits[i] (physical positions >= n_local) with local bits local_bits[i].
+// Peer-memory path: any distinct local positions.  NCCL path: the TOP n_swap local bits in order
+// (contiguous blocks), in place, chunked.  Collective over the group of 2^n_swap ranks.
 extern "C" int qsv_swap_global_local(qsv_handle *h, int n_swap, const int *global_bits, const int *local_bits) {
     if (!h) return QSV_EINVAL;
     if (n_swap == 0) return QSV_OK;
@@ -233,13 +247,17 @@ extern "C" int qsv_swap_global_local(qsv_handle *h, int n_swap, const int *globa
     if (n_swap < 0 || n_swap > g || !global_bits || !local_bits) QSVX_FAIL(h, QSV_EINVAL, "swap: n_swap=%d with %d rank bits", n_swap, g);
     for (int i = 0; i < n_swap; ++i) {
         if (global_bits[i] < h->n_local || global_bits[i] >= h->n_qubits) QSVX_FAIL(h, QSV_EINVAL, "swap: global bit %d is not a rank bit", global_bits[i]);
-        if (local_bits[i] != h->n_local - n_swap + i) QSVX_FAIL(h, QSV_EINVAL, "swap: local bits must be the top %d local positions in order", n_swap);
-        for (int j = 0; j < i; ++j) if (global_bits[i] == global_bits[j]) QSVX_FAIL(h, QSV_EINVAL, "swap: repeated global bit");
+        if (local_bits[i] < 0 || local_bits[i] >= h->n_local) QSVX_FAIL(h, QSV_EINVAL, "swap: local bit %d outside the shard", local_bits[i]);
+        for (int j = 0; j < i; ++j)
+            if (global_bits[i] == global_bits[j] || local_bits[i] == local_bits[j]) QSVX_FAIL(h, QSV_EINVAL, "swap: repeated bit");
     }
     auto *c = (qsvx::Comm *)h->comm;
     if (!c) QSVX_FAIL(h, QSV_ECOMM, "swap: qsv_comm_init was not called");
     QSVX_CUDA(h, cudaSetDevice(h->device));
     auto &N = qsvx::nccl();
+    bool top = true;                               // contiguous blocks: the top n_swap local bits in order
+    for (int i = 0; i < n_swap; ++i) top = top && local_bits[i] == h->n_local - n_swap + i;
+    if (n_swap > 3) QSVX_FAIL(h, QSV_EINVAL, "swap: at most 3 bits per exchange (one box)");
 
     const int peers = 1 << n_swap;
     int me = 0;                                    // my value of the swapped rank bits
@@ -261,14 +279,20 @@ extern "C" int qsv_swap_global_local(qsv_handle *h, int n_swap, const int *globa
         if (rc) return rc;
         const uint64_t block_amps = h->n_amps >> n_swap;
         const int grid = h->sm_count * 4;
-        if (h->dtype == QSV_C128) k_swap_peer<double2, 4><<<grid, 512, 0, h->stream>>>((double2 *)h->d_state, pt, peers, me, block_amps);
-        else k_swap_peer<float2, 8><<<grid, 512, 0, h->stream>>>((float2 *)h->d_state, pt, peers, me, block_amps);
+        SwapBits sbits;
+        sbits.n = n_swap;
+        for (int i = 0; i < 3; ++i) { sbits.bit[i] = i < n_swap ? local_bits[i] : 0; sbits.sorted[i] = sbits.bit[i]; }
+        std::sort(sbits.sorted, sbits.sorted + n_swap);
+        if (h->dtype == QSV_C128) k_swap_peer<double2, 4><<<grid, 512, 0, h->stream>>>((double2 *)h->d_state, pt, peers, me, block_amps, sbits);
+        else k_swap_peer<float2, 8><<<grid, 512, 0, h->stream>>>((float2 *)h->d_state, pt, peers, me, block_amps, sbits);
         QSVX_CUDA(h, cudaGetLastError());
         rc = swap_barrier(h, c);                     // nobody reads its shard before all exchanges landed
         if (rc) return rc;
         qsvx_timer_end(h, 20 + n_swap);
         return QSV_OK;
     }
+    if (!top) QSVX_FAIL(h, QSV_EINVAL, "swap: the ncclSend/ncclRecv path needs the top %d local positions in order "
+                                       "(arbitrary positions are served by the peer-memory kernel)", n_swap);
     size_t chunk = std::min(block_bytes, (size_t)256 << 20);
     const size_t need = 2 * (size_t)(peers - 1) * chunk;
     if (c->bounce_bytes < need) {

@@ -157,19 +157,30 @@ class ShardedSimulator:
         uid = share_unique_id(self.dist, self.rank) if self.world > 1 else None
         self.shard = CudaShard(n_qubits, self.rank, self.world, dtype, self.local_rank, uid)
         self.peer_swap = self.shard.map_peers(self.dist) if self.world > 1 else False
+        self.logical_rank, self._flip_mask = self.rank, 0
 
     def plan(self, circuit_dict: dict, **compiler_kw) -> Program:
         from quantum_simulations_b200.kernel.cuda_dense import circuit_ops
         cd = validate_circuit_dict(circuit_dict)
         if cd["number_of_qubits"] != self.n:
             raise ValueError("circuit size differs from the simulator's")
+        compiler_kw.setdefault("swap_anywhere", bool(self.peer_swap))     # peer kernel: no relabel before a swap
+        compiler_kw.setdefault("rank_flips", True)                        # X pending on a rank bit renames shards
         return sharding.plan(circuit_ops(cd), self.n, self.n - self.g, self.dtype.name, **compiler_kw)
 
     def simulate(self, circuit_dict: dict, out: np.ndarray | None = None, **compiler_kw) -> np.ndarray:
+        """Returns the amplitudes of LOGICAL shard ``self.logical_rank`` (= rank ^ the program's
+        rank_flip_mask: an X gate left pending on a rank bit is a renaming of the shards, not a
+        data movement); index of amplitude i of the result = (logical_rank << n_local) | i."""
         prog = self.plan(circuit_dict, **compiler_kw)
+        self.run(prog)
+        return self.shard.state.download(out)
+
+    def run(self, prog: Program) -> None:
         self.shard.state.init_zero()
         execute(prog, self.shard)
-        return self.shard.state.download(out)
+        self.logical_rank = self.rank ^ prog.rank_flip_mask
+        self._flip_mask = prog.rank_flip_mask
 
     def sample(self, seed: int, shots: int) -> np.ndarray:
         """Measurement samples of the sharded state, identical on every rank and bit-exact with
@@ -187,7 +198,7 @@ class ShardedSimulator:
         if self.world > 1:
             parts = [torch.empty(n_leaves, dtype=torch.float64) for _ in range(self.world)]
             self.dist.all_gather(parts, torch.from_numpy(mine))
-            sums = np.concatenate([p.numpy() for p in parts])
+            sums = np.concatenate([parts[l ^ self._flip_mask].numpy() for l in range(self.world)])   # logical order
         else:
             sums = mine
         offs = np.empty(len(sums) + 1)
@@ -199,7 +210,7 @@ class ShardedSimulator:
         out = np.zeros(shots, dtype=np.int64)
         over = b >= len(sums)
         out[over] = (1 << self.n) - 1
-        lo, hi = self.rank * n_leaves, (self.rank + 1) * n_leaves
+        lo, hi = self.logical_rank * n_leaves, (self.logical_rank + 1) * n_leaves
         sel = np.nonzero((b >= lo) & (b < hi) & ~over)[0]
         if len(sel):
             lidx = np.ascontiguousarray(b[sel] - lo, dtype=np.uint64)
@@ -210,7 +221,7 @@ class ShardedSimulator:
                                             loff.ctypes.data_as(C.POINTER(C.c_double)),
                                             xs.ctypes.data_as(C.POINTER(C.c_double)),
                                             got.ctypes.data_as(C.POINTER(C.c_uint64))))
-            out[sel] = got.astype(np.int64) + (self.rank << n_loc)
+            out[sel] = got.astype(np.int64) + (self.logical_rank << n_loc)
         if self.world > 1:
             t = torch.from_numpy(out)
             if self.rank != 0:

@@ -30,7 +30,8 @@ def main():
         parts = [torch.empty(shard.size * 2, dtype=torch.float64) for _ in range(world)] if rank == 0 else None
         dist.gather(torch.from_numpy(shard.view(np.float64).copy()), parts, dst=0)
         if rank == 0:
-            got = np.concatenate([p.numpy().view(np.complex128) for p in parts])
+            mask = sim.logical_rank ^ sim.rank           # physical shard r holds logical shard r ^ mask
+            got = np.concatenate([parts[l ^ mask].numpy().view(np.complex128) for l in range(world)])
             want = CO.simulate_c(cd)
             err = float(np.abs(got - want).max())
             print(f"{name}: n={n} world={world} max|d|={err:.3e}", flush=True)

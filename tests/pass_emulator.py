@@ -166,7 +166,7 @@ def run_program_sharded(prog: Program, psi: np.ndarray) -> np.ndarray:
                 run_pass(shards[r], step.desc, step.ops, n_loc, r, step.tables)
         elif isinstance(step, SwapStep):
             assert all(g >= n_loc for g in step.global_bits)
-            assert list(step.local_bits) == [n_loc - len(step.local_bits) + i for i in range(len(step.local_bits))]
+            assert all(0 <= l < n_loc for l in step.local_bits) and len(set(step.local_bits)) == len(step.local_bits)
             psi = swap_bits_full(psi, n, step.global_bits, step.local_bits)
         else:
             raise AssertionError(type(step))

@@ -23,7 +23,12 @@ def check(cd, g, **kw):
     psi[0] = 1
     psi = run_program_sharded(prog, psi)
     want = O.simulate(validate_circuit_dict(cd))
-    assert prog.final_pos == list(range(n)) and not any(prog.final_flips)
+    if prog.rank_flip_mask:                       # rank_flips=True: shard r holds logical shard r ^ mask
+        world = 1 << g
+        shards = psi.reshape(world, -1)
+        psi = np.concatenate([shards[r ^ prog.rank_flip_mask] for r in range(world)])
+    assert prog.final_pos == list(range(n))
+    assert not any(f for q, f in enumerate(prog.final_flips) if prog.final_pos[q] < n - g)
     assert np.abs(psi - want).max() <= 1e-12
     return prog
 
@@ -41,6 +46,26 @@ def test_sharded_matches_oracle(workload, g):
 @pytest.mark.parametrize("seed", range(6))
 def test_sharded_random_mixed_seeds(seed):
     check(W.random_mixed(11, 120, seed), 2, tile_bits=6, low_bits=2)
+
+
+@pytest.mark.parametrize("g", [1, 2, 3])
+def test_swap_anywhere_names_arbitrary_local_positions(g):
+    """The peer-memory swap kernel takes any local positions: no relabel pass before the swap."""
+    n = 13
+    prog = check(W.random_1q_cz(n, 20, 1234), g, tile_bits=7, low_bits=2, swap_anywhere=True)
+    assert prog.stats["swaps"] >= 1
+    check(W.random_mixed(n, 150, 3), g, tile_bits=7, low_bits=2, swap_anywhere=True)
+
+
+@pytest.mark.parametrize("g", [1, 2, 3])
+@pytest.mark.parametrize("seed", range(4))
+def test_rank_flips_rename_shards_instead_of_moving_data(g, seed):
+    n = 12
+    check(W.random_1q_cz(n, 20, seed), g, tile_bits=7, low_bits=2, swap_anywhere=True, rank_flips=True)
+    check(W.random_mixed(n, 150, seed), g, tile_bits=7, low_bits=2, rank_flips=True)
+    gates = [{"qubits": [n - 1], "gate": "X"}, {"qubits": [0], "gate": "H"}, {"qubits": [n - 1, 0], "gate": "CNOT"}]
+    prog = check({"number_of_qubits": n, "gates": gates}, 1, tile_bits=7, low_bits=2, rank_flips=True)
+    assert prog.rank_flip_mask == 1 and prog.stats["swaps"] == 0
 
 
 def test_diagonal_only_use_of_rank_bits_needs_no_swap():
