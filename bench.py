@@ -353,19 +353,22 @@ def bench_multi(args) -> None:
 
     # end to end through the public object: plan + (cached) specialisation + run + D2H of the shard
     n_loc = n - g
-    host = PinnedBuffer((1 << n_loc) * amp_bytes)
-    out = host.array(dtype, 1 << n_loc)
-    sim.simulate(cd, out, **ckw)
-    dist.barrier()
-    reps = max(1, min(args.steps, 3))
-    t0 = time.perf_counter()
-    for _ in range(reps):
+    shard_bytes = amp_bytes * (1 << n_loc)
+    e2e_s = None
+    if not args.no_e2e:
+        host = PinnedBuffer((1 << n_loc) * amp_bytes)
+        out = host.array(dtype, 1 << n_loc)
         sim.simulate(cd, out, **ckw)
-    dist.barrier()
-    e2e_s = torch.tensor([(time.perf_counter() - t0) / reps], dtype=torch.float64)
-    dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_s = float(e2e_s.item())
-    host.free()
+        dist.barrier()
+        reps = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            sim.simulate(cd, out, **ckw)
+        dist.barrier()
+        e2e_t = torch.tensor([(time.perf_counter() - t0) / reps], dtype=torch.float64)
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+        e2e_s = float(e2e_t.item())
+        host.free()
 
     if rank == 0:
         ms_per_step = total_ms / args.steps
@@ -375,7 +378,6 @@ def bench_multi(args) -> None:
         alg_bytes = 2 * amp_bytes * (1 << n_loc)
         peak, peak_src = _peaks()
         achieved = alg_bytes / (avg_pass_ms * 1e-3) / 1e9
-        shard_bytes = amp_bytes * (1 << n_loc)
         nv = [{"bits": b, "ms": round(ms, 3),
                "sent_gb_per_gpu": round((1 - 0.5 ** b) * shard_bytes / 1e9, 3),
                "gbs_per_direction": round((1 - 0.5 ** b) * shard_bytes / (ms * 1e-3) / 1e9, 1),
@@ -406,7 +408,8 @@ def bench_multi(args) -> None:
                        "peak_gbs_per_direction": 900.0},
             "gpu_launches": len(per_launch) + 2 * args.steps,
             "clocks": clk,
-            "e2e": {"value": updates_per_step / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3,
+            "e2e": None if e2e_s is None else
+                   {"value": updates_per_step / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3,
                     "h2d_bytes_per_step": int(prog_bytes) * world, "d2h_bytes_per_step": int(shard_bytes) * world,
                     "what": "ShardedSimulator.simulate(circuit, out=pinned host shard) on every rank: validate + "
                             "stage planning + (cached) kernel specialisation + |0> + passes + swaps + D2H of the "
