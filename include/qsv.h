@@ -221,6 +221,13 @@ int qsv_leaf_sums(qsv_handle *h, double *out_host);
 int qsv_sample_in_leaves(qsv_handle *h, int shots, const uint64_t *leaf_idx, const double *leaf_off,
                          const double *x, uint64_t *out_local_index);
 
+/* Observables after the path (new; definitions in oracle/ref_dense.py): contributions of the LOCAL
+ * shard, the caller sums over shards.  qubits are physical positions (rank bits allowed).
+ *   qsv_probabilities  marginal distribution over nq <= 20 qubits, out[o] with bit k of o = qubit qubits[k]
+ *   qsv_expect_z       <prod_{q in mask} Z_q> = sum_i |amp_i|^2 (-1)^parity(i & mask)               */
+int qsv_probabilities(qsv_handle *h, int nq, const int *qubits, double *out_host);
+int qsv_expect_z(qsv_handle *h, uint64_t mask, double *out);
+
 /* ---------------------------------------------------- multi-GPU qubit remap ----
  * HiSVSIM-style redistribution (hisvsim_repo/mpi_redistributer.hpp:265-344,
  * svsim-mpi.hpp:123-173): swap `n_swap` (<= 3) rank bits with local bits.  local_bits may be any

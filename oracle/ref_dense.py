@@ -265,3 +265,24 @@ def sample_indices(psi: np.ndarray, seed: int, shots: int) -> np.ndarray:
                 break
         out[s] = b * leaf + hit
     return out
+
+
+def marginal_probabilities(psi: np.ndarray, qubits) -> np.ndarray:
+    """out[o] = sum of |psi_i|^2 over the indices i whose bit qubits[k] equals bit k of o.
+    (Not in the reference: HiSVSIM-style observable; definition is ours.)"""
+    p = psi.real.astype(np.float64) ** 2 + psi.imag.astype(np.float64) ** 2
+    idx = np.arange(len(p), dtype=np.int64)
+    o = np.zeros(len(p), dtype=np.int64)
+    for k, q in enumerate(qubits):
+        o |= ((idx >> q) & 1) << k
+    return np.bincount(o, weights=p, minlength=1 << len(qubits))
+
+
+def expectation_z(psi: np.ndarray, qubits) -> float:
+    """<prod_q Z_q> = sum_i |psi_i|^2 (-1)^(number of listed qubits set in i)."""
+    p = psi.real.astype(np.float64) ** 2 + psi.imag.astype(np.float64) ** 2
+    idx = np.arange(len(p), dtype=np.int64)
+    par = np.zeros(len(p), dtype=np.int64)
+    for q in qubits:
+        par ^= (idx >> q) & 1
+    return float(np.sum(np.where(par == 1, -p, p)))

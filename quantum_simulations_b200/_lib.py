@@ -85,6 +85,8 @@ SIGNATURES = {
     "qsv_jit_build_pass": (C.c_int, [C.POINTER(QsvPass), C.POINTER(QsvOp), C.c_int, C.POINTER(C.c_size_t), C.c_char_p, C.c_size_t]),
     "qsv_norm2": (C.c_int, [_H, _dp]),
     "qsv_sample": (C.c_int, [_H, C.c_uint64, C.c_int, _dp, C.POINTER(C.c_uint64)]),
+    "qsv_probabilities": (C.c_int, [_H, C.c_int, _ip, _dp]),
+    "qsv_expect_z": (C.c_int, [_H, C.c_uint64, _dp]),
     "qsv_leaf_sums": (C.c_int, [_H, _dp]),
     "qsv_sample_in_leaves": (C.c_int, [_H, C.c_int, C.POINTER(C.c_uint64), _dp, _dp, C.POINTER(C.c_uint64)]),
     "qsv_comm_unique_id": (C.c_int, [C.c_void_p]),

@@ -695,6 +695,53 @@ int qsv_sample(qsv_handle *h, uint64_t, int shots, const double *sorted_u, uint6
     return QSV_OK;
 }
 
+// ---------------------------------------------------------------- observables ----
+int qsv_probabilities(qsv_handle *h, int nq, const int *qubits, double *out_host) {
+    QSV_CHECK_H(h);
+    if (nq < 0 || nq > 20 || (nq && !qubits) || !out_host) QSV_FAIL(h, QSV_EINVAL, "probabilities: need 0..20 qubits");
+    MarginalArgs a;
+    memset(&a, 0, sizeof(a));
+    a.nq = nq;
+    for (int i = 0; i < nq; ++i) {
+        if (qubits[i] < 0 || qubits[i] >= h->n_qubits) QSV_FAIL(h, QSV_EINVAL, "probabilities: qubit %d out of range", qubits[i]);
+        for (int j = 0; j < i; ++j) if (qubits[i] == qubits[j]) QSV_FAIL(h, QSV_EINVAL, "probabilities: repeated qubit %d", qubits[i]);
+        a.qs[i] = qubits[i];
+    }
+    QSV_CUDA(h, cudaSetDevice(h->device));
+    const size_t bins = (size_t)1 << nq;
+    double *d = nullptr;
+    QSV_CUDA(h, cudaMalloc((void **)&d, bins * sizeof(double)));
+    cudaError_t e = cudaMemsetAsync(d, 0, bins * sizeof(double), h->stream);
+    if (e == cudaSuccess) {
+        const size_t smem = nq <= 10 ? bins * sizeof(double) : 0;
+        const uint64_t rank_bits = (uint64_t)h->rank << h->n_local;
+        const int grid = grid_for(h->n_amps, 256, h->sm_count * 8);
+        if (h->dtype == QSV_C128) k_marginal<double><<<grid, 256, smem, h->stream>>>((const double2 *)h->d_state, h->n_amps, rank_bits, a, d);
+        else k_marginal<float><<<grid, 256, smem, h->stream>>>((const float2 *)h->d_state, h->n_amps, rank_bits, a, d);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_host, d, bins * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d);
+    QSV_CUDA(h, e);
+    return QSV_OK;
+}
+
+int qsv_expect_z(qsv_handle *h, uint64_t mask, double *out) {
+    QSV_CHECK_H(h);
+    if (!out) QSV_FAIL(h, QSV_EINVAL, "expect_z: null out");
+    if (h->n_qubits < 64 && (mask >> h->n_qubits)) QSV_FAIL(h, QSV_EINVAL, "expect_z: mask names a qubit >= %d", h->n_qubits);
+    QSV_CUDA(h, cudaSetDevice(h->device));
+    const uint64_t rank_bits = (uint64_t)h->rank << h->n_local;
+    if (h->dtype == QSV_C128) k_expect_z_partial<double><<<kNormBlocks, 256, 0, h->stream>>>((const double2 *)h->d_state, h->n_amps, rank_bits, mask, h->d_partials);
+    else k_expect_z_partial<float><<<kNormBlocks, 256, 0, h->stream>>>((const float2 *)h->d_state, h->n_amps, rank_bits, mask, h->d_partials);
+    k_sum_partials<<<1, 256, 0, h->stream>>>(h->d_partials, kNormBlocks, h->d_partials + kNormBlocks);
+    QSV_CUDA(h, cudaGetLastError());
+    QSV_CUDA(h, cudaMemcpyAsync(out, h->d_partials + kNormBlocks, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    QSV_CUDA(h, cudaStreamSynchronize(h->stream));
+    return QSV_OK;
+}
+
 // --------------------------------------------------------------------- timing ----
 int qsv_timing_enable(qsv_handle *h, int on) {
     QSV_CHECK_H(h);

@@ -235,6 +235,22 @@ class DeviceState:
         self._ck(self.lib.qsv_norm2(self._h, C.byref(out)))
         return out.value
 
+    def probabilities(self, qubits) -> np.ndarray:
+        """Marginal distribution of this shard over `qubits` (bit k of the outcome = qubits[k])."""
+        qs = (C.c_int * max(len(qubits), 1))(*qubits)
+        out = np.zeros(1 << len(qubits), dtype=np.float64)
+        self._ck(self.lib.qsv_probabilities(self._h, len(qubits), qs, out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def expect_z(self, qubits) -> float:
+        """<Z_q1 Z_q2 ...> contribution of this shard."""
+        mask = 0
+        for q in qubits:
+            mask |= 1 << q
+        out = C.c_double()
+        self._ck(self.lib.qsv_expect_z(self._h, mask, C.byref(out)))
+        return out.value
+
     def sample(self, seed: int, shots: int) -> np.ndarray:
         """Measurement samples (basis-state indices, ascending), bit-exact with
         oracle/ref_dense.py::sample_indices: u = sort(default_rng(seed).random(shots))."""

@@ -53,6 +53,12 @@ def _crash_after() -> int | None:
     return None if val is None else int(val)
 
 
+def _crash_at_checkpoint() -> int:
+    """Which checkpoint of the run WE_CRASH_AFTER_CHUNK applies to (extension: the reference always
+    dies in its first step; resuming from a COMMITTED checkpoint needs a later one)."""
+    return int(os.environ.get("WE_CRASH_AT_CHECKPOINT", "0"))
+
+
 def _wipe_buf(buf_dir: Path) -> None:
     shutil.rmtree(buf_dir / "chunks", ignore_errors=True)
     (buf_dir / "manifest.json").unlink(missing_ok=True)
@@ -144,6 +150,7 @@ def _run_inner(cd, n, chunk_size, work, steps, use_wal, np_dtype, device, checkp
         else:
             st.init_zero()
         last_ckpt = start
+        n_ckpt = 0
         for idx in range(start, len(steps)):
             step = steps[idx]
             if step["nonlocal_ops"]:
@@ -153,7 +160,8 @@ def _run_inner(cd, n, chunk_size, work, steps, use_wal, np_dtype, device, checkp
             if final or (checkpoint_every and (idx + 1 - last_ckpt) >= checkpoint_every):
                 # durable checkpoint into the buffer that is NOT the committed one
                 dst = _other(current)
-                _write_checkpoint(st, _buf_dir(work, dst), man, np_dtype)
+                _write_checkpoint(st, _buf_dir(work, dst), man, np_dtype, inject=(n_ckpt == _crash_at_checkpoint()))
+                n_ckpt += 1
                 current, last_ckpt = dst, idx + 1
                 if wal:
                     wal.commit_step(idx, current)
@@ -164,13 +172,13 @@ def _run_inner(cd, n, chunk_size, work, steps, use_wal, np_dtype, device, checkp
     return _buf_dir(work, current)
 
 
-def _write_checkpoint(st, dst_dir: Path, man: Manifest, np_dtype) -> None:
+def _write_checkpoint(st, dst_dir: Path, man: Manifest, np_dtype, inject: bool = True) -> None:
     """Shard -> chunk files through two pinned staging buffers: the D2H copy of chunk c+1 is
     in flight while chunk c is written and fsynced (reference _writer thread, pipeline.py:73-82)."""
     from quantum_simulations_b200.storage.pinned import PinnedBuffer
 
     _wipe_buf(dst_dir)
-    crash_after = _crash_after()
+    crash_after = _crash_after() if inject else None
     cs = man.chunk_size
     nbytes = cs * np_dtype.itemsize
     bufs = [PinnedBuffer(nbytes), PinnedBuffer(nbytes)]

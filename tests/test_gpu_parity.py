@@ -260,6 +260,32 @@ def test_sample_indices_bit_exact(n, dtype):
         assert set(s.tolist()) <= {0, (1 << n) - 1} and len(set(s.tolist())) == 2
 
 
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+def test_observables_match_oracle(dtype):
+    """Marginal probabilities and <Z..Z> of a random state, incl. a sharded handle (rank bits)."""
+    from quantum_simulations_b200.kernel.cuda import DeviceState
+    n = 14
+    rng = np.random.default_rng(3)
+    psi = (rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)).astype(dtype)
+    psi /= np.linalg.norm(psi)
+    tol = 1e-12 if dtype == "complex128" else 1e-6
+    with DeviceState(n, dtype) as st:
+        st.upload(psi)
+        for qs in ([0], [3, 9], [13, 0, 7, 2], list(range(12)), []):
+            assert np.abs(st.probabilities(qs) - O.marginal_probabilities(psi, qs)).max() <= tol
+        for qs in ([5], [0, 13], [1, 2, 3, 4, 10]):
+            assert abs(st.expect_z(qs) - O.expectation_z(psi, qs)) <= tol
+    world, n_local = 4, n - 2
+    acc_p, acc_z = np.zeros(8), 0.0
+    for rank in range(world):
+        with DeviceState(n, dtype, rank=rank, world=world) as st:
+            st.upload(psi[rank << n_local:(rank + 1) << n_local])
+            acc_p += st.probabilities([13, 1, 12])
+            acc_z += st.expect_z([12, 13, 4])
+    assert np.abs(acc_p - O.marginal_probabilities(psi, [13, 1, 12])).max() <= tol
+    assert abs(acc_z - O.expectation_z(psi, [12, 13, 4])) <= tol
+
+
 def test_ghz20_config0_known_answer():
     from quantum_simulations_b200.kernel.cuda_dense import simulate
     got = simulate(W.ghz(20))
@@ -283,7 +309,7 @@ def test_program_replay_matches_one_shot():
 
 
 # ------------------------------------------------------- size-independent properties
-@pytest.mark.parametrize("n", [24, 27])
+@pytest.mark.parametrize("n", [24, 27, 30])
 def test_large_invariants(n):
     """Sizes the NumPy oracle cannot reach cheaply: norm, QFT|0> uniform, GHZ, U U^dagger."""
     cuda = _cuda()
@@ -307,6 +333,28 @@ def test_large_invariants(n):
         st.init_zero(); st.run_program(PassCompiler(n).compile(ops + inv))
         assert abs(st.norm2() - 1.0) < 1e-10
         assert abs(st.download(count=1)[0] - 1.0) < 1e-10
+
+
+def test_baseline_config_full_size_round_trip():
+    """BASELINE.json configs[2] at FULL size (30 qubits, complex128, depth 20, seed 1234): the circuit
+    followed by its inverse must return |0...0>, the forward state must be normalised, and the
+    measurement samples of a GHZ-30 state are its two basis states."""
+    cuda = _cuda()
+    from quantum_simulations_b200.kernel.cuda_dense import circuit_ops, compile_circuit
+    from quantum_simulations_b200.circuit.passes import PassCompiler
+    n = 30
+    cd = validate_circuit_dict(W.random_1q_cz(n, 20, 1234))
+    ops = circuit_ops(cd)
+    inv = [(qs, U.conj().T) for qs, U in reversed(ops)]
+    with cuda.DeviceState(n) as st:
+        st.init_zero(); st.run_program(PassCompiler(n).compile(ops))
+        assert abs(st.norm2() - 1.0) < 1e-10
+        st.run_program(PassCompiler(n).compile(inv))
+        assert abs(st.norm2() - 1.0) < 1e-10
+        assert abs(st.download(count=1)[0] - 1.0) < 1e-9
+        st.init_zero(); st.run_program(compile_circuit(W.ghz(n)))
+        s = st.sample(seed=3, shots=32)
+        assert set(s.tolist()) == {0, (1 << n) - 1}
 
 
 def test_n26_matches_c_oracle_sampled():
