@@ -278,13 +278,18 @@ extern "C" int qsv_swap_global_local(qsv_handle *h, int n_swap, const int *globa
         int rc = swap_barrier(h, c);                 // every peer has finished its previous pass
         if (rc) return rc;
         const uint64_t block_amps = h->n_amps >> n_swap;
-        const int grid = h->sm_count * 4;
+        const char *eg = getenv("QSV_SWAP_GRID"), *eu = getenv("QSV_SWAP_UNROLL");
+        const int grid = h->sm_count * (eg ? atoi(eg) : 4);
+        const int unroll = eu ? atoi(eu) : 4;
         SwapBits sbits;
         sbits.n = n_swap;
         for (int i = 0; i < 3; ++i) { sbits.bit[i] = i < n_swap ? local_bits[i] : 0; sbits.sorted[i] = sbits.bit[i]; }
         std::sort(sbits.sorted, sbits.sorted + n_swap);
-        if (h->dtype == QSV_C128) k_swap_peer<double2, 4><<<grid, 512, 0, h->stream>>>((double2 *)h->d_state, pt, peers, me, block_amps, sbits);
-        else k_swap_peer<float2, 8><<<grid, 512, 0, h->stream>>>((float2 *)h->d_state, pt, peers, me, block_amps, sbits);
+        if (h->dtype == QSV_C128) {
+            if (unroll == 2) k_swap_peer<double2, 2><<<grid, 512, 0, h->stream>>>((double2 *)h->d_state, pt, peers, me, block_amps, sbits);
+            else if (unroll == 8) k_swap_peer<double2, 8><<<grid, 512, 0, h->stream>>>((double2 *)h->d_state, pt, peers, me, block_amps, sbits);
+            else k_swap_peer<double2, 4><<<grid, 512, 0, h->stream>>>((double2 *)h->d_state, pt, peers, me, block_amps, sbits);
+        } else k_swap_peer<float2, 8><<<grid, 512, 0, h->stream>>>((float2 *)h->d_state, pt, peers, me, block_amps, sbits);
         QSVX_CUDA(h, cudaGetLastError());
         rc = swap_barrier(h, c);                     // nobody reads its shard before all exchanges landed
         if (rc) return rc;

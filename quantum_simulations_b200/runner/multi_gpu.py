@@ -242,3 +242,71 @@ def simulate_sharded(circuit_dict: dict, dtype="complex128", out: np.ndarray | N
         return sim.simulate(cd, out, **compiler_kw)
     finally:
         sim.close()
+
+
+def run(circuit_dict: dict, work_dir, chunk_size: int = 1 << 20, dtype: str = "complex128",
+        use_wal: bool = True, **compiler_kw):
+    """Multi-GPU form of ``runner.single_node.run`` (reference single_node.py:78-138), launched
+    with one process per GPU: simulate from |0...0>, then every rank writes the chunk files of
+    its (logical) shard through two pinned staging buffers; rank 0 publishes the manifest and
+    commits the WAL after all chunks are durable.  Returns the buffer path (``collect_state``
+    reads it exactly like a single-device run).  A restart re-runs the circuit: intermediate
+    states are laid out stage by stage, only the final one is in logical order."""
+    from pathlib import Path
+
+    from quantum_simulations_b200.runner.single_node import _buf_dir, _other, _wipe_buf
+    from quantum_simulations_b200.storage.block_store import chunk_filename, write_chunk_atomic
+    from quantum_simulations_b200.storage.manifest import Manifest, write_manifest_atomic
+    from quantum_simulations_b200.storage.pinned import PinnedBuffer
+    from quantum_simulations_b200.wal.wal import WAL
+
+    cd = validate_circuit_dict(circuit_dict)
+    n = cd["number_of_qubits"]
+    sim = ShardedSimulator(n, dtype)
+    try:
+        n_loc = n - sim.g
+        chunk_size = min(chunk_size, 1 << n_loc)
+        if (1 << n_loc) % chunk_size:
+            raise ValueError("2^n must be divisible by chunk_size")
+        work = Path(work_dir)
+        wal = WAL(work / "wal.json", circuit_dict=cd) if (use_wal and sim.rank == 0) else None
+        current = wal.committed_buf if wal else "a"
+        if sim.dist is not None:
+            box = [current]
+            sim.dist.broadcast_object_list(box, src=0)
+            current = box[0]
+        dst = _buf_dir(work, _other(current))
+        if sim.rank == 0:
+            _wipe_buf(dst)
+        if sim.dist is not None:
+            sim.dist.barrier()
+        sim.run(sim.plan(cd, **compiler_kw))
+        per_rank = (1 << n_loc) // chunk_size
+        first = sim.logical_rank * per_rank                     # logical shard order = index order
+        st, np_dtype = sim.shard.state, sim.dtype
+        bufs = [PinnedBuffer(chunk_size * np_dtype.itemsize), PinnedBuffer(chunk_size * np_dtype.itemsize)]
+        try:
+            st._ck(st.lib.qsv_download_async(st._h, bufs[0].ptr, 0, chunk_size))
+            for c in range(per_rank):
+                st.sync()
+                if c + 1 < per_rank:
+                    st._ck(st.lib.qsv_download_async(st._h, bufs[(c + 1) & 1].ptr, (c + 1) * chunk_size, chunk_size))
+                write_chunk_atomic(dst / "chunks" / chunk_filename(first + c), bufs[c & 1].array(np_dtype, chunk_size), np_dtype)
+            st.sync()
+        finally:
+            for b in bufs:
+                b.free()
+        if sim.dist is not None:
+            sim.dist.barrier()
+        if sim.rank == 0:
+            total = per_rank * sim.world
+            write_manifest_atomic(dst, Manifest(n_qubits=n, chunk_size=chunk_size, n_chunks=total, dtype=np_dtype.name,
+                                                chunks=[chunk_filename(i) for i in range(total)]))
+            if wal:
+                wal.commit_step(len(cd["gates"]) - 1 if cd["gates"] else 0, _other(current))
+                wal.close()
+        if sim.dist is not None:
+            sim.dist.barrier()
+        return dst
+    finally:
+        sim.close()

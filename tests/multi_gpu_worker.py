@@ -44,6 +44,20 @@ def main():
                 raise SystemExit(f"{name}: sharded samples differ from oracle.sample_indices on the same state")
     sim.close()
     dist.barrier()
+    # the runner surface: chunk files + manifest + WAL written by all ranks, read back by collect_state
+    import tempfile, os
+    from quantum_simulations_b200.runner import multi_gpu as MG
+    from quantum_simulations_b200.runner.single_node import collect_state
+    box = [tempfile.mkdtemp(prefix="qsv_mg_") if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    cd = validate_circuit_dict(W.random_1q_cz(n, 10, 21))
+    buf = MG.run(cd, box[0], chunk_size=1 << (n - 5), dtype="complex128")
+    if rank == 0:
+        got = collect_state(buf)
+        err = float(np.abs(got - CO.simulate_c(cd)).max())
+        print(f"runner.multi_gpu.run: {len(os.listdir(buf / 'chunks'))} chunk files, max|d|={err:.3e}", flush=True)
+        worst = max(worst, err)
+    dist.barrier()
     dist.destroy_process_group()
     if rank == 0 and worst > 1e-12:
         raise SystemExit(f"multi-GPU parity failed: {worst}")
