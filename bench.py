@@ -259,8 +259,9 @@ def bench_single(args) -> None:
         simulate(cd, dtype=dtype, device=args.device, out=out, **ckw)       # warm-up
         reps = max(1, min(args.steps, 3))
         t0 = time.perf_counter()
+        phases: dict = {}
         for _ in range(reps):
-            simulate(cd, dtype=dtype, device=args.device, out=out, **ckw)
+            simulate(cd, dtype=dtype, device=args.device, out=out, phases=phases, **ckw)
         e2e_s = (time.perf_counter() - t0) / reps
         import ctypes
         from quantum_simulations_b200 import _lib as L
@@ -271,6 +272,14 @@ def bench_single(args) -> None:
                        "cudaMalloc + |0> + passes + D2H of the full state, host perf_counter"}
         nrm = float(np.vdot(out[: 1 << 20], out[: 1 << 20]).real)
         e2e["host_prefix_norm"] = nrm
+        with DeviceState(n, dtype, args.device) as st2:           # what the PCIe copy alone costs on this box
+            st2.init_zero(); st2.sync()
+            t0 = time.perf_counter()
+            st2.download(out)
+            d2h_s = time.perf_counter() - t0
+        e2e["phases_ms"] = {k: round(v / reps, 2) for k, v in phases.items()}
+        e2e["d2h_only_ms"] = d2h_s * 1e3
+        e2e["d2h_gbs"] = (1 << n) * amp_bytes / d2h_s / 1e9
         host.free()
 
     line = {

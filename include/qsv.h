@@ -64,6 +64,9 @@ int qsv_device_count(void);
 /* Allocate the shard `rank` of `world` (power of two) of an n_qubits state on `device`. */
 int qsv_create(qsv_handle **out, int n_qubits, int dtype, int device, int rank, int world);
 int qsv_destroy(qsv_handle *h);
+/* qsv_destroy parks a shard buffer >= 64 MiB (one per device) for the next qsv_create of the same
+ * size: cudaFree + cudaMalloc of a 16 GiB buffer cost ~150 ms.  This frees the parked buffers. */
+int qsv_release_cached(void);
 /* Message of the last failure on h (h == NULL: last failure of qsv_create). */
 const char *qsv_last_error(const qsv_handle *h);
 int qsv_sync(qsv_handle *h);

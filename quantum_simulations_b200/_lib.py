@@ -59,6 +59,7 @@ SIGNATURES = {
     "qsv_device_count": (C.c_int, []),
     "qsv_create": (C.c_int, [C.POINTER(_H), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "qsv_destroy": (C.c_int, [_H]),
+    "qsv_release_cached": (C.c_int, []),
     "qsv_last_error": (C.c_char_p, [_H]),
     "qsv_sync": (C.c_int, [_H]),
     "qsv_device_ptr": (C.c_int, [_H, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p)]),

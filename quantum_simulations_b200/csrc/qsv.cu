@@ -3,8 +3,10 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
 
 #include "common.cuh"
@@ -16,6 +18,35 @@
 #include "sample.cuh"
 
 static thread_local std::string g_create_error;
+
+// One cached shard allocation per device: cudaFree / cudaMalloc of a multi-GiB buffer costs up to
+// ~150 ms (page unmapping), which would dominate back-to-back simulations of the same size.  A
+// destroyed handle parks its buffer here; the next qsv_create of the same size on that device takes
+// it, any other size frees it first (so the cache never adds to the peak).  qsv_release_cached()
+// empties it.
+namespace {
+struct CachedShard { void *ptr = nullptr; size_t bytes = 0; };
+std::mutex g_cache_mu;
+CachedShard g_cache[64];
+
+void *cache_take(int device, size_t bytes) {
+    std::lock_guard<std::mutex> g(g_cache_mu);
+    CachedShard &c = g_cache[device & 63];
+    if (!c.ptr) return nullptr;
+    void *p = c.ptr;
+    const bool fit = c.bytes == bytes;
+    c = CachedShard();
+    if (fit) return p;
+    cudaFree(p);
+    return nullptr;
+}
+void cache_put(int device, void *ptr, size_t bytes) {
+    std::lock_guard<std::mutex> g(g_cache_mu);
+    CachedShard &c = g_cache[device & 63];
+    if (c.ptr) cudaFree(c.ptr);
+    c.ptr = ptr; c.bytes = bytes;
+}
+}  // namespace
 
 #define QSV_FAIL(h, code, ...)                                  \
     do {                                                        \
@@ -33,6 +64,22 @@ static thread_local std::string g_create_error;
     } while (0)
 
 #define QSV_CHECK_H(h) do { if (!(h)) return QSV_EINVAL; } while (0)
+
+// Small device buffers come from the stream-ordered pool (cudaMallocAsync): no device-wide
+// synchronisation and no page unmapping on free — a plain cudaFree was measured to stall for up to
+// 0.7 s after a 16 GiB device-to-host copy.
+static inline cudaError_t dev_alloc(qsv_handle *h, void **ptr, size_t bytes) { return cudaMallocAsync(ptr, bytes, h->stream); }
+static inline void dev_free(qsv_handle *h, void *ptr) { if (ptr) cudaFreeAsync(ptr, h->stream); }
+static void keep_pool_memory(int device) {
+    static bool done[64] = {};
+    if (done[device & 63]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    done[device & 63] = true;
+}
 
 static inline int grid_for(uint64_t items, int threads, int max_blocks = 148 * 16) {
     uint64_t b = (items + threads - 1) / threads;
@@ -105,15 +152,19 @@ int qsv_create(qsv_handle **out, int n_qubits, int dtype, int device, int rank, 
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaMalloc(&h->d_state, h->n_amps * h->amp_bytes);
-    if (e == cudaSuccess) { h->n_partials = kNormBlocks + 8; e = cudaMalloc(&h->d_partials, h->n_partials * sizeof(double)); }
-    if (e == cudaSuccess) e = cudaMalloc(&h->d_pass_scratch, sizeof(qsv_pass));
+    if (e == cudaSuccess) {
+        h->d_state = cache_take(device, h->n_amps * h->amp_bytes);
+        if (!h->d_state) e = cudaMalloc(&h->d_state, h->n_amps * h->amp_bytes);
+    }
+    if (e == cudaSuccess) keep_pool_memory(device);
+    if (e == cudaSuccess) { h->n_partials = kNormBlocks + 8; e = dev_alloc(h, (void **)&h->d_partials, h->n_partials * sizeof(double)); }
+    if (e == cudaSuccess) e = dev_alloc(h, (void **)&h->d_pass_scratch, sizeof(qsv_pass));
     if (e != cudaSuccess) {
         g_create_error = std::string("qsv_create: ") + cudaGetErrorString(e);
         int code = (e == cudaErrorMemoryAllocation) ? QSV_ENOMEM : QSV_ECUDA;
         cudaGetLastError();
         if (h->d_state) cudaFree(h->d_state);
-        if (h->d_partials) cudaFree(h->d_partials);
+        if (h->stream) { dev_free(h, h->d_partials); dev_free(h, h->d_pass_scratch); }
         if (h->stream) cudaStreamDestroy(h->stream);
         delete h;
         return code;
@@ -124,15 +175,38 @@ int qsv_create(qsv_handle **out, int n_qubits, int dtype, int device, int rank, 
 
 int qsv_destroy(qsv_handle *h) {
     QSV_CHECK_H(h);
+    const bool trace = getenv("QSV_TRACE") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::milli>(b - a).count(); };
+    auto t0 = now();
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    auto t1 = now();
     qsv_comm_teardown(h);
     for (auto &t : h->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     if (h->t0) { cudaEventDestroy(h->t0); cudaEventDestroy(h->t1); }
-    cudaFree(h->d_state); cudaFree(h->d_partials); cudaFree(h->d_pass_scratch);
-    if (h->d_ops_scratch) cudaFree(h->d_ops_scratch);
+    auto t2 = now();
+    if (h->n_amps * h->amp_bytes >= ((size_t)64 << 20)) cache_put(h->device, h->d_state, h->n_amps * h->amp_bytes);
+    else cudaFree(h->d_state);
+    auto t3 = now();
+    dev_free(h, h->d_partials); dev_free(h, h->d_pass_scratch); dev_free(h, h->d_ops_scratch);
+    auto t4 = now();
     cudaStreamDestroy(h->stream);
+    auto t5 = now();
+    if (trace) fprintf(stderr, "[qsv] destroy: sync %.2f teardown %.2f state %.2f scratch %.2f stream %.2f ms\n",
+                       ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4), ms(t4, t5));
     delete h;
+    return QSV_OK;
+}
+
+int qsv_release_cached(void) {
+    std::lock_guard<std::mutex> g(g_cache_mu);
+    int dev0 = 0;
+    cudaGetDevice(&dev0);
+    for (int d = 0; d < 64; ++d)
+        if (g_cache[d].ptr) { cudaSetDevice(d); cudaFree(g_cache[d].ptr); g_cache[d] = CachedShard(); }
+    cudaSetDevice(dev0);
     return QSV_OK;
 }
 
@@ -267,9 +341,9 @@ static int launch_diag(qsv_handle *h, int nq, const int *qs, const double *phase
     for (int i = 0; i < (1 << nq); ++i) { a.phase[i].x = (R)phases[2 * i]; a.phase[i].y = (R)phases[2 * i + 1]; }
     // args travel through the ops scratch buffer (stream ordered)
     if (h->ops_scratch_cap < sizeof(a)) {
-        if (h->d_ops_scratch) cudaFree(h->d_ops_scratch);
+        dev_free(h, h->d_ops_scratch);
         h->ops_scratch_cap = 1 << 20;
-        QSV_CUDA(h, cudaMalloc((void **)&h->d_ops_scratch, h->ops_scratch_cap));
+        QSV_CUDA(h, dev_alloc(h, (void **)&h->d_ops_scratch, h->ops_scratch_cap));
     }
     QSV_CUDA(h, cudaMemcpyAsync(h->d_ops_scratch, &a, sizeof(a), cudaMemcpyHostToDevice, h->stream));
     QSV_CUDA(h, cudaStreamSynchronize(h->stream));   // `a` is a stack object
@@ -327,9 +401,9 @@ int qsv_apply_kq(qsv_handle *h, int k, const int *qs, const double *U) {
     const size_t mat_elems = (size_t)D * D;
     const size_t need = 64 + mat_elems * 16;
     if (h->ops_scratch_cap < need) {
-        if (h->d_ops_scratch) cudaFree(h->d_ops_scratch);
+        dev_free(h, h->d_ops_scratch);
         h->ops_scratch_cap = 1 << 20;
-        QSV_CUDA(h, cudaMalloc((void **)&h->d_ops_scratch, h->ops_scratch_cap));
+        QSV_CUDA(h, dev_alloc(h, (void **)&h->d_ops_scratch, h->ops_scratch_cap));
     }
     char *scratch = (char *)h->d_ops_scratch;
     std::vector<char> stage(need);
@@ -446,9 +520,9 @@ int qsv_apply_pass(qsv_handle *h, const qsv_pass *pass, const qsv_op *ops, const
     const size_t need = tab_off + sizeof(double2) * (size_t)std::max(pass->n_fold, 1);
     if (h->ops_scratch_cap < need) {
         QSV_CUDA(h, cudaStreamSynchronize(h->stream));
-        if (h->d_ops_scratch) cudaFree(h->d_ops_scratch);
+        dev_free(h, h->d_ops_scratch);
         h->ops_scratch_cap = std::max(need, (size_t)1 << 20);
-        QSV_CUDA(h, cudaMalloc((void **)&h->d_ops_scratch, h->ops_scratch_cap));
+        QSV_CUDA(h, dev_alloc(h, (void **)&h->d_ops_scratch, h->ops_scratch_cap));
     }
     // stream order protects the scratch against the previous one-shot pass; the host buffers
     // are pageable, so cudaMemcpyAsync stages them before returning.
@@ -479,18 +553,17 @@ int qsv_program_create(qsv_handle *h, const qsv_pass *passes, int n_passes, cons
     }
     if (total_fold > 0 && !tables) { delete p; QSV_FAIL(h, QSV_EINVAL, "program_create: fold tables missing"); }
     cudaError_t e = cudaSuccess;
-    if (n_passes) e = cudaMalloc((void **)&p->d_passes, sizeof(qsv_pass) * n_passes);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_ops, sizeof(qsv_op) * std::max(total_ops, 1));
-    if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_tables, sizeof(double2) * std::max(total_fold, 1));
-    if (e == cudaSuccess && total_fold) e = cudaMemcpy(p->d_tables, tables, sizeof(double2) * total_fold, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess && n_passes) e = cudaMemcpy(p->d_passes, passes, sizeof(qsv_pass) * n_passes, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess && total_ops) e = cudaMemcpy(p->d_ops, ops, sizeof(qsv_op) * total_ops, cudaMemcpyHostToDevice);
+    if (n_passes) e = dev_alloc(h, (void **)&p->d_passes, sizeof(qsv_pass) * n_passes);
+    if (e == cudaSuccess) e = dev_alloc(h, (void **)&p->d_ops, sizeof(qsv_op) * std::max(total_ops, 1));
+    if (e == cudaSuccess) e = dev_alloc(h, (void **)&p->d_tables, sizeof(double2) * std::max(total_fold, 1));
+    if (e == cudaSuccess && total_fold) e = cudaMemcpyAsync(p->d_tables, tables, sizeof(double2) * total_fold, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess && n_passes) e = cudaMemcpyAsync(p->d_passes, passes, sizeof(qsv_pass) * n_passes, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess && total_ops) e = cudaMemcpyAsync(p->d_ops, ops, sizeof(qsv_op) * total_ops, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);          // the host arrays belong to the caller
     if (e != cudaSuccess) {
         h->err = std::string("program_create: ") + cudaGetErrorString(e);
         cudaGetLastError();
-        if (p->d_passes) cudaFree(p->d_passes);
-        if (p->d_ops) cudaFree(p->d_ops);
-        if (p->d_tables) cudaFree(p->d_tables);
+        dev_free(h, p->d_passes); dev_free(h, p->d_ops); dev_free(h, p->d_tables);
         delete p;
         return QSV_ECUDA;
     }
@@ -592,9 +665,8 @@ int qsv_program_destroy(qsv_handle *h, qsv_program *p) {
     QSV_CHECK_H(h);
     if (!p) return QSV_OK;
     cudaSetDevice(h->device);
-    cudaStreamSynchronize(h->stream);
     if (p->graph) cudaGraphExecDestroy(p->graph);
-    cudaFree(p->d_passes); cudaFree(p->d_ops); cudaFree(p->d_tables);
+    dev_free(h, p->d_passes); dev_free(h, p->d_ops); dev_free(h, p->d_tables);   // stream-ordered after the last run
     delete p;
     return QSV_OK;
 }
@@ -622,14 +694,14 @@ int qsv_leaf_sums(qsv_handle *h, double *out_host) {
     const int leaf = 1 << leaf_log2;
     const uint64_t n_leaves = h->n_amps >> leaf_log2;
     double *d = nullptr;
-    QSV_CUDA(h, cudaMalloc((void **)&d, n_leaves * sizeof(double)));
+    QSV_CUDA(h, dev_alloc(h, (void **)&d, n_leaves * sizeof(double)));
     const unsigned grid = (unsigned)((n_leaves + 127) / 128);
     if (h->dtype == QSV_C128) k_leaf_sums<double><<<grid, 128, 0, h->stream>>>((const double2 *)h->d_state, n_leaves, leaf, d);
     else k_leaf_sums<float><<<grid, 128, 0, h->stream>>>((const float2 *)h->d_state, n_leaves, leaf, d);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(out_host, d, n_leaves * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    cudaFree(d);
+    dev_free(h, d);
     QSV_CUDA(h, e);
     return QSV_OK;
 }
@@ -645,7 +717,7 @@ int qsv_sample_in_leaves(qsv_handle *h, int shots, const uint64_t *leaf_idx, con
     for (int i = 0; i < shots; ++i) if (leaf_idx[i] >= n_leaves) QSV_FAIL(h, QSV_EINVAL, "sample_in_leaves: leaf %llu outside the shard", (unsigned long long)leaf_idx[i]);
     char *d = nullptr;
     const size_t n8 = (size_t)shots * 8;
-    QSV_CUDA(h, cudaMalloc((void **)&d, 4 * n8));
+    QSV_CUDA(h, dev_alloc(h, (void **)&d, 4 * n8));
     cudaError_t e = cudaMemcpyAsync(d, leaf_idx, n8, cudaMemcpyHostToDevice, h->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d + n8, leaf_off, n8, cudaMemcpyHostToDevice, h->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d + 2 * n8, x, n8, cudaMemcpyHostToDevice, h->stream);
@@ -661,7 +733,7 @@ int qsv_sample_in_leaves(qsv_handle *h, int shots, const uint64_t *leaf_idx, con
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(out_local_index, d + 3 * n8, n8, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    cudaFree(d);
+    dev_free(h, d);
     QSV_CUDA(h, e);
     return QSV_OK;
 }
@@ -710,7 +782,7 @@ int qsv_probabilities(qsv_handle *h, int nq, const int *qubits, double *out_host
     QSV_CUDA(h, cudaSetDevice(h->device));
     const size_t bins = (size_t)1 << nq;
     double *d = nullptr;
-    QSV_CUDA(h, cudaMalloc((void **)&d, bins * sizeof(double)));
+    QSV_CUDA(h, dev_alloc(h, (void **)&d, bins * sizeof(double)));
     cudaError_t e = cudaMemsetAsync(d, 0, bins * sizeof(double), h->stream);
     if (e == cudaSuccess) {
         const size_t smem = nq <= 10 ? bins * sizeof(double) : 0;
@@ -722,7 +794,7 @@ int qsv_probabilities(qsv_handle *h, int nq, const int *qubits, double *out_host
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(out_host, d, bins * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    cudaFree(d);
+    dev_free(h, d);
     QSV_CUDA(h, e);
     return QSV_OK;
 }

@@ -25,18 +25,40 @@ def compile_circuit(circuit_dict: dict, dtype="complex128", **compiler_kw) -> Pr
 
 
 def simulate(circuit_dict: dict, dtype="complex128", device: int = 0, out: np.ndarray | None = None,
-             fused: bool = True, jit: bool | None = None, **compiler_kw) -> np.ndarray:
-    """Run the circuit on the GPU and return the final state vector (host, `dtype`)."""
+             fused: bool = True, jit: bool | None = None, phases: dict | None = None, **compiler_kw) -> np.ndarray:
+    """Run the circuit on the GPU and return the final state vector (host, `dtype`).
+    `phases` (optional dict) receives the host time of each phase in milliseconds."""
+    import time
     from quantum_simulations_b200.kernel.cuda import DeviceState
+
+    t = [time.perf_counter()]
+
+    def mark(name):
+        if phases is not None:
+            t.append(time.perf_counter())
+            phases[name] = phases.get(name, 0.0) + (t[-1] - t[-2]) * 1e3
 
     cd = validate_circuit_dict(circuit_dict)
     n = cd["number_of_qubits"]
     ops = circuit_ops(cd)
+    mark("validate+gate_matrices")
     with DeviceState(n, dtype, device) as st:
+        mark("create(cudaMalloc)")
         st.init_zero()
         if fused and n >= REG_BITS:
-            st.run_program(PassCompiler(n, dtype=st.dtype.name, **compiler_kw).compile(ops), jit=jit)
+            prog = PassCompiler(n, dtype=st.dtype.name, **compiler_kw).compile(ops)
+            mark("pass_compiler")
+            st.run_program(prog, jit=jit)
+            if phases is not None:
+                st.sync()
+            mark("upload+specialise+run")
         else:
             for qs, U in ops:
                 st.apply_op(qs, U)
-        return st.download(out)
+            if phases is not None:
+                st.sync()
+            mark("per_gate_run")
+        res = st.download(out)
+        mark("download(D2H)")
+    mark("destroy(cudaFree)")
+    return res

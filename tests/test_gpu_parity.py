@@ -141,6 +141,28 @@ def test_a1_a2_host_callables_and_nonlocal_raise():
         cuda.apply_2q(small, 0, 2, G.CNOT())
 
 
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+def test_nonlocal_butterfly_drop_ins_match_oracle(dtype):
+    """kernel.cuda_nonlocal mirrors cpu_nonlocal.py:22-67 (same names, in place on host chunks)."""
+    from quantum_simulations_b200.kernel import cuda_nonlocal as KN
+    rng = np.random.default_rng(11)
+    tol = TOL[dtype] * 10
+
+    def chunks(m):
+        return [(rng.standard_normal(256) + 1j * rng.standard_normal(256)).astype(dtype) for _ in range(m)]
+
+    U1 = G.gate_matrix("RY", {"theta": 0.7}) @ G.H()
+    U2 = np.kron(G.H(), G.gate_matrix("RY", {"theta": 1.1})) @ G.CNOT()
+    for fn, m, args in ((KN.apply_1q_pair, 2, (U1,)), (KN.apply_2q_pair_qa_local, 2, (3, U2)),
+                        (KN.apply_2q_pair_qb_local, 2, (2, U2)), (KN.apply_2q_quad, 4, (U2,))):
+        got = chunks(m)
+        want = [c.astype(np.complex128) for c in got]
+        getattr(O, fn.__name__)(*want, *args)
+        fn(*got, *args)
+        for a, b in zip(got, want):
+            assert a.dtype == np.dtype(dtype) and np.abs(a - b).max() <= tol, fn.__name__
+
+
 def test_sharded_handle_semantics_on_one_gpu():
     """4 shards of an 8-qubit state as 4 handles on one device: rank bits as controls /
     diagonal qubits work without communication; mixing one raises QSV_ENONLOCAL."""
