@@ -416,6 +416,16 @@ def test_runner_dtypes_and_manifest(dtype):
     assert np.abs(got - O.simulate(validate_circuit_dict(cd))).max() <= TOL[dtype]
 
 
+def test_pipeline_runner_surface(tmp_path):
+    """reference tests/test_out_of_core_e2e.py:38 / test_fusion.py:149: pipeline.run == single_node.run."""
+    from quantum_simulations_b200.runner import pipeline
+    from quantum_simulations_b200.runner.single_node import collect_state
+    cd = W.qft(6)
+    for fusion in (False, True):
+        final = pipeline.run(cd, tmp_path / f"f{int(fusion)}", chunk_size=16, buffer_depth=2, use_wal=False, use_fusion=fusion)
+        assert np.abs(collect_state(final) - O.simulate(validate_circuit_dict(cd))).max() <= 1e-12
+
+
 def test_runner_errors():
     from quantum_simulations_b200.runner.single_node import run
     with tempfile.TemporaryDirectory() as td:
