@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define QSV_ABI_VERSION 2
+#define QSV_ABI_VERSION 3
 
 /* dtypes (wenbo_engine/storage/block_store.py:11 fixes complex64; the oracle is complex128) */
 #define QSV_C64  0
@@ -135,7 +135,15 @@ int qsv_apply_kq(qsv_handle *h, int k, const int *qs, const double *U);
                             m[0] = tan(phi/2), m[1] = sin(phi), m[2] = cos(phi), m[3] = sin(phi) */
 #define QSV_OP_SIGN   5  /* no target: amp = -amp where all controls are 1 (Z, CZ)            */
 #define QSV_OP_SCALE  6  /* no target, no controls: amp *= m[0] (real)                        */
-#define QSV_OP_KINDS  7
+#define QSV_OP_TPHASE 7  /* TABLE PHASE on the b half of a register slot (target): every amplitude whose
+                            target bit is 1 is multiplied by the unit complex number
+                                T_thr[thread] * prod_k T_run_k[(global_index >> 8 r_k) & 255]
+                            read from the pass's table array: m[0] = offset of the 2^(n_tile-4)-entry
+                            per-thread table (-1: none), m[1] = offset of the first 256-entry table of
+                            the 8-bit index runs r_k named by the bit mask m[2] (ascending; -1: none).
+                            One op replaces ALL controlled-phase gates (CR, CZ) between the target and
+                            qubits that are not register-resident in the round (the QFT pattern).     */
+#define QSV_OP_KINDS  8
 
 /* PRE-OPS of an UNCONTROLLED HAD / ROT (qsv_op.flags).  Diagonal gates that sit right before a
  * mixing gate on its target are folded into it by the compiler, so they cost no dispatch:

@@ -15,7 +15,7 @@ LIB_PATH = _CSRC / os.environ.get("QSV_LIB_NAME", "libqsv.so")   # env override:
 QSV_C64, QSV_C128 = 0, 1
 QSV_OK, QSV_EINVAL, QSV_ENONLOCAL, QSV_ECUDA, QSV_ENOMEM, QSV_ECOMM, QSV_EIO = 0, -1, -2, -3, -4, -5, -6
 QSV_MAX_TILE_BITS, QSV_REG_BITS, QSV_MAX_ROUNDS = 14, 4, 16
-OP_HAD, OP_ROT, OP_XSWAP, OP_YSWAP, OP_PHASE, OP_SIGN, OP_SCALE = range(7)
+OP_HAD, OP_ROT, OP_XSWAP, OP_YSWAP, OP_PHASE, OP_SIGN, OP_SCALE, OP_TPHASE = range(8)
 OP_WITH_TARGET = (OP_HAD, OP_ROT, OP_XSWAP, OP_YSWAP)
 OPF_PRESIGN, OPF_PRENEG, OPF_PREPHASE = 1, 2, 4
 OPT_JIT, OPT_SIMPLE_PASS, OPT_PEER_SWAP = 1, 2, 3

@@ -97,6 +97,11 @@ k_pass(typename CxT<R>::V *__restrict__ state, const qsv_pass *__restrict__ pass
         }
         for (int o = rd.op_begin; o < rd.op_end; ++o) {
             const qsv_op &op = ops[o];
+            if (op.kind == QSV_OP_TPHASE) {
+                const double2 f = tphase_factor(tables, op.m, tid, glob);
+                QSV_DISPATCH_TB(op.target, (op_cmul_slot<V, R, TB>(v, (R)f.x, (R)f.y)));
+                continue;
+            }
             if (op.flags) {     // HAD / ROT with pre-ops: the control fields are parity masks
                 const int sm = (int)(((uint32_t)__popc(xb & op.tile_ctrl) + (uint32_t)__popcll(glob & op.glob_ctrl) +
                                       ((uint32_t)op.flags >> 1)) << 31);

@@ -130,6 +130,36 @@ __device__ __forceinline__ void op_sign_slot(V (&v)[kRegAmps]) {
     for (int j = 0; j < kRegAmps; ++j) if (j & (1 << TB)) { v[j].x = flip_sign(v[j].x); v[j].y = flip_sign(v[j].y); }
 }
 
+// TABLE PHASE: the b half of slot TB times a unit complex number (general product: 4 FP64 per amplitude)
+template <typename V, typename R, int TB>
+__device__ __forceinline__ void op_cmul_slot(V (&v)[kRegAmps], const R fr, const R fi) {
+#pragma unroll
+    for (int j = 0; j < kRegAmps; ++j) if (j & (1 << TB)) {
+        const R x = v[j].x, y = v[j].y;
+        v[j].x = fma(-y, fi, x * fr);
+        v[j].y = fma(y, fr, x * fi);
+    }
+}
+// the factor of a QSV_OP_TPHASE op for this thread / tile
+__device__ __forceinline__ double2 tphase_factor(const double2 *__restrict__ tables, const double *__restrict__ m,
+                                                 const uint32_t thread, const uint64_t glob) {
+    double2 f = make_double2(1.0, 0.0);
+    const int toff = (int)m[0], goff = (int)m[1];
+    uint32_t mask = (uint32_t)m[2];
+    if (toff >= 0) f = tables[toff + thread];
+    if (goff >= 0) {
+        int k = 0;
+        while (mask) {
+            const int r = __ffs((int)mask) - 1;
+            mask &= mask - 1;
+            const double2 g = tables[goff + 256 * k + (int)((glob >> (8 * r)) & 255ull)];
+            f = make_double2(f.x * g.x - f.y * g.y, f.x * g.y + f.y * g.x);
+            ++k;
+        }
+    }
+    return f;
+}
+
 // SIGN controlled by exactly TWO register slots (a CZ between two register-resident qubits)
 template <typename V, int A, int B>
 __device__ __forceinline__ void op_sign_slot2(V (&v)[kRegAmps]) {

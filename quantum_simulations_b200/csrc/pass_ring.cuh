@@ -54,7 +54,7 @@ struct RingSmem {
 
 // dense dispatch codes (kept in bits 2..7 of qsv_op.target while the ops are staged in shared memory)
 enum : int { RC_HAD = 0, RC_ROT = 4, RC_MIX_END = 8, RC_PHASE1 = 8, RC_SIGN1 = 12, RC_SIGN2 = 16,
-             RC_FOLD_SIGN = 22, RC_FOLD_PHASE = 23, RC_SCALE = 24, RC_XSWAP = 25, RC_YSWAP = 29, RC_GENERIC = 33 };
+             RC_FOLD_SIGN = 22, RC_FOLD_PHASE = 23, RC_SCALE = 24, RC_XSWAP = 25, RC_YSWAP = 29, RC_TPHASE = 33, RC_GENERIC = 37 };
 
 __device__ __forceinline__ int ring_dispatch_code(int kind, int tb, uint32_t rc, uint32_t fl, bool other_ctrl) {
     const bool one = rc != 0 && (rc & (rc - 1)) == 0;
@@ -74,6 +74,7 @@ __device__ __forceinline__ int ring_dispatch_code(int kind, int tb, uint32_t rc,
             }
             return RC_GENERIC;
         case QSV_OP_SCALE: return RC_SCALE;
+        case QSV_OP_TPHASE: return RC_TPHASE + tb;
         default: return RC_GENERIC;
     }
 }
@@ -280,6 +281,8 @@ k_pass_ring(double2 *__restrict__ state, const qsv_pass *__restrict__ pass_ptr,
                     }
                     continue;
                 }
+                double2 tf = make_double2(1.0, 0.0);
+                if (code >= RC_TPHASE && code < RC_TPHASE + 4) tf = tphase_factor(tables, S.ops[o].m, gt, glob);
                 if (hd.y | hd.z | hd.w) {
                     const uint64_t gc = ((uint64_t)hd.w << 32) | hd.z;
                     if ((glob & gc) != gc) continue;                       // group-uniform
@@ -288,6 +291,7 @@ k_pass_ring(double2 *__restrict__ state, const qsv_pass *__restrict__ pass_ptr,
                 switch (code) {
                     RING_CASE4(RC_PHASE1, (op_phase_slot<V, R, TB>(v, c.x, c.y)))
                     RING_CASE4(RC_SIGN1, (op_sign_slot<V, TB>(v)))
+                    RING_CASE4(RC_TPHASE, (op_cmul_slot<V, R, TB>(v, tf.x, tf.y)))
                     RING_CASE4(RC_XSWAP, (op_xswap<V, TB, false>(v, 0u)))
                     RING_CASE4(RC_YSWAP, (op_yswap<V, TB, false>(v, 0u)))
 #undef RING_CASE4

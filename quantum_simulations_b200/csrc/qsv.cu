@@ -457,7 +457,15 @@ static int validate_pass(qsv_handle *h, const qsv_pass *p, const qsv_op *ops) {
             const qsv_op &op = ops[o];
             if (op.kind >= QSV_OP_KINDS) QSV_FAIL(h, QSV_EINVAL, "pass: op %d bad kind %d", o, (int)op.kind);
             const bool has_target = op.kind == QSV_OP_HAD || op.kind == QSV_OP_ROT || op.kind == QSV_OP_XSWAP ||
-                                    op.kind == QSV_OP_YSWAP;
+                                    op.kind == QSV_OP_YSWAP || op.kind == QSV_OP_TPHASE;
+            if (op.kind == QSV_OP_TPHASE) {
+                const int toff = (int)op.m[0], goff = (int)op.m[1];
+                const unsigned mask = (unsigned)op.m[2];
+                if (op.reg_ctrl || op.tile_ctrl || op.glob_ctrl || op.flags) QSV_FAIL(h, QSV_EINVAL, "pass: op %d: TPHASE takes no controls", o);
+                if (toff < -1 || (toff >= 0 && toff + (1 << (T - QSV_REG_BITS)) > p->n_fold)) QSV_FAIL(h, QSV_EINVAL, "pass: op %d: thread table outside the pass's tables", o);
+                if (mask > 255u || goff < -1 || (goff >= 0 && goff + 256 * __builtin_popcount(mask) > p->n_fold) || (goff < 0 && mask))
+                    QSV_FAIL(h, QSV_EINVAL, "pass: op %d: run tables outside the pass's tables", o);
+            }
             if (has_target && op.target >= QSV_REG_BITS) QSV_FAIL(h, QSV_EINVAL, "pass: op %d target", o);
             const bool any_ctrl = op.reg_ctrl || op.tile_ctrl || op.glob_ctrl;
             if (op.flags & ~(QSV_OPF_PRESIGN | QSV_OPF_PRENEG | QSV_OPF_PREPHASE)) QSV_FAIL(h, QSV_EINVAL, "pass: op %d: unknown flags", o);

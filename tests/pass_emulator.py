@@ -65,6 +65,27 @@ def run_pass(psi: np.ndarray, desc: L.QsvPass, ops, n_local: int, rank: int = 0,
             cols = (x & need) == need
             m = [op.m[k] for k in range(4)]
             ctrl_any = bool(op.reg_ctrl or op.tile_ctrl or op.glob_ctrl)
+            if op.kind == L.OP_TPHASE:
+                assert not ctrl_any and not op.flags and 0 <= op.target < R and tables is not None
+                toff, goff, mask = int(m[0]), int(m[1]), int(m[2])
+                nthr = 1 << (t - R)
+                tix = np.zeros(1 << t, dtype=np.int64)
+                for k, i in enumerate(thr):
+                    tix |= ((x >> i) & 1) << k
+                fac = np.ones((len(glob), 1 << t), dtype=np.complex128)
+                if toff >= 0:
+                    assert toff + nthr <= desc.n_fold
+                    fac *= tables[toff:toff + nthr][tix][None, :]
+                k = 0
+                for r_ in range(8):
+                    if mask >> r_ & 1:
+                        assert goff >= 0 and goff + 256 * (k + 1) <= desc.n_fold
+                        fac *= tables[goff + 256 * k + ((glob >> (8 * r_)) & 255)][:, None]
+                        k += 1
+                tb = 1 << regs[op.target]
+                sel = (x & tb) != 0
+                work[:, sel] *= fac[:, sel]
+                continue
             if op.flags:
                 # HAD / ROT with pre-ops: the control fields are parity masks of a sign on the b half
                 assert op.kind in (L.OP_HAD, L.OP_ROT) and not op.reg_ctrl
