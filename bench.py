@@ -382,7 +382,8 @@ def bench_multi(args) -> None:
     if rank == 0:
         ms_per_step = total_ms / args.steps
         pass_ms = [ms for ms, kind, _ in per_launch if kind == 10]
-        swap_ms = [(ms, kind - 20) for ms, kind, _ in per_launch if kind >= 20]
+        swap_ms = [(ms, kind - 20) for ms, kind, _ in per_launch if 20 <= kind < 30]
+        fused_ms = [(ms, kind - 30) for ms, kind, _ in per_launch if kind >= 30]
         avg_pass_ms = float(np.mean(pass_ms))
         alg_bytes = 2 * amp_bytes * (1 << n_loc)
         peak, peak_src = _peaks()
@@ -412,8 +413,12 @@ def bench_multi(args) -> None:
                          "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
                          "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_pass_ms,
                          "launches_timed": len(pass_ms), "share_of_step": sum(pass_ms) / total_ms},
+            "overlapped_pass_swap": {"count_per_step": len(fused_ms) // max(args.steps, 1),
+                                     "ms": [round(ms, 3) for ms, _ in fused_ms[-max(1, len(fused_ms) // max(args.steps, 1)):]] if fused_ms else [],
+                                     "what": "last pass of a stage split into 2^s blocks, exchange of each block pair on a second "
+                                             "stream while the next block is computed (qsv_pass_swap_overlapped)"},
             "nvlink": {"path": "peer-memory kernel (CUDA IPC, loads/stores over NVLink)" if sim.peer_swap
-                       else f"chunked ncclSend/ncclRecv ({sim.shard.peer_error or 'QSV_SWAP=nccl'})", "swaps": nv, "share_of_step": sum(ms for ms, _ in swap_ms) / total_ms if swap_ms else 0.0,
+                       else f"chunked ncclSend/ncclRecv ({sim.shard.peer_error or 'QSV_SWAP=nccl'})", "swaps": nv, "share_of_step": (sum(ms for ms, _ in swap_ms) + sum(ms for ms, _ in fused_ms)) / total_ms,
                        "peak_gbs_per_direction": 900.0},
             "gpu_launches": len(per_launch) + 2 * args.steps,
             "clocks": clk,

@@ -201,6 +201,13 @@ int qsv_program_create(qsv_handle *h, const qsv_pass *passes, int n_passes,
                        qsv_program **out);
 int qsv_program_run(qsv_handle *h, qsv_program *p);
 int qsv_program_destroy(qsv_handle *h, qsv_program *p);
+int qsv_program_run_range(qsv_handle *h, qsv_program *p, int first_pass, int n_passes);
+/* Pass `pass_index` followed by the swap of the top n_swap local bits, with the NVLink exchange
+ * OVERLAPPED with the pass on a second stream: the shard is processed block by block in the order the
+ * exchange consumes the blocks (see csrc/qsv.cu).  *overlapped = 0 if it had to fall back to
+ * "pass, then swap" (pass not specialised / tile touches the swapped bits / peers not mapped). */
+int qsv_pass_swap_overlapped(qsv_handle *h, qsv_program *p, int pass_index, int n_swap, const int *global_bits,
+                             const int *local_bits, int *overlapped);
 /* qsv_program_create SPECIALISES each 2^11-amplitude pass (complex128 and complex64) at run time (NVRTC, sm_100a): the same ring
  * kernel with the pass's bit positions and op sequence as straight-line code and the coefficients
  * in the kernel-parameter bank; cubins are cached by pass STRUCTURE (in memory and under

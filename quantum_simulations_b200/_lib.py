@@ -80,6 +80,8 @@ SIGNATURES = {
     "qsv_program_create": (C.c_int, [_H, C.POINTER(QsvPass), C.c_int, C.POINTER(QsvOp), _dp, C.POINTER(_P)]),
     "qsv_program_run": (C.c_int, [_H, _P]),
     "qsv_program_destroy": (C.c_int, [_H, _P]),
+    "qsv_program_run_range": (C.c_int, [_H, _P, C.c_int, C.c_int]),
+    "qsv_pass_swap_overlapped": (C.c_int, [_H, _P, C.c_int, C.c_int, _ip, _ip, _ip]),
     "qsv_set_option": (C.c_int, [_H, C.c_int, C.c_longlong]),
     "qsv_jit_stats": (C.c_int, [_ip, _ip, _ip, _ip, _dp]),
     "qsv_jit_source": (C.c_int, [C.POINTER(QsvPass), C.POINTER(QsvOp), C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),

@@ -636,7 +636,9 @@ class PassCompiler:
             park = []
             if remaining and self.a:
                 wish = self._choose_tile(remaining, pos, forced=[], pool=set(tile))
-                cand = [c for c in wish if c in set(tile)]
+                # contents whose home is a rank bit wait on the top local slots for the swap that takes
+                # them there: they are never parked (a swap of untouched top bits overlaps with the pass)
+                cand = [c for c in wish if c in set(tile) and home[c] < self.n_local]
                 if self.park_off_last_round and rounds:
                     # a content that is register-resident in the LAST round cannot be stored to a low
                     # position without an extra idle round (the lanes must cover the low positions for

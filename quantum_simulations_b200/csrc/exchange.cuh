@@ -167,9 +167,9 @@ __device__ __forceinline__ uint64_t swap_addr(const SwapBits &sb, uint64_t off, 
 template <typename V, int U>
 __global__ void __launch_bounds__(512)
 k_swap_peer(V *__restrict__ mine, PeerTable peers, const int n_peers, const int me, const uint64_t block_amps,
-            const SwapBits sb) {
+            const SwapBits sb, const int only_phase) {
     const uint64_t half = block_amps >> 1;
-    const uint64_t total = (uint64_t)(n_peers - 1) * half;
+    const uint64_t total = (uint64_t)(only_phase >= 0 ? 1 : n_peers - 1) * half;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t e0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e0 < total; e0 += stride * U) {
         V x[U], y[U];
@@ -178,8 +178,9 @@ k_swap_peer(V *__restrict__ mine, PeerTable peers, const int n_peers, const int 
         for (int u = 0; u < U; ++u) {
             const uint64_t e = e0 + (uint64_t)u * stride;
             const uint64_t ee = e < total ? e : e0;
-            const int k = (int)(ee / half);                 // phase 0 .. n_peers-2
-            const uint64_t i = ee - (uint64_t)k * half;
+            const int k0 = (int)(ee / half);                // phase 0 .. n_peers-2
+            const uint64_t i = ee - (uint64_t)k0 * half;
+            const int k = only_phase >= 0 ? only_phase : k0;
             const int d = me ^ (k + 1);                     // phase k pairs me with me^(k+1): a perfect
                                                             // matching of the group, so no GPU is the
                                                             // target of two others at the same time
@@ -237,6 +238,45 @@ static int swap_barrier(qsv_handle *h, qsvx::Comm *c) {
     return QSV_OK;
 }
 
+static int qsvx_swap_barrier_on(qsv_handle *h, qsvx::Comm *c, cudaStream_t stream) {
+    double *d = h->d_partials + h->n_partials - 3;
+    QSVX_NCCL(h, qsvx::nccl().AllReduce(d, d, 1, /*ncclDouble*/ 8, /*ncclSum*/ 0, c->comm, stream));
+    return QSV_OK;
+}
+
+// One phase of the peer-memory exchange on `stream` (used by qsv_pass_swap_overlapped): a barrier
+// (every rank has finished the blocks of this phase), then the pair (me, me ^ (phase+1)) only.
+static int qsvx_swap_phase(qsv_handle *h, qsvx::Comm *c, cudaStream_t stream, int n_swap, const int *global_bits,
+                           const int *local_bits, int phase) {
+    const int peers = 1 << n_swap;
+    int me = 0;
+    for (int i = 0; i < n_swap; ++i) me |= ((h->rank >> (global_bits[i] - h->n_local)) & 1) << i;
+    PeerTable pt;
+    for (int d = 0; d < 8; ++d) {
+        pt.ptr[d] = nullptr;
+        if (d < peers) {
+            int r = h->rank;
+            for (int i = 0; i < n_swap; ++i) {
+                const int rb = global_bits[i] - h->n_local;
+                r = (r & ~(1 << rb)) | (((d >> i) & 1) << rb);
+            }
+            pt.ptr[d] = c->peer[r];
+        }
+    }
+    SwapBits sbits;
+    sbits.n = n_swap;
+    for (int i = 0; i < 3; ++i) { sbits.bit[i] = i < n_swap ? local_bits[i] : 0; sbits.sorted[i] = sbits.bit[i]; }
+    std::sort(sbits.sorted, sbits.sorted + n_swap);
+    int rc = qsvx_swap_barrier_on(h, c, stream);
+    if (rc) return rc;
+    const uint64_t block_amps = h->n_amps >> n_swap;
+    const int grid = h->sm_count * 2;                       // leave SMs to the pass running beside it
+    if (h->dtype == QSV_C128) k_swap_peer<double2, 4><<<grid, 512, 0, stream>>>((double2 *)h->d_state, pt, peers, me, block_amps, sbits, phase);
+    else k_swap_peer<float2, 8><<<grid, 512, 0, stream>>>((float2 *)h->d_state, pt, peers, me, block_amps, sbits, phase);
+    QSVX_CUDA(h, cudaGetLastError());
+    return QSV_OK;
+}
+
 // Swap rank bits global_bits[i] (physical positions >= n_local) with local bits local_bits[i].
 // Peer-memory path: any distinct local positions.  NCCL path: the TOP n_swap local bits in order
 // (contiguous blocks), in place, chunked.  Collective over the group of 2^n_swap ranks.
@@ -286,10 +326,10 @@ extern "C" int qsv_swap_global_local(qsv_handle *h, int n_swap, const int *globa
         for (int i = 0; i < 3; ++i) { sbits.bit[i] = i < n_swap ? local_bits[i] : 0; sbits.sorted[i] = sbits.bit[i]; }
         std::sort(sbits.sorted, sbits.sorted + n_swap);
         if (h->dtype == QSV_C128) {
-            if (unroll == 2) k_swap_peer<double2, 2><<<grid, 512, 0, h->stream>>>((double2 *)h->d_state, pt, peers, me, block_amps, sbits);
-            else if (unroll == 8) k_swap_peer<double2, 8><<<grid, 512, 0, h->stream>>>((double2 *)h->d_state, pt, peers, me, block_amps, sbits);
-            else k_swap_peer<double2, 4><<<grid, 512, 0, h->stream>>>((double2 *)h->d_state, pt, peers, me, block_amps, sbits);
-        } else k_swap_peer<float2, 8><<<grid, 512, 0, h->stream>>>((float2 *)h->d_state, pt, peers, me, block_amps, sbits);
+            if (unroll == 2) k_swap_peer<double2, 2><<<grid, 512, 0, h->stream>>>((double2 *)h->d_state, pt, peers, me, block_amps, sbits, -1);
+            else if (unroll == 8) k_swap_peer<double2, 8><<<grid, 512, 0, h->stream>>>((double2 *)h->d_state, pt, peers, me, block_amps, sbits, -1);
+            else k_swap_peer<double2, 4><<<grid, 512, 0, h->stream>>>((double2 *)h->d_state, pt, peers, me, block_amps, sbits, -1);
+        } else k_swap_peer<float2, 8><<<grid, 512, 0, h->stream>>>((float2 *)h->d_state, pt, peers, me, block_amps, sbits, -1);
         QSVX_CUDA(h, cudaGetLastError());
         rc = swap_barrier(h, c);                     // nobody reads its shard before all exchanges landed
         if (rc) return rc;

@@ -596,20 +596,25 @@ int qsv_program_create(qsv_handle *h, const qsv_pass *passes, int n_passes, cons
     return QSV_OK;
 }
 
-static int launch_pass_jit(qsv_handle *h, qsv_program *p, int i) {
-    const uint32_t n_tiles = (uint32_t)(h->n_amps >> qsvjit::kT);
-    const unsigned grid = n_tiles < (uint32_t)h->sm_count ? n_tiles : (unsigned)h->sm_count;
+// tiles [tile_begin, tile_end) of pass i on `stream` (the whole pass: 0 .. n_amps >> 11)
+static int launch_pass_jit_range(qsv_handle *h, qsv_program *p, int i, uint32_t tile_begin, uint32_t tile_end, cudaStream_t stream) {
+    const uint32_t count = tile_end - tile_begin;
+    const unsigned grid = count < (uint32_t)h->sm_count ? count : (unsigned)h->sm_count;
     void *state = h->d_state;
     const double2 *tables = p->d_tables + p->fold_offset[i];
     unsigned long long rank_bits = (unsigned long long)h->rank << h->n_local;
-    unsigned nt = n_tiles;
+    unsigned tb = tile_begin, te = tile_end;
     static const double zero = 0.0;
     void *coefs = p->jit_coefs[i].empty() ? (void *)&zero
                 : (h->dtype == QSV_C64 ? (void *)p->jit_coefs_f[i].data() : (void *)p->jit_coefs[i].data());
-    void *args[] = {&state, &tables, &rank_bits, &nt, coefs};
-    ScopedTimer t(h, 10, i);
-    QSV_CUDA(h, cudaLaunchKernel((const void *)p->jit[i], dim3(grid), dim3(128 * (qsvjit::groups() + 1)), args, qsvjit::kSmemBytes, h->stream));
+    void *args[] = {&state, &tables, &rank_bits, &tb, &te, coefs};
+    QSV_CUDA(h, cudaLaunchKernel((const void *)p->jit[i], dim3(grid), dim3(128 * (qsvjit::groups() + 1)), args, qsvjit::kSmemBytes, stream));
     return QSV_OK;
+}
+
+static int launch_pass_jit(qsv_handle *h, qsv_program *p, int i) {
+    ScopedTimer t(h, 10, i);
+    return launch_pass_jit_range(h, p, i, 0u, (uint32_t)(h->n_amps >> qsvjit::kT), h->stream);
 }
 
 int qsv_program_run(qsv_handle *h, qsv_program *p) {
@@ -622,6 +627,84 @@ int qsv_program_run(qsv_handle *h, qsv_program *p) {
                                          p->d_tables + p->fold_offset[i], (int)i);
         if (rc) return rc;
     }
+    return QSV_OK;
+}
+
+int qsv_program_run_range(qsv_handle *h, qsv_program *p, int first, int count) {
+    QSV_CHECK_H(h);
+    if (!p || first < 0 || count < 0 || (size_t)(first + count) > p->passes.size()) QSV_FAIL(h, QSV_EINVAL, "program_run_range: bad slice");
+    QSV_CUDA(h, cudaSetDevice(h->device));
+    for (int i = first; i < first + count; ++i) {
+        int rc = p->jit[i] ? launch_pass_jit(h, p, i)
+                           : launch_pass(h, &p->passes[i], p->d_passes + i, p->d_ops + p->op_offset[i],
+                                         p->d_tables + p->fold_offset[i], i);
+        if (rc) return rc;
+    }
+    return QSV_OK;
+}
+
+// Pass `pass_index` of the program followed by the swap of the TOP n_swap local bits with rank bits
+// global_bits[], with the exchange OVERLAPPED with the pass: when the pass's tile does not contain
+// the swapped local bits, the shard splits into 2^n_swap blocks that the pass processes one by one,
+// in the order in which the swap needs them (phase k: block me ^ (k+1)); the peer-memory exchange
+// of a block pair runs on the copy stream as soon as both owners have finished that block, while
+// the compute stream continues with the next block.  Falls back to "pass, then swap" when the
+// conditions do not hold (pass not specialised, bits not on top, peers not mapped).
+int qsv_pass_swap_overlapped(qsv_handle *h, qsv_program *p, int pass_index, int n_swap, const int *global_bits,
+                             const int *local_bits, int *overlapped) {
+    QSV_CHECK_H(h);
+    if (overlapped) *overlapped = 0;
+    if (!p || pass_index < 0 || (size_t)pass_index >= p->passes.size()) QSV_FAIL(h, QSV_EINVAL, "pass_swap_overlapped: bad pass");
+    auto *c = (qsvx::Comm *)h->comm;
+    bool ok = c && c->peers_ready && h->use_peer_swap && p->jit[pass_index] && n_swap >= 1 && n_swap <= 3 &&
+              global_bits && local_bits && (h->n_local - n_swap) >= qsvjit::kT + 1;
+    unsigned seen = 0;                                           // the TOP n_swap local positions, any order
+    for (int i = 0; ok && i < n_swap; ++i) {
+        const int rel = local_bits[i] - (h->n_local - n_swap);
+        ok = rel >= 0 && rel < n_swap && !((seen >> rel) & 1u);
+        if (ok) seen |= 1u << rel;
+    }
+    const qsv_pass &P = p->passes[pass_index];
+    for (int i = 0; ok && i < P.n_tile; ++i)
+        ok = P.load_bits[i] < h->n_local - n_swap && P.store_bits[i] < h->n_local - n_swap;
+    if (!ok) {
+        int rc = qsv_program_run_range(h, p, pass_index, 1);
+        if (rc) return rc;
+        return qsv_swap_global_local(h, n_swap, global_bits, local_bits);
+    }
+    QSV_CUDA(h, cudaSetDevice(h->device));
+    const int peers = 1 << n_swap;
+    int me = 0;
+    for (int i = 0; i < n_swap; ++i) me |= ((h->rank >> (global_bits[i] - h->n_local)) & 1) << i;
+    const uint32_t n_tiles = (uint32_t)(h->n_amps >> qsvjit::kT);
+    const uint32_t per_block = n_tiles >> n_swap;            // the top local bits are the top tile-index bits
+    cudaStream_t S = h->stream, X = c->copy_stream;
+    ScopedTimer t(h, 30 + n_swap, pass_index);
+    cudaEvent_t ev;
+    QSV_CUDA(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    // block value d (bit i = local bit local_bits[i]) -> index of its contiguous range of tiles
+    auto tile_block = [&](int d) {
+        uint32_t b = 0;
+        for (int i = 0; i < n_swap; ++i) b |= (uint32_t)((d >> i) & 1) << (local_bits[i] - (h->n_local - n_swap));
+        return b;
+    };
+    for (int k = 0; k < peers - 1; ++k) {
+        const int d = me ^ (k + 1);
+        int rc = launch_pass_jit_range(h, p, pass_index, tile_block(d) * per_block, (tile_block(d) + 1) * per_block, S);
+        if (rc) return rc;
+        QSV_CUDA(h, cudaEventRecord(ev, S));
+        QSV_CUDA(h, cudaStreamWaitEvent(X, ev, 0));
+        rc = qsvx_swap_phase(h, c, X, n_swap, global_bits, local_bits, k);       // barrier + one phase of the exchange
+        if (rc) return rc;
+    }
+    int rc = launch_pass_jit_range(h, p, pass_index, tile_block(me) * per_block, (tile_block(me) + 1) * per_block, S);
+    if (rc) return rc;
+    rc = qsvx_swap_barrier_on(h, c, X);                       // every exchange has landed everywhere
+    if (rc) return rc;
+    QSV_CUDA(h, cudaEventRecord(ev, X));
+    QSV_CUDA(h, cudaStreamWaitEvent(S, ev, 0));
+    QSV_CUDA(h, cudaEventDestroy(ev));
+    if (overlapped) *overlapped = 1;
     return QSV_OK;
 }
 

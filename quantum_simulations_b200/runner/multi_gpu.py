@@ -32,6 +32,10 @@ def execute(prog: Program, backend) -> None:
         if isinstance(step, PassStep):
             run.append(step)
             continue
+        if run and isinstance(step, SwapStep) and hasattr(backend, "run_passes_then_swap"):
+            backend.run_passes_then_swap(run, list(step.global_bits), list(step.local_bits))
+            run = []
+            continue
         if run:
             backend.run_passes(run)
             run = []
@@ -51,6 +55,7 @@ class CudaShard:
         self.rank, self.world = rank, world
         self._uploaded: dict = {}
         self.peer_swap, self.peer_error = False, None
+        self.swaps = self.overlapped_swaps = 0
         if world > 1:
             if unique_id is None or len(unique_id) != 128:
                 raise ValueError("world > 1 needs the 128-byte NCCL unique id of rank 0 (nccl_unique_id())")
@@ -101,7 +106,28 @@ class CudaShard:
         else:
             self.state.replay(h)
 
+    def run_passes_then_swap(self, steps, global_bits, local_bits) -> None:
+        """All passes but the last as usual; the last one overlapped with the exchange
+        (qsv_pass_swap_overlapped) when its tile leaves the swapped bits alone."""
+        h = self._uploaded.get(id(steps[0]))
+        temp = h is None
+        if temp:
+            h = self.state.upload_steps(steps)
+        st, lib = self.state, self.state.lib
+        s = len(global_bits)
+        g = (C.c_int * s)(*global_bits)
+        l = (C.c_int * s)(*local_bits)
+        ov = C.c_int(0)
+        if len(steps) > 1:
+            st._ck(lib.qsv_program_run_range(st._h, h, 0, len(steps) - 1))
+        st._ck(lib.qsv_pass_swap_overlapped(st._h, h, len(steps) - 1, s, g, l, C.byref(ov)))
+        self.overlapped_swaps += int(ov.value)
+        self.swaps += 1
+        if temp:
+            self.state.release_program(h)
+
     def swap(self, global_bits, local_bits) -> None:
+        self.swaps += 1
         s = len(global_bits)
         g = (C.c_int * s)(*global_bits)
         l = (C.c_int * s)(*local_bits)

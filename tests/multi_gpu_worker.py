@@ -22,10 +22,28 @@ def main():
     sim = ShardedSimulator(n)
     dist, rank, world = sim.dist, sim.rank, sim.world
     worst = 0.0
-    for name, cd in (("random_1q_cz", W.random_1q_cz(n, 20, 1234)), ("qft", W.qft(n)), ("ghz", W.ghz(n)),
-                     ("random_mixed", W.random_mixed(n, 300, 8))):
+    g = world.bit_length() - 1
+    # work on the low qubits, then mix every rank-bit qubit: the last pass before the swap leaves the
+    # top local bits alone, so the exchange must run OVERLAPPED with it (qsv_pass_swap_overlapped)
+    low_then_top = {"number_of_qubits": n, "gates":
+                    [{"qubits": [q], "gate": "RY", "params": {"theta": 0.3 + 0.1 * q}} for q in range(10)]
+                    + [{"qubits": [q, q + 1], "gate": "CZ"} for q in range(9)]
+                    + [{"qubits": [q], "gate": "H"} for q in range(10)]
+                    + [{"qubits": [q], "gate": "H"} for q in range(n - g, n)]
+                    + [{"qubits": [n - 1, 0], "gate": "CNOT"}]}
+    overlapped_seen = 0
+    for name, cd in (("low_then_top", low_then_top), ("random_1q_cz", W.random_1q_cz(n, 20, 1234)), ("qft", W.qft(n)),
+                     ("ghz", W.ghz(n)), ("random_mixed", W.random_mixed(n, 300, 8))):
         cd = validate_circuit_dict(cd)
-        shard = sim.simulate(cd)
+        if name == "low_then_top":
+            # identity placement (as after an upload / resume): the planner cannot dodge the swap
+            from quantum_simulations_b200.circuit.passes import PassCompiler
+            from quantum_simulations_b200.kernel.cuda_dense import circuit_ops
+            prog = PassCompiler(n, n - g, swap_anywhere=sim.peer_swap, rank_flips=True).compile(circuit_ops(cd))
+            sim.run(prog)
+            shard = sim.shard.state.download()
+        else:
+            shard = sim.simulate(cd)
         samples = sim.sample(seed=7, shots=257)
         parts = [torch.empty(shard.size * 2, dtype=torch.float64) for _ in range(world)] if rank == 0 else None
         dist.gather(torch.from_numpy(shard.view(np.float64).copy()), parts, dst=0)
@@ -34,8 +52,10 @@ def main():
             got = np.concatenate([parts[l ^ mask].numpy().view(np.complex128) for l in range(world)])
             want = CO.simulate_c(cd)
             err = float(np.abs(got - want).max())
-            print(f"{name}: n={n} world={world} max|d|={err:.3e}", flush=True)
+            print(f"{name}: n={n} world={world} max|d|={err:.3e} swaps={sim.shard.swaps} overlapped={sim.shard.overlapped_swaps}", flush=True)
             worst = max(worst, err)
+            if name == "low_then_top":
+                overlapped_seen = sim.shard.overlapped_swaps
             from oracle import ref_dense as O
             want_s = O.sample_indices(got, 7, 257)
             if not np.array_equal(samples, want_s):
@@ -61,6 +81,8 @@ def main():
     dist.destroy_process_group()
     if rank == 0 and worst > 1e-12:
         raise SystemExit(f"multi-GPU parity failed: {worst}")
+    if rank == 0 and sim.peer_swap and overlapped_seen < 1:
+        raise SystemExit("the overlapped pass+swap path was never taken")
 
 
 if __name__ == "__main__":

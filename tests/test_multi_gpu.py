@@ -23,3 +23,4 @@ def test_sharded_gpus_match_oracle(world):
            str(ROOT / "tests" / "multi_gpu_worker.py"), "20"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    print(r.stdout[-1500:])
