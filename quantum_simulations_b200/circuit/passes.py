@@ -939,7 +939,8 @@ class PassCompiler:
         vacate = [p for p in low if occ[p] not in parked][: len(movers)]
         movers = movers[: len(vacate)]
         if not movers:
-            return [self._send_home(new, content, home, finished, parked)[c] for c in content]
+            sent = self._send_home(new, content, home, finished, parked)      # ONE call: it mutates
+            return [sent[c] for c in content]
 
         def assign(order):
             out = dict(cur)
@@ -958,7 +959,8 @@ class PassCompiler:
             sc = score(asg)
             if sc > best_s:
                 best, best_s = asg, sc
-        return [self._send_home(best, content, home, finished, parked)[c] for c in content]
+        sent = self._send_home(best, content, home, finished, parked)
+        return [sent[c] for c in content]
 
     def _send_home(self, asg: dict, content, home, finished, parked) -> dict:
         """Finished contents (no remaining use) swap into their home slot when that slot is in
