@@ -30,7 +30,7 @@ k_pass(typename CxT<R>::V *__restrict__ state, const qsv_pass *__restrict__ pass
        const qsv_op *__restrict__ ops, const double2 *__restrict__ tables, const uint64_t rank_bits) {
     using V = typename CxT<R>::V;
     constexpr int W = (sizeof(V) == 16) ? 3 : 4;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     V *tile = reinterpret_cast<V *>(smem_raw);
 
     const qsv_pass &P = *pass_ptr;
