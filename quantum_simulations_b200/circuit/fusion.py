@@ -98,3 +98,78 @@ def fusion_stats(levels: list[list[dict]], k: int) -> dict:
         "ops_before": sum(len(lv) for lv in levels),
         "ops_after": sum(len(s["local_ops"]) + len(s["nonlocal_ops"]) for s in steps),
     }
+
+
+def fuse_2q_blocks(ops: list[Op], only_diagonal: bool = True) -> list[Op]:
+    """Merge runs of gates that stay inside one qubit PAIR into a single 4x4 unitary (the 2-qubit
+    analogue of fuse_1q_ops, reference fusion.py:41-81).
+
+    only_diagonal=True (default): a run is merged only if its product is exactly DIAGONAL.  That is
+    the case front ends create when they decompose controlled phases into CNOT ladders
+    (QASMBench: u1 / cx / u1 / cx / u1): the product of such a run has exact zeros off the diagonal
+    (permutations and diagonals multiply without rounding), and the pass compiler then treats it as
+    a phase gate instead of two controlled swaps.  Everything else is emitted unchanged, because a
+    dense 4x4 block would cost the lifting form its structure (a general 1-qubit gate is 4.5 FP64 /
+    amplitude, a dense 2-qubit block 16).  only_diagonal=False merges every run (dense blocks)."""
+    out: list[Op] = []
+    block_of: dict[int, int] = {}                 # qubit -> index into `blocks`
+    blocks: list = []                             # [a, b, [(qs, U, U4)]] or None once emitted
+    I2 = np.eye(2, dtype=np.complex128)
+    swap = np.eye(4)[[0, 2, 1, 3]]
+
+    def emit_block(a: int, b: int, members: list) -> None:
+        if not only_diagonal:
+            U = np.eye(4, dtype=np.complex128)
+            for _, _, U4 in members:
+                U = U4 @ U
+            out.append(([a, b], U)) if any(len(q) == 2 for q, _, _ in members) else out.extend((q, u) for q, u, _ in members)
+            return
+        i = 0
+        while i < len(members):
+            best, prod = None, np.eye(4, dtype=np.complex128)
+            for j in range(i, len(members)):
+                prod = members[j][2] @ prod
+                if j > i and not np.any(prod - np.diag(np.diag(prod))) and any(len(members[k][0]) == 2 for k in range(i, j + 1)):
+                    best = (j, prod.copy())
+            if best is None:
+                out.append((members[i][0], members[i][1]))
+                i += 1
+            else:
+                out.append(([a, b], best[1]))
+                i = best[0] + 1
+
+    def close(q: int) -> None:
+        i = block_of.pop(q, None)
+        if i is None or blocks[i] is None:
+            return
+        a, b, members = blocks[i]
+        blocks[i] = None
+        block_of.pop(a, None)
+        block_of.pop(b, None)
+        emit_block(a, b, members)
+
+    for qs, U in ops:
+        U = np.asarray(U, dtype=np.complex128)
+        if len(qs) == 1:
+            q = qs[0]
+            i = block_of.get(q)
+            if i is not None and blocks[i] is not None:
+                a, b, members = blocks[i]
+                members.append((list(qs), U, np.kron(U, I2) if q == a else np.kron(I2, U)))
+            else:
+                out.append((list(qs), U))          # not inside a pair run: nothing to merge with
+            continue
+        a, b = qs
+        ia, ib = block_of.get(a), block_of.get(b)
+        if ia is not None and ia == ib and blocks[ia] is not None:
+            x, y, members = blocks[ia]
+            members.append((list(qs), U, U if (x, y) == (a, b) else swap @ U @ swap))
+            continue
+        close(a)
+        close(b)
+        blocks.append([a, b, [(list(qs), U, U)]])
+        block_of[a] = block_of[b] = len(blocks) - 1
+    for blk in blocks:
+        if blk is not None:
+            emit_block(*blk)
+    return out

@@ -62,3 +62,22 @@ def simulate(circuit_dict: dict, dtype="complex128", device: int = 0, out: np.nd
         mark("download(D2H)")
     mark("destroy(cudaFree)")
     return res
+
+
+def simulate_qasm(text: str, dtype="complex128", device: int = 0, out: np.ndarray | None = None, **compiler_kw) -> np.ndarray:
+    """OpenQASM 2.0 program -> final state on the GPU (circuit/qasm.py front end; CNOT-ladder
+    decompositions of controlled phases are fused back into diagonal blocks first)."""
+    from quantum_simulations_b200.circuit.fusion import fuse_2q_blocks
+    from quantum_simulations_b200.circuit.qasm import qasm_to_ops
+    from quantum_simulations_b200.kernel.cuda import DeviceState
+
+    n, ops = qasm_to_ops(text)
+    ops = fuse_2q_blocks(ops)
+    with DeviceState(n, dtype, device) as st:
+        st.init_zero()
+        if n >= REG_BITS:
+            st.run_program(PassCompiler(n, dtype=st.dtype.name, **compiler_kw).compile(ops))
+        else:
+            for qs, U in ops:
+                st.apply_op(qs, U)
+        return st.download(out)

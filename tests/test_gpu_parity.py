@@ -426,6 +426,28 @@ def test_pipeline_runner_surface(tmp_path):
         assert np.abs(collect_state(final) - O.simulate(validate_circuit_dict(cd))).max() <= 1e-12
 
 
+def test_qasm_front_end_on_the_device():
+    """A QASMBench-style QFT (u1 / cx ladders) through simulate_qasm equals the reference QFT."""
+    import math
+    from quantum_simulations_b200.kernel.cuda_dense import simulate_qasm
+    n = 16
+    src = ['OPENQASM 2.0;', 'include "qelib1.inc";', f'qreg q[{n}];']
+    for j in range(n):
+        src.append(f"h q[{j}];")
+        for k in range(j + 1, n):
+            lam = 2 * math.pi / 2 ** (k - j + 1)
+            src += [f"u1({lam / 2}) q[{k}];", f"cx q[{k}],q[{j}];", f"u1({-lam / 2}) q[{j}];", f"cx q[{k}],q[{j}];",
+                    f"u1({lam / 2}) q[{j}];"]
+    src += ["ccx q[0],q[1],q[2];", "rx(0.3) q[5];", "cswap q[3],q[4],q[5];"]
+    got = simulate_qasm("\n".join(src))
+    from quantum_simulations_b200.circuit.qasm import qasm_to_ops
+    _, ops = qasm_to_ops("\n".join(src))
+    want = np.zeros(1 << n, dtype=np.complex128)
+    want[0] = 1
+    O.apply_ops(want, ops)
+    assert np.abs(got - want).max() <= 1e-12
+
+
 def test_runner_errors():
     from quantum_simulations_b200.runner.single_node import run
     with tempfile.TemporaryDirectory() as td:

@@ -1,0 +1,136 @@
+"""OpenQASM 2.0 front end (circuit/qasm.py): parsed programs against the oracle."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import ref_dense as O
+from quantum_simulations_b200 import workloads as W
+from quantum_simulations_b200.circuit.io import validate_circuit_dict
+from quantum_simulations_b200.circuit.passes import PassCompiler
+from quantum_simulations_b200.circuit.qasm import QasmError, qasm_to_dict, qasm_to_ops
+from tests.pass_emulator import run_program
+
+HEAD = 'OPENQASM 2.0;\ninclude "qelib1.inc";\n'
+
+
+def state(n, ops):
+    psi = np.zeros(1 << n, dtype=np.complex128)
+    psi[0] = 1
+    O.apply_ops(psi, ops)
+    return psi
+
+
+def qft_qasm(n):
+    """The decomposition QASMBench uses (qft_n20.qasm: u1 / cx ladders), on qubits in our order."""
+    out = [HEAD, f"qreg q[{n}];", f"creg c[{n}];"]
+    for j in range(n):
+        out.append(f"h q[{j}];")
+        for k in range(j + 1, n):
+            lam = 2 * math.pi / 2 ** (k - j + 1)
+            out += [f"u1({lam / 2}) q[{k}];", f"cx q[{k}],q[{j}];", f"u1({-lam / 2}) q[{j}];", f"cx q[{k}],q[{j}];",
+                    f"u1({lam / 2}) q[{j}];"]
+    out.append("measure q -> c;")
+    return "\n".join(out)
+
+
+def test_bell_and_dict_form():
+    src = HEAD + "qreg q[2]; creg c[2];\nh q[0];\ncx q[0],q[1]; // entangle\nbarrier q;\nmeasure q[0] -> c[0];"
+    n, ops = qasm_to_ops(src)
+    assert n == 2 and np.abs(state(n, ops) - np.array([1, 0, 0, 1]) / np.sqrt(2)).max() < 1e-15
+    cd = qasm_to_dict(src)
+    assert cd == {"number_of_qubits": 2, "gates": [{"qubits": [0], "gate": "H", "params": {}},
+                                                   {"qubits": [0, 1], "gate": "CNOT", "params": {}}]}
+    assert np.abs(O.simulate(validate_circuit_dict(cd)) - state(n, ops)).max() < 1e-15
+
+
+def test_qasmbench_style_qft_equals_the_reference_qft():
+    n = 6
+    _, ops = qasm_to_ops(qft_qasm(n))
+    want = O.simulate(validate_circuit_dict(W.qft(n)))
+    assert np.abs(state(n, ops) - want).max() < 1e-12
+    # and through the pass compiler (emulated passes)
+    psi = np.zeros(1 << n, dtype=np.complex128)
+    psi[0] = 1
+    run_program(PassCompiler(n, tile_bits=5, low_bits=2).compile(ops), psi)
+    assert np.abs(psi - want).max() < 1e-12
+
+
+def test_two_qubit_fusion_recovers_controlled_phases():
+    """cx / u1 ladders fuse back into diagonal 2-qubit blocks: same state, far fewer mixing ops."""
+    from quantum_simulations_b200.circuit.fusion import fuse_2q_blocks
+    n = 8
+    _, ops = qasm_to_ops(qft_qasm(n))
+    fused = fuse_2q_blocks(ops)
+    want = O.simulate(validate_circuit_dict(W.qft(n)))
+    assert np.abs(state(n, fused) - want).max() < 1e-12
+    assert len(fused) < len(ops) / 2
+    two_q = [U for q, U in fused if len(q) == 2]
+    assert two_q and all(not np.any(U - np.diag(np.diag(U))) for U in two_q)                   # diagonal again
+    plain = PassCompiler(n, tile_bits=6, low_bits=2).compile(ops)
+    better = PassCompiler(n, tile_bits=6, low_bits=2).compile(fused)
+    psi = np.zeros(1 << n, dtype=np.complex128)
+    psi[0] = 1
+    run_program(better, psi)
+    assert np.abs(psi - want).max() < 1e-12
+    assert better.stats["micro_ops"] < plain.stats["micro_ops"] / 2
+    dense = fuse_2q_blocks(ops, only_diagonal=False)                 # every pair run -> one 4x4 block
+    assert np.abs(state(n, dense) - want).max() < 1e-12 and len(dense) < len(fused)
+    # random mixed circuits: fusion never changes the state
+    for seed in range(5):
+        cd = validate_circuit_dict(W.random_mixed(7, 120, seed))
+        from quantum_simulations_b200.kernel import gates as G
+        ir = [(g["qubits"], G.gate_matrix(g["gate"], g["params"])) for g in cd["gates"]]
+        assert np.abs(state(7, fuse_2q_blocks(ir)) - O.simulate(cd)).max() < 1e-12
+
+
+def test_parametrised_gates_registers_and_broadcast():
+    src = HEAD + """qreg a[2]; qreg b[1];
+    h a; rx(pi/2) b[0]; u3(0.1,0.2,0.3) a[1]; rz(-pi/4) a[0]; cu1(pi/8) a[0],b[0]; crz(0.3) b[0],a[1];
+    swap a[0],a[1]; sdg a[0]; tdg b[0]; rzz(0.4) a[1],b[0]; cz a[0],b[0]; p(0.7) a[1]; u2(0.1,0.2) b[0];"""
+    n, ops = qasm_to_ops(src)
+    assert n == 3 and [q for q, _ in ops[:2]] == [[0], [1]]          # h broadcast over register a
+    psi = state(n, ops)
+    assert abs(np.vdot(psi, psi).real - 1) < 1e-12
+    for _, U in ops:
+        assert np.abs(U.conj().T @ U - np.eye(len(U))).max() < 1e-12
+
+
+def test_toffoli_cswap_and_user_gates():
+    src = HEAD + """qreg q[3];
+    gate majority a,b,c { cx c,b; cx c,a; ccx a,b,c; }
+    gate myrot(t) x { ry(t/2) x; ry(t/2) x; }
+    x q[0]; x q[1]; ccx q[0],q[1],q[2]; myrot(pi) q[0]; majority q[0],q[1],q[2]; cswap q[2],q[0],q[1];"""
+    n, ops = qasm_to_ops(src)
+    psi = state(n, ops)
+    # reference evaluation with explicit permutation / rotation matrices
+    ref = np.zeros(8, dtype=np.complex128)
+    ref[0] = 1
+
+    def perm(f):
+        nonlocal ref
+        new = np.zeros_like(ref)
+        for i in range(8):
+            new[f(i)] += ref[i]
+        ref = new
+
+    bit = lambda i, q: (i >> q) & 1                                   # noqa: E731
+    perm(lambda i: i ^ 1); perm(lambda i: i ^ 2)
+    perm(lambda i: i ^ (4 if bit(i, 0) and bit(i, 1) else 0))
+    ry = np.array([[math.cos(math.pi / 2), -math.sin(math.pi / 2)], [math.sin(math.pi / 2), math.cos(math.pi / 2)]])
+    O.apply_1q(ref, 0, ry.astype(np.complex128))
+    perm(lambda i: i ^ (2 if bit(i, 2) else 0)); perm(lambda i: i ^ (1 if bit(i, 2) else 0))
+    perm(lambda i: i ^ (4 if bit(i, 0) and bit(i, 1) else 0))
+    perm(lambda i: (i & 4) | (((i >> 1) & 1) | ((i & 1) << 1)) if bit(i, 2) else i)
+    assert np.abs(psi - ref).max() < 1e-12
+
+
+def test_errors():
+    with pytest.raises(QasmError, match="unsupported gate"):
+        qasm_to_ops(HEAD + "qreg q[1]; foo q[0];")
+    with pytest.raises(QasmError, match="not supported"):
+        qasm_to_ops(HEAD + "qreg q[1]; reset q[0];")
+    with pytest.raises(QasmError, match="out of range"):
+        qasm_to_ops(HEAD + "qreg q[1]; h q[3];")
+    with pytest.raises(QasmError, match="no name in the reference"):
+        qasm_to_dict(HEAD + "qreg q[1]; rz(0.1) q[0];")
