@@ -100,7 +100,7 @@ def fusion_stats(levels: list[list[dict]], k: int) -> dict:
     }
 
 
-def fuse_2q_blocks(ops: list[Op], only_diagonal: bool = True) -> list[Op]:
+def fuse_2q_blocks(ops: list[Op], only_diagonal: bool = True, tol: float = 0.0) -> list[Op]:
     """Merge runs of gates that stay inside one qubit PAIR into a single 4x4 unitary (the 2-qubit
     analogue of fuse_1q_ops, reference fusion.py:41-81).
 
@@ -110,10 +110,14 @@ def fuse_2q_blocks(ops: list[Op], only_diagonal: bool = True) -> list[Op]:
     (permutations and diagonals multiply without rounding), and the pass compiler then treats it as
     a phase gate instead of two controlled swaps.  Everything else is emitted unchanged, because a
     dense 4x4 block would cost the lifting form its structure (a general 1-qubit gate is 4.5 FP64 /
-    amplitude, a dense 2-qubit block 16).  only_diagonal=False merges every run (dense blocks)."""
+    amplitude, a dense 2-qubit block 16).  only_diagonal=False merges every run (dense blocks).
+    tol > 0 also accepts runs whose product is diagonal up to `tol` (compiled ZZ interactions: three
+    CNOTs and rotations by multiples of pi/2, exact only in exact arithmetic); the off-diagonal
+    residue is dropped and the diagonal renormalised, an error of order tol per merged run."""
     out: list[Op] = []
     block_of: dict[int, int] = {}                 # qubit -> index into `blocks`
     blocks: list = []                             # [a, b, [(qs, U, U4)]] or None once emitted
+    pending: dict[int, list] = {}                 # 1-qubit ops waiting for a pair run on their qubit
     I2 = np.eye(2, dtype=np.complex128)
     swap = np.eye(4)[[0, 2, 1, 3]]
 
@@ -129,8 +133,13 @@ def fuse_2q_blocks(ops: list[Op], only_diagonal: bool = True) -> list[Op]:
             best, prod = None, np.eye(4, dtype=np.complex128)
             for j in range(i, len(members)):
                 prod = members[j][2] @ prod
-                if j > i and not np.any(prod - np.diag(np.diag(prod))) and any(len(members[k][0]) == 2 for k in range(i, j + 1)):
-                    best = (j, prod.copy())
+                if j > i and any(len(members[k][0]) == 2 for k in range(i, j + 1)):
+                    off = prod - np.diag(np.diag(prod))
+                    if not np.any(off):
+                        best = (j, prod.copy())
+                    elif tol > 0 and np.abs(off).max() <= tol:
+                        d = np.diag(prod)
+                        best = (j, np.diag(d / np.abs(d)))
             if best is None:
                 out.append((members[i][0], members[i][1]))
                 i += 1
@@ -157,7 +166,7 @@ def fuse_2q_blocks(ops: list[Op], only_diagonal: bool = True) -> list[Op]:
                 a, b, members = blocks[i]
                 members.append((list(qs), U, np.kron(U, I2) if q == a else np.kron(I2, U)))
             else:
-                out.append((list(qs), U))          # not inside a pair run: nothing to merge with
+                pending.setdefault(q, []).append((list(qs), U))     # may lead a pair run that starts later
             continue
         a, b = qs
         ia, ib = block_of.get(a), block_of.get(b)
@@ -167,9 +176,13 @@ def fuse_2q_blocks(ops: list[Op], only_diagonal: bool = True) -> list[Op]:
             continue
         close(a)
         close(b)
-        blocks.append([a, b, [(list(qs), U, U)]])
+        lead = [(q_, u_, np.kron(u_, I2)) for q_, u_ in pending.pop(a, [])] + \
+               [(q_, u_, np.kron(I2, u_)) for q_, u_ in pending.pop(b, [])]
+        blocks.append([a, b, lead + [(list(qs), U, U)]])
         block_of[a] = block_of[b] = len(blocks) - 1
     for blk in blocks:
         if blk is not None:
             emit_block(*blk)
+    for q_ops in pending.values():
+        out.extend(q_ops)
     return out

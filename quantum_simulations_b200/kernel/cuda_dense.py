@@ -72,7 +72,7 @@ def simulate_qasm(text: str, dtype="complex128", device: int = 0, out: np.ndarra
     from quantum_simulations_b200.kernel.cuda import DeviceState
 
     n, ops = qasm_to_ops(text)
-    ops = fuse_2q_blocks(ops)
+    ops = fuse_2q_blocks(ops, tol=1e-14)
     with DeviceState(n, dtype, device) as st:
         st.init_zero()
         if n >= REG_BITS:
