@@ -727,6 +727,15 @@ int qsv_jit_build_pass(const qsv_pass *pass, const qsv_op *ops, int dtype, size_
     if (!qsvjit::generate(*pass, ops, src, coefs, dtype == QSV_C64)) { msg = "pass is not eligible for specialisation"; rc = QSV_EINVAL; }
     else if (!qsvjit::nvrtc().load()) { msg = "NVRTC unavailable: " + qsvjit::nvrtc().why; rc = QSV_EIO; }
     else if (!qsvjit::compile(src, cubin, msg)) rc = QSV_ECUDA;
+    if (rc == QSV_OK && getenv("QSV_JIT_WARM")) {            // build-time cache warm-up (no device needed)
+        const std::string dir = qsvjit::cache_dir();
+        if (!dir.empty()) {
+            mkdir(dir.c_str(), 0755);
+            char name[64];
+            snprintf(name, sizeof(name), "/%016llx.cubin", (unsigned long long)qsvjit::source_key(src));
+            qsvjit::write_file_atomic(dir + name, cubin);
+        }
+    }
     if (cubin_bytes) *cubin_bytes = cubin.size();
     if (log && log_cap) { snprintf(log, log_cap, "%s", msg.c_str()); }
     return rc;

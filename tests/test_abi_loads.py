@@ -71,3 +71,13 @@ def test_product_never_imports_the_oracle():
     for py in pkg.rglob("*.py"):
         text = py.read_text()
         assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), py
+
+
+def test_graft_entry_has_build_and_smoke():
+    """The driver imports __graft_entry__ and calls build() / smoke(): both must exist (an editing
+    accident once left the file empty)."""
+    import importlib
+    ge = importlib.import_module("__graft_entry__")
+    assert callable(ge.build) and callable(ge.smoke) and callable(ge.warm_jit_cache)
+    src = (ROOT / "__graft_entry__.py").read_text()
+    assert "compute_100a" in src or "make" in src
