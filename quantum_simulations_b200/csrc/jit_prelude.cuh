@@ -28,14 +28,18 @@ __device__ __forceinline__ uint64_t insert_zero_bit(uint64_t x, int pos) {
 #ifdef JIT_F32
 typedef float2 JV;
 typedef float JR;
-#define JIT_NBUF 12          // 12 x 16 KB: four private buffers per consumer group
+#ifndef JIT_NBUF
+#define JIT_NBUF 12          // 12 x 16 KB: four buffers per consumer group
+#endif
 // shared slot of tile index x: the 16-byte PAIR index is swizzled, the pair stays in order, so a
 // 16-byte cp.async still lands two consecutive amplitudes correctly
 __device__ __forceinline__ uint32_t jit_slot(uint32_t x) { return (tile_swizzle<3>(x >> 1) << 1) | (x & 1u); }
 #else
 typedef double2 JV;
 typedef double JR;
-#define JIT_NBUF 6           //  6 x 32 KB: two private buffers per consumer group
+#ifndef JIT_NBUF
+#define JIT_NBUF 6           //  6 x 32 KB: two buffers per consumer group
+#endif
 __device__ __forceinline__ uint32_t jit_slot(uint32_t x) { return tile_swizzle<3>(x); }
 #endif
 
