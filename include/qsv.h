@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define QSV_ABI_VERSION 3
+#define QSV_ABI_VERSION 4
 
 /* dtypes (wenbo_engine/storage/block_store.py:11 fixes complex64; the oracle is complex128) */
 #define QSV_C64  0
@@ -117,6 +117,7 @@ int qsv_apply_kq(qsv_handle *h, int k, const int *qs, const double *U);
 #define QSV_MAX_TILE_BITS 14
 #define QSV_REG_BITS       4
 #define QSV_MAX_ROUNDS    16
+#define QSV_MAX_ACTIVE_BITS 52
 
 /* op kinds.  Every op is an IN-PLACE update of register-resident amplitudes (each arithmetic
  * statement overwrites one of its own operands), which is what lets the kernel interpret a gate
@@ -187,6 +188,15 @@ typedef struct {
     qsv_round rounds[QSV_MAX_ROUNDS];
     int32_t   n_ops;
     int32_t   n_fold;                          /* complex entries in this pass's fold-table array */
+    int32_t   n_active;                        /* -1: the pass visits every tile.  >= 0: ZERO-SUPPORT SKIPPING — the
+                                                  caller guarantees that every amplitude with a 1 at a non-tile
+                                                  position outside active_bits[0..n_active) is exactly zero (a
+                                                  run from |0...0> before those qubits were touched); the pass
+                                                  then visits only the 2^n_active tiles that can hold data.
+                                                  Zero tiles stay zero under any gate list, so the result is
+                                                  identical.  Honoured by the specialised kernels; the
+                                                  interpreting kernels visit every tile.                        */
+    int32_t   active_bits[QSV_MAX_ACTIVE_BITS];/* ascending non-tile local positions                          */
     uint64_t  store_flip;                      /* physical tile bits XOR-ed into every store address:
                                                   pending X gates are never executed on data — the
                                                   compiler carries them as a Pauli frame and the last

@@ -14,7 +14,7 @@ LIB_PATH = _CSRC / os.environ.get("QSV_LIB_NAME", "libqsv.so")   # env override:
 
 QSV_C64, QSV_C128 = 0, 1
 QSV_OK, QSV_EINVAL, QSV_ENONLOCAL, QSV_ECUDA, QSV_ENOMEM, QSV_ECOMM, QSV_EIO = 0, -1, -2, -3, -4, -5, -6
-QSV_MAX_TILE_BITS, QSV_REG_BITS, QSV_MAX_ROUNDS = 14, 4, 16
+QSV_MAX_TILE_BITS, QSV_REG_BITS, QSV_MAX_ROUNDS, QSV_MAX_ACTIVE_BITS = 14, 4, 16, 52
 OP_HAD, OP_ROT, OP_XSWAP, OP_YSWAP, OP_PHASE, OP_SIGN, OP_SCALE, OP_TPHASE = range(8)
 OP_WITH_TARGET = (OP_HAD, OP_ROT, OP_XSWAP, OP_YSWAP)
 OPF_PRESIGN, OPF_PRENEG, OPF_PREPHASE = 1, 2, 4
@@ -35,6 +35,7 @@ class QsvPass(C.Structure):
     _fields_ = [("n_tile", C.c_int32), ("load_bits", C.c_int32 * QSV_MAX_TILE_BITS),
                 ("store_bits", C.c_int32 * QSV_MAX_TILE_BITS), ("n_rounds", C.c_int32),
                 ("rounds", QsvRound * QSV_MAX_ROUNDS), ("n_ops", C.c_int32), ("n_fold", C.c_int32),
+                ("n_active", C.c_int32), ("active_bits", C.c_int32 * QSV_MAX_ACTIVE_BITS),
                 ("store_flip", C.c_uint64)]
 
 

@@ -478,9 +478,14 @@ class PassCompiler:
         self.table_phases = table_phases
 
     # ---- public -----------------------------------------------------------------------
-    def compile(self, ir_ops, init_pos=None, init_flips=None, home_pos=None) -> Program:
+    def compile(self, ir_ops, init_pos=None, init_flips=None, home_pos=None, zero_state: bool = False) -> Program:
         """init_pos[q]: physical position of IR qubit q before the first op (default q);
-        home_pos[q]: position it must have after the last one (default: init_pos[q])."""
+        home_pos[q]: position it must have after the last one (default: init_pos[q]).
+        zero_state=True: the caller guarantees the state is |0...0> when the program starts (rank 0
+        holds amp[0] = 1): passes then visit only the tiles that can hold data (qsv_pass.n_active) —
+        index bits of qubits no pass has had in its tile yet are still 0 everywhere."""
+        # positions whose index bit may be 1 somewhere in the stored state; None = all (no skipping)
+        self._support = set() if (zero_state and self.n_local == self.n) else None
         n = self.n
         alias = list(range(n))                      # IR qubit -> content
         xf = list(init_flips) if init_flips is not None else [0] * n   # Pauli-X frame per content
@@ -883,6 +888,15 @@ class PassCompiler:
                     flip |= 1 << store[i]
                     xf[content[i]] = 0
         desc.store_flip = flip
+        desc.n_active = -1
+        support = getattr(self, "_support", None)
+        if support is not None:
+            active = sorted(support - set(load_bits))
+            if len(active) <= L.QSV_MAX_ACTIVE_BITS and len(active) < self.n_local - t:
+                desc.n_active = len(active)
+                for k, b in enumerate(active):
+                    desc.active_bits[k] = b
+            support |= set(load_bits)                     # a pass may leave data on all its tile positions
         for i in range(t):                                # commit the relabelling
             pos[content[i]] = store[i]
         return PassStep(desc, arr, len(flat), srcs, list(tile), tab, n_folded, n_absorbed)

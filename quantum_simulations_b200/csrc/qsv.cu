@@ -436,6 +436,13 @@ static int validate_pass(qsv_handle *h, const qsv_pass *p, const qsv_op *ops) {
     }
     if (tile_mask != store_mask) QSV_FAIL(h, QSV_EINVAL, "pass: store_bits is not a permutation of load_bits");
     if (p->store_flip & ~tile_mask) QSV_FAIL(h, QSV_EINVAL, "pass: store_flip names a bit outside the tile");
+    if (p->n_active < -1 || p->n_active > QSV_MAX_ACTIVE_BITS || p->n_active > h->n_local - T)
+        QSV_FAIL(h, QSV_EINVAL, "pass: n_active=%d", p->n_active);
+    for (int k = 0; k < p->n_active; ++k) {
+        const int b = p->active_bits[k];
+        if (b < 0 || b >= h->n_local || ((tile_mask >> b) & 1) || (k && b <= p->active_bits[k - 1]))
+            QSV_FAIL(h, QSV_EINVAL, "pass: active_bits must be ascending local non-tile positions (entry %d = %d)", k, b);
+    }
     if (p->n_rounds < 1 || p->n_rounds > QSV_MAX_ROUNDS) QSV_FAIL(h, QSV_EINVAL, "pass: n_rounds=%d", p->n_rounds);
     if (p->n_ops < 0 || p->n_fold < 0) QSV_FAIL(h, QSV_EINVAL, "pass: n_ops / n_fold < 0");
     for (int r = 0; r < p->n_rounds; ++r) {
@@ -614,7 +621,9 @@ static int launch_pass_jit_range(qsv_handle *h, qsv_program *p, int i, uint32_t 
 
 static int launch_pass_jit(qsv_handle *h, qsv_program *p, int i) {
     ScopedTimer t(h, 10, i);
-    return launch_pass_jit_range(h, p, i, 0u, (uint32_t)(h->n_amps >> qsvjit::kT), h->stream);
+    const int na = p->passes[i].n_active;                      // zero-support skipping: 2^n_active tiles
+    const uint32_t tiles = na >= 0 ? (uint32_t)1 << na : (uint32_t)(h->n_amps >> qsvjit::kT);
+    return launch_pass_jit_range(h, p, i, 0u, tiles, h->stream);
 }
 
 int qsv_program_run(qsv_handle *h, qsv_program *p) {
@@ -665,6 +674,7 @@ int qsv_pass_swap_overlapped(qsv_handle *h, qsv_program *p, int pass_index, int 
         if (ok) seen |= 1u << rel;
     }
     const qsv_pass &P = p->passes[pass_index];
+    ok = ok && P.n_active < 0;
     for (int i = 0; ok && i < P.n_tile; ++i)
         ok = P.load_bits[i] < h->n_local - n_swap && P.store_bits[i] < h->n_local - n_swap;
     if (!ok) {

@@ -25,9 +25,13 @@ def compile_circuit(circuit_dict: dict, dtype="complex128", **compiler_kw) -> Pr
 
 
 def simulate(circuit_dict: dict, dtype="complex128", device: int = 0, out: np.ndarray | None = None,
-             fused: bool = True, jit: bool | None = None, phases: dict | None = None, **compiler_kw) -> np.ndarray:
+             fused: bool = True, jit: bool | None = None, phases: dict | None = None,
+             skip_zero_support: bool = False, **compiler_kw) -> np.ndarray:
     """Run the circuit on the GPU and return the final state vector (host, `dtype`).
-    `phases` (optional dict) receives the host time of each phase in milliseconds."""
+    `phases` (optional dict) receives the host time of each phase in milliseconds.
+    skip_zero_support=True: the run starts from |0...0>, so index bits of qubits no pass has touched
+    yet are 0 everywhere; passes visit only the tiles that can hold data (exact: zero tiles stay
+    zero).  Off by default so that every pass streams the whole state (the roofline accounting)."""
     import time
     from quantum_simulations_b200.kernel.cuda import DeviceState
 
@@ -46,7 +50,7 @@ def simulate(circuit_dict: dict, dtype="complex128", device: int = 0, out: np.nd
         mark("create(cudaMalloc)")
         st.init_zero()
         if fused and n >= REG_BITS:
-            prog = PassCompiler(n, dtype=st.dtype.name, **compiler_kw).compile(ops)
+            prog = PassCompiler(n, dtype=st.dtype.name, **compiler_kw).compile(ops, zero_state=skip_zero_support)
             mark("pass_compiler")
             st.run_program(prog, jit=jit)
             if phases is not None:

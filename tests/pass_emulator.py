@@ -37,6 +37,14 @@ def run_pass(psi: np.ndarray, desc: L.QsvPass, ops, n_local: int, rank: int = 0,
         base = _insert_zero(base, p)
     glob = (rank << n_local) | base
     tile_mask = sum(1 << b for b in load)
+    if desc.n_active >= 0:
+        # zero-support skipping: every tile outside the active set must be exactly zero (the kernel
+        # does not visit it); a planner bug shows up here
+        act = [desc.active_bits[k] for k in range(desc.n_active)]
+        assert act == sorted(act) and all(0 <= b < n_local and not (tile_mask >> b) & 1 for b in act)
+        amask = sum(1 << b for b in act)
+        dead = (base & ~amask) != 0
+        assert not np.any(psi[base[dead][:, None] + off_l[None, :]]), "skipped tile holds data"
     work = psi[base[:, None] + off_l[None, :]]
     for r in range(desc.n_rounds):
         rd = desc.rounds[r]

@@ -232,6 +232,19 @@ def test_specialised_and_interpreted_passes_agree_with_oracle(workload, jit, dty
     assert got.dtype == np.dtype(dtype) and np.abs(got - want).max() <= TOL[dtype]
 
 
+@pytest.mark.parametrize("workload", ["random_1q_cz", "random_mixed", "qft", "ghz"])
+def test_zero_support_skipping_matches_oracle(workload):
+    """simulate(skip_zero_support=True): early passes visit only the tiles that can hold data."""
+    from quantum_simulations_b200.kernel.cuda_dense import simulate
+    n = 20
+    cd = {"random_1q_cz": lambda: W.random_1q_cz(n, 20, 1234), "random_mixed": lambda: W.random_mixed(n, 400, 5),
+          "qft": lambda: W.qft(n), "ghz": lambda: W.ghz(n)}[workload]()
+    want = CO.simulate_c(validate_circuit_dict(cd))
+    for dtype in ("complex128", "complex64"):
+        got = simulate(cd, dtype=dtype, skip_zero_support=True)
+        assert np.abs(got - want).max() <= TOL[dtype]
+
+
 def test_jit_kernels_are_cached_by_structure():
     """Two circuits with the same structure but different angles share compiled kernels."""
     import ctypes as C

@@ -185,3 +185,18 @@ def test_x_and_y_gates_never_touch_data():
         {"qubits": [3, 4], "gate": "CU", "params": {"U": [[0.6, -0.8], [0.8, 0.6]], "exponent": 1}}]}
     check(cd, tile_bits=4, low_bits=0)
     check(cd, tile_bits=6, low_bits=2, x_frame=False)
+
+
+@pytest.mark.parametrize("n,t,a", [(9, 6, 2), (11, 7, 3), (12, 8, 3)])
+def test_zero_support_skipping_is_exact(n, t, a):
+    """compile(zero_state=True): early passes name only the tiles that can hold data; the emulator
+    asserts that every skipped tile is exactly zero, and the result equals the oracle's."""
+    for cd in (W.random_1q_cz(n, 20, 1234), W.qft(n), W.ghz(n), W.random_mixed(n, 150, 4)):
+        ops = ir_ops(cd)
+        prog = PassCompiler(n, tile_bits=t, low_bits=a).compile(ops, zero_state=True)
+        assert prog.passes[0].desc.n_active == 0                     # first pass: one tile
+        assert any(s.desc.n_active == -1 for s in prog.passes) or n - t <= 3
+        psi = np.zeros(1 << n, dtype=np.complex128)
+        psi[0] = 1
+        run_program(prog, psi)
+        assert np.abs(psi - O.simulate(validate_circuit_dict(cd))).max() <= 1e-12
