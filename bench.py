@@ -214,7 +214,8 @@ def bench_single(args) -> None:
     t0 = time.perf_counter()
     ckw = dict(tile_bits=args.tile_bits, low_bits=args.low_bits, max_rounds=args.max_rounds,
                defer_diagonals=args.defer_diagonals, fold_tables=not args.no_fold_tables)
-    prog = PassCompiler(n, dtype=dtype, **ckw).compile(circuit_ops(cd))
+    from quantum_simulations_b200.circuit.sharding import plan_single
+    prog = plan_single(circuit_ops(cd), n, dtype, True, False, **ckw)      # from |0...0>: free initial placement
     compile_s = time.perf_counter() - t0
     n_pass = len(prog.passes)
     updates_per_step = len(cd["gates"]) * (1 << n)
@@ -244,7 +245,7 @@ def bench_single(args) -> None:
     # headline, never as the headline — the roofline accounting assumes every pass streams the state
     zs = None
     if not args.no_zero_support:
-        prog_z = PassCompiler(n, dtype=dtype, **ckw).compile(circuit_ops(cd), zero_state=True)
+        prog_z = plan_single(circuit_ops(cd), n, dtype, True, True, **ckw)
         with DeviceState(n, dtype, args.device) as st:
             hz = st.upload_program(prog_z)
             for _ in range(args.warmup):

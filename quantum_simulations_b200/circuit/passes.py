@@ -53,11 +53,12 @@ class MicroOp:
     pre_phase: complex = 1.0 + 0.0j    # pending diag(1, e^{i phi}) on the target
     tph: dict | None = None            # OP_TPHASE: {partner content: unit phase applied when target AND partner are 1}
 
-    @property
-    def looks(self) -> tuple:
-        """Contents the op inspects without mixing them (controls + pre-sign partners)."""
+    looks: tuple = field(init=False, repr=False, compare=False, default=())
+
+    def __post_init__(self):
+        # contents the op inspects without mixing them (controls + pre-sign partners + table partners)
         out = self.ctrls + tuple(self.pre_par) if self.pre_par else self.ctrls
-        return out + tuple(self.tph) if self.tph else out
+        self.looks = out + tuple(self.tph) if self.tph else out
 
 
 @dataclass
@@ -436,7 +437,7 @@ class PassCompiler:
                  merge_diagonals: bool = True, fold_tables: bool = True,
                  defer_diagonals: bool = False, absorb: bool = True, allow_swaps: bool = True,
                  swap_anywhere: bool = False, rank_flips: bool = False, park_off_last_round: bool = True,
-                 table_phases: bool = True):
+                 table_phases: bool = True, eager_flips: bool = True):
         self.n = n_qubits
         self.n_local = n_qubits if n_local is None else n_local
         self.dtype = np.dtype(dtype).name
@@ -476,6 +477,9 @@ class PassCompiler:
         self.rank_flips = rank_flips
         self.park_off_last_round = park_off_last_round
         self.table_phases = table_phases
+        # materialise a pending X as soon as its qubit will never be MIXED again (instead of waiting
+        # until nothing inspects it either): the not-yet-scheduled ops that inspect it are re-conjugated
+        self.eager_flips = eager_flips
 
     # ---- public -----------------------------------------------------------------------
     def compile(self, ir_ops, init_pos=None, init_flips=None, home_pos=None, zero_state: bool = False) -> Program:
@@ -487,10 +491,17 @@ class PassCompiler:
         # positions whose index bit may be 1 somewhere in the stored state; None = all (no skipping)
         self._support = set() if (zero_state and self.n_local == self.n) else None
         n = self.n
+        # the lowering depends only on the op list and the initial frame: planning the same circuit
+        # for several initial placements (sharding.plan / plan_single) lowers it once
+        lkey = (id(ir_ops), len(ir_ops), tuple(init_flips) if init_flips is not None else None)
+        cached = getattr(self, "_lowered", None)
         alias = list(range(n))                      # IR qubit -> content
         xf = list(init_flips) if init_flips is not None else [0] * n   # Pauli-X frame per content
         segments: list = [[]]
         seq = 0
+        if cached is not None and cached[0] == lkey:
+            segments, alias, xf = cached[1], list(cached[2]), list(cached[3])
+            ir_ops = ()                              # skip the lowering loop below
         # Diagonal micro-ops commute with each other and with everything that only INSPECTS
         # their contents, so they are pooled per control set (phases multiply, signs cancel)
         # and only emitted right before an op that MIXES one of their contents.
@@ -532,7 +543,9 @@ class PassCompiler:
                             item = self._absorb_pool(pool, item)
                         flush({item.target}, item.src)
                     emit(item)
-        flush()
+        if cached is None or cached[0] != lkey:
+            flush()
+            self._lowered = (lkey, segments, list(alias), list(xf))
         pos = list(init_pos) if init_pos is not None else list(range(n))
         home = [0] * n                              # home[content] = position it must end at
         for q in range(n):
@@ -637,6 +650,16 @@ class PassCompiler:
                     for c in op.looks + ((op.target,) if op.target is not None else ()):
                         self._uses[c] -= 1
             remaining = [op for op in remaining if id(op) not in done]
+            eager: set = set()
+            if self.eager_flips and self.x_frame and self.restore_layout and last_segment and remaining:
+                mixed_later = {op.target for op in remaining if op.target is not None}
+                # ... and is only inspected by DIAGONAL ops from here on (a flipped control of a mixing
+                # op would turn into an X on its target, i.e. a frame change of another content)
+                ctrl_of_mixing = {c for op in remaining if op.target is not None for c in op.ctrls}
+                eager = {c for c in tile if xf[c] and self._uses[c] > 0 and c not in mixed_later
+                         and c not in ctrl_of_mixing}
+                if eager:
+                    remaining = self._reconjugate(remaining, eager)
             final = not remaining and last_segment and self.restore_layout
             park = []
             if remaining and self.a:
@@ -651,7 +674,36 @@ class PassCompiler:
                     last_regs = set(rounds[-1][0])
                     cand = [c for c in cand if c not in last_regs] + [c for c in cand if c in last_regs]
                 park = cand[: self.a]
-            prog.steps.append(self._emit_pass(tile, rounds, pos, home, park, final, xf))
+            prog.steps.append(self._emit_pass(tile, rounds, pos, home, park, final, xf, eager=eager))
+
+    def _reconjugate(self, remaining: list, flipped: set) -> list:
+        """The stored bit of every content in `flipped` is about to be inverted (its pending X is
+        materialised by this pass's store).  Rewrite the unscheduled ops that INSPECT such a content
+        so that they act the same on the new storage: a pre-sign partner toggles the constant sign;
+        an AND-control c turns C_c(O) into O . C_c(O^-1) (the rule of frame_transform).  None of the
+        contents is mixed again (caller's condition), so targets are unaffected."""
+        out: list = []
+        for op in remaining:
+            items = [op]
+            for c in flipped:
+                nxt = []
+                for it in items:
+                    if c in it.pre_par:
+                        it = replace(it, pre_neg=not it.pre_neg)
+                    if c in it.ctrls:
+                        one = [0] * self.n
+                        one[c] = 1
+                        nxt += frame_transform(it, one)
+                    else:
+                        nxt.append(it)
+                items = nxt
+            out += items
+        # uses[] counts the unscheduled ops per content: recount (an op may have become two)
+        self._uses = [0] * self.n
+        for op in out:
+            for c in op.looks + ((op.target,) if op.target is not None else ()):
+                self._uses[c] += 1
+        return out
 
     def _low_contents(self, pos):
         at = {p: c for c, p in enumerate(pos)}
@@ -746,7 +798,7 @@ class PassCompiler:
         return rounds, pend
 
     # ---- pass emission ----------------------------------------------------------------
-    def _emit_pass(self, tile, rounds, pos, home, park, final, xf=None, explicit_store=None) -> PassStep:
+    def _emit_pass(self, tile, rounds, pos, home, park, final, xf=None, explicit_store=None, eager=frozenset()) -> PassStep:
         t, W = self.t, min(self.W, self.t - REG_BITS)
         load_bits = sorted(pos[c] for c in tile)
         at = {p: c for c, p in enumerate(pos)}
@@ -884,7 +936,7 @@ class PassCompiler:
         flip = 0
         if xf is not None:                                # materialise pending X gates for free:
             for i in range(t):                            # safe once nothing later looks at the bit
-                if xf[content[i]] and (final or content[i] in finished):
+                if xf[content[i]] and (final or content[i] in finished or content[i] in eager):
                     flip |= 1 << store[i]
                     xf[content[i]] = 0
         desc.store_flip = flip

@@ -76,15 +76,56 @@ def candidate_placements(n: int, g: int) -> list[list[int]]:
     return uniq
 
 
+def plan_single(ir_ops, n_qubits: int, dtype: str = "complex128", zero_init: bool = True,
+                skip_zero_support: bool = False, **compiler_kw) -> Program:
+    """One device.  From |0...0> the initial placement is free, which removes the layout-restoring
+    pass at the end: plan once without restoration, read off where every qubit ended up, and start
+    the qubits there instead (the plan is driven by qubit contents, so it repeats itself up to the
+    choice of the always-resident low positions).  A couple of such iterations are tried and the
+    plan with the fewest passes (then rounds) wins; the final layout is always the identity."""
+    comp = PassCompiler(n_qubits, n_qubits, dtype, **compiler_kw)
+    ident = list(range(n_qubits))
+    if not zero_init or not comp.restore_layout:
+        return comp.compile(ir_ops, zero_state=skip_zero_support and zero_init)
+    probe = PassCompiler(n_qubits, n_qubits, dtype, **dict(compiler_kw, restore_layout=False))
+    try:
+        bare = probe.compile(ir_ops)                        # where does every qubit end up?
+        f = bare.final_pos
+        if f == ident and not any(bare.final_flips):
+            comp._lowered = probe._lowered
+            best = comp.compile(ir_ops, zero_state=True) if skip_zero_support else bare   # nothing to restore
+            best.stats["init_pos"] = ident
+            return best
+        inv = [0] * n_qubits                                # inv[p] = qubit that ended on position p
+        for q in range(n_qubits):
+            inv[f[q]] = q
+        init = [inv[q] for q in range(n_qubits)]
+        comp._lowered = probe._lowered                      # same op list: lowered once
+        cand = comp.compile(ir_ops, init_pos=init, home_pos=ident, zero_state=skip_zero_support)
+        if cand.stats["passes"] <= bare.stats["passes"]:   # no restoring pass had to be added
+            cand.stats["init_pos"] = init
+            return cand
+    except (NotImplementedError, RuntimeError):
+        cand = None
+    best = comp.compile(ir_ops, zero_state=skip_zero_support)
+    best.stats["init_pos"] = ident
+    if cand is not None and (cand.stats["passes"], cand.stats["rounds"]) < (best.stats["passes"], best.stats["rounds"]):
+        cand.stats["init_pos"] = init
+        return cand
+    return best
+
+
 def plan(ir_ops, n_qubits: int, n_local: int, dtype: str = "complex128", zero_init: bool = True,
          **compiler_kw) -> Program:
     """Compile `ir_ops` for shards of 2^n_local amplitudes.  With zero_init the initial
     placement is chosen among a few candidates by the cost model; the final layout is always
     the identity (logical qubit q on physical bit q)."""
-    comp = PassCompiler(n_qubits, n_local, dtype, **compiler_kw)
     g = n_qubits - n_local
+    if g == 0:
+        return plan_single(ir_ops, n_qubits, dtype, zero_init, **compiler_kw)
+    comp = PassCompiler(n_qubits, n_local, dtype, **compiler_kw)
     ident = list(range(n_qubits))
-    if g == 0 or not zero_init:
+    if not zero_init:
         return comp.compile(ir_ops)
     best, best_t = None, None
     for init in candidate_placements(n_qubits, g):

@@ -19,9 +19,15 @@ def circuit_ops(cd: dict) -> list:
     return [(g["qubits"], gmod.gate_matrix(g["gate"], g["params"])) for g in cd["gates"]]
 
 
-def compile_circuit(circuit_dict: dict, dtype="complex128", **compiler_kw) -> Program:
+def compile_circuit(circuit_dict: dict, dtype="complex128", zero_init: bool = True, skip_zero_support: bool = False,
+                    **compiler_kw) -> Program:
+    """Passes for a run of the whole circuit.  zero_init=True (the run starts from |0...0>, like the
+    reference's simulate): the initial qubit placement is free and is chosen so that no
+    layout-restoring pass is needed (circuit/sharding.plan_single)."""
+    from quantum_simulations_b200.circuit.sharding import plan_single
     cd = validate_circuit_dict(circuit_dict)
-    return PassCompiler(cd["number_of_qubits"], dtype=np.dtype(dtype).name, **compiler_kw).compile(circuit_ops(cd))
+    return plan_single(circuit_ops(cd), cd["number_of_qubits"], np.dtype(dtype).name, zero_init,
+                       skip_zero_support, **compiler_kw)
 
 
 def simulate(circuit_dict: dict, dtype="complex128", device: int = 0, out: np.ndarray | None = None,
@@ -50,7 +56,8 @@ def simulate(circuit_dict: dict, dtype="complex128", device: int = 0, out: np.nd
         mark("create(cudaMalloc)")
         st.init_zero()
         if fused and n >= REG_BITS:
-            prog = PassCompiler(n, dtype=st.dtype.name, **compiler_kw).compile(ops, zero_state=skip_zero_support)
+            from quantum_simulations_b200.circuit.sharding import plan_single
+            prog = plan_single(ops, n, st.dtype.name, True, skip_zero_support, **compiler_kw)
             mark("pass_compiler")
             st.run_program(prog, jit=jit)
             if phases is not None:

@@ -25,7 +25,7 @@ def _case(seed: int):
           W.qft(n)][kind]
     kw = dict(tile_bits=t, low_bits=a, max_rounds=int(rng.integers(2, 6)), swap_anywhere=bool(rng.integers(0, 2)),
               rank_flips=bool(rng.integers(0, 2)), table_phases=bool(rng.integers(0, 2)), absorb=bool(rng.integers(0, 2)))
-    return n, g, validate_circuit_dict(cd), kw, bool(g and rng.integers(0, 2))
+    return n, g, validate_circuit_dict(cd), kw, bool(rng.integers(0, 2))
 
 
 @pytest.mark.parametrize("block", range(8))
@@ -33,7 +33,14 @@ def test_fuzz_block(block):
     for seed in list(range(block * 40, block * 40 + 40)) + [5746, 7444]:      # + two seeds that once failed
         n, g, cd, kw, planned = _case(seed)
         ops = [(q["qubits"], G.gate_matrix(q["gate"], q["params"])) for q in cd["gates"]]
-        prog = sharding.plan(ops, n, n - g, **kw) if planned else PassCompiler(n, n - g, **kw).compile(ops)
+        # planned: free initial placement from |0...0> (sharding.plan / plan_single), every other seed
+        # with zero-support skipping on one device
+        if planned and g == 0:
+            prog = sharding.plan_single(ops, n, "complex128", True, seed % 2 == 0, **kw)
+        elif planned:
+            prog = sharding.plan(ops, n, n - g, **kw)
+        else:
+            prog = PassCompiler(n, n - g, **kw).compile(ops)
         psi = np.zeros(1 << n, dtype=np.complex128)
         psi[0] = 1
         psi = run_program_sharded(prog, psi) if g else run_program(prog, psi)
