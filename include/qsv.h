@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define QSV_ABI_VERSION 4
+#define QSV_ABI_VERSION 5
 
 /* dtypes (wenbo_engine/storage/block_store.py:11 fixes complex64; the oracle is complex128) */
 #define QSV_C64  0
@@ -197,6 +197,11 @@ typedef struct {
                                                   identical.  Honoured by the specialised kernels; the
                                                   interpreting kernels visit every tile.                        */
     int32_t   active_bits[QSV_MAX_ACTIVE_BITS];/* ascending non-tile local positions                          */
+    int32_t   zero_input;                      /* 1: FUSED |0...0> INITIALISATION — the pass does not read the
+                                                  shard: it behaves as if it held |0...0> (amp[0] = 1 on rank 0,
+                                                  zeros elsewhere), so a run from the zero state needs neither
+                                                  the memset nor the read half of its first pass.  The
+                                                  interpreting kernels initialise the shard themselves first.   */
     uint64_t  store_flip;                      /* physical tile bits XOR-ed into every store address:
                                                   pending X gates are never executed on data — the
                                                   compiler carries them as a Pauli frame and the last

@@ -35,7 +35,7 @@ class QsvPass(C.Structure):
     _fields_ = [("n_tile", C.c_int32), ("load_bits", C.c_int32 * QSV_MAX_TILE_BITS),
                 ("store_bits", C.c_int32 * QSV_MAX_TILE_BITS), ("n_rounds", C.c_int32),
                 ("rounds", QsvRound * QSV_MAX_ROUNDS), ("n_ops", C.c_int32), ("n_fold", C.c_int32),
-                ("n_active", C.c_int32), ("active_bits", C.c_int32 * QSV_MAX_ACTIVE_BITS),
+                ("n_active", C.c_int32), ("active_bits", C.c_int32 * QSV_MAX_ACTIVE_BITS), ("zero_input", C.c_int32),
                 ("store_flip", C.c_uint64)]
 
 

@@ -396,6 +396,7 @@ class Program:
     final_pos: list = field(default_factory=list)   # final_pos[q] = position of IR qubit q
     final_flips: list = field(default_factory=list) # final_flips[q] = 1: qubit q is still stored flipped
     rank_flip_mask: int = 0                          # shard r holds logical shard r ^ rank_flip_mask
+    fused_init: bool = False                         # the first pass creates |0...0> itself (zero_input)
     stats: dict = field(default_factory=dict)
 
     @property
@@ -482,12 +483,15 @@ class PassCompiler:
         self.eager_flips = eager_flips
 
     # ---- public -----------------------------------------------------------------------
-    def compile(self, ir_ops, init_pos=None, init_flips=None, home_pos=None, zero_state: bool = False) -> Program:
+    def compile(self, ir_ops, init_pos=None, init_flips=None, home_pos=None, zero_state: bool = False,
+                fuse_init: bool = False) -> Program:
         """init_pos[q]: physical position of IR qubit q before the first op (default q);
         home_pos[q]: position it must have after the last one (default: init_pos[q]).
         zero_state=True: the caller guarantees the state is |0...0> when the program starts (rank 0
         holds amp[0] = 1): passes then visit only the tiles that can hold data (qsv_pass.n_active) —
-        index bits of qubits no pass has had in its tile yet are still 0 everywhere."""
+        index bits of qubits no pass has had in its tile yet are still 0 everywhere.
+        fuse_init=True: the program STARTS from |0...0> whatever the shard holds: its first pass does not
+        read its input (qsv_pass.zero_input), so neither a memset nor the read half of that pass is paid."""
         # positions whose index bit may be 1 somewhere in the stored state; None = all (no skipping)
         self._support = set() if (zero_state and self.n_local == self.n) else None
         n = self.n
@@ -587,6 +591,9 @@ class PassCompiler:
                 self._plan_segment(seg, pos, home, prog, xf, last_segment=(k == len(live) - 1))
         if self.restore_layout:
             self._restore(prog, pos, home, xf)
+        if fuse_init and prog.steps and isinstance(prog.steps[0], PassStep):
+            prog.steps[0].desc.zero_input = 1
+            prog.fused_init = True
         prog.final_pos = [pos[alias[q]] for q in range(n)]
         prog.final_flips = [xf[alias[q]] for q in range(n)]
         prog.rank_flip_mask = sum(1 << (prog.final_pos[q] - self.n_local) for q in range(n)

@@ -25,6 +25,15 @@ HBM_BW = 5.8e12          # achieved by a pass kernel, B/s (profiles/r01)
 NVLINK_BW = 0.55e12      # achieved by the chunked in-place exchange, B/s per direction
 
 
+def fuse_init(prog: Program) -> Program:
+    """The program starts from |0...0>: let its first pass create that state itself
+    (qsv_pass.zero_input) instead of reading a memset shard."""
+    if prog.steps and isinstance(prog.steps[0], PassStep):
+        prog.steps[0].desc.zero_input = 1
+        prog.fused_init = True
+    return prog
+
+
 def estimate_seconds(prog: Program) -> float:
     amp = 16 if prog.dtype == "complex128" else 8
     shard = amp * (1 << prog.n_local)
@@ -85,8 +94,10 @@ def plan_single(ir_ops, n_qubits: int, dtype: str = "complex128", zero_init: boo
     plan with the fewest passes (then rounds) wins; the final layout is always the identity."""
     comp = PassCompiler(n_qubits, n_qubits, dtype, **compiler_kw)
     ident = list(range(n_qubits))
-    if not zero_init or not comp.restore_layout:
-        return comp.compile(ir_ops, zero_state=skip_zero_support and zero_init)
+    if not zero_init:
+        return comp.compile(ir_ops)
+    if not comp.restore_layout:
+        return fuse_init(comp.compile(ir_ops, zero_state=skip_zero_support))
     probe = PassCompiler(n_qubits, n_qubits, dtype, **dict(compiler_kw, restore_layout=False))
     try:
         bare = probe.compile(ir_ops)                        # where does every qubit end up?
@@ -95,7 +106,7 @@ def plan_single(ir_ops, n_qubits: int, dtype: str = "complex128", zero_init: boo
             comp._lowered = probe._lowered
             best = comp.compile(ir_ops, zero_state=True) if skip_zero_support else bare   # nothing to restore
             best.stats["init_pos"] = ident
-            return best
+            return fuse_init(best)
         inv = [0] * n_qubits                                # inv[p] = qubit that ended on position p
         for q in range(n_qubits):
             inv[f[q]] = q
@@ -104,15 +115,15 @@ def plan_single(ir_ops, n_qubits: int, dtype: str = "complex128", zero_init: boo
         cand = comp.compile(ir_ops, init_pos=init, home_pos=ident, zero_state=skip_zero_support)
         if cand.stats["passes"] <= bare.stats["passes"]:   # no restoring pass had to be added
             cand.stats["init_pos"] = init
-            return cand
+            return fuse_init(cand)
     except (NotImplementedError, RuntimeError):
         cand = None
     best = comp.compile(ir_ops, zero_state=skip_zero_support)
     best.stats["init_pos"] = ident
     if cand is not None and (cand.stats["passes"], cand.stats["rounds"]) < (best.stats["passes"], best.stats["rounds"]):
         cand.stats["init_pos"] = init
-        return cand
-    return best
+        return fuse_init(cand)
+    return fuse_init(best)
 
 
 def plan(ir_ops, n_qubits: int, n_local: int, dtype: str = "complex128", zero_init: bool = True,
@@ -138,6 +149,6 @@ def plan(ir_ops, n_qubits: int, n_local: int, dtype: str = "complex128", zero_in
             best, best_t = prog, t
             best.stats["init_pos"] = init
     if best is None:
-        return comp.compile(ir_ops)
+        return fuse_init(comp.compile(ir_ops))
     best.stats["estimated_s"] = best_t
-    return best
+    return fuse_init(best)

@@ -443,6 +443,7 @@ static int validate_pass(qsv_handle *h, const qsv_pass *p, const qsv_op *ops) {
         if (b < 0 || b >= h->n_local || ((tile_mask >> b) & 1) || (k && b <= p->active_bits[k - 1]))
             QSV_FAIL(h, QSV_EINVAL, "pass: active_bits must be ascending local non-tile positions (entry %d = %d)", k, b);
     }
+    if (p->zero_input != 0 && p->zero_input != 1) QSV_FAIL(h, QSV_EINVAL, "pass: zero_input=%d", p->zero_input);
     if (p->n_rounds < 1 || p->n_rounds > QSV_MAX_ROUNDS) QSV_FAIL(h, QSV_EINVAL, "pass: n_rounds=%d", p->n_rounds);
     if (p->n_ops < 0 || p->n_fold < 0) QSV_FAIL(h, QSV_EINVAL, "pass: n_ops / n_fold < 0");
     for (int r = 0; r < p->n_rounds; ++r) {
@@ -498,6 +499,10 @@ static int validate_pass(qsv_handle *h, const qsv_pass *p, const qsv_op *ops) {
 static int launch_pass(qsv_handle *h, const qsv_pass *host_pass, const qsv_pass *dev_pass, const qsv_op *dev_ops,
                        const double2 *dev_tables, int pass_index) {
     const int T = host_pass->n_tile;
+    if (host_pass->zero_input) {          // the interpreting kernels read the shard: give them |0...0>
+        int rc = qsv_init_zero(h);
+        if (rc) return rc;
+    }
     const uint64_t rank_bits = (uint64_t)h->rank << h->n_local;
     ScopedTimer t(h, 10, pass_index);
     if (h->dtype == QSV_C128 && T == kRingT && host_pass->n_ops <= kRingMaxOps && !h->force_simple_pass) {
@@ -674,7 +679,7 @@ int qsv_pass_swap_overlapped(qsv_handle *h, qsv_program *p, int pass_index, int 
         if (ok) seen |= 1u << rel;
     }
     const qsv_pass &P = p->passes[pass_index];
-    ok = ok && P.n_active < 0;
+    ok = ok && P.n_active < 0 && !P.zero_input;
     for (int i = 0; ok && i < P.n_tile; ++i)
         ok = P.load_bits[i] < h->n_local - n_swap && P.store_bits[i] < h->n_local - n_swap;
     if (!ok) {

@@ -54,16 +54,18 @@ def simulate(circuit_dict: dict, dtype="complex128", device: int = 0, out: np.nd
     mark("validate+gate_matrices")
     with DeviceState(n, dtype, device) as st:
         mark("create(cudaMalloc)")
-        st.init_zero()
         if fused and n >= REG_BITS:
             from quantum_simulations_b200.circuit.sharding import plan_single
             prog = plan_single(ops, n, st.dtype.name, True, skip_zero_support, **compiler_kw)
             mark("pass_compiler")
+            if not prog.fused_init:            # otherwise the first pass creates |0...0> itself
+                st.init_zero()
             st.run_program(prog, jit=jit)
             if phases is not None:
                 st.sync()
             mark("upload+specialise+run")
         else:
+            st.init_zero()
             for qs, U in ops:
                 st.apply_op(qs, U)
             if phases is not None:

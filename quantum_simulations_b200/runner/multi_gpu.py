@@ -203,7 +203,8 @@ class ShardedSimulator:
         return self.shard.state.download(out)
 
     def run(self, prog: Program) -> None:
-        self.shard.state.init_zero()
+        if not prog.fused_init:                # otherwise the first pass creates |0...0> itself
+            self.shard.state.init_zero()
         execute(prog, self.shard)
         self.logical_rank = self.rank ^ prog.rank_flip_mask
         self._flip_mask = prog.rank_flip_mask

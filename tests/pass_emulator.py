@@ -37,6 +37,10 @@ def run_pass(psi: np.ndarray, desc: L.QsvPass, ops, n_local: int, rank: int = 0,
         base = _insert_zero(base, p)
     glob = (rank << n_local) | base
     tile_mask = sum(1 << b for b in load)
+    if desc.zero_input:                                    # fused |0...0> initialisation: input ignored
+        psi[:] = 0
+        if rank == 0:
+            psi[0] = 1
     if desc.n_active >= 0:
         # zero-support skipping: every tile outside the active set must be exactly zero (the kernel
         # does not visit it); a planner bug shows up here

@@ -49,7 +49,7 @@ def test_constants_match_header():
 def test_struct_layouts():
     assert C.sizeof(L.QsvOp) == 4 + 4 + 8 + 32
     assert C.sizeof(L.QsvRound) == 4 + 14 + 2 + 12         # uint8[4], uint8[14], pad, 3 x int32
-    assert C.sizeof(L.QsvPass) == 4 + 14 * 4 * 2 + 4 + 16 * C.sizeof(L.QsvRound) + 4 + 4 + 4 + 52 * 4 + 4 + 8   # + pad to 8
+    assert C.sizeof(L.QsvPass) == 4 + 14 * 4 * 2 + 4 + 16 * C.sizeof(L.QsvRound) + 4 + 4 + 4 + 52 * 4 + 4 + 8   # n_active, active_bits, zero_input, store_flip
 
 
 def test_no_gpu_means_loud_failure_not_fallback():

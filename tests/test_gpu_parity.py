@@ -245,6 +245,23 @@ def test_zero_support_skipping_matches_oracle(workload):
         assert np.abs(got - want).max() <= TOL[dtype]
 
 
+@pytest.mark.parametrize("jit", [True, False])
+def test_fused_initialisation_on_the_device(jit):
+    """A program whose first pass has zero_input starts from |0...0> whatever the shard holds —
+    on the specialised kernels (no read at all) and on the interpreting ones (they initialise first)."""
+    from quantum_simulations_b200.kernel.cuda import DeviceState
+    from quantum_simulations_b200.kernel.cuda_dense import compile_circuit
+    n = 18
+    cd = W.random_1q_cz(n, 20, 1234)
+    prog = compile_circuit(cd)
+    assert prog.fused_init
+    with DeviceState(n) as st:
+        st.upload(np.full(1 << n, 0.5 + 0.25j))            # junk that must be ignored
+        st.run_program(prog, jit=jit)
+        got = st.download()
+    assert np.abs(got - CO.simulate_c(validate_circuit_dict(cd))).max() <= 1e-12
+
+
 def test_jit_kernels_are_cached_by_structure():
     """Two circuits with the same structure but different angles share compiled kernels."""
     import ctypes as C

@@ -200,3 +200,27 @@ def test_zero_support_skipping_is_exact(n, t, a):
         psi[0] = 1
         run_program(prog, psi)
         assert np.abs(psi - O.simulate(validate_circuit_dict(cd))).max() <= 1e-12
+
+
+def test_fused_initialisation_ignores_the_input():
+    """plan_single / sharding.plan mark the first pass zero_input: the program starts from |0...0>
+    whatever the shard holds (no memset, no read in the first pass)."""
+    from quantum_simulations_b200.circuit import sharding
+    from tests.pass_emulator import run_program_sharded
+    n = 11
+    cd = W.random_1q_cz(n, 20, 1234)
+    ops = ir_ops(cd)
+    want = O.simulate(validate_circuit_dict(cd))
+    prog = sharding.plan_single(ops, n, tile_bits=7, low_bits=2)
+    assert prog.fused_init and prog.passes[0].desc.zero_input == 1 and all(s.desc.zero_input == 0 for s in prog.passes[1:])
+    junk = np.random.default_rng(0).standard_normal(1 << n) + 1j
+    run_program(prog, junk)
+    assert np.abs(junk - want).max() <= 1e-12
+    prog = sharding.plan(ops, n, n - 2, tile_bits=7, low_bits=2)
+    assert prog.fused_init
+    junk = run_program_sharded(prog, np.random.default_rng(1).standard_normal(1 << n) + 1j)
+    if prog.rank_flip_mask:
+        sh = junk.reshape(4, -1)
+        junk = np.concatenate([sh[r ^ prog.rank_flip_mask] for r in range(4)])
+    assert np.abs(junk - want).max() <= 1e-12
+    assert not PassCompiler(n, tile_bits=7, low_bits=2).compile(ops).fused_init          # plain compile: never
