@@ -591,8 +591,8 @@ class PassCompiler:
                 self._plan_segment(seg, pos, home, prog, xf, last_segment=(k == len(live) - 1))
         if self.restore_layout:
             self._restore(prog, pos, home, xf)
-        if fuse_init and prog.steps and isinstance(prog.steps[0], PassStep):
-            prog.steps[0].desc.zero_input = 1
+        if fuse_init and prog.steps and isinstance(prog.steps[0], PassStep) and self._support is None:
+            prog.steps[0].desc.zero_input = 1        # (zero-support skipping needs a really zeroed shard)
             prog.fused_init = True
         prog.final_pos = [pos[alias[q]] for q in range(n)]
         prog.final_flips = [xf[alias[q]] for q in range(n)]

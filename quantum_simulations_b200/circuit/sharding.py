@@ -28,7 +28,9 @@ NVLINK_BW = 0.55e12      # achieved by the chunked in-place exchange, B/s per di
 def fuse_init(prog: Program) -> Program:
     """The program starts from |0...0>: let its first pass create that state itself
     (qsv_pass.zero_input) instead of reading a memset shard."""
-    if prog.steps and isinstance(prog.steps[0], PassStep):
+    # (not with zero-support skipping: tiles that are never visited must really hold zeros)
+    if prog.steps and isinstance(prog.steps[0], PassStep) and all(
+            s.desc.n_active < 0 for s in prog.steps if isinstance(s, PassStep)):
         prog.steps[0].desc.zero_input = 1
         prog.fused_init = True
     return prog

@@ -37,8 +37,12 @@ def run_pass(psi: np.ndarray, desc: L.QsvPass, ops, n_local: int, rank: int = 0,
         base = _insert_zero(base, p)
     glob = (rank << n_local) | base
     tile_mask = sum(1 << b for b in load)
-    if desc.zero_input:                                    # fused |0...0> initialisation: input ignored
-        psi[:] = 0
+    if desc.zero_input:
+        # fused |0...0> initialisation: the tiles the pass VISITS are not read (treated as |0...0>);
+        # tiles it skips (zero-support) keep whatever they hold, so that combination needs a real memset
+        live = np.ones(len(base), dtype=bool) if desc.n_active < 0 else \
+            (base & ~sum(1 << desc.active_bits[k] for k in range(desc.n_active))) == 0
+        psi[(base[live][:, None] + off_l[None, :]).ravel()] = 0
         if rank == 0:
             psi[0] = 1
     if desc.n_active >= 0:
