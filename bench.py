@@ -452,7 +452,7 @@ def bench_multi(args) -> None:
             "nvlink": {"path": "peer-memory kernel (CUDA IPC, loads/stores over NVLink)" if sim.peer_swap
                        else f"chunked ncclSend/ncclRecv ({sim.shard.peer_error or 'QSV_SWAP=nccl'})", "swaps": nv, "share_of_step": (sum(ms for ms, _ in swap_ms) + sum(ms for ms, _ in fused_ms)) / total_ms,
                        "peak_gbs_per_direction": 900.0},
-            "gpu_launches": len(per_launch) + 2 * args.steps,
+            "gpu_launches": len(per_launch) + (0 if prog.fused_init else 2 * args.steps),
             "clocks": clk,
             "e2e": None if e2e_s is None else
                    {"value": updates_per_step / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3,
