@@ -177,7 +177,13 @@ def atlas_stages(circuit_dict: dict, k: int, method: str = "heuristic",
         raise ValueError(f"unknown staging method: {method!r}")
     if method == "ilp":
         from quantum_simulations_b200.circuit.staging_ilp import local_sets_ilp
-        plan = iter(local_sets_ilp(gates, n, k))
+        # upper bound on the number of stages: what the heuristic needs (bisection starts below it)
+        heur_steps, _ = atlas_stages(cd, k, method="heuristic", lookahead=lookahead)
+        bound = 1 + sum(1 for st in heur_steps if st["nonlocal_ops"] and not st["local_ops"])
+        try:
+            plan = iter(local_sets_ilp(gates, n, k, max_stages=max(1, bound)))
+        except (ValueError, RuntimeError):
+            plan = iter(())                              # e.g. a gate wider than k: heuristic picks below
     else:
         plan = None
 

@@ -58,7 +58,7 @@ def test_qubit_map():
     assert m.to_list() == [3, 1, 2, 0]
 
 
-@pytest.mark.parametrize("method", ["heuristic", "greedy"])
+@pytest.mark.parametrize("method", ["heuristic", "greedy", "ilp"])
 def test_reference_bug_repro(method):
     """n=3, k=1: H(2) H(0) CZ(2,0) H(0) H(1) -> the reference gives max|delta| = 0.5."""
     cd = {"number_of_qubits": 3, "gates": [
@@ -99,3 +99,18 @@ def test_stats_keys():
 def test_unknown_method():
     with pytest.raises(ValueError, match="unknown staging method"):
         atlas_stages(W.qft(4), 2, method="nope")
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_ilp_staging_matches_oracle(seed):
+    """method="ilp" (SciPy HiGHS instead of the reference's PuLP): the plan executes to the oracle's
+    state, and the ILP itself needs no more stages than the bound it was given."""
+    from quantum_simulations_b200 import workloads as W
+    cd = validate_circuit_dict(W.random_mixed(5, 24, seed))
+    for k in (2, 3):
+        got, _ = run_steps(cd, k, "ilp")
+        assert np.abs(got - O.simulate(cd)).max() <= 1e-12
+        from quantum_simulations_b200.circuit.staging_ilp import local_sets_ilp
+        sets = local_sets_ilp(cd["gates"], 5, k, max_stages=len(cd["gates"]))
+        assert all(len(s_) == k for s_ in sets) and 1 <= len(sets) <= len(cd["gates"])
+        assert staging_stats(cd, k, "ilp")["staged_steps"] >= 1
