@@ -69,7 +69,7 @@ def _solve(gates, n: int, k: int, S: int, ni, pred, time_limit: float):
 
 
 def local_sets_ilp(gates: list[dict], n: int, k: int, max_stages: int | None = None,
-                   time_limit: float = 30.0) -> list[set[int]]:
+                   time_limit: float = 10.0) -> list[set[int]]:
     """Local-qubit set of every stage, fewest stages first, then fewest side changes."""
     from quantum_simulations_b200.circuit.staging import non_insular_qubits
 

@@ -110,7 +110,13 @@ def test_ilp_staging_matches_oracle(seed):
     for k in (2, 3):
         got, _ = run_steps(cd, k, "ilp")
         assert np.abs(got - O.simulate(cd)).max() <= 1e-12
-        from quantum_simulations_b200.circuit.staging_ilp import local_sets_ilp
-        sets = local_sets_ilp(cd["gates"], 5, k, max_stages=len(cd["gates"]))
-        assert all(len(s_) == k for s_ in sets) and 1 <= len(sets) <= len(cd["gates"])
         assert staging_stats(cd, k, "ilp")["staged_steps"] >= 1
+
+
+def test_ilp_local_sets_on_a_known_case():
+    """GHZ-4 with 2 local qubits: q0,q1 first, then every later CNOT needs its own pair local; the ILP
+    finds the 3-stage plan {0,1} -> {1,2} -> {2,3} (one qubit changes side per transition)."""
+    from quantum_simulations_b200.circuit.staging_ilp import local_sets_ilp
+    cd = validate_circuit_dict(W.ghz(4))
+    sets = local_sets_ilp(cd["gates"], 4, 2, max_stages=4, time_limit=10.0)
+    assert [sorted(s_) for s_ in sets] == [[0, 1], [1, 2], [2, 3]]
