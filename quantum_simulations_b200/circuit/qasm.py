@@ -87,12 +87,17 @@ def _split_args(s: str) -> list[str]:
     return [a.strip() for a in out]
 
 
-def qasm_to_ops(text: str) -> tuple[int, list]:
-    """Parse an OpenQASM 2.0 program -> (n_qubits, [(qubits, U)]) in program order."""
+def qasm_to_ops(text: str, with_statement_index: bool = False):
+    """Parse an OpenQASM 2.0 program -> (n_qubits, [(qubits, U)]) in program order.
+    with_statement_index=True adds a third value: for every op the 0-based index of the gate
+    STATEMENT it came from (a broadcast or a ccx yields several ops of one statement; barrier /
+    measure / declarations are not counted) — what HiSVSIM's part files number."""
     text = re.sub(r"//[^\n]*", "", text)
     regs: dict[str, tuple[int, int]] = {}           # name -> (offset, size)
     gates: dict[str, tuple[list, list, list]] = {}  # name -> (params, qargs, body statements)
     ops: list = []
+    stmt_of: list = []
+    n_stmt = 0
     n = 0
 
     # pull out gate definitions first (they contain braces)
@@ -186,11 +191,14 @@ def qasm_to_ops(text: str) -> tuple[int, list]:
                     raise QasmError(f"{a.strip()}: index out of range")
                 args.append([off + int(am.group(2))])
         width = max(len(a) for a in args)
+        before = len(ops)
         for i in range(width):
             emit(m.group(1), params, [a[i] if len(a) > 1 else a[0] for a in args])
+        stmt_of += [n_stmt] * (len(ops) - before)
+        n_stmt += 1
     if n == 0:
         raise QasmError("no qreg declared")
-    return n, ops
+    return (n, ops, stmt_of) if with_statement_index else (n, ops)
 
 
 def qasm_to_dict(text: str) -> dict:
