@@ -251,6 +251,23 @@ class DeviceState:
         self._ck(self.lib.qsv_expect_z(self._h, mask, C.byref(out)))
         return out.value
 
+    def project(self, qubit: int, outcome: int, renormalise: bool = True) -> float:
+        """Partial measurement with a known outcome (HiSVSIM ``StateVector::project``,
+        hisvsim_repo/state_vector.hpp:829-922): keep the amplitudes whose bit `qubit` equals `outcome`,
+        zero the others and (optionally) renormalise.  Returns the probability of the outcome.
+        One branch-free diagonal sweep (qsv_apply_diag with the table (s, 0) or (0, s))."""
+        if outcome not in (0, 1):
+            raise ValueError("outcome must be 0 or 1")
+        p = float(self.probabilities([qubit])[outcome])
+        if self.world > 1:
+            raise NotImplementedError("project on a sharded state: sum the probabilities over the shards first "
+                                      "(ShardedSimulator.project)")
+        if p <= 0.0:
+            raise ValueError(f"outcome {outcome} of qubit {qubit} has probability 0")
+        s = 1.0 / np.sqrt(p) if renormalise else 1.0
+        self.apply_diag([qubit], [s, 0.0] if outcome == 0 else [0.0, s])
+        return p
+
     def sample(self, seed: int, shots: int) -> np.ndarray:
         """Measurement samples (basis-state indices, ascending), bit-exact with
         oracle/ref_dense.py::sample_indices: u = sort(default_rng(seed).random(shots))."""

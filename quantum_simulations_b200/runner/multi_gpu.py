@@ -209,6 +209,33 @@ class ShardedSimulator:
         self.logical_rank = self.rank ^ prog.rank_flip_mask
         self._flip_mask = prog.rank_flip_mask
 
+    def probabilities(self, qubits) -> np.ndarray:
+        """Marginal distribution over logical `qubits` of the whole sharded state (identical on every
+        rank): per-shard marginals (qsv_probabilities, rank bits allowed) summed over the shards."""
+        import torch
+        p = self.shard.state.probabilities(self._physical(qubits))
+        if self.world > 1:
+            t = torch.from_numpy(p)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+            p = t.numpy()
+        return p
+
+    def expect_z(self, qubits) -> float:
+        import torch
+        v = torch.tensor([self.shard.state.expect_z(self._physical(qubits))], dtype=torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(v, op=self.dist.ReduceOp.SUM)
+        return float(v.item())
+
+    def _physical(self, qubits) -> list:
+        """After a run the layout is the identity except for the shard renaming of rank_flip_mask: a
+        flipped rank bit is seen inverted by the shard-local kernels, which read the PHYSICAL rank."""
+        n_loc = self.n - self.g
+        if any(q >= n_loc and (self._flip_mask >> (q - n_loc)) & 1 for q in qubits):
+            raise NotImplementedError("observable on a qubit whose rank bit is renamed (rank_flip_mask): "
+                                      "use sample() or gather the shards")
+        return list(qubits)
+
     def sample(self, seed: int, shots: int) -> np.ndarray:
         """Measurement samples of the sharded state, identical on every rank and bit-exact with
         oracle/ref_dense.py::sample_indices.  The exclusive scan over leaf sums is one sequential

@@ -338,6 +338,29 @@ def test_observables_match_oracle(dtype):
     assert abs(acc_z - O.expectation_z(psi, [12, 13, 4])) <= tol
 
 
+def test_project_partial_measurement():
+    """DeviceState.project == HiSVSIM-style collapse: keep one outcome of a qubit, renormalise."""
+    from quantum_simulations_b200.kernel.cuda import DeviceState
+    n = 12
+    rng = np.random.default_rng(9)
+    psi = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
+    psi /= np.linalg.norm(psi)
+    for q, b in ((0, 1), (7, 0), (11, 1)):
+        keep = ((np.arange(1 << n) >> q) & 1) == b
+        p_want = float(np.sum(np.abs(psi[keep]) ** 2))
+        want = np.where(keep, psi, 0) / np.sqrt(p_want)
+        with DeviceState(n) as st:
+            st.upload(psi)
+            p = st.project(q, b)
+            got = st.download()
+            assert abs(st.norm2() - 1.0) < 1e-12
+        assert abs(p - p_want) < 1e-12 and np.abs(got - want).max() < 1e-12
+    with DeviceState(3) as st:
+        st.init_zero()
+        with pytest.raises(ValueError, match="probability 0"):
+            st.project(1, 1)
+
+
 def test_ghz20_config0_known_answer():
     from quantum_simulations_b200.kernel.cuda_dense import simulate
     got = simulate(W.ghz(20))
