@@ -55,10 +55,18 @@ class MicroOp:
 
     looks: tuple = field(init=False, repr=False, compare=False, default=())
 
+    tmask: int = field(init=False, repr=False, compare=False, default=0)    # 1 << target (0: none)
+    lmask: int = field(init=False, repr=False, compare=False, default=0)    # OR of 1 << c over `looks`
+
     def __post_init__(self):
         # contents the op inspects without mixing them (controls + pre-sign partners + table partners)
         out = self.ctrls + tuple(self.pre_par) if self.pre_par else self.ctrls
         self.looks = out + tuple(self.tph) if self.tph else out
+        self.tmask = 0 if self.target is None else 1 << self.target
+        m = 0
+        for c in self.looks:
+            m |= 1 << c
+        self.lmask = m
 
 
 @dataclass
@@ -200,6 +208,38 @@ def lower_op(qubits, U, src: int = -1) -> list:
         low = lower_1q(U[np.ix_(od, od)], qa, (qb,), src)    # control = qubits[1]
         return [Dense2Q(qa, qb, U, src)] if any(isinstance(x, Dense1Q) for x in low) else low
     return [Dense2Q(qa, qb, U, src)]
+
+
+_LOWER_CACHE: dict = {}
+
+
+def lower_op_cached(qubits, U, src: int = -1) -> list:
+    """lower_op with the decomposition cached by matrix: circuits repeat a handful of gates (H, X, S,
+    T, CZ, ...), and the structure detection + ZYZ of lower_op is most of the lowering time.  The
+    cache holds the items for the symbolic qubits (0, 1); they are re-targeted per use."""
+    U = np.ascontiguousarray(U, dtype=np.complex128)
+    key = (len(qubits), U.tobytes())
+    tmpl = _LOWER_CACHE.get(key)
+    if tmpl is None:
+        if len(_LOWER_CACHE) > 4096:
+            _LOWER_CACHE.clear()
+        tmpl = lower_op(list(range(len(qubits))), U, -1)
+        _LOWER_CACHE[key] = tmpl
+    qs = list(qubits)
+    if len(qs) == 2 and qs[0] == qs[1]:
+        raise ValueError("2-qubit op on a repeated qubit")
+    out = []
+    for it in tmpl:
+        if isinstance(it, tuple):                       # ('swap', 0, 1)
+            out.append((it[0], qs[it[1]], qs[it[2]]))
+        elif isinstance(it, MicroOp):
+            out.append(replace(it, target=None if it.target is None else qs[it.target],
+                               ctrls=tuple(qs[c] for c in it.ctrls), src=src))
+        elif isinstance(it, Dense2Q):
+            out.append(replace(it, qa=qs[it.qa], qb=qs[it.qb], src=src))
+        else:                                           # Dense1Q
+            out.append(replace(it, q=qs[it.q], ctrl=None if it.ctrl is None else qs[it.ctrl], src=src))
+    return out
 
 
 def absorb_diagonals(rops: list, regset: set) -> tuple[list, int]:
@@ -408,23 +448,24 @@ class Program:
 def _scan(ops, mixable, lookahead: int | None = None):
     """(run, missing): ops that can execute, in order, when exactly the contents in `mixable`
     may be mixed; and the dependency-free ops that only lack their target in `mixable`."""
-    bt: set = set()      # contents an earlier pending op MIXES
-    bc: set = set()      # contents an earlier pending op INSPECTS
+    bt = 0               # contents an earlier pending op MIXES      (bit masks over contents)
+    bc = 0               # contents an earlier pending op INSPECTS
+    mix = 0
+    for c in mixable:
+        mix |= 1 << c
     run: list = []
     missing: list = []
+    if lookahead is not None and lookahead < len(ops):
+        ops = ops[:lookahead]
     for i, op in enumerate(ops):
-        if lookahead is not None and i >= lookahead:
-            break
-        t = op.target
-        free = (t is None or (t not in bt and t not in bc)) and not any(c in bt for c in op.looks)
-        if free and (t is None or t in mixable):
-            run.append(i)
-            continue
-        if free:
+        tm = op.tmask
+        if not (tm & (bt | bc)) and not (op.lmask & bt):      # dependency-free
+            if not tm or tm & mix:
+                run.append(i)
+                continue
             missing.append(i)
-        if t is not None:
-            bt.add(t)
-        bc.update(op.looks)
+        bt |= tm
+        bc |= op.lmask
     return run, missing
 
 
@@ -527,7 +568,7 @@ class PassCompiler:
                     emit(op)
 
         for i, (qs, U) in enumerate(ir_ops):
-            for low in lower_op([alias[q] for q in qs], U, i):
+            for low in lower_op_cached([alias[q] for q in qs], U, i):
                 if isinstance(low, tuple):          # swap: rename, no data movement
                     qa, qb = list(qs)
                     alias[qa], alias[qb] = alias[qb], alias[qa]
