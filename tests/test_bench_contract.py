@@ -1,0 +1,48 @@
+"""The bench line the driver parses: checked on the line committed under profiles/ (produced by
+``python bench.py`` on a B200) and on the argument parser, so a refactor cannot silently drop a key."""
+import json
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _line(name):
+    return json.loads((ROOT / "profiles" / "r01" / name).read_text().strip().splitlines()[-1])
+
+
+def test_single_gpu_line_has_every_contract_key():
+    r = _line("bench_n30_jit.json")
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert k in r, k
+    assert r["metric"] == "amplitude-updates/s" and r["n_gpus"] == 1 and r["higher_is_better"] is True
+    assert r["dtype"] == "complex128" and r["data"] == "synthetic" and r["vs_baseline"] is None
+    assert "workload" in r["config"] and "model" not in r["config"] and r["config"]["n_qubits"] == 30
+    rf = r["roofline"]
+    assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
+    assert 0 < rf["frac"] <= 1.0 and rf["traffic"] and abs(rf["traffic"] / rf["algorithmic_bytes_per_launch"] - 1) < 0.01
+    cb = r["cpu_baseline"]
+    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["sample"] and cb["value"] > 0
+    e = r["e2e"]
+    assert e["value"] > 0 and e["d2h_bytes_per_step"] == 16 * 2 ** 30 and e["h2d_bytes_per_step"] > 0
+    assert e["value"] < r["value"]                       # end to end includes the copies
+    assert r["gpu_launches"] > 0
+    assert set(r["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    assert abs(r["value"] - r["config"]["gates"] * 2 ** 30 / (r["ms_per_step"] * 1e-3)) / r["value"] < 1e-6
+
+
+def test_multi_gpu_lines():
+    for name, n_gpus in (("bench_n31_2gpu_peer_swap.json", 2), ("bench_n32_4gpu.json", 4), ("bench_n33_8gpu.json", 8),
+                         ("bench_n36_8gpu_1TiB.json", 8)):
+        r = _line(name)
+        assert r["n_gpus"] == n_gpus and r["scaling"] == "weak" and r["metric"] == "amplitude-updates/s"
+        assert r["roofline"]["bound"] == "hbm" and "nvlink" in r and r["config"]["swaps_per_step"] >= 1
+
+
+def test_cli_surface():
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--help"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0
+    for flag in ("--gpus", "--steps", "--warmup", "--impl"):
+        assert flag in out.stdout
