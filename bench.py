@@ -371,7 +371,22 @@ def bench_multi(args) -> None:
     def step():
         sim.run(prog)
 
-    for _ in range(args.warmup):
+    def global_norm() -> float:
+        v = torch.tensor([st.norm2()], dtype=torch.float64)
+        dist.all_reduce(v, op=dist.ReduceOp.SUM)
+        return float(v.item())
+
+    tol = 1e-9 if dtype == "complex128" else 1e-4
+    step()
+    plan_note = "default planner options"
+    if abs(global_norm() - 1.0) > tol:
+        # insurance: a plan that does not even conserve the norm is replaced by the conservative planner
+        # (swaps on the top positions after a relabel pass, no eager flips, no table phases) before timing
+        prog = sim.plan(cd, swap_anywhere=False, rank_flips=False, eager_flips=False, table_phases=False, **ckw)
+        sim.shard.prepare(prog)
+        plan_note = "FALLBACK: conservative planner options (the default plan failed the norm check)"
+        step()
+    for _ in range(max(args.warmup - 1, 0)):
         step()
     st.sync(); dist.barrier()
     clocks = ClockSampler(sim.local_rank).start() if rank == 0 else None
@@ -387,10 +402,9 @@ def bench_multi(args) -> None:
     tmax = torch.tensor([total_ms], dtype=torch.float64)
     dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     total_ms = float(tmax.item())
-    nrm = torch.tensor([st.norm2()], dtype=torch.float64)
-    dist.all_reduce(nrm, op=dist.ReduceOp.SUM)
-    if abs(float(nrm.item()) - 1.0) > (1e-9 if dtype == "complex128" else 1e-4):
-        raise SystemExit(f"bench: state norm {float(nrm.item())} != 1 — result invalid")
+    nrm = global_norm()
+    if abs(nrm - 1.0) > tol:
+        raise SystemExit(f"bench: state norm {nrm} != 1 — result invalid")
 
     # end to end through the public object: plan + (cached) specialisation + run + D2H of the shard
     n_loc = n - g
@@ -438,7 +452,8 @@ def bench_multi(args) -> None:
                        "step_sequence": "".join(("S%d" % len(s_.global_bits)) if isinstance(s_, SwapStep)
                                                 else ("P" if s_.n_micro_ops else "p") for s_ in prog.steps),
                        "l2_hygiene": f"shard {(1 << n_loc) * amp_bytes / 2**30:.0f} GiB >> 126 MB L2",
-                       "host_compile_s": compile_s, "timing": "CUDA events on each rank's stream, max over ranks"},
+                       "host_compile_s": compile_s, "plan": plan_note,
+                       "timing": "CUDA events on each rank's stream, max over ranks"},
             "gate_layers_per_s": info["levels"] / (ms_per_step * 1e-3),
             "hbm_gbs_per_gate_layer_per_gpu": info["levels"] * alg_bytes / (ms_per_step * 1e-3) / 1e9,
             "roofline": {"bound": "hbm", "kernel": "k_pass_jit / k_pass_ring", "achieved": achieved, "peak": peak,
