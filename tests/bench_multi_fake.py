@@ -1,0 +1,96 @@
+"""Runs bench.py's N>1 control flow on CPU: the GPU objects are replaced by NumPy-emulator fakes
+(test infrastructure), the process group is real gloo.  Checks that the JSON line is assembled."""
+from __future__ import annotations
+
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+import quantum_simulations_b200.runner.multi_gpu as MG          # noqa: E402
+import quantum_simulations_b200.storage.pinned as PIN            # noqa: E402
+from gloo_worker import EmuShard                                 # noqa: E402
+
+
+class FakeState:
+    def __init__(self, emu):
+        self.emu, self._t0, self._timed, self._timing = emu, 0.0, [], False
+
+    def init_zero(self):
+        self.emu.psi[:] = 0
+        if self.emu.rank == 0:
+            self.emu.psi[0] = 1
+
+    def sync(self): pass
+    def timing(self, on): self._timing = on
+    def timer_start(self): self._t0 = time.perf_counter()
+    def timer_stop(self): return (time.perf_counter() - self._t0) * 1e3
+    def take_timings(self): out, self._timed = self._timed, []; return out
+    def norm2(self): return float(np.vdot(self.emu.psi, self.emu.psi).real)
+
+    def download(self, out=None):
+        if out is None:
+            return self.emu.psi.copy()
+        out[:] = self.emu.psi
+        return out
+
+
+class FakeShard:
+    peer_error = "emulated"
+
+    def __init__(self, emu, state):
+        self.emu, self.state = emu, state
+
+    def prepare(self, prog): pass
+
+    def run_passes(self, steps):
+        t0 = time.perf_counter()
+        self.emu.run_passes(steps)
+        if self.state._timing:
+            self.state._timed += [((time.perf_counter() - t0) * 1e3 / len(steps), 10, i) for i in range(len(steps))]
+
+    def swap(self, g, l):
+        t0 = time.perf_counter()
+        self.emu.swap(g, l)
+        if self.state._timing:
+            self.state._timed.append(((time.perf_counter() - t0) * 1e3, 20 + len(g), -1))
+
+
+class FakeSim:
+    def __init__(self, n, dtype="complex128"):
+        self.rank, self.local_rank, self.world = MG.dist_env()
+        self.n, self.g, self.dtype = n, self.world.bit_length() - 1, np.dtype(dtype)
+        self.dist = MG.init_plumbing()
+        emu = EmuShard(n, self.rank, self.world, self.dist)
+        self.shard = FakeShard(emu, FakeState(emu))
+        self.peer_swap, self.logical_rank, self._flip_mask = False, self.rank, 0
+
+    plan = MG.ShardedSimulator.plan
+    run = MG.ShardedSimulator.run
+
+    def simulate(self, cd, out=None, **kw):
+        self.run(self.plan(cd, **kw))
+        return self.shard.state.download(out)
+
+    def close(self): pass
+
+
+class FakePinned:
+    def __init__(self, nbytes): self.buf = np.zeros(nbytes, dtype=np.uint8)
+    def array(self, dtype, count): return self.buf.view(dtype)[:count]
+    def free(self): pass
+
+
+MG.ShardedSimulator = FakeSim
+PIN.PinnedBuffer = FakePinned
+
+if __name__ == "__main__":
+    import bench
+    sys.argv = ["bench.py", "--gpus", sys.argv[1], "--qubits", "12", "--steps", "2", "--warmup", "3",
+                "--tile-bits", "6", "--low-bits", "2"]
+    bench.main()

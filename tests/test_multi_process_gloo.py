@@ -31,3 +31,24 @@ def test_sharded_run_across_processes(tmp_path, world):
         want = O.simulate(validate_circuit_dict(cd))
         assert np.abs(got - want).max() <= 1e-12, name
         assert int((tmp_path / f"{name}_swaps.txt").read_text()) >= 1, name
+
+
+def test_bench_multi_control_flow_on_cpu(tmp_path):
+    """bench.py --gpus 2 with the GPU objects replaced by emulator fakes (tests/bench_multi_fake.py):
+    the N > 1 code path runs end to end over gloo and prints one well-formed JSON line."""
+    import json
+    world = 2
+    port = 29800 + (os.getpid() % 150)
+    procs = []
+    for rank in range(world):
+        env = dict(os.environ, RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world),
+                   MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1")
+        procs.append(subprocess.Popen([sys.executable, str(ROOT / "tests" / "bench_multi_fake.py"), str(world)],
+                                      env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=300) for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(o[1][-2000:] for o in outs)
+    line = json.loads(outs[0][0].strip().splitlines()[-1])
+    assert line["n_gpus"] == 2 and line["scaling"] == "weak" and line["config"]["n_qubits"] == 12
+    assert line["config"]["swaps_per_step"] >= 1 and line["config"]["plan"] == "default planner options"
+    assert line["e2e"]["value"] > 0 and line["roofline"]["bound"] == "hbm" and "nvlink" in line
+    assert outs[1][0].strip() == ""                                  # only rank 0 prints
