@@ -359,7 +359,7 @@ def bench_multi(args) -> None:
     g = int(math.log2(world))
     n = args.qubits if args.qubits is not None else 30 + g
     cd, info = workload(n)
-    sim = ShardedSimulator(n, dtype)
+    sim = ShardedSimulator(n, dtype, fused_exchange=True) if args.fused_exchange else ShardedSimulator(n, dtype)
     rank, dist, st = sim.rank, sim.dist, sim.shard.state
     ckw = dict(tile_bits=args.tile_bits, low_bits=args.low_bits, max_rounds=args.max_rounds)
     t0 = time.perf_counter()
@@ -429,7 +429,8 @@ def bench_multi(args) -> None:
         ms_per_step = total_ms / args.steps
         pass_ms = [ms for ms, kind, _ in per_launch if kind == 10]
         swap_ms = [(ms, kind - 20) for ms, kind, _ in per_launch if 20 <= kind < 30]
-        fused_ms = [(ms, kind - 30) for ms, kind, _ in per_launch if kind >= 30]
+        fused_ms = [(ms, kind - 30) for ms, kind, _ in per_launch if 30 <= kind < 40]
+        scatter_ms = [(ms, kind - 40) for ms, kind, _ in per_launch if kind >= 40]
         avg_pass_ms = float(np.mean(pass_ms))
         alg_bytes = 2 * amp_bytes * (1 << n_loc)
         peak, peak_src = _peaks()
@@ -464,8 +465,13 @@ def bench_multi(args) -> None:
                                      "ms": [round(ms, 3) for ms, _ in fused_ms[-max(1, len(fused_ms) // max(args.steps, 1)):]] if fused_ms else [],
                                      "what": "last pass of a stage split into 2^s blocks, exchange of each block pair on a second "
                                              "stream while the next block is computed (qsv_pass_swap_overlapped)"},
+            "scatter_pass": {"enabled": bool(getattr(sim, "fused_exchange", False)),
+                             "count_per_step": len(scatter_ms) // max(args.steps, 1),
+                             "ms": [round(ms, 3) for ms, _ in scatter_ms[-max(1, len(scatter_ms) // max(args.steps, 1)):]] if scatter_ms else [],
+                             "what": "last pass of a stage fused with the exchange: its stores go straight into the second "
+                                     "buffers of the peers over NVLink (qsv_pass_scatter, --fused-exchange; 2x shard memory)"},
             "nvlink": {"path": "peer-memory kernel (CUDA IPC, loads/stores over NVLink)" if sim.peer_swap
-                       else f"chunked ncclSend/ncclRecv ({sim.shard.peer_error or 'QSV_SWAP=nccl'})", "swaps": nv, "share_of_step": (sum(ms for ms, _ in swap_ms) + sum(ms for ms, _ in fused_ms)) / total_ms,
+                       else f"chunked ncclSend/ncclRecv ({sim.shard.peer_error or 'QSV_SWAP=nccl'})", "swaps": nv, "share_of_step": (sum(ms for ms, _ in swap_ms) + sum(ms for ms, _ in fused_ms) + sum(ms for ms, _ in scatter_ms)) / total_ms,
                        "peak_gbs_per_direction": 900.0},
             "gpu_launches": len(per_launch) + (0 if prog.fused_init else 2 * args.steps),
             "clocks": clk,
@@ -501,6 +507,8 @@ def main() -> None:
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-zero-support", action="store_true")
+    ap.add_argument("--fused-exchange", action="store_true",
+                    help="N > 1: second buffer per shard, the pass before a swap stores straight into the peers (qsv_pass_scatter)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     global WORKLOAD

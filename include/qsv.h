@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define QSV_ABI_VERSION 5
+#define QSV_ABI_VERSION 6
 
 /* dtypes (wenbo_engine/storage/block_store.py:11 fixes complex64; the oracle is complex128) */
 #define QSV_C64  0
@@ -223,6 +223,28 @@ int qsv_program_run_range(qsv_handle *h, qsv_program *p, int first_pass, int n_p
  * "pass, then swap" (pass not specialised / tile touches the swapped bits / peers not mapped). */
 int qsv_pass_swap_overlapped(qsv_handle *h, qsv_program *p, int pass_index, int n_swap, const int *global_bits,
                              const int *local_bits, int *overlapped);
+/* SCATTER PASS: pass `pass_index` FUSED with the exchange that follows it — one kernel computes the pass
+ * and stores every amplitude where it lives AFTER the swap of local bits local_bits[i] with rank bits
+ * global_bits[i]: into the second buffer ("shadow") of this GPU or, by plain stores through NVLink,
+ * of a peer.  No separate swap kernel, no additional HBM sweep; the shard and its shadow exchange
+ * roles afterwards (qsv_device_ptr changes).  Needs 2x the shard in HBM and the specialised kernels.
+ *   qsv_shadow_ptr               allocate the shadow (first call) and return its device pointer
+ *   qsv_comm_shadow_ipc_handle   64-byte CUDA IPC handle of the shadow (one process per GPU)
+ *   qsv_comm_set_shadow_peers    world x 64 bytes of those handles; after qsv_comm_set_peers
+ *   qsv_scatter_set_targets      the same wiring from raw device pointers valid in THIS process
+ *                                (current[r], shadow[r] for every rank r; several shards of one process)
+ *   qsv_pass_scatter_prepare     build / load the kernel ahead of time
+ *   qsv_pass_scatter             run it; collective over the 2^n_swap ranks.  With an NCCL communicator
+ *                                a stream-ordered barrier follows the kernel; without one (same-process
+ *                                shards) the caller synchronises all handles before the next step.
+ *                                *fused = 0: conditions not met, "pass, then qsv_swap_global_local" ran. */
+int qsv_shadow_ptr(qsv_handle *h, void **ptr);
+int qsv_comm_shadow_ipc_handle(qsv_handle *h, void *out64);
+int qsv_comm_set_shadow_peers(qsv_handle *h, const void *handles);
+int qsv_scatter_set_targets(qsv_handle *h, void *const *current, void *const *shadow);
+int qsv_pass_scatter_prepare(qsv_handle *h, qsv_program *p, int pass_index, int n_swap, const int *local_bits);
+int qsv_pass_scatter(qsv_handle *h, qsv_program *p, int pass_index, int n_swap, const int *global_bits,
+                     const int *local_bits, int *fused);
 /* qsv_program_create SPECIALISES each 2^11-amplitude pass (complex128 and complex64) at run time (NVRTC, sm_100a): the same ring
  * kernel with the pass's bit positions and op sequence as straight-line code and the coefficients
  * in the kernel-parameter bank; cubins are cached by pass STRUCTURE (in memory and under
@@ -238,6 +260,11 @@ int qsv_jit_stats(int *compiled, int *disk_hits, int *mem_hits, int *failed, dou
 /* The CUDA source qsv_program_create would hand to NVRTC for this pass (inspection / profiling). */
 int qsv_jit_source(const qsv_pass *pass, const qsv_op *ops, int dtype, char *out, size_t cap, size_t *needed);
 int qsv_jit_build_pass(const qsv_pass *pass, const qsv_op *ops, int dtype, size_t *cubin_bytes, char *log, size_t log_cap);
+/* The same two for the SCATTER variant of the pass (stores redirected by the swapped local bits). */
+int qsv_jit_source_scatter(const qsv_pass *pass, const qsv_op *ops, int dtype, int n_swap, const int *local_bits,
+                           char *out, size_t cap, size_t *needed);
+int qsv_jit_build_scatter(const qsv_pass *pass, const qsv_op *ops, int dtype, int n_swap, const int *local_bits,
+                          size_t *cubin_bytes, char *log, size_t log_cap);
 
 /* --------------------------------------------------------------- reductions ---- */
 int qsv_norm2(qsv_handle *h, double *out);   /* sum |amp|^2 of the LOCAL shard */

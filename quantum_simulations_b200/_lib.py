@@ -83,10 +83,20 @@ SIGNATURES = {
     "qsv_program_destroy": (C.c_int, [_H, _P]),
     "qsv_program_run_range": (C.c_int, [_H, _P, C.c_int, C.c_int]),
     "qsv_pass_swap_overlapped": (C.c_int, [_H, _P, C.c_int, C.c_int, _ip, _ip, _ip]),
+    "qsv_shadow_ptr": (C.c_int, [_H, C.POINTER(C.c_void_p)]),
+    "qsv_comm_shadow_ipc_handle": (C.c_int, [_H, C.c_void_p]),
+    "qsv_comm_set_shadow_peers": (C.c_int, [_H, C.c_void_p]),
+    "qsv_scatter_set_targets": (C.c_int, [_H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "qsv_pass_scatter_prepare": (C.c_int, [_H, _P, C.c_int, C.c_int, _ip]),
+    "qsv_pass_scatter": (C.c_int, [_H, _P, C.c_int, C.c_int, _ip, _ip, _ip]),
     "qsv_set_option": (C.c_int, [_H, C.c_int, C.c_longlong]),
     "qsv_jit_stats": (C.c_int, [_ip, _ip, _ip, _ip, _dp]),
     "qsv_jit_source": (C.c_int, [C.POINTER(QsvPass), C.POINTER(QsvOp), C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "qsv_jit_build_pass": (C.c_int, [C.POINTER(QsvPass), C.POINTER(QsvOp), C.c_int, C.POINTER(C.c_size_t), C.c_char_p, C.c_size_t]),
+    "qsv_jit_source_scatter": (C.c_int, [C.POINTER(QsvPass), C.POINTER(QsvOp), C.c_int, C.c_int, _ip, C.c_char_p, C.c_size_t,
+                                        C.POINTER(C.c_size_t)]),
+    "qsv_jit_build_scatter": (C.c_int, [C.POINTER(QsvPass), C.POINTER(QsvOp), C.c_int, C.c_int, _ip, C.POINTER(C.c_size_t),
+                                       C.c_char_p, C.c_size_t]),
     "qsv_norm2": (C.c_int, [_H, _dp]),
     "qsv_sample": (C.c_int, [_H, C.c_uint64, C.c_int, _dp, C.POINTER(C.c_uint64)]),
     "qsv_probabilities": (C.c_int, [_H, C.c_int, _ip, _dp]),

@@ -53,6 +53,11 @@ struct qsv_program {
     std::vector<cudaKernel_t> jit;
     std::vector<std::vector<double>> jit_coefs;
     std::vector<std::vector<float>> jit_coefs_f;      // the same values for complex64 kernels
+    // scatter passes (pass fused with the exchange after it): host copy of the ops for their
+    // generator, kernels keyed by (pass index, swapped local bits)
+    std::vector<qsv_op> h_ops;
+    struct ScatterKernel { int pass_index; int n; int bits[3]; cudaKernel_t fn; };
+    std::vector<ScatterKernel> scatter;
 };
 
 struct qsv_handle {
@@ -63,6 +68,12 @@ struct qsv_handle {
     size_t n_amps = 0;            // local amplitudes
     size_t amp_bytes = 16;
     void *d_state = nullptr;
+    // scatter passes write into a second buffer of the same size (allocated on demand); the two
+    // exchange roles after every scatter pass.  scat_cur[r] / scat_other[r] = rank r's current and
+    // second buffer as seen from this process (same-process pointers or CUDA IPC mappings).
+    void *d_shadow = nullptr;
+    std::vector<void *> scat_cur, scat_other;
+    bool scat_ready = false, scat_ipc = false;
     cudaStream_t stream = nullptr;
     // scratch for reductions / one-shot passes
     double *d_partials = nullptr; size_t n_partials = 0;

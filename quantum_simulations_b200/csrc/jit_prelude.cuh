@@ -43,6 +43,10 @@ typedef double JR;
 __device__ __forceinline__ uint32_t jit_slot(uint32_t x) { return tile_swizzle<3>(x); }
 #endif
 
+// targets of a scatter pass (pass fused with the exchange that follows it): p[x] = the second buffer
+// of the rank whose swapped rank bits equal x, keep = this rank's swapped bits at the local positions
+struct JitDst { JV *p[8]; unsigned long long keep; };
+
 struct JitRingSmem {
     JV buf[JIT_NBUF][2048];
     unsigned long long full[JIT_NBUF];

@@ -183,7 +183,13 @@ int qsv_destroy(qsv_handle *h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     auto t1 = now();
+    if (h->scat_ipc) {                              // every mapped peer buffer is in one of the two tables
+        for (auto *tab : {&h->scat_cur, &h->scat_other})
+            for (size_t r = 0; r < tab->size(); ++r) if ((*tab)[r] && (int)r != h->rank) cudaIpcCloseMemHandle((*tab)[r]);
+        if (h->comm) ((qsvx::Comm *)h->comm)->peer.clear();
+    }
     qsv_comm_teardown(h);
+    if (h->d_shadow) cudaFree(h->d_shadow);
     for (auto &t : h->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     if (h->t0) { cudaEventDestroy(h->t0); cudaEventDestroy(h->t1); }
     auto t2 = now();
@@ -587,6 +593,7 @@ int qsv_program_create(qsv_handle *h, const qsv_pass *passes, int n_passes, cons
         delete p;
         return QSV_ECUDA;
     }
+    if (ops && total_ops) p->h_ops.assign(ops, ops + total_ops);      // scatter kernels are generated on demand
     // specialise every eligible pass (complex128 ring tiles); the rest is interpreted
     p->jit.assign(n_passes, nullptr);
     p->jit_coefs.assign(n_passes, {});
@@ -721,6 +728,204 @@ int qsv_pass_swap_overlapped(qsv_handle *h, qsv_program *p, int pass_index, int 
     QSV_CUDA(h, cudaEventDestroy(ev));
     if (overlapped) *overlapped = 1;
     return QSV_OK;
+}
+
+// ------------------------------------------------------------------ scatter pass ----
+int qsv_shadow_ptr(qsv_handle *h, void **ptr) {
+    QSV_CHECK_H(h);
+    QSV_CUDA(h, cudaSetDevice(h->device));
+    if (!h->d_shadow) {
+        cudaError_t e = cudaMalloc(&h->d_shadow, h->n_amps * h->amp_bytes);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            h->d_shadow = nullptr;
+            QSV_FAIL(h, e == cudaErrorMemoryAllocation ? QSV_ENOMEM : QSV_ECUDA, "shadow buffer (%zu bytes): %s",
+                     h->n_amps * h->amp_bytes, cudaGetErrorString(e));
+        }
+    }
+    if (ptr) *ptr = h->d_shadow;
+    return QSV_OK;
+}
+
+int qsv_comm_shadow_ipc_handle(qsv_handle *h, void *out64) {
+    QSV_CHECK_H(h);
+    if (!out64) QSV_FAIL(h, QSV_EINVAL, "shadow_ipc_handle: null output");
+    int rc = qsv_shadow_ptr(h, nullptr);
+    if (rc) return rc;
+    cudaIpcMemHandle_t mh;
+    QSV_CUDA(h, cudaIpcGetMemHandle(&mh, h->d_shadow));
+    memcpy(out64, &mh, 64);
+    return QSV_OK;
+}
+
+int qsv_comm_set_shadow_peers(qsv_handle *h, const void *handles) {
+    QSV_CHECK_H(h);
+    auto *c = (qsvx::Comm *)h->comm;
+    if (!handles || !c || !c->peers_ready) QSV_FAIL(h, QSV_ECOMM, "set_shadow_peers: call qsv_comm_set_peers first");
+    if (h->scat_ready) QSV_FAIL(h, QSV_EINVAL, "set_shadow_peers: targets are already wired");
+    int rc = qsv_shadow_ptr(h, nullptr);
+    if (rc) return rc;
+    std::vector<void *> other(h->world, nullptr);
+    for (int r = 0; r < h->world; ++r) {
+        if (r == h->rank) { other[r] = h->d_shadow; continue; }
+        cudaIpcMemHandle_t mh;
+        memcpy(&mh, (const char *)handles + 64 * r, 64);
+        cudaError_t e = cudaIpcOpenMemHandle(&other[r], mh, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            for (int q = 0; q < r; ++q) if (q != h->rank && other[q]) cudaIpcCloseMemHandle(other[q]);
+            QSV_FAIL(h, QSV_ECOMM, "cudaIpcOpenMemHandle(shadow of rank %d): %s", r, cudaGetErrorString(e));
+        }
+    }
+    h->scat_cur = c->peer;
+    h->scat_other = other;
+    h->scat_ready = h->scat_ipc = true;
+    return QSV_OK;
+}
+
+int qsv_scatter_set_targets(qsv_handle *h, void *const *current, void *const *shadow) {
+    QSV_CHECK_H(h);
+    if (!current || !shadow) QSV_FAIL(h, QSV_EINVAL, "scatter_set_targets: null tables");
+    if (h->scat_ipc) QSV_FAIL(h, QSV_EINVAL, "scatter_set_targets: targets are already wired through CUDA IPC");
+    int rc = qsv_shadow_ptr(h, nullptr);
+    if (rc) return rc;
+    if (current[h->rank] != h->d_state || shadow[h->rank] != h->d_shadow)
+        QSV_FAIL(h, QSV_EINVAL, "scatter_set_targets: entry %d must be this handle's own buffers", h->rank);
+    h->scat_cur.assign(current, current + h->world);
+    h->scat_other.assign(shadow, shadow + h->world);
+    h->scat_ready = true;
+    return QSV_OK;
+}
+
+static bool scatter_bits_ok(qsv_handle *h, int n_swap, const int *local_bits) {
+    if (n_swap < 1 || n_swap > 3 || !local_bits) return false;
+    for (int i = 0; i < n_swap; ++i) {
+        if (local_bits[i] < 0 || local_bits[i] >= h->n_local) return false;
+        for (int j = 0; j < i; ++j) if (local_bits[i] == local_bits[j]) return false;
+    }
+    return true;
+}
+
+// kernel of (pass, swapped local bits): program cache, then the cubin caches / NVRTC of jit.cuh
+static cudaKernel_t scatter_kernel(qsv_handle *h, qsv_program *p, int i, int n_swap, const int *local_bits) {
+    for (auto &k : p->scatter)
+        if (k.pass_index == i && k.n == n_swap && !memcmp(k.bits, local_bits, sizeof(int) * n_swap)) return k.fn;
+    if (!h->jit || !qsvjit::enabled() || h->force_simple_pass || !p->jit[i]) return nullptr;
+    qsvjit::Scatter sc;
+    sc.n = n_swap;
+    for (int k = 0; k < n_swap; ++k) sc.local_bits[k] = local_bits[k];
+    std::vector<std::string> srcs(1);
+    std::vector<double> coefs;                      // same op order as the plain kernel: p->jit_coefs[i] is reused
+    const qsv_op *ops = p->h_ops.empty() ? nullptr : p->h_ops.data() + p->op_offset[i];
+    if (!qsvjit::generate(p->passes[i], ops, srcs[0], coefs, h->dtype == QSV_C64, &sc)) return nullptr;
+    std::vector<qsvjit::Kernel> ks;
+    std::string err;
+    qsvjit::resolve(h->device, srcs, ks, err);
+    if (!err.empty()) h->err = "jit (scatter pass): " + err;
+    qsv_program::ScatterKernel e{i, n_swap, {0, 0, 0}, ks[0].fn};
+    for (int k = 0; k < n_swap; ++k) e.bits[k] = local_bits[k];
+    p->scatter.push_back(e);                        // a failed build is remembered as well (fn == nullptr)
+    return ks[0].fn;
+}
+
+int qsv_pass_scatter_prepare(qsv_handle *h, qsv_program *p, int pass_index, int n_swap, const int *local_bits) {
+    QSV_CHECK_H(h);
+    if (!p || pass_index < 0 || (size_t)pass_index >= p->passes.size() || !scatter_bits_ok(h, n_swap, local_bits))
+        QSV_FAIL(h, QSV_EINVAL, "pass_scatter_prepare: bad arguments");
+    QSV_CUDA(h, cudaSetDevice(h->device));
+    return scatter_kernel(h, p, pass_index, n_swap, local_bits) ? QSV_OK : QSV_EINVAL;
+}
+
+int qsv_pass_scatter(qsv_handle *h, qsv_program *p, int pass_index, int n_swap, const int *global_bits,
+                     const int *local_bits, int *fused) {
+    QSV_CHECK_H(h);
+    if (fused) *fused = 0;
+    if (!p || pass_index < 0 || (size_t)pass_index >= p->passes.size()) QSV_FAIL(h, QSV_EINVAL, "pass_scatter: bad pass");
+    const int g = h->n_qubits - h->n_local;
+    if (!scatter_bits_ok(h, n_swap, local_bits) || !global_bits || n_swap > g) QSV_FAIL(h, QSV_EINVAL, "pass_scatter: bad swap bits");
+    for (int i = 0; i < n_swap; ++i) {
+        if (global_bits[i] < h->n_local || global_bits[i] >= h->n_qubits) QSV_FAIL(h, QSV_EINVAL, "pass_scatter: global bit %d is not a rank bit", global_bits[i]);
+        for (int j = 0; j < i; ++j) if (global_bits[i] == global_bits[j]) QSV_FAIL(h, QSV_EINVAL, "pass_scatter: repeated bit");
+    }
+    QSV_CUDA(h, cudaSetDevice(h->device));
+    auto *c = (qsvx::Comm *)h->comm;
+    cudaKernel_t fn = nullptr;
+    if (h->scat_ready && p->passes[pass_index].n_active < 0) fn = scatter_kernel(h, p, pass_index, n_swap, local_bits);
+    if (!fn) {                                       // every rank takes the same decision: same program, same wiring
+        int rc = qsv_program_run_range(h, p, pass_index, 1);
+        if (rc) return rc;
+        return qsv_swap_global_local(h, n_swap, global_bits, local_bits);
+    }
+    struct { void *p[8]; unsigned long long keep; } dst;
+    dst.keep = 0;
+    for (int i = 0; i < n_swap; ++i)
+        dst.keep |= (unsigned long long)((h->rank >> (global_bits[i] - h->n_local)) & 1) << local_bits[i];
+    for (int x = 0; x < 8; ++x) {
+        dst.p[x] = nullptr;
+        if (x >= (1 << n_swap)) continue;
+        int r = h->rank;
+        for (int i = 0; i < n_swap; ++i) {
+            const int rb = global_bits[i] - h->n_local;
+            r = (r & ~(1 << rb)) | (((x >> i) & 1) << rb);
+        }
+        dst.p[x] = h->scat_other[r];
+        if (!dst.p[x]) QSV_FAIL(h, QSV_ECOMM, "pass_scatter: the second buffer of rank %d is not mapped", r);
+    }
+    {
+        ScopedTimer t(h, 40 + n_swap, pass_index);
+        const uint32_t tiles = (uint32_t)(h->n_amps >> qsvjit::kT);
+        const unsigned grid = tiles < (uint32_t)h->sm_count ? tiles : (unsigned)h->sm_count;
+        void *state = h->d_state;
+        const double2 *tables = p->d_tables + p->fold_offset[pass_index];
+        unsigned long long rank_bits = (unsigned long long)h->rank << h->n_local;
+        unsigned tb = 0, te = tiles;
+        static const double zero = 0.0;
+        void *coefs = p->jit_coefs[pass_index].empty() ? (void *)&zero
+                    : (h->dtype == QSV_C64 ? (void *)p->jit_coefs_f[pass_index].data() : (void *)p->jit_coefs[pass_index].data());
+        void *args[] = {&state, &tables, &rank_bits, &tb, &te, coefs, &dst};
+        QSV_CUDA(h, cudaLaunchKernel((const void *)fn, dim3(grid), dim3(128 * (qsvjit::groups() + 1)), args, qsvjit::kSmemBytes, h->stream));
+        if (c && c->comm) {                          // all stores of all ranks have landed before anyone reads
+            int rc = swap_barrier(h, c);
+            if (rc) return rc;
+        }
+    }
+    std::swap(h->d_state, h->d_shadow);
+    std::swap(h->scat_cur, h->scat_other);
+    if (c && c->peers_ready) c->peer = h->scat_cur;
+    if (fused) *fused = 1;
+    return QSV_OK;
+}
+
+int qsv_jit_source_scatter(const qsv_pass *pass, const qsv_op *ops, int dtype, int n_swap, const int *local_bits,
+                           char *out, size_t cap, size_t *needed) {
+    if (!pass || (pass->n_ops > 0 && !ops) || n_swap < 1 || n_swap > 3 || !local_bits) return QSV_EINVAL;
+    qsvjit::Scatter sc;
+    sc.n = n_swap;
+    for (int k = 0; k < n_swap; ++k) sc.local_bits[k] = local_bits[k];
+    std::string src;
+    std::vector<double> coefs;
+    if (!qsvjit::generate(*pass, ops, src, coefs, dtype == QSV_C64, &sc)) return QSV_EINVAL;
+    if (needed) *needed = src.size() + 1;
+    if (out && cap) snprintf(out, cap, "%s", src.c_str());
+    return QSV_OK;
+}
+
+int qsv_jit_build_scatter(const qsv_pass *pass, const qsv_op *ops, int dtype, int n_swap, const int *local_bits,
+                          size_t *cubin_bytes, char *log, size_t log_cap) {
+    if (!pass || (pass->n_ops > 0 && !ops) || n_swap < 1 || n_swap > 3 || !local_bits) return QSV_EINVAL;
+    qsvjit::Scatter sc;
+    sc.n = n_swap;
+    for (int k = 0; k < n_swap; ++k) sc.local_bits[k] = local_bits[k];
+    std::string src, msg;
+    std::vector<double> coefs;
+    std::vector<char> cubin;
+    int rc = QSV_OK;
+    if (!qsvjit::generate(*pass, ops, src, coefs, dtype == QSV_C64, &sc)) { msg = "pass is not eligible for a scatter kernel"; rc = QSV_EINVAL; }
+    else if (!qsvjit::nvrtc().load()) { msg = "NVRTC unavailable: " + qsvjit::nvrtc().why; rc = QSV_EIO; }
+    else if (!qsvjit::compile(src, cubin, msg)) rc = QSV_ECUDA;
+    if (cubin_bytes) *cubin_bytes = cubin.size();
+    if (log && log_cap) { snprintf(log, log_cap, "%s", msg.c_str()); }
+    return rc;
 }
 
 int qsv_set_option(qsv_handle *h, int option, long long value) {

@@ -55,7 +55,8 @@ class CudaShard:
         self.rank, self.world = rank, world
         self._uploaded: dict = {}
         self.peer_swap, self.peer_error = False, None
-        self.swaps = self.overlapped_swaps = 0
+        self.fused_exchange, self.fused_error = False, None
+        self.swaps = self.overlapped_swaps = self.fused_swaps = 0
         if world > 1:
             if unique_id is None or len(unique_id) != 128:
                 raise ValueError("world > 1 needs the 128-byte NCCL unique id of rank 0 (nccl_unique_id())")
@@ -87,6 +88,31 @@ class CudaShard:
         lib.qsv_set_option(h, L.OPT_PEER_SWAP, int(self.peer_swap))     # all ranks must take the same path
         return self.peer_swap
 
+    def map_shadows(self, dist) -> bool:
+        """Opt-in (after map_peers): give every shard a second buffer and map the peers' second buffers
+        too, so that a pass followed by a swap runs as ONE kernel that stores its results where they live
+        after the swap (qsv_pass_scatter).  Costs 2x the shard in HBM; returns False, and changes
+        nothing, if any rank cannot allocate or map."""
+        self.fused_error = None
+        if self.world == 1 or not self.peer_swap:
+            return False
+        lib, h = self.state.lib, self.state._h
+        mine = C.create_string_buffer(64)
+        ok = lib.qsv_comm_shadow_ipc_handle(h, mine) == 0
+        if not ok:
+            self.fused_error = (lib.qsv_last_error(h) or b"?").decode(errors="replace")
+        box = [None] * self.world
+        dist.all_gather_object(box, mine.raw if ok else None)
+        mapped = False
+        if all(b is not None for b in box):
+            mapped = lib.qsv_comm_set_shadow_peers(h, C.create_string_buffer(b"".join(box), 64 * self.world)) == 0
+            if not mapped:
+                self.fused_error = (lib.qsv_last_error(h) or b"?").decode(errors="replace")
+        flags = [None] * self.world
+        dist.all_gather_object(flags, bool(mapped))
+        self.fused_exchange = all(flags)                 # all ranks must take the same path
+        return self.fused_exchange
+
     def prepare(self, prog: Program) -> None:
         """Upload (and specialise) every run of passes once; execute() then only replays."""
         run: list = []
@@ -94,7 +120,10 @@ class CudaShard:
             if isinstance(step, PassStep):
                 run.append(step)
             elif run:
-                self._uploaded[id(run[0])] = self.state.upload_steps(run)
+                h = self._uploaded[id(run[0])] = self.state.upload_steps(run)
+                if self.fused_exchange and isinstance(step, SwapStep):
+                    l = (C.c_int * len(step.local_bits))(*step.local_bits)
+                    self.state.lib.qsv_pass_scatter_prepare(self.state._h, h, len(run) - 1, len(step.local_bits), l)
                 run = []
 
     def run_passes(self, steps) -> None:
@@ -120,8 +149,12 @@ class CudaShard:
         ov = C.c_int(0)
         if len(steps) > 1:
             st._ck(lib.qsv_program_run_range(st._h, h, 0, len(steps) - 1))
-        st._ck(lib.qsv_pass_swap_overlapped(st._h, h, len(steps) - 1, s, g, l, C.byref(ov)))
-        self.overlapped_swaps += int(ov.value)
+        if self.fused_exchange:
+            st._ck(lib.qsv_pass_scatter(st._h, h, len(steps) - 1, s, g, l, C.byref(ov)))
+            self.fused_swaps += int(ov.value)
+        else:
+            st._ck(lib.qsv_pass_swap_overlapped(st._h, h, len(steps) - 1, s, g, l, C.byref(ov)))
+            self.overlapped_swaps += int(ov.value)
         self.swaps += 1
         if temp:
             self.state.release_program(h)
@@ -172,7 +205,9 @@ class ShardedSimulator:
     the one-time work (rendezvous, NCCL communicator, shard allocation); ``simulate`` runs one
     circuit from |0...0> and returns THIS rank's shard in host memory."""
 
-    def __init__(self, n_qubits: int, dtype="complex128"):
+    def __init__(self, n_qubits: int, dtype="complex128", fused_exchange: bool | None = None):
+        """fused_exchange (default: env QSV_FUSED_EXCHANGE=1): second buffer per shard, passes before a
+        swap run as scatter passes (see CudaShard.map_shadows)."""
         self.rank, self.local_rank, self.world = dist_env()
         self.n = n_qubits
         self.g = int(math.log2(self.world))
@@ -183,6 +218,9 @@ class ShardedSimulator:
         uid = share_unique_id(self.dist, self.rank) if self.world > 1 else None
         self.shard = CudaShard(n_qubits, self.rank, self.world, dtype, self.local_rank, uid)
         self.peer_swap = self.shard.map_peers(self.dist) if self.world > 1 else False
+        if fused_exchange is None:
+            fused_exchange = os.environ.get("QSV_FUSED_EXCHANGE", "0") == "1"
+        self.fused_exchange = bool(fused_exchange) and self.peer_swap and self.shard.map_shadows(self.dist)
         self.logical_rank, self._flip_mask = self.rank, 0
 
     def plan(self, circuit_dict: dict, **compiler_kw) -> Program:

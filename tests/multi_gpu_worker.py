@@ -52,10 +52,11 @@ def main():
             got = np.concatenate([parts[l ^ mask].numpy().view(np.complex128) for l in range(world)])
             want = CO.simulate_c(cd)
             err = float(np.abs(got - want).max())
-            print(f"{name}: n={n} world={world} max|d|={err:.3e} swaps={sim.shard.swaps} overlapped={sim.shard.overlapped_swaps}", flush=True)
+            print(f"{name}: n={n} world={world} max|d|={err:.3e} swaps={sim.shard.swaps} overlapped={sim.shard.overlapped_swaps} "
+                  f"scatter_passes={sim.shard.fused_swaps}", flush=True)
             worst = max(worst, err)
             if name == "low_then_top":
-                overlapped_seen = sim.shard.overlapped_swaps
+                overlapped_seen = sim.shard.overlapped_swaps + sim.shard.fused_swaps
             from oracle import ref_dense as O
             want_s = O.sample_indices(got, 7, 257)
             if not np.array_equal(samples, want_s):
@@ -82,7 +83,9 @@ def main():
     if rank == 0 and worst > 1e-12:
         raise SystemExit(f"multi-GPU parity failed: {worst}")
     if rank == 0 and sim.peer_swap and overlapped_seen < 1:
-        raise SystemExit("the overlapped pass+swap path was never taken")
+        raise SystemExit("the overlapped pass+swap path (or, with QSV_FUSED_EXCHANGE=1, the scatter pass) was never taken")
+    if rank == 0 and os.environ.get("QSV_FUSED_EXCHANGE") == "1" and not sim.fused_exchange:
+        raise SystemExit(f"QSV_FUSED_EXCHANGE=1 but the second buffers could not be wired: {sim.shard.fused_error}")
 
 
 if __name__ == "__main__":

@@ -1,4 +1,5 @@
 """Real multi-GPU parity (needs >= 2 GPUs on the box; skipped otherwise)."""
+import os
 import subprocess
 import sys
 from pathlib import Path
@@ -24,3 +25,97 @@ def test_sharded_gpus_match_oracle(world):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     print(r.stdout[-1500:])
+
+
+# Scatter passes (ABI v6: the pass before a swap stores straight into the peers' second buffers) were
+# written after this round's GPU budget was spent: they build, their addressing is checked on the CPU
+# (tests/test_jit_build.py), but they have not run on hardware yet, so the tests are opt-in.
+scatter_opt_in = pytest.mark.skipif(os.environ.get("QSV_TEST_SCATTER") != "1",
+                                    reason="scatter passes: opt-in until validated on hardware (QSV_TEST_SCATTER=1)")
+
+
+@pytest.mark.gpu
+@scatter_opt_in
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_gpus_with_scatter_passes_match_oracle(world):
+    if _gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(29720 + world),
+           str(ROOT / "tests" / "multi_gpu_worker.py"), "20"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, QSV_FUSED_EXCHANGE="1"))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    first = [ln for ln in r.stdout.splitlines() if ln.startswith("low_then_top")]
+    assert first and "scatter_passes=0" not in first[0]
+    print(r.stdout[-1500:])
+
+
+@pytest.mark.gpu
+@scatter_opt_in
+@pytest.mark.parametrize("dtype,world", [("complex128", 2), ("complex128", 4), ("complex64", 2)])
+def test_scatter_pass_shards_of_one_process_on_one_device(dtype, world):
+    """All shards as handles of THIS process on device 0 (qsv_scatter_set_targets wires raw pointers):
+    every (pass, swap) pair of a sharded plan runs as a scatter pass; the result must equal the oracle."""
+    import ctypes as C
+    import numpy as np
+    from oracle import ref_dense as O
+    from quantum_simulations_b200 import _lib as L, workloads as W
+    from quantum_simulations_b200.circuit import sharding
+    from quantum_simulations_b200.circuit.io import validate_circuit_dict
+    from quantum_simulations_b200.circuit.passes import PassStep, SwapStep
+    from quantum_simulations_b200.kernel.cuda import DeviceState
+    from quantum_simulations_b200.kernel.cuda_dense import circuit_ops
+
+    n, g = 17, world.bit_length() - 1
+    lib = L.load()
+    for cd in (W.random_1q_cz(n, 16, 99), W.qft(n), W.random_mixed(n, 200, 4)):
+        cd = validate_circuit_dict(cd)
+        prog = sharding.plan(circuit_ops(cd), n, n - g, dtype, swap_anywhere=True, rank_flips=True)
+        assert prog.stats["swaps"] >= 1
+        shards = [DeviceState(n, dtype, 0, r, world) for r in range(world)]
+        try:
+            cur = (C.c_void_p * world)(*[s.device_ptr()[0] for s in shards])
+            sh = (C.c_void_p * world)()
+            for r, s in enumerate(shards):
+                p = C.c_void_p()
+                s._ck(lib.qsv_shadow_ptr(s._h, C.byref(p)))
+                sh[r] = p.value
+            for s in shards:
+                s._ck(lib.qsv_scatter_set_targets(s._h, cur, sh))
+                if not prog.fused_init:
+                    s.init_zero()
+            run, fused_total = [], 0
+            for step in list(prog.steps) + [None]:
+                if isinstance(step, PassStep):
+                    run.append(step)
+                    continue
+                if isinstance(step, SwapStep):
+                    assert run, "a swap with no pass before it: nothing to fuse in this plan"
+                    k = len(step.global_bits)
+                    gb, lb = (C.c_int * k)(*step.global_bits), (C.c_int * k)(*step.local_bits)
+                    for s in shards:
+                        h = s.upload_steps(run)
+                        if len(run) > 1:
+                            s._ck(lib.qsv_program_run_range(s._h, h, 0, len(run) - 1))
+                        fused = C.c_int(0)
+                        s._ck(lib.qsv_pass_scatter(s._h, h, len(run) - 1, k, gb, lb, C.byref(fused)))
+                        assert fused.value == 1, (lib.qsv_last_error(s._h) or b"").decode()
+                        fused_total += 1
+                        s.release_program(h)
+                    for s in shards:                      # no communicator: the caller is the barrier
+                        s.sync()
+                elif run:
+                    for s in shards:
+                        h = s.upload_steps(run)
+                        s.replay(h)
+                        s.release_program(h)
+                        s.sync()
+                run = []
+            got = np.concatenate([shards[l ^ prog.rank_flip_mask].download() for l in range(world)])
+        finally:
+            for s in shards:
+                s.close()
+        want = O.simulate(cd).astype(got.dtype)
+        tol = 1e-12 if dtype == "complex128" else 2e-5
+        assert fused_total == world * prog.stats["swaps"]
+        assert np.abs(got - want).max() <= tol
