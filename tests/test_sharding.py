@@ -82,3 +82,44 @@ def test_x_on_rank_bit_is_materialised():
     n = 9
     gates = [{"qubits": [n - 1], "gate": "X"}, {"qubits": [0], "gate": "H"}, {"qubits": [n - 1, 0], "gate": "CNOT"}]
     check({"number_of_qubits": n, "gates": gates}, 1, tile_bits=6, low_bits=2)
+
+
+@pytest.mark.parametrize("g", [1, 2, 3])
+@pytest.mark.parametrize("workload", ["random_1q_cz", "random_mixed", "qft"])
+def test_planned_placements_incl_exchange_candidates_match_oracle(workload, g):
+    """sharding.plan from |0...0>: the initial placement is chosen among block and (with swap_anywhere)
+    plain-exchange candidates; whatever wins must give the oracle's state in the identity layout."""
+    from quantum_simulations_b200.circuit import sharding
+    picked_exchange = 0
+    for n, seed in ((14, 1234), (15, 5), (16, 77)):
+        cd = {"random_1q_cz": lambda: W.random_1q_cz(n, 20, seed), "random_mixed": lambda: W.random_mixed(n, 160, seed),
+              "qft": lambda: W.qft(n)}[workload]()
+        kw = dict(tile_bits=7, low_bits=2, swap_anywhere=True, rank_flips=True)
+        prog = sharding.plan(ir_ops(cd), n, n - g, **kw)
+        base = sharding.candidate_placements(n, g)
+        assert prog.stats["init_pos"] in sharding.candidate_placements(n, g, direct=True)
+        picked_exchange += prog.stats["init_pos"] not in base
+        psi = np.zeros(1 << n, dtype=np.complex128)
+        psi[0] = 1
+        psi = run_program_sharded(prog, psi)
+        if prog.rank_flip_mask:
+            shards = psi.reshape(1 << g, -1)
+            psi = np.concatenate([shards[r ^ prog.rank_flip_mask] for r in range(1 << g)])
+        assert prog.final_pos == list(range(n))
+        assert np.abs(psi - O.simulate(validate_circuit_dict(cd))).max() <= 1e-12
+    # every exchange candidate on its own, not only when the cost model picks it
+    n = 14
+    cd = {"random_1q_cz": lambda: W.random_1q_cz(n, 20, 3), "random_mixed": lambda: W.random_mixed(n, 160, 3),
+          "qft": lambda: W.qft(n)}[workload]()
+    extra = [p for p in sharding.candidate_placements(n, g, direct=True) if p not in sharding.candidate_placements(n, g)]
+    assert extra
+    for init in extra:
+        prog = PassCompiler(n, n - g, tile_bits=7, low_bits=2, swap_anywhere=True, rank_flips=True).compile(
+            ir_ops(cd), init_pos=init, home_pos=list(range(n)))
+        psi = np.zeros(1 << n, dtype=np.complex128)
+        psi[0] = 1
+        psi = run_program_sharded(prog, psi)
+        if prog.rank_flip_mask:
+            shards = psi.reshape(1 << g, -1)
+            psi = np.concatenate([shards[r ^ prog.rank_flip_mask] for r in range(1 << g)])
+        assert np.abs(psi - O.simulate(validate_circuit_dict(cd))).max() <= 1e-12
