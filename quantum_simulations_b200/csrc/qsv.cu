@@ -633,6 +633,15 @@ static int launch_pass_jit_range(qsv_handle *h, qsv_program *p, int i, uint32_t 
 
 static int launch_pass_jit(qsv_handle *h, qsv_program *p, int i) {
     ScopedTimer t(h, 10, i);
+    if (p->passes[i].zero_input && !getenv("QSV_INIT_PASS_FULL")) {
+        // Fused |0...0> initialisation: the pass reads nothing, and every tile but the one that holds
+        // amplitude 0 (tile 0 of rank 0) is identically zero before AND after it (gates are linear;
+        // the store flips only move whole tiles).  So: zero-fill the shard at write bandwidth and run
+        // the arithmetic for that one tile only.  QSV_INIT_PASS_FULL=1 runs every tile as before.
+        QSV_CUDA(h, cudaMemsetAsync(h->d_state, 0, h->n_amps * h->amp_bytes, h->stream));
+        if (h->rank != 0) return QSV_OK;
+        return launch_pass_jit_range(h, p, i, 0u, 1u, h->stream);
+    }
     const int na = p->passes[i].n_active;                      // zero-support skipping: 2^n_active tiles
     const uint32_t tiles = na >= 0 ? (uint32_t)1 << na : (uint32_t)(h->n_amps >> qsvjit::kT);
     return launch_pass_jit_range(h, p, i, 0u, tiles, h->stream);
