@@ -236,22 +236,32 @@ def bench_single(args) -> None:
             st_.init_zero()
         st_.replay(handle_)
 
-    with DeviceState(n, dtype, args.device) as st:
-        handle = st.upload_program(prog)
-        for _ in range(args.warmup):
-            one_step(st, handle, prog)
-        st.sync()
-        clocks = ClockSampler(args.device).start()
-        st.timing(True)
-        st.timer_start()
-        for _ in range(args.steps):
-            one_step(st, handle, prog)
-        total_ms = st.timer_stop()
-        per_launch = st.take_timings()
-        st.timing(False)
-        clk = clocks.stop()
-        norm = st.norm2()
-    if abs(norm - 1.0) > (1e-9 if dtype == "complex128" else 1e-4):
+    def timed_run():
+        with DeviceState(n, dtype, args.device) as st:
+            handle = st.upload_program(prog)
+            for _ in range(args.warmup):
+                one_step(st, handle, prog)
+            st.sync()
+            clocks = ClockSampler(args.device).start()
+            st.timing(True)
+            st.timer_start()
+            for _ in range(args.steps):
+                one_step(st, handle, prog)
+            total_ms_ = st.timer_stop()
+            per_launch_ = st.take_timings()
+            st.timing(False)
+            return total_ms_, per_launch_, clocks.stop(), st.norm2()
+
+    norm_tol = 1e-9 if dtype == "complex128" else 1e-4
+    total_ms, per_launch, clk, norm = timed_run()
+    init_note = None
+    if abs(norm - 1.0) > norm_tol and prog.fused_init and "QSV_INIT_PASS_FULL" not in os.environ:
+        # insurance for the zero-fill + one-tile form of the first pass (written after the last GPU run
+        # of round 1): fall back to the full zero-input launch, which is the measured and tested one
+        os.environ["QSV_INIT_PASS_FULL"] = "1"
+        init_note = f"FALLBACK: QSV_INIT_PASS_FULL=1 (norm was {norm} with the zero-fill form of the first pass)"
+        total_ms, per_launch, clk, norm = timed_run()
+    if abs(norm - 1.0) > norm_tol:
         raise SystemExit(f"bench: state norm {norm} != 1 — result invalid")
 
     ms_per_step = total_ms / args.steps
@@ -336,7 +346,7 @@ def bench_single(args) -> None:
                             "the tile that holds amplitude 0 is computed, every other tile is zero before and after a linear "
                             "pass) — per_pass_ms[0]; not part of the roofline average") if prog.fused_init
                            else "cudaMemset + set amp[0] before the passes",
-                   "init_pass_ms": round(float(np.mean(init_ms)), 3) if init_ms else None,
+                   "init_pass_ms": round(float(np.mean(init_ms)), 3) if init_ms else None, "init_note": init_note,
                    "l2_hygiene": f"state {(1 << n) * amp_bytes / 2**30:.0f} GiB >> 126 MB L2: every pass streams from HBM",
                    "host_compile_s": compile_s},
         "gate_layers_per_s": info["levels"] / (ms_per_step * 1e-3),

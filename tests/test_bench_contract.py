@@ -46,3 +46,15 @@ def test_cli_surface():
     assert out.returncode == 0
     for flag in ("--gpus", "--steps", "--warmup", "--impl"):
         assert flag in out.stdout
+
+
+def test_single_gpu_control_flow_on_cpu():
+    """bench.py at N = 1 with the GPU objects replaced by emulator fakes (tests/bench_single_fake.py):
+    the code path the driver runs assembles a well-formed line (incl. roofline without the init pass)."""
+    out = subprocess.run([sys.executable, str(ROOT / "tests" / "bench_single_fake.py")], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-3000:]
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    assert r["n_gpus"] == 1 and r["config"]["n_qubits"] == 12 and r["e2e"]["value"] > 0 and r["cpu_baseline"]["value"] > 0
+    assert r["config"]["init_note"] is None and r["config"]["init_pass_ms"] is not None
+    assert r["roofline"]["launches_timed"] == (r["config"]["passes_per_step"] - 1) * r["steps"]
+    assert r["zero_support_skipping"]["ms_per_step"] > 0
