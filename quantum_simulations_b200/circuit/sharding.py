@@ -36,15 +36,23 @@ def fuse_init(prog: Program) -> Program:
     return prog
 
 
-def estimate_seconds(prog: Program) -> float:
+def estimate_seconds(prog: Program, fused_exchange: bool = False) -> float:
+    """fused_exchange: a swap right after a pass runs inside that pass (scatter pass, qsv_pass_scatter):
+    the pair costs the longer of the two instead of their sum."""
     amp = 16 if prog.dtype == "complex128" else 8
     shard = amp * (1 << prog.n_local)
     t = 0.0
+    last_pass = None
     for s in prog.steps:
         if isinstance(s, PassStep):
-            t += 2 * shard / HBM_BW * (1.0 + 0.012 * s.n_micro_ops)
+            last_pass = 2 * shard / HBM_BW * (1.0 + 0.012 * s.n_micro_ops)
+            t += last_pass
         elif isinstance(s, SwapStep):
-            t += (1.0 - 0.5 ** len(s.global_bits)) * shard / NVLINK_BW
+            x = (1.0 - 0.5 ** len(s.global_bits)) * shard / NVLINK_BW
+            if fused_exchange and last_pass is not None:
+                x = max(0.0, x - last_pass)
+            t += x
+            last_pass = None
     return t
 
 
@@ -149,6 +157,7 @@ def plan(ir_ops, n_qubits: int, n_local: int, dtype: str = "complex128", zero_in
     placement is chosen among a few candidates by the cost model; the final layout is always
     the identity (logical qubit q on physical bit q)."""
     g = n_qubits - n_local
+    fused_exchange = bool(compiler_kw.pop("fused_exchange", False))     # cost model only
     if g == 0:
         return plan_single(ir_ops, n_qubits, dtype, zero_init, **compiler_kw)
     comp = PassCompiler(n_qubits, n_local, dtype, **compiler_kw)
@@ -162,7 +171,7 @@ def plan(ir_ops, n_qubits: int, n_local: int, dtype: str = "complex128", zero_in
             prog = comp.compile(ir_ops, init_pos=init, home_pos=ident)
         except (NotImplementedError, RuntimeError):
             continue
-        t = estimate_seconds(prog)
+        t = estimate_seconds(prog, fused_exchange)
         # the exchange placements must win clearly (a pass saved, not model noise): the block
         # placements are the ones whose swaps overlap with the pass before them
         if best is None or t < best_t * (1.0 if init in base else 0.97):

@@ -230,6 +230,8 @@ class ShardedSimulator:
             raise ValueError("circuit size differs from the simulator's")
         compiler_kw.setdefault("swap_anywhere", bool(self.peer_swap))     # peer kernel: no relabel before a swap
         compiler_kw.setdefault("rank_flips", True)                        # X pending on a rank bit renames shards
+        if getattr(self, "fused_exchange", False):
+            compiler_kw.setdefault("fused_exchange", True)                # cost model: a swap hides the pass before it
         return sharding.plan(circuit_ops(cd), self.n, self.n - self.g, self.dtype.name, **compiler_kw)
 
     def simulate(self, circuit_dict: dict, out: np.ndarray | None = None, **compiler_kw) -> np.ndarray:
