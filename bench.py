@@ -225,6 +225,8 @@ def bench_single(args) -> None:
     t0 = time.perf_counter()
     ckw = dict(tile_bits=args.tile_bits, low_bits=args.low_bits, max_rounds=args.max_rounds,
                defer_diagonals=args.defer_diagonals, fold_tables=not args.no_fold_tables)
+    if args.no_low_store_round:
+        ckw["low_store_round"] = False
     from quantum_simulations_b200.circuit.sharding import plan_single
     prog = plan_single(circuit_ops(cd), n, dtype, True, False, **ckw)      # from |0...0>: free initial placement
     compile_s = time.perf_counter() - t0
@@ -388,6 +390,8 @@ def bench_multi(args) -> None:
     sim = ShardedSimulator(n, dtype, fused_exchange=True) if args.fused_exchange else ShardedSimulator(n, dtype)
     rank, dist, st = sim.rank, sim.dist, sim.shard.state
     ckw = dict(tile_bits=args.tile_bits, low_bits=args.low_bits, max_rounds=args.max_rounds)
+    if args.no_low_store_round:
+        ckw["low_store_round"] = False
     t0 = time.perf_counter()
     prog = sim.plan(cd, **ckw)
     compile_s = time.perf_counter() - t0
@@ -535,6 +539,8 @@ def main() -> None:
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-zero-support", action="store_true")
+    ap.add_argument("--no-low-store-round", action="store_true",
+                    help="experiment: no idle round before stores whose registers hold a low (row) position")
     ap.add_argument("--fused-exchange", action="store_true",
                     help="N > 1: second buffer per shard, the pass before a swap stores straight into the peers (qsv_pass_scatter)")
     args = ap.parse_args()

@@ -479,7 +479,7 @@ class PassCompiler:
                  merge_diagonals: bool = True, fold_tables: bool = True,
                  defer_diagonals: bool = False, absorb: bool = True, allow_swaps: bool = True,
                  swap_anywhere: bool = False, rank_flips: bool = False, park_off_last_round: bool = True,
-                 table_phases: bool = True, eager_flips: bool = True):
+                 table_phases: bool = True, eager_flips: bool = True, low_store_round: bool = True):
         self.n = n_qubits
         self.n_local = n_qubits if n_local is None else n_local
         self.dtype = np.dtype(dtype).name
@@ -518,6 +518,11 @@ class PassCompiler:
         # of the ranks by the runner).  False: such a qubit is swapped in and its flip materialised.
         self.rank_flips = rank_flips
         self.park_off_last_round = park_off_last_round
+        # True: a last round whose registers hold a content that is stored to one of the low (128-byte
+        # row) positions is followed by an idle round that moves the registers elsewhere, so that the
+        # lanes cover whole rows.  False (experiment): store as is — half-row stores that L2 merges,
+        # against one shared-memory round trip less.
+        self.low_store_round = low_store_round
         self.table_phases = table_phases
         # materialise a pending X as soon as its qubit will never be MIXED again (instead of waiting
         # until nothing inspects it either): the not-yet-scheduled ops that inspect it are re-conjugated
@@ -875,7 +880,7 @@ class PassCompiler:
             plan.append((self._idle_regs(lo_store if self.ring else lo_load | lo_store), []))
         if set(plan[0][0]) & lo_load and not self.ring:
             plan.insert(0, (self._idle_regs(lo_load), []))
-        if set(plan[-1][0]) & lo_store:
+        if set(plan[-1][0]) & lo_store and self.low_store_round:
             plan.append((self._idle_regs(lo_store), []))
         if len(plan) == 1:
             # one round = same thread mapping for load and store: only coalesced on both

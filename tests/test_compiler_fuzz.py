@@ -25,7 +25,9 @@ def _case(seed: int):
           W.qft(n)][kind]
     kw = dict(tile_bits=t, low_bits=a, max_rounds=int(rng.integers(2, 6)), swap_anywhere=bool(rng.integers(0, 2)),
               rank_flips=bool(rng.integers(0, 2)), table_phases=bool(rng.integers(0, 2)), absorb=bool(rng.integers(0, 2)))
-    return n, g, validate_circuit_dict(cd), kw, bool(rng.integers(0, 2))
+    planned = bool(rng.integers(0, 2))
+    kw["low_store_round"] = bool(rng.integers(0, 2))        # drawn last: earlier seeds keep their cases
+    return n, g, validate_circuit_dict(cd), kw, planned
 
 
 @pytest.mark.parametrize("block", range(8))
