@@ -27,3 +27,6 @@ run init_full "QSV_INIT_PASS_FULL=1" ""
 run no_low_store_round "QSV_X=0" "--no-low-store-round"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches_r02.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e --no-zero-support > $out/ncu_launches_r02.log 2>&1; echo "ncu list rc=$?"
+# 6. do DFMA and DMMA run on separate pipes?  (mixed_mode* sum_tflops above either single peak = yes)
+mkdir -p tools/_build && nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/_build/fp64_peak tools/fp64_peak.cu \
+  && tools/_build/fp64_peak | tee $out/fp64_peak_mixed.json
