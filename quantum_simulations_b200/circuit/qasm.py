@@ -99,6 +99,8 @@ def qasm_to_ops(text: str, with_statement_index: bool = False):
     stmt_of: list = []
     n_stmt = 0
     n = 0
+    touched: set = set()                            # qubits some gate has acted on (for leading resets)
+    scanned = [0]
 
     # pull out gate definitions first (they contain braces)
     def take_gate(m):
@@ -171,6 +173,18 @@ def qasm_to_ops(text: str, with_statement_index: bool = False):
             n += int(m.group(2))
             continue
         if re.match(r"(creg|barrier|measure)\b", st):
+            continue
+        m = re.fullmatch(r"reset\s+(\w+)\s*(?:\[\s*(\d+)\s*\])?", st)
+        if m and m.group(1) in regs:
+            # reset of a qubit no gate has acted on yet: the run starts from |0...0>, so it is the identity
+            # (QASMBench's bwt / square_root open with such resets); anywhere else it is not unitary
+            off, size = regs[m.group(1)]
+            which = range(off, off + size) if m.group(2) is None else [off + int(m.group(2))]
+            for qs_, _ in ops[scanned[0]:]:                 # incremental: every op is looked at once
+                touched.update(qs_)
+            scanned[0] = len(ops)
+            if any(q in touched for q in which):
+                raise QasmError("'reset' after a gate on the same qubit is not supported (not a unitary gate)")
             continue
         if re.match(r"(reset|if)\b", st):
             raise QasmError(f"'{st.split()[0]}' is not supported (not a unitary gate)")

@@ -129,8 +129,19 @@ def test_errors():
     with pytest.raises(QasmError, match="unsupported gate"):
         qasm_to_ops(HEAD + "qreg q[1]; foo q[0];")
     with pytest.raises(QasmError, match="not supported"):
-        qasm_to_ops(HEAD + "qreg q[1]; reset q[0];")
+        qasm_to_ops(HEAD + "qreg q[1]; h q[0]; reset q[0];")
     with pytest.raises(QasmError, match="out of range"):
         qasm_to_ops(HEAD + "qreg q[1]; h q[3];")
     with pytest.raises(QasmError, match="no name in the reference"):
         qasm_to_dict(HEAD + "qreg q[1]; rz(0.1) q[0];")
+
+
+def test_reset_before_any_gate_is_the_identity_and_later_resets_are_refused():
+    from quantum_simulations_b200.circuit.qasm import QasmError, qasm_to_ops
+    head = 'OPENQASM 2.0;\ninclude "qelib1.inc";\nqreg q[3];\ncreg c[3];\n'
+    n, ops = qasm_to_ops(head + "reset q[0];\nreset q;\nh q[0];\ncx q[0],q[1];\nreset q[2];\n")
+    assert n == 3 and [qs for qs, _ in ops] == [[0], [0, 1]]
+    with pytest.raises(QasmError, match="after a gate on the same qubit"):
+        qasm_to_ops(head + "h q[1];\nreset q[1];\n")
+    with pytest.raises(QasmError, match="not a unitary gate"):
+        qasm_to_ops(head + "h q[1];\nmeasure q[1] -> c[1];\nif(c==1) x q[0];\n")
