@@ -137,10 +137,15 @@ def qasm_to_ops(text: str, with_statement_index: bool = False):
         elif name == "rzz":                          # exp(-i t/2 Z(x)Z): diagonal
             t = params[0]
             ops.append(([qs[0], qs[1]], np.diag([np.exp(-0.5j * t), np.exp(0.5j * t), np.exp(0.5j * t), np.exp(-0.5j * t)]).astype(C128)))
-        elif name in ("rxx", "ryy"):                 # exp(-i t/2 P(x)P), P = X or Y
-            pp = np.kron(_FIXED_1Q[name[1]], _FIXED_1Q[name[1]])
-            t = params[0]
-            ops.append(([qs[0], qs[1]], (math.cos(t / 2) * np.eye(4) - 1j * math.sin(t / 2) * pp).astype(C128)))
+        elif name in ("rxx", "ryy"):                 # exp(-i t/2 P(x)P), P = X or Y, as (W(x)W) RZZ(t) (W(x)W)^-1
+            # with W Z W^-1 = +-P: 1-qubit gates around a DIAGONAL 2-qubit gate, which the pass compiler
+            # runs inside fused passes (a dense non-controlled 4x4 would cost a sweep of its own)
+            before, after = (("h", []), ("h", [])) if name == "rxx" else (("rx", [-math.pi / 2]), ("rx", [math.pi / 2]))
+            for q in qs:
+                emit(before[0], before[1], [q])
+            emit("rzz", params, qs)
+            for q in qs:
+                emit(after[0], after[1], [q])
         elif name == "ccx":                          # standard 6-CNOT decomposition (qelib1.inc)
             a, b, c = qs
             for g_, q_ in (("h", [c]), ("cx", [b, c]), ("tdg", [c]), ("cx", [a, c]), ("t", [c]), ("cx", [b, c]),

@@ -145,3 +145,26 @@ def test_reset_before_any_gate_is_the_identity_and_later_resets_are_refused():
         qasm_to_ops(head + "h q[1];\nreset q[1];\n")
     with pytest.raises(QasmError, match="not a unitary gate"):
         qasm_to_ops(head + "h q[1];\nmeasure q[1] -> c[1];\nif(c==1) x q[0];\n")
+
+
+@pytest.mark.parametrize("name", ["rxx", "ryy"])
+def test_rxx_ryy_lower_to_one_qubit_gates_around_a_diagonal(name):
+    """exp(-i t/2 P(x)P) arrives as 1-qubit gates around RZZ (diagonal), so that it plans into fused
+    passes instead of a dense 4x4 sweep; the product must be the same unitary."""
+    import math
+    from oracle import ref_dense as O
+    from quantum_simulations_b200.circuit.passes import PassCompiler
+    P = {"rxx": np.array([[0, 1], [1, 0]], complex), "ryy": np.array([[0, -1j], [1j, 0]])}[name]
+    t = 0.613
+    n, ops = qasm_to_ops(HEAD + f"qreg q[3]; h q[0]; ry(0.4) q[2]; {name}({t}) q[2],q[0];")
+    assert all(len(qs) == 1 or np.count_nonzero(U - np.diag(np.diag(U))) == 0 for qs, U in ops)
+    psi = np.zeros(8, complex); psi[0] = 1
+    for qs, U in ops:
+        O.apply_1q(psi, qs[0], U) if len(qs) == 1 else O.apply_2q(psi, qs[0], qs[1], U)
+    phi = np.zeros(8, complex); phi[0] = 1
+    for qs, U in ops[:2]:
+        O.apply_1q(phi, qs[0], U)
+    O.apply_2q(phi, 2, 0, math.cos(t / 2) * np.eye(4) - 1j * math.sin(t / 2) * np.kron(P, P))
+    assert np.abs(psi - phi).max() <= 1e-14
+    prog = PassCompiler(12, tile_bits=7, low_bits=2).compile(qasm_to_ops(HEAD + f"qreg q[12]; h q; {name}(0.3) q[11],q[1];")[1])
+    assert prog.stats["dense2q_steps"] == 0
