@@ -121,13 +121,52 @@ def fuse_2q_blocks(ops: list[Op], only_diagonal: bool = True, tol: float = 0.0) 
     I2 = np.eye(2, dtype=np.complex128)
     swap = np.eye(4)[[0, 2, 1, 3]]
 
-    def emit_block(a: int, b: int, members: list) -> None:
+    def diagonal_run(seq: list):
+        """Longest prefix of `seq` (with a 2-qubit member) whose product is diagonal -> (length, diag) | None."""
+        best, prod, has2 = None, np.eye(4, dtype=np.complex128), False
+        for j, m in enumerate(seq):
+            prod = m[2] @ prod
+            has2 = has2 or len(m[0]) == 2
+            if j > 0 and has2:
+                off = prod - np.diag(np.diag(prod))
+                if not np.any(off):
+                    best = (j + 1, prod.copy())
+                elif tol > 0 and np.abs(off).max() <= tol:
+                    d = np.diag(prod)
+                    best = (j + 1, np.diag(d / np.abs(d)))
+        return best
+
+    def emit_block(a: int, b: int, members: list, na: int = 0, nb: int = 0) -> None:
+        if only_diagonal and (na or nb):
+            # the block opens with 1-qubit gates that were waiting on its two qubits (members[:na] on a,
+            # members[na:na+nb] on b; the two groups commute): a merged run may start anywhere in EACH
+            # group, e.g. skip the Hadamard layer before a compiled ZZ block on one qubit only
+            la, lb, rest = members[:na], members[na:na + nb], members[na + nb:]
+            found = None
+            for skip in range(na + nb + 1):                      # fewest skipped gates first
+                for sa in range(max(0, skip - nb), min(na, skip) + 1):
+                    sb = skip - sa
+                    hit = diagonal_run(la[sa:] + lb[sb:] + rest)
+                    if hit is not None and hit[0] > (na - sa) + (nb - sb):
+                        found = (sa, sb, hit)
+                        break
+                if found:
+                    break
+            if found:
+                sa, sb, (length, diag) = found
+                out.extend((m[0], m[1]) for m in la[:sa] + lb[:sb])
+                out.append(([a, b], diag))
+                members = (la[sa:] + lb[sb:] + rest)[length:]
         if not only_diagonal:
             U = np.eye(4, dtype=np.complex128)
             for _, _, U4 in members:
                 U = U4 @ U
             out.append(([a, b], U)) if any(len(q) == 2 for q, _, _ in members) else out.extend((q, u) for q, u, _ in members)
             return
+        # 1-qubit gates after the block's last 2-qubit gate that do not end up in a merged run go back to
+        # `pending`: they may LEAD the next pair run on their qubit (compiled ZZ / CPHASE blocks open with
+        # 1-qubit gates, and a gate on a qubit of an open block joins that block first)
+        last2 = max((k for k, m in enumerate(members) if len(m[0]) == 2), default=-1)
         i = 0
         while i < len(members):
             best, prod = None, np.eye(4, dtype=np.complex128)
@@ -141,7 +180,10 @@ def fuse_2q_blocks(ops: list[Op], only_diagonal: bool = True, tol: float = 0.0) 
                         d = np.diag(prod)
                         best = (j, np.diag(d / np.abs(d)))
             if best is None:
-                out.append((members[i][0], members[i][1]))
+                if i > last2:
+                    pending.setdefault(members[i][0][0], []).append((members[i][0], members[i][1]))
+                else:
+                    out.append((members[i][0], members[i][1]))
                 i += 1
             else:
                 out.append(([a, b], best[1]))
@@ -151,11 +193,11 @@ def fuse_2q_blocks(ops: list[Op], only_diagonal: bool = True, tol: float = 0.0) 
         i = block_of.pop(q, None)
         if i is None or blocks[i] is None:
             return
-        a, b, members = blocks[i]
+        a, b, members, na, nb = blocks[i]
         blocks[i] = None
         block_of.pop(a, None)
         block_of.pop(b, None)
-        emit_block(a, b, members)
+        emit_block(a, b, members, na, nb)
 
     for qs, U in ops:
         U = np.asarray(U, dtype=np.complex128)
@@ -163,7 +205,7 @@ def fuse_2q_blocks(ops: list[Op], only_diagonal: bool = True, tol: float = 0.0) 
             q = qs[0]
             i = block_of.get(q)
             if i is not None and blocks[i] is not None:
-                a, b, members = blocks[i]
+                a, b, members = blocks[i][:3]
                 members.append((list(qs), U, np.kron(U, I2) if q == a else np.kron(I2, U)))
             else:
                 pending.setdefault(q, []).append((list(qs), U))     # may lead a pair run that starts later
@@ -171,14 +213,14 @@ def fuse_2q_blocks(ops: list[Op], only_diagonal: bool = True, tol: float = 0.0) 
         a, b = qs
         ia, ib = block_of.get(a), block_of.get(b)
         if ia is not None and ia == ib and blocks[ia] is not None:
-            x, y, members = blocks[ia]
+            x, y, members = blocks[ia][:3]
             members.append((list(qs), U, U if (x, y) == (a, b) else swap @ U @ swap))
             continue
         close(a)
         close(b)
-        lead = [(q_, u_, np.kron(u_, I2)) for q_, u_ in pending.pop(a, [])] + \
-               [(q_, u_, np.kron(I2, u_)) for q_, u_ in pending.pop(b, [])]
-        blocks.append([a, b, lead + [(list(qs), U, U)]])
+        lead_a = [(q_, u_, np.kron(u_, I2)) for q_, u_ in pending.pop(a, [])]
+        lead_b = [(q_, u_, np.kron(I2, u_)) for q_, u_ in pending.pop(b, [])]
+        blocks.append([a, b, lead_a + lead_b + [(list(qs), U, U)], len(lead_a), len(lead_b)])
         block_of[a] = block_of[b] = len(blocks) - 1
     for blk in blocks:
         if blk is not None:

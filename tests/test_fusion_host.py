@@ -71,3 +71,58 @@ def test_fused_matrices_match_the_reference_golden():
     for key, (qs, U) in zip(keys, fused):
         assert key.split("/")[2] == "q" + "_".join(map(str, qs))
         np.testing.assert_allclose(U, gold[key], atol=1e-14)
+
+
+# ------------------------------------------------------------------ fuse_2q_blocks (diagonal pair runs)
+def _run(n, ops):
+    psi = np.zeros(1 << n, dtype=np.complex128)
+    psi[0] = 1
+    for qs, U in ops:
+        O.apply_1q(psi, qs[0], U) if len(qs) == 1 else O.apply_2q(psi, qs[0], qs[1], U)
+    return psi
+
+
+def _compiled_zz(a, b, t):
+    """exp(-i t/2 Z(x)Z) the way a transpiler emits it: Rx(pi/2)-conjugated RYY ... here the common
+    three-gate form with basis changes on BOTH sides, so the run opens and closes with 1-qubit gates."""
+    import math
+    from quantum_simulations_b200.circuit.qasm import qasm_to_ops
+    txt = ('OPENQASM 2.0;\ninclude "qelib1.inc";\nqreg q[4];\n'
+           f"rz(0.3) q[{a}];\nrz(-0.2) q[{b}];\ncx q[{a}],q[{b}];\nrz({t}) q[{b}];\ncx q[{a}],q[{b}];\nrz(0.11) q[{a}];\n")
+    return qasm_to_ops(txt)[1]
+
+
+def test_pair_runs_start_inside_the_waiting_one_qubit_gates_and_return_their_tail():
+    """A Hadamard layer, then compiled ZZ blocks that share qubits: every block must come out as ONE
+    diagonal gate — the run may skip the H that waits on one of its qubits only, and the 1-qubit gates
+    that follow a block must be free to lead the next block on their qubit."""
+    from quantum_simulations_b200.circuit.fusion import fuse_2q_blocks
+    H = G.gate_matrix("H", {})
+    ops = [([q], H) for q in range(4)] + _compiled_zz(0, 1, 0.7) + _compiled_zz(1, 2, -0.4) + _compiled_zz(2, 3, 1.1) \
+        + _compiled_zz(0, 1, 0.2)
+    fused = fuse_2q_blocks(ops, tol=1e-14)
+    two = [(qs, U) for qs, U in fused if len(qs) == 2]
+    assert len(two) == 4 and all(np.count_nonzero(U - np.diag(np.diag(U))) == 0 for _, U in two)
+    assert len(fused) == 4 + 4                                 # the H layer + one diagonal per block
+    assert np.abs(_run(4, fused) - _run(4, ops)).max() <= 1e-14
+
+
+def test_pair_run_fusion_preserves_the_state_on_random_circuits():
+    from quantum_simulations_b200.circuit.fusion import fuse_2q_blocks
+    rng = np.random.default_rng(11)
+    names1, n = ["H", "T", "S", "X", "Z"], 5
+    for trial in range(60):
+        ops = []
+        for _ in range(int(rng.integers(10, 60))):
+            k = rng.random()
+            if k < 0.45:
+                ops.append(([int(rng.integers(n))], G.gate_matrix(names1[int(rng.integers(len(names1)))], {})))
+            elif k < 0.6:
+                ops.append(([int(rng.integers(n))], G.gate_matrix("RY", {"theta": float(rng.normal())})))
+            else:
+                a, b = (int(x) for x in rng.choice(n, 2, replace=False))
+                ops.append(([a, b], G.gate_matrix(["CNOT", "CZ", "CR"][int(rng.integers(3))], {"k": 3})))
+        want = _run(n, ops)
+        for kw in (dict(), dict(tol=1e-12), dict(only_diagonal=False)):
+            got = _run(n, fuse_2q_blocks(ops, **kw))
+            assert np.abs(got - want).max() <= 1e-12, (trial, kw)

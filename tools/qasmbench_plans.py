@@ -16,7 +16,7 @@ for f in files:
     if len(ops)>60000: print(name,'skip',len(ops)); continue
     try:
         t0=time.time()
-        fops=fuse_2q_blocks(ops)
+        fops=fuse_2q_blocks(ops, tol=1e-14)        # what kernel.cuda_dense.simulate_qasm uses
         g=max(0,n-30)
         if n<11:
             prog=sharding.plan_single(fops,n)
