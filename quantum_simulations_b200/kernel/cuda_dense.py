@@ -87,10 +87,14 @@ def simulate_qasm(text: str, dtype="complex128", device: int = 0, out: np.ndarra
     n, ops = qasm_to_ops(text)
     ops = fuse_2q_blocks(ops, tol=1e-14)
     with DeviceState(n, dtype, device) as st:
-        st.init_zero()
         if n >= REG_BITS:
-            st.run_program(PassCompiler(n, dtype=st.dtype.name, **compiler_kw).compile(ops))
+            from quantum_simulations_b200.circuit.sharding import plan_single
+            prog = plan_single(ops, n, st.dtype.name, True, False, **compiler_kw)    # as simulate(): free initial
+            if not prog.fused_init:                                                  # placement, fused |0...0>
+                st.init_zero()
+            st.run_program(prog)
         else:
+            st.init_zero()
             for qs, U in ops:
                 st.apply_op(qs, U)
         return st.download(out)
