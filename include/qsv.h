@@ -260,6 +260,8 @@ int qsv_jit_stats(int *compiled, int *disk_hits, int *mem_hits, int *failed, dou
 /* The CUDA source qsv_program_create would hand to NVRTC for this pass (inspection / profiling). */
 int qsv_jit_source(const qsv_pass *pass, const qsv_op *ops, int dtype, char *out, size_t cap, size_t *needed);
 int qsv_jit_build_pass(const qsv_pass *pass, const qsv_op *ops, int dtype, size_t *cubin_bytes, char *log, size_t log_cap);
+/* The coefficient bank (C.c[i], in op order) the specialised kernel of this pass is launched with. */
+int qsv_jit_coefs(const qsv_pass *pass, const qsv_op *ops, int dtype, double *out, size_t cap, size_t *needed);
 /* The same two for the SCATTER variant of the pass (stores redirected by the swapped local bits). */
 int qsv_jit_source_scatter(const qsv_pass *pass, const qsv_op *ops, int dtype, int n_swap, const int *local_bits,
                            char *out, size_t cap, size_t *needed);

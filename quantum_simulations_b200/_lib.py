@@ -93,6 +93,7 @@ SIGNATURES = {
     "qsv_jit_stats": (C.c_int, [_ip, _ip, _ip, _ip, _dp]),
     "qsv_jit_source": (C.c_int, [C.POINTER(QsvPass), C.POINTER(QsvOp), C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "qsv_jit_build_pass": (C.c_int, [C.POINTER(QsvPass), C.POINTER(QsvOp), C.c_int, C.POINTER(C.c_size_t), C.c_char_p, C.c_size_t]),
+    "qsv_jit_coefs": (C.c_int, [C.POINTER(QsvPass), C.POINTER(QsvOp), C.c_int, _dp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "qsv_jit_source_scatter": (C.c_int, [C.POINTER(QsvPass), C.POINTER(QsvOp), C.c_int, C.c_int, _ip, C.c_char_p, C.c_size_t,
                                         C.POINTER(C.c_size_t)]),
     "qsv_jit_build_scatter": (C.c_int, [C.POINTER(QsvPass), C.POINTER(QsvOp), C.c_int, C.c_int, _ip, C.POINTER(C.c_size_t),

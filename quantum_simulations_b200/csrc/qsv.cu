@@ -980,6 +980,16 @@ int qsv_jit_source(const qsv_pass *pass, const qsv_op *ops, int dtype, char *out
     return QSV_OK;
 }
 
+int qsv_jit_coefs(const qsv_pass *pass, const qsv_op *ops, int dtype, double *out, size_t cap, size_t *needed) {
+    if (!pass || (pass->n_ops > 0 && !ops)) return QSV_EINVAL;
+    std::string src;
+    std::vector<double> coefs;
+    if (!qsvjit::generate(*pass, ops, src, coefs, dtype == QSV_C64)) return QSV_EINVAL;
+    if (needed) *needed = coefs.size();
+    if (out) for (size_t i = 0; i < coefs.size() && i < cap; ++i) out[i] = coefs[i];
+    return QSV_OK;
+}
+
 int qsv_jit_stats(int *compiled, int *disk_hits, int *mem_hits, int *failed, double *compile_seconds) {
     const qsvjit::Stats &s = qsvjit::stats();
     if (compiled) *compiled = s.compiled;

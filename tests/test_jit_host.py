@@ -1,0 +1,130 @@
+"""The run-time specialised kernels, executed on the CPU (tests/jit_host_run.py: the generated CUDA
+source compiled with g++ against a host stand-in for the device prelude, one OS thread per CUDA
+thread).  Compared with the NumPy pass emulator, which the GPU kernels are compared with on hardware."""
+import numpy as np
+import pytest
+
+from quantum_simulations_b200 import workloads as W
+from quantum_simulations_b200.circuit import sharding
+from quantum_simulations_b200.circuit.io import validate_circuit_dict
+from quantum_simulations_b200.circuit.passes import PassCompiler, PassStep, SwapStep
+from quantum_simulations_b200.kernel import gates as G
+from quantum_simulations_b200.kernel.cuda_dense import compile_circuit
+from tests.jit_host_run import run_pass_on_host
+from tests.pass_emulator import run_pass, swap_bits_full
+
+
+def _random_state(n, seed, dtype=np.complex128):
+    rng = np.random.default_rng(seed)
+    psi = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
+    return (psi / np.linalg.norm(psi)).astype(dtype)
+
+
+def _ops(cd):
+    cd = validate_circuit_dict(cd)
+    return [(g["qubits"], G.gate_matrix(g["gate"], g["params"])) for g in cd["gates"]]
+
+
+@pytest.mark.parametrize("workload", ["random_1q_cz", "random_mixed", "qft"])
+def test_specialised_kernels_match_the_emulator(workload):
+    n = 13
+    cd = {"random_1q_cz": lambda: W.random_1q_cz(n, 20, 1234), "random_mixed": lambda: W.random_mixed(n, 220, 5),
+          "qft": lambda: W.qft(n)}[workload]()
+    prog = compile_circuit(cd, zero_init=False)
+    psi = _random_state(n, 1)
+    for step in prog.passes[:4]:
+        want, got = psi.copy(), psi.copy()
+        run_pass(want, step.desc, step.ops, n, 0, step.tables)
+        run_pass_on_host(step, got, n, grid=2)
+        assert np.abs(got - want).max() <= 1e-13
+        psi = want
+
+
+def test_complex64_kernel_and_low_position_register_stores():
+    n = 13
+    prog = compile_circuit(W.random_1q_cz(n, 20, 7), dtype="complex64", zero_init=False, low_store_round=False)
+    psi = _random_state(n, 2)
+    for step in prog.passes[:2]:
+        want = psi.copy()
+        run_pass(want, step.desc, step.ops, n, 0, step.tables)
+        got = psi.astype(np.complex64)
+        run_pass_on_host(step, got, n, grid=1)
+        assert np.abs(got - want).max() <= 2e-6
+        psi = want
+    prog = compile_circuit(W.random_1q_cz(n, 20, 7), zero_init=False, low_store_round=False)
+    assert prog.stats["rounds"] < compile_circuit(W.random_1q_cz(n, 20, 7), zero_init=False).stats["rounds"]
+    psi = _random_state(n, 3)
+    for step in prog.passes[:3]:
+        want, got = psi.copy(), psi.copy()
+        run_pass(want, step.desc, step.ops, n, 0, step.tables)
+        run_pass_on_host(step, got, n, grid=2)
+        assert np.abs(got - want).max() <= 1e-13
+        psi = want
+
+
+def test_zero_input_pass_full_launch_and_zero_fill_plus_one_tile():
+    """The first pass of a run from |0...0> ignores what the shard holds.  Two launch forms must give the
+    same shard: every tile (the round-1 form) and zero-fill + the one tile that holds amplitude 0."""
+    n = 14
+    prog = compile_circuit(W.random_1q_cz(n, 20, 1234))
+    assert prog.fused_init and prog.passes[0].desc.zero_input == 1
+    step = prog.passes[0]
+    want = np.zeros(1 << n, dtype=np.complex128)
+    want[0] = 1
+    run_pass(want, step.desc, step.ops, n, 0, step.tables)
+    full = _random_state(n, 4)                       # junk that must be ignored
+    run_pass_on_host(step, full, n, grid=3)
+    assert np.abs(full - want).max() <= 1e-13
+    one = np.zeros(1 << n, dtype=np.complex128)      # = cudaMemsetAsync
+    run_pass_on_host(step, one, n, grid=1, tile_range=(0, 1))
+    assert np.abs(one - want).max() <= 1e-13
+    other_rank = _random_state(n, 5)                 # a shard of rank != 0 is all zero after the pass
+    run_pass_on_host(step, other_rank, n, rank=1, grid=2)
+    assert not other_rank.any()
+
+
+@pytest.mark.parametrize("g", [1, 2])
+def test_scatter_kernels_do_the_pass_and_the_swap(g):
+    """qsv_pass_scatter on the CPU: every rank runs the scatter variant of the pass before a swap; its
+    stores go to the second buffers of all ranks.  Afterwards the second buffers must hold what
+    'pass, then swap' leaves in the shards."""
+    n = 13 + g
+    n_loc = n - g
+    world = 1 << g
+    checked = 0
+    for cd in (W.random_1q_cz(n, 20, 1234), W.qft(n), W.random_mixed(n, 200, 9)):
+        prog = sharding.plan(_ops(cd), n, n_loc, swap_anywhere=True, rank_flips=True)
+        state = np.zeros(1 << n, dtype=np.complex128)
+        state[0] = 1
+        steps = list(prog.steps)
+        for k, step in enumerate(steps):
+            shards = state.reshape(world, -1)
+            if isinstance(step, SwapStep):
+                state = swap_bits_full(state, n, step.global_bits, step.local_bits)
+                continue
+            nxt = steps[k + 1] if k + 1 < len(steps) else None
+            if isinstance(nxt, SwapStep) and checked < 2:
+                gb, lb = list(nxt.global_bits), list(nxt.local_bits)
+                second = [np.full(1 << n_loc, np.nan + 0j) for _ in range(world)]      # every slot must be written
+                for r in range(world):
+                    targets, keep = [], 0
+                    for i, (gbit, lbit) in enumerate(zip(gb, lb)):
+                        keep |= ((r >> (gbit - n_loc)) & 1) << lbit
+                    for x in range(1 << len(gb)):
+                        rr = r
+                        for i, gbit in enumerate(gb):
+                            rb = gbit - n_loc
+                            rr = (rr & ~(1 << rb)) | (((x >> i) & 1) << rb)
+                        targets.append(second[rr])
+                    run_pass_on_host(step, shards[r].copy(), n_loc, rank=r, grid=2, scatter=(lb, targets, keep))
+                want = state.copy().reshape(world, -1)
+                for r in range(world):
+                    run_pass(want[r], step.desc, step.ops, n_loc, r, step.tables)
+                want = swap_bits_full(want.reshape(-1), n, gb, lb)
+                got = np.concatenate(second)
+                assert not np.isnan(got).any()
+                assert np.abs(got - want).max() <= 1e-13
+                checked += 1
+            for r in range(world):
+                run_pass(shards[r], step.desc, step.ops, n_loc, r, step.tables)
+    assert checked == 2
