@@ -128,3 +128,21 @@ def test_scatter_kernels_do_the_pass_and_the_swap(g):
             for r in range(world):
                 run_pass(shards[r], step.desc, step.ops, n_loc, r, step.tables)
     assert checked == 2
+
+
+def test_whole_program_through_host_kernels_equals_the_oracle():
+    """Every pass of a planned run from |0...0> (fused initialisation in its zero-fill form, table phases,
+    pre-ops, store flips, free initial placement) on the host-built specialised kernels."""
+    from oracle import ref_dense as O
+    n = 14
+    cd = validate_circuit_dict(W.random_mixed(n, 260, 21))
+    prog = compile_circuit(cd)
+    assert prog.fused_init and all(isinstance(s, PassStep) for s in prog.steps)
+    psi = _random_state(n, 6)
+    for i, step in enumerate(prog.passes):
+        if step.desc.zero_input:
+            psi[:] = 0
+            run_pass_on_host(step, psi, n, grid=1, tile_range=(0, 1))
+        else:
+            run_pass_on_host(step, psi, n, grid=2)
+    assert np.abs(psi - O.simulate(cd)).max() <= 1e-12
