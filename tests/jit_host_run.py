@@ -63,12 +63,17 @@ def host_kernel(step, dtype="complex128", scatter_bits=None):
         _BUILD.mkdir(exist_ok=True)
         cpp, so = _BUILD / f"k_{key}.cpp", _BUILD / f"k_{key}.so"
         if not so.exists():
+            import os
+            cpp = _BUILD / f"k_{key}.{os.getpid()}.cpp"             # several test processes may build the same kernel
+            tmp = _BUILD / f"k_{key}.{os.getpid()}.so"
             cpp.write_text(full)
             cmd = ["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-pthread", "-Wno-unknown-pragmas", "-Wno-attributes",
-                   f"-I{HOST_INC}", f"-I{CSRC}", "-o", str(so), str(cpp)]
+                   f"-I{HOST_INC}", f"-I{CSRC}", "-o", str(tmp), str(cpp)]
             r = subprocess.run(cmd, capture_output=True, text=True)
             if r.returncode != 0:
                 raise RuntimeError("g++ failed on the generated kernel:\n" + r.stderr[-4000:])
+            os.replace(tmp, so)
+            cpp.unlink()
         lib = C.CDLL(str(so))
         fn = lib.jit_host_run
         fn.restype = C.c_int
