@@ -227,6 +227,9 @@ def bench_single(args) -> None:
                defer_diagonals=args.defer_diagonals, fold_tables=not args.no_fold_tables)
     if args.no_low_store_round:
         ckw["low_store_round"] = False
+    if args.warp_local_rounds:
+        ckw["warp_local_rounds"] = True
+        os.environ["QSV_JIT_WARP_SYNC"] = "1"
     from quantum_simulations_b200.circuit.sharding import plan_single
     prog = plan_single(circuit_ops(cd), n, dtype, True, False, **ckw)      # from |0...0>: free initial placement
     compile_s = time.perf_counter() - t0
@@ -541,6 +544,8 @@ def main() -> None:
     ap.add_argument("--no-zero-support", action="store_true")
     ap.add_argument("--no-low-store-round", action="store_true",
                     help="experiment: no idle round before stores whose registers hold a low (row) position")
+    ap.add_argument("--warp-local-rounds", action="store_true",
+                    help="experiment (N = 1): warp-local round exchanges with __syncwarp() instead of the group barrier")
     ap.add_argument("--fused-exchange", action="store_true",
                     help="N > 1: second buffer per shard, the pass before a swap stores straight into the peers (qsv_pass_scatter)")
     args = ap.parse_args()

@@ -479,7 +479,8 @@ class PassCompiler:
                  merge_diagonals: bool = True, fold_tables: bool = True,
                  defer_diagonals: bool = False, absorb: bool = True, allow_swaps: bool = True,
                  swap_anywhere: bool = False, rank_flips: bool = False, park_off_last_round: bool = True,
-                 table_phases: bool = True, eager_flips: bool = True, low_store_round: bool = True):
+                 table_phases: bool = True, eager_flips: bool = True, low_store_round: bool = True,
+                 warp_local_rounds: bool = False):
         self.n = n_qubits
         self.n_local = n_qubits if n_local is None else n_local
         self.dtype = np.dtype(dtype).name
@@ -523,6 +524,11 @@ class PassCompiler:
         # lanes cover whole rows.  False (experiment): store as is — half-row stores that L2 merges,
         # against one shared-memory round trip less.
         self.low_store_round = low_store_round
+        # experiment: keep the two tile positions that select the WARP inside a consumer group (thread
+        # bits 5, 6) the same from one round to the next wherever both rounds leave them out of the
+        # registers.  The shared-memory exchange between such rounds stays inside each warp, and the
+        # specialised kernel (QSV_JIT_WARP_SYNC=1) replaces the group's named barrier by __syncwarp().
+        self.warp_local_rounds = warp_local_rounds
         self.table_phases = table_phases
         # materialise a pending X as soon as its qubit will never be MIXED again (instead of waiting
         # until nothing inspects it either): the not-yet-scheduled ops that inspect it are re-conjugated
@@ -906,19 +912,47 @@ class PassCompiler:
         n_absorbed = 0
         g_scale = 1.0                 # product of SCALE micro-ops (1/sqrt2 per Hadamard)
         g_phase = _ONE                # product of uncontrolled PHASE / SIGN micro-ops
+        def thread_order(r, regs):
+            free = [i for i in range(t) if i not in regs]
+            if r == len(plan) - 1:
+                return sorted(free, key=lambda i: store[i])
+            if r == 0 and not self.ring:
+                return sorted(free, key=lambda i: load_bits[i])
+            return self._bank_friendly(free)
+
+        thr_of = [thread_order(r, regs) for r, (regs, _) in enumerate(plan)]
+        if self.warp_local_rounds and t - REG_BITS == 7:
+            # thread bits 0..2 are fixed by coalescing / bank groups; any two of the other four thread
+            # positions may sit on bits 5, 6.  Walk the round boundaries backwards and give both rounds a
+            # common pair there whenever one exists.
+            # (middle rounds of the specialised kernels may use ANY thread position: their bank-group codes
+            # are chosen per pass for whatever sits on thread bits 0..2)
+            pinned = [False] * len(plan)
+            last = len(plan) - 1
+
+            def movable(k):
+                return thr_of[k][3:7] if k == last else thr_of[k]
+
+            for r in range(last - 1, -1, -1):
+                if r == 0 and not self.ring:
+                    break
+                nxt = thr_of[r + 1]
+                pool = movable(r + 1)
+                options = [tuple(nxt[5:7])] if pinned[r + 1] else [(a, b) for a in pool for b in pool if a < b]
+                mine = set(movable(r))
+                pair = next((p_ for p_ in options if p_[0] in mine and p_[1] in mine), None)
+                if pair is None:
+                    continue
+                for k in (r, r + 1):
+                    thr_of[k] = [i for i in thr_of[k] if i not in pair] + list(pair)
+                pinned[r] = pinned[r + 1] = True
         for r, (regs, rops) in enumerate(plan):
             rd = desc.rounds[r]
             slot_of = {}
             for b, i in enumerate(sorted(regs)):
                 rd.reg_pos[b] = i
                 slot_of[content[i]] = b
-            free = [i for i in range(t) if i not in regs]
-            if r == len(plan) - 1:
-                thr = sorted(free, key=lambda i: store[i])
-            elif r == 0 and not self.ring:
-                thr = sorted(free, key=lambda i: load_bits[i])
-            else:
-                thr = self._bank_friendly(free)
+            thr = thr_of[r]
             for k, i in enumerate(thr):
                 rd.thr_pos[k] = i
             rd.op_begin = len(flat)

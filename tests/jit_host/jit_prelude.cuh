@@ -124,10 +124,11 @@ struct SpinBarrier {
         }
     }
 };
-static SpinBarrier g_cta_bar, g_group_bar[4];
+static SpinBarrier g_cta_bar, g_group_bar[4], g_warp_bar[32];
 static JitRingSmem *g_smem = nullptr;
 static inline void __syncthreads() { g_cta_bar.wait(); }
 static inline void group_bar(int grp) { g_group_bar[grp].wait(); }
+static inline void __syncwarp() { g_warp_bar[threadIdx.x >> 5].wait(); }
 
 static inline void apply_fold(JV (&v)[16], const double2 f) {
     JR pr = (JR)f.x, pi = (JR)f.y;

@@ -27,6 +27,7 @@ def _case(seed: int):
               rank_flips=bool(rng.integers(0, 2)), table_phases=bool(rng.integers(0, 2)), absorb=bool(rng.integers(0, 2)))
     planned = bool(rng.integers(0, 2))
     kw["low_store_round"] = bool(rng.integers(0, 2))        # drawn last: earlier seeds keep their cases
+    kw["warp_local_rounds"] = bool(rng.integers(0, 2))
     return n, g, validate_circuit_dict(cd), kw, planned
 
 

@@ -528,3 +528,18 @@ def test_low_position_register_stores(workload, jit):
     for dtype in ("complex128", "complex64"):
         got = simulate(cd, dtype=dtype, jit=jit, low_store_round=False)
         assert np.abs(got - want).max() <= TOL[dtype]
+
+
+@pytest.mark.skipif(__import__("os").environ.get("QSV_TEST_SCATTER") != "1",
+                    reason="generator switch added after the round's last GPU minute: opt-in until it has run on hardware")
+def test_warp_local_rounds_on_the_device(monkeypatch):
+    """warp_local_rounds + QSV_JIT_WARP_SYNC=1: __syncwarp() instead of the group barrier between rounds
+    whose exchange stays inside each warp (tests/test_jit_host.py checks the same kernels on the CPU)."""
+    from quantum_simulations_b200.kernel.cuda_dense import simulate
+    monkeypatch.setenv("QSV_JIT_WARP_SYNC", "1")
+    n = 20
+    for cd in (W.random_1q_cz(n, 20, 1234), W.random_mixed(n, 400, 5), W.qft(n)):
+        want = CO.simulate_c(validate_circuit_dict(cd))
+        for dtype in ("complex128", "complex64"):
+            got = simulate(cd, dtype=dtype, warp_local_rounds=True, low_store_round=False)
+            assert np.abs(got - want).max() <= TOL[dtype]

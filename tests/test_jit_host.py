@@ -146,3 +146,28 @@ def test_whole_program_through_host_kernels_equals_the_oracle():
         else:
             run_pass_on_host(step, psi, n, grid=2)
     assert np.abs(psi - O.simulate(cd)).max() <= 1e-12
+
+
+def test_warp_local_rounds_with_syncwarp(monkeypatch):
+    """PassCompiler(warp_local_rounds=True) keeps the tile positions behind thread bits 5, 6 (the warp
+    inside a consumer group) fixed across a round boundary where it can; with QSV_JIT_WARP_SYNC=1 the
+    kernel then replaces the group barrier of that boundary by __syncwarp().  On the host every warp is
+    32 free-running OS threads, so a boundary that is wrongly declared warp-local gives wrong amplitudes
+    (checked once by replacing EVERY barrier: errors of 0.03-0.1)."""
+    from tests.jit_host_run import kernel_source
+    monkeypatch.setenv("QSV_JIT_WARP_SYNC", "1")
+    n = 13
+    prog = compile_circuit(W.random_1q_cz(n, 20, 1234), zero_init=False, warp_local_rounds=True)
+    assert prog.stats["rounds"] == compile_circuit(W.random_1q_cz(n, 20, 1234), zero_init=False).stats["rounds"]
+    psi = _random_state(n, 8)
+    local = 0
+    for step in prog.passes[:3]:
+        local += kernel_source(step).count("__syncwarp();")
+        want, got = psi.copy(), psi.copy()
+        run_pass(want, step.desc, step.ops, n, 0, step.tables)
+        run_pass_on_host(step, got, n, grid=2)
+        assert np.abs(got - want).max() <= 1e-13
+        psi = want
+    assert local >= 2
+    monkeypatch.delenv("QSV_JIT_WARP_SYNC")
+    assert "__syncwarp();" not in kernel_source(prog.passes[0])          # the default kernels are unchanged
