@@ -228,11 +228,27 @@ class ShardedSimulator:
         cd = validate_circuit_dict(circuit_dict)
         if cd["number_of_qubits"] != self.n:
             raise ValueError("circuit size differs from the simulator's")
+        return self.plan_ops(circuit_ops(cd), **compiler_kw)
+
+    def plan_ops(self, ops: list, **compiler_kw) -> Program:
+        """Stage plan for a step-IR op list [(qubits, U)] (what the front ends produce: circuit dicts,
+        circuit/qasm.qasm_to_ops, circuit/hisvsim_parts)."""
         compiler_kw.setdefault("swap_anywhere", bool(self.peer_swap))     # peer kernel: no relabel before a swap
         compiler_kw.setdefault("rank_flips", True)                        # X pending on a rank bit renames shards
         if getattr(self, "fused_exchange", False):
             compiler_kw.setdefault("fused_exchange", True)                # cost model: a swap hides the pass before it
-        return sharding.plan(circuit_ops(cd), self.n, self.n - self.g, self.dtype.name, **compiler_kw)
+        return sharding.plan(ops, self.n, self.n - self.g, self.dtype.name, **compiler_kw)
+
+    def simulate_qasm(self, text: str, out: np.ndarray | None = None, **compiler_kw) -> np.ndarray:
+        """OpenQASM 2.0 program from |0...0> on the sharded state (front end as in
+        kernel.cuda_dense.simulate_qasm); returns this rank's logical shard like ``simulate``."""
+        from quantum_simulations_b200.circuit.fusion import fuse_2q_blocks
+        from quantum_simulations_b200.circuit.qasm import qasm_to_ops
+        n, ops = qasm_to_ops(text)
+        if n != self.n:
+            raise ValueError("circuit size differs from the simulator's")
+        self.run(self.plan_ops(fuse_2q_blocks(ops, tol=1e-14), **compiler_kw))
+        return self.shard.state.download(out)
 
     def simulate(self, circuit_dict: dict, out: np.ndarray | None = None, **compiler_kw) -> np.ndarray:
         """Returns the amplitudes of LOGICAL shard ``self.logical_rank`` (= rank ^ the program's

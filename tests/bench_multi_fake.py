@@ -71,6 +71,8 @@ class FakeSim:
         self.peer_swap, self.logical_rank, self._flip_mask = False, self.rank, 0
 
     plan = MG.ShardedSimulator.plan
+    plan_ops = MG.ShardedSimulator.plan_ops
+    simulate_qasm = MG.ShardedSimulator.simulate_qasm
     run = MG.ShardedSimulator.run
 
     def simulate(self, cd, out=None, **kw):

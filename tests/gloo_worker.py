@@ -78,8 +78,29 @@ def main():
         np.save(out_dir / f"{name}_rank{rank}.npy", shard.psi)
         if rank == 0:
             (out_dir / f"{name}_swaps.txt").write_text(str(shard.swaps))
+    # the OpenQASM front end on a sharded state (what ShardedSimulator.simulate_qasm does): compiled ZZ
+    # blocks behind a Hadamard layer fuse into diagonals, the rest plans into passes and swaps
+    from quantum_simulations_b200.circuit.fusion import fuse_2q_blocks
+    from quantum_simulations_b200.circuit.qasm import qasm_to_ops
+    nq, ops = qasm_to_ops(qasm_text(n))
+    g = world.bit_length() - 1
+    prog = sharding.plan(fuse_2q_blocks(ops, tol=1e-14), nq, nq - g, tile_bits=6, low_bits=2, rank_flips=True)
+    shard = EmuShard(nq, rank, world, dist)
+    execute(prog, shard)
+    np.save(out_dir / f"qasm_rank{rank ^ prog.rank_flip_mask}.npy", shard.psi)
     dist.barrier()
     dist.destroy_process_group()
+
+
+def qasm_text(n: int) -> str:
+    src = ["OPENQASM 2.0;", 'include "qelib1.inc";', f"qreg q[{n}];", f"h q;"]
+    for layer in range(3):
+        for a in range(layer % 2, n - 1, 2):
+            b = a + 1
+            src += [f"rz(0.2) q[{a}];", f"cx q[{a}],q[{b}];", f"rz({0.3 + 0.1 * a}) q[{b}];", f"cx q[{a}],q[{b}];"]
+        src += [f"rx({0.4 + 0.05 * q}) q[{q}];" for q in range(n)]
+    src += [f"ryy(0.7) q[{n - 1}],q[0];", f"ccx q[0],q[{n // 2}],q[{n - 1}];"]
+    return "\n".join(src)
 
 
 if __name__ == "__main__":

@@ -31,6 +31,19 @@ def test_sharded_run_across_processes(tmp_path, world):
         want = O.simulate(validate_circuit_dict(cd))
         assert np.abs(got - want).max() <= 1e-12, name
         assert int((tmp_path / f"{name}_swaps.txt").read_text()) >= 1, name
+    _check_qasm(tmp_path, world, n)
+
+
+def _check_qasm(tmp_path, world, n):
+    sys.path.insert(0, str(ROOT / "tests"))
+    from gloo_worker import qasm_text
+    from quantum_simulations_b200.circuit.qasm import qasm_to_ops
+    _, ops = qasm_to_ops(qasm_text(n))
+    want = np.zeros(1 << n, dtype=np.complex128)
+    want[0] = 1
+    O.apply_ops(want, ops)
+    got = np.concatenate([np.load(tmp_path / f"qasm_rank{r}.npy") for r in range(world)])
+    assert np.abs(got - want).max() <= 1e-12
 
 
 def test_bench_multi_control_flow_on_cpu(tmp_path):
