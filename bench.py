@@ -352,6 +352,9 @@ def bench_single(args) -> None:
                             "pass) — per_pass_ms[0]; not part of the roofline average") if prog.fused_init
                            else "cudaMemset + set amp[0] before the passes",
                    "init_pass_ms": round(float(np.mean(init_ms)), 3) if init_ms else None, "init_note": init_note,
+                   "planner_switches": {"low_store_round": not args.no_low_store_round,
+                                        "warp_local_rounds": bool(args.warp_local_rounds),
+                                        "init_pass_full": "QSV_INIT_PASS_FULL" in os.environ},
                    "l2_hygiene": f"state {(1 << n) * amp_bytes / 2**30:.0f} GiB >> 126 MB L2: every pass streams from HBM",
                    "host_compile_s": compile_s},
         "gate_layers_per_s": info["levels"] / (ms_per_step * 1e-3),
