@@ -272,6 +272,19 @@ def bench_single(args) -> None:
     ms_per_step = total_ms / args.steps
     value = updates_per_step / (ms_per_step * 1e-3)
 
+    # beside the headline: the same run with the first pass launched over EVERY tile (no zero-fill
+    # shortcut), i.e. seven full sweeps of the pass kernel — the conservative reading of the step
+    full_first = None
+    if prog.fused_init and "QSV_INIT_PASS_FULL" not in os.environ:
+        os.environ["QSV_INIT_PASS_FULL"] = "1"
+        try:
+            f_ms, _, _, f_norm = timed_run()
+        finally:
+            os.environ.pop("QSV_INIT_PASS_FULL", None)
+        if abs(f_norm - 1.0) <= norm_tol:
+            full_first = {"ms_per_step": f_ms / args.steps, "value": updates_per_step / (f_ms / args.steps * 1e-3), "unit": UNIT,
+                          "what": "QSV_INIT_PASS_FULL=1: the zero-input first pass runs its arithmetic on every tile"}
+
     # the same circuit with ZERO-SUPPORT SKIPPING (compile(zero_state=True)): reported beside the
     # headline, never as the headline — the roofline accounting assumes every pass streams the state
     zs = None
@@ -367,6 +380,7 @@ def bench_single(args) -> None:
                      "launches_timed": len(streamed_ms), "share_of_step": pass_share,
                      "launches": "every pass that reads and writes the state once (the write-only init pass is excluded)"},
         "zero_support_skipping": zs,
+        "full_first_pass": full_first,
         "jit": jit_stats(),
         "gpu_launches": len(per_launch) + (0 if prog.fused_init else 2 * args.steps),   # + memset & set-amp of |0> unless fused
         "clocks": clk,

@@ -58,3 +58,4 @@ def test_single_gpu_control_flow_on_cpu():
     assert r["config"]["init_note"] is None and r["config"]["init_pass_ms"] is not None
     assert r["roofline"]["launches_timed"] == (r["config"]["passes_per_step"] - 1) * r["steps"]
     assert r["zero_support_skipping"]["ms_per_step"] > 0
+    assert r["full_first_pass"]["ms_per_step"] > 0 and r["config"]["planner_switches"]["low_store_round"] is True
