@@ -230,6 +230,8 @@ def bench_single(args) -> None:
     if args.warp_local_rounds:
         ckw["warp_local_rounds"] = True
         os.environ["QSV_JIT_WARP_SYNC"] = "1"
+    if args.streaming_stores:
+        os.environ["QSV_JIT_STCS"] = "1"
     from quantum_simulations_b200.circuit.sharding import plan_single
     prog = plan_single(circuit_ops(cd), n, dtype, True, False, **ckw)      # from |0...0>: free initial placement
     compile_s = time.perf_counter() - t0
@@ -367,6 +369,7 @@ def bench_single(args) -> None:
                    "init_pass_ms": round(float(np.mean(init_ms)), 3) if init_ms else None, "init_note": init_note,
                    "planner_switches": {"low_store_round": not args.no_low_store_round,
                                         "warp_local_rounds": bool(args.warp_local_rounds),
+                                        "streaming_stores": os.environ.get("QSV_JIT_STCS") == "1",
                                         "init_pass_full": "QSV_INIT_PASS_FULL" in os.environ},
                    "l2_hygiene": f"state {(1 << n) * amp_bytes / 2**30:.0f} GiB >> 126 MB L2: every pass streams from HBM",
                    "host_compile_s": compile_s},
@@ -563,6 +566,8 @@ def main() -> None:
                     help="experiment: no idle round before stores whose registers hold a low (row) position")
     ap.add_argument("--warp-local-rounds", action="store_true",
                     help="experiment (N = 1): warp-local round exchanges with __syncwarp() instead of the group barrier")
+    ap.add_argument("--streaming-stores", action="store_true",
+                    help="experiment (N = 1): st.global.cs (evict-first) for the final stores of a pass")
     ap.add_argument("--fused-exchange", action="store_true",
                     help="N > 1: second buffer per shard, the pass before a swap stores straight into the peers (qsv_pass_scatter)")
     args = ap.parse_args()

@@ -59,6 +59,7 @@ static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
 static inline int __ffs(int x) { return __builtin_ffs(x); }
 template <typename T> static inline T __ldg(const T *p) { return *p; }
+template <typename T> static inline void __stcs(T *p, const T &v) { *p = v; }
 using std::fma;
 
 static inline uint64_t insert_zero_bit(uint64_t x, int pos) {

@@ -27,6 +27,7 @@ run init_full "QSV_INIT_PASS_FULL=1" ""
 run no_low_store_round "QSV_X=0" "--no-low-store-round"
 run warp_local_rounds "QSV_X=0" "--warp-local-rounds"
 run both "QSV_X=0" "--no-low-store-round --warp-local-rounds"
+run streaming_stores "QSV_X=0" "--streaming-stores"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches_r02.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e --no-zero-support > $out/ncu_launches_r02.log 2>&1; echo "ncu list rc=$?"
 # 6. do DFMA and DMMA run on separate pipes?  (mixed_mode* sum_tflops above either single peak = yes)
