@@ -8,7 +8,7 @@
 #   5. ncu launch list of (2)
 cd "$(dirname "$0")/.."
 out=gpurun_out; mkdir -p $out
-QSV_TEST_SCATTER=1 timeout 1500 python -m pytest tests -m gpu -x -q > $out/pytest_gpu_r2.log 2>&1; echo "pytest rc=$?"; tail -n 6 $out/pytest_gpu_r2.log
+QSV_TEST_SCATTER=1 timeout 1500 python -m pytest tests -m gpu -q > $out/pytest_gpu_r2.log 2>&1; echo "pytest rc=$?"; grep -E "FAILED|ERROR|passed|failed" $out/pytest_gpu_r2.log | tail -n 12
 run() {  # name, env, flags
   env $2 timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e $3 > $out/bench_r2_$1.log 2>$out/bench_r2_$1.err; echo "bench $1 rc=$?"
   python - $out/bench_r2_$1.log <<'PY'
