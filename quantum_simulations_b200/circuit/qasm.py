@@ -11,7 +11,9 @@ user `gate` definitions (expanded), broadcast over whole registers, `barrier` / 
 (ignored: the engine returns the state).  `reset` and `if` are rejected (not unitary / classical)."""
 from __future__ import annotations
 
+import ast
 import math
+import operator
 import re
 
 import numpy as np
@@ -60,15 +62,53 @@ class QasmError(ValueError):
     pass
 
 
+_FUNCS = {"sin": math.sin, "cos": math.cos, "tan": math.tan, "exp": math.exp, "ln": math.log, "sqrt": math.sqrt}
+_BINOPS = {ast.Add: operator.add, ast.Sub: operator.sub, ast.Mult: operator.mul, ast.Div: operator.truediv,
+           ast.Pow: operator.pow}
+
+
 def _eval(expr: str, env: dict) -> float:
+    """Parameter expression of OpenQASM 2.0 (numbers, pi, formal parameters, + - * / ^, unary minus, and the
+    six built-in functions).  The text is parsed to a Python AST and walked over a closed set of node types:
+    attribute access, subscripts, calls of anything but the six functions, comparisons etc. are rejected, so a
+    .qasm file cannot reach interpreter internals (nothing is ever passed to eval())."""
     expr = expr.strip()
-    if not re.fullmatch(r"[0-9a-zA-Z_+\-*/().\s^]*", expr):
-        raise QasmError(f"bad parameter expression {expr!r}")
-    names = {"pi": math.pi, "sin": math.sin, "cos": math.cos, "tan": math.tan, "exp": math.exp,
-             "ln": math.log, "sqrt": math.sqrt, **env}
     try:
-        return float(eval(expr.replace("^", "**"), {"__builtins__": {}}, names))   # noqa: S307 (whitelisted chars / names)
-    except Exception as e:
+        tree = ast.parse(expr.replace("^", "**"), mode="eval")
+    except (SyntaxError, ValueError, MemoryError, RecursionError):
+        raise QasmError(f"bad parameter expression {expr!r}") from None
+
+    def walk(node, depth=0):
+        if depth > 64:
+            raise QasmError(f"parameter expression {expr!r} is nested too deeply")
+        if isinstance(node, ast.Expression):
+            return walk(node.body, depth + 1)
+        if isinstance(node, ast.Constant) and type(node.value) in (int, float):
+            return float(node.value)
+        if isinstance(node, ast.Name):
+            if node.id == "pi":
+                return math.pi
+            if node.id in env:
+                return float(env[node.id])
+            raise QasmError(f"unknown name {node.id!r} in parameter expression {expr!r}")
+        if isinstance(node, ast.UnaryOp) and isinstance(node.op, (ast.USub, ast.UAdd)):
+            v = walk(node.operand, depth + 1)
+            return -v if isinstance(node.op, ast.USub) else v
+        if isinstance(node, ast.BinOp) and type(node.op) in _BINOPS:
+            a, b = walk(node.left, depth + 1), walk(node.right, depth + 1)
+            if isinstance(node.op, ast.Pow) and abs(b) > 1024:
+                raise QasmError(f"exponent too large in {expr!r}")
+            return float(_BINOPS[type(node.op)](a, b))
+        if (isinstance(node, ast.Call) and isinstance(node.func, ast.Name) and node.func.id in _FUNCS
+                and len(node.args) == 1 and not node.keywords):
+            return float(_FUNCS[node.func.id](walk(node.args[0], depth + 1)))
+        raise QasmError(f"bad parameter expression {expr!r}: {type(node).__name__} is not allowed")
+
+    try:
+        return walk(tree)
+    except QasmError:
+        raise
+    except (ArithmeticError, ValueError, TypeError) as e:
         raise QasmError(f"cannot evaluate {expr!r}: {e}") from None
 
 

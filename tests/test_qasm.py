@@ -136,6 +136,24 @@ def test_errors():
         qasm_to_dict(HEAD + "qreg q[1]; rz(0.1) q[0];")
 
 
+def test_parameter_expressions_are_walked_not_evaluated():
+    """A .qasm file is untrusted input: attribute chains, subscripts, lambdas, foreign calls are refused
+    (they used to reach interpreter internals through eval()); the arithmetic of the spec still works."""
+    import math
+    from quantum_simulations_b200.circuit.qasm import _eval
+    for bad in ("().__class__.__base__.__subclasses__().__len__()", "pi.real", "[1][0]", "(lambda: 1)()",
+                "__import__('os')", "open('x')", "1 if 1 else 2", "1 < 2", "sin(1, 2)", "sin.__name__", "foo", "2 ** 99999",
+                "'a'", "True", "1j"):
+        with pytest.raises(QasmError):
+            _eval(bad, {})
+        with pytest.raises(QasmError):
+            qasm_to_ops(HEAD + f"qreg q[1]; rz({bad}) q[0];")
+    assert _eval("-pi/2 + 2^3*sin(pi/6) - sqrt(4)*ln(exp(1))", {}) == pytest.approx(-math.pi / 2 + 8 * 0.5 - 2.0)
+    assert _eval("theta/2 + 1e-3", {"theta": 0.5}) == pytest.approx(0.251)
+    with pytest.raises(QasmError, match="cannot evaluate"):
+        _eval("1/0", {})
+
+
 def test_reset_before_any_gate_is_the_identity_and_later_resets_are_refused():
     from quantum_simulations_b200.circuit.qasm import QasmError, qasm_to_ops
     head = 'OPENQASM 2.0;\ninclude "qelib1.inc";\nqreg q[3];\ncreg c[3];\n'
