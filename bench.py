@@ -418,7 +418,7 @@ def bench_multi(args) -> None:
     t0 = time.perf_counter()
     prog = sim.plan(cd, **ckw)
     compile_s = time.perf_counter() - t0
-    sim.shard.prepare(prog)
+    sim.prepare(prog)
     updates_per_step = len(cd["gates"]) * (1 << n)
 
     def step():
@@ -436,7 +436,7 @@ def bench_multi(args) -> None:
         # insurance: a plan that does not even conserve the norm is replaced by the conservative planner
         # (swaps on the top positions after a relabel pass, no eager flips, no table phases) before timing
         prog = sim.plan(cd, swap_anywhere=False, rank_flips=False, eager_flips=False, table_phases=False, **ckw)
-        sim.shard.prepare(prog)
+        sim.prepare(prog)
         plan_note = "FALLBACK: conservative planner options (the default plan failed the norm check)"
         step()
     for _ in range(max(args.warmup - 1, 0)):
@@ -483,7 +483,8 @@ def bench_multi(args) -> None:
         pass_ms, init_ms = split_init_pass(per_launch, args.steps, prog.fused_init)
         swap_ms = [(ms, kind - 20) for ms, kind, _ in per_launch if 20 <= kind < 30]
         fused_ms = [(ms, kind - 30) for ms, kind, _ in per_launch if 30 <= kind < 40]
-        scatter_ms = [(ms, kind - 40) for ms, kind, _ in per_launch if kind >= 40]
+        scatter_ms = [(ms, kind - 40) for ms, kind, _ in per_launch if 40 <= kind < 50]
+        piped = [(ms, kind - 50, pi) for ms, kind, pi in per_launch if 50 <= kind < 60]
         avg_pass_ms = float(np.mean(pass_ms))
         alg_bytes = 2 * amp_bytes * (1 << n_loc)
         peak, peak_src = _peaks()
@@ -520,6 +521,13 @@ def bench_multi(args) -> None:
                                      "ms": [round(ms, 3) for ms, _ in fused_ms[-max(1, len(fused_ms) // max(args.steps, 1)):]] if fused_ms else [],
                                      "what": "last pass of a stage split into 2^s blocks, exchange of each block pair on a second "
                                              "stream while the next block is computed (qsv_pass_swap_overlapped)"},
+            "pipelined_swap": {"count_per_step": len(piped) // max(args.steps, 1),
+                               "regions": [{"bits": b, "ms": round(ms, 3), "passes_before": pi // 16, "passes_after": pi % 16}
+                                           for ms, b, pi in piped[-max(1, len(piped) // max(args.steps, 1)):]] if piped else [],
+                               "xchg_sms": getattr(sim.shard, "xchg_sms", None), "enabled": bool(getattr(sim.shard, "pipeline", False)),
+                               "what": "stage transition executed chunk by chunk (qsv_swap_pipelined): the TMA exchange kernel of "
+                                       "chunk j on xchg_sms SMs beside the pass kernels of the neighbouring chunks on the other SMs; "
+                                       "ms = the whole region (its passes included)"},
             "scatter_pass": {"enabled": bool(getattr(sim, "fused_exchange", False)),
                              "count_per_step": len(scatter_ms) // max(args.steps, 1),
                              "ms": [round(ms, 3) for ms, _ in scatter_ms[-max(1, len(scatter_ms) // max(args.steps, 1)):]] if scatter_ms else [],
@@ -527,6 +535,7 @@ def bench_multi(args) -> None:
                                      "buffers of the peers over NVLink (qsv_pass_scatter, --fused-exchange; 2x shard memory)"},
             "nvlink": {"path": "peer-memory kernel (CUDA IPC, loads/stores over NVLink)" if sim.peer_swap
                        else f"chunked ncclSend/ncclRecv ({sim.shard.peer_error or 'QSV_SWAP=nccl'})", "swaps": nv, "share_of_step": (sum(ms for ms, _ in swap_ms) + sum(ms for ms, _ in fused_ms) + sum(ms for ms, _ in scatter_ms)) / total_ms,
+                       "pipelined_regions_share_of_step": sum(ms for ms, _, _ in piped) / total_ms,
                        "peak_gbs_per_direction": 900.0},
             "gpu_launches": len(per_launch) + (0 if prog.fused_init else 2 * args.steps),
             "clocks": clk,

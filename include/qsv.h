@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define QSV_ABI_VERSION 6
+#define QSV_ABI_VERSION 7
 
 /* dtypes (wenbo_engine/storage/block_store.py:11 fixes complex64; the oracle is complex128) */
 #define QSV_C64  0
@@ -217,12 +217,23 @@ int qsv_program_create(qsv_handle *h, const qsv_pass *passes, int n_passes,
 int qsv_program_run(qsv_handle *h, qsv_program *p);
 int qsv_program_destroy(qsv_handle *h, qsv_program *p);
 int qsv_program_run_range(qsv_handle *h, qsv_program *p, int first_pass, int n_passes);
-/* Pass `pass_index` followed by the swap of the top n_swap local bits, with the NVLink exchange
- * OVERLAPPED with the pass on a second stream: the shard is processed block by block in the order the
- * exchange consumes the blocks (see csrc/qsv.cu).  *overlapped = 0 if it had to fall back to
- * "pass, then swap" (pass not specialised / tile touches the swapped bits / peers not mapped). */
-int qsv_pass_swap_overlapped(qsv_handle *h, qsv_program *p, int pass_index, int n_swap, const int *global_bits,
-                             const int *local_bits, int *overlapped);
+/* Which passes of a program run on a specialised kernel (flags[i] = 1) — the host plumbing reduces this
+ * over all ranks before it chooses a collective execution path (pipelined transitions need every rank to
+ * take the same one). */
+int qsv_program_specialised(qsv_handle *h, qsv_program *p, int *flags, int n_flags);
+/* PIPELINED STAGE TRANSITION (replaces the reference's read / compute / write overlap,
+ * wenbo_engine/runner/pipeline.py:50-82, and HiSVSIM's gather_qubits between parts,
+ * hisvsim_repo/execute.hpp:665-685): the swap of rank bits global_bits[] with local bits local_bits[],
+ * executed chunk by chunk together with the passes next to it.  chunk_bits[] (1..4 ascending local
+ * positions, not swapped, in no tile of the named passes) cut the shard into 2^n_chunk chunks; for each
+ * chunk: passes [a_first, a_first + a_count) of `pa`, then the exchange, then passes [0, b_count) of `pb`.
+ * The pass launches use sm_count - xchg_sms SMs, the exchange kernels (TMA bulk copies through shared
+ * memory, csrc/xchg.cuh) xchg_sms SMs on a second stream; cross-GPU ordering is by flag words in peer
+ * memory (no NCCL, no host synchronisation).  Collective over the ranks of the swap group; every
+ * condition that does not hold is an error (nothing has run then), never a per-rank fallback. */
+int qsv_swap_pipelined(qsv_handle *h, qsv_program *pa, int a_first, int a_count, qsv_program *pb, int b_count,
+                       int n_swap, const int *global_bits, const int *local_bits, int n_chunk, const int *chunk_bits,
+                       int xchg_sms);
 /* SCATTER PASS: pass `pass_index` FUSED with the exchange that follows it — one kernel computes the pass
  * and stores every amplitude where it lives AFTER the swap of local bits local_bits[i] with rank bits
  * global_bits[i]: into the second buffer ("shadow") of this GPU or, by plain stores through NVLink,
@@ -305,6 +316,11 @@ int qsv_swap_global_local(qsv_handle *h, int n_swap, const int *global_bits, con
  * Without it (or QSV_OPT_PEER_SWAP=0) the chunked ncclSend/ncclRecv exchange is used. */
 int qsv_comm_ipc_handle(qsv_handle *h, void *out64);
 int qsv_comm_set_peers(qsv_handle *h, const void *handles /* world x 64 bytes */);
+/* The same wiring for SHARDS OF ONE PROCESS (handles of all ranks created by this process, on one or
+ * several devices it can address): no NCCL communicator, no IPC — shards[r] = qsv_device_ptr of rank r.
+ * Swaps then run on the exchange kernels of csrc/xchg.cuh, which order themselves through flag words. */
+int qsv_comm_init_local(qsv_handle *h);
+int qsv_comm_set_peers_local(qsv_handle *h, void *const *shards /* world pointers */);
 /* Sum one double across all shards (norm, sampling offsets). world==1: no-op. */
 int qsv_allreduce_sum(qsv_handle *h, double *value);
 

@@ -82,7 +82,8 @@ SIGNATURES = {
     "qsv_program_run": (C.c_int, [_H, _P]),
     "qsv_program_destroy": (C.c_int, [_H, _P]),
     "qsv_program_run_range": (C.c_int, [_H, _P, C.c_int, C.c_int]),
-    "qsv_pass_swap_overlapped": (C.c_int, [_H, _P, C.c_int, C.c_int, _ip, _ip, _ip]),
+    "qsv_program_specialised": (C.c_int, [_H, _P, _ip, C.c_int]),
+    "qsv_swap_pipelined": (C.c_int, [_H, _P, C.c_int, C.c_int, _P, C.c_int, C.c_int, _ip, _ip, C.c_int, _ip, C.c_int]),
     "qsv_shadow_ptr": (C.c_int, [_H, C.POINTER(C.c_void_p)]),
     "qsv_comm_shadow_ipc_handle": (C.c_int, [_H, C.c_void_p]),
     "qsv_comm_set_shadow_peers": (C.c_int, [_H, C.c_void_p]),
@@ -109,6 +110,8 @@ SIGNATURES = {
     "qsv_swap_global_local": (C.c_int, [_H, C.c_int, _ip, _ip]),
     "qsv_comm_ipc_handle": (C.c_int, [_H, C.c_void_p]),
     "qsv_comm_set_peers": (C.c_int, [_H, C.c_void_p]),
+    "qsv_comm_init_local": (C.c_int, [_H]),
+    "qsv_comm_set_peers_local": (C.c_int, [_H, C.POINTER(C.c_void_p)]),
     "qsv_allreduce_sum": (C.c_int, [_H, _dp]),
     "qsv_timing_enable": (C.c_int, [_H, C.c_int]),
     "qsv_get_timings": (C.c_int, [_H, C.POINTER(QsvTiming), C.c_int, _ip]),

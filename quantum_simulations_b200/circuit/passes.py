@@ -210,6 +210,18 @@ def lower_op(qubits, U, src: int = -1) -> list:
     return [Dense2Q(qa, qb, U, src)]
 
 
+def _ops_fingerprint(ir_ops) -> bytes:
+    """Content hash of a step-IR op list [(qubits, U)]: the key of the per-compiler lowering cache."""
+    import hashlib
+    h = hashlib.blake2b(digest_size=16)
+    h.update(len(ir_ops).to_bytes(8, "little"))
+    for qs, U in ir_ops:
+        h.update(bytes([len(qs)]))
+        h.update(np.asarray(list(qs), dtype=np.int64).tobytes())
+        h.update(np.ascontiguousarray(U, dtype=np.complex128).tobytes())
+    return h.digest()
+
+
 _LOWER_CACHE: dict = {}
 
 
@@ -549,7 +561,8 @@ class PassCompiler:
         n = self.n
         # the lowering depends only on the op list and the initial frame: planning the same circuit
         # for several initial placements (sharding.plan / plan_single) lowers it once
-        lkey = (id(ir_ops), len(ir_ops), tuple(init_flips) if init_flips is not None else None)
+        # (keyed by CONTENT: an id() can be recycled by a new list, and a list can be mutated in place)
+        lkey = (_ops_fingerprint(ir_ops), tuple(init_flips) if init_flips is not None else None)
         cached = getattr(self, "_lowered", None)
         alias = list(range(n))                      # IR qubit -> content
         xf = list(init_flips) if init_flips is not None else [0] * n   # Pauli-X frame per content

@@ -19,6 +19,8 @@ Cost model (seconds, per device), used only to rank candidate placements:
 """
 from __future__ import annotations
 
+from dataclasses import dataclass
+
 from quantum_simulations_b200.circuit.passes import PassCompiler, PassStep, Program, SwapStep
 
 HBM_BW = 5.8e12          # achieved by a pass kernel, B/s (profiles/r01)
@@ -181,3 +183,90 @@ def plan(ir_ops, n_qubits: int, n_local: int, dtype: str = "complex128", zero_in
         return fuse_init(comp.compile(ir_ops))
     best.stats["estimated_s"] = best_t
     return fuse_init(best)
+
+
+# ------------------------------------------------------------------ pipelined stage transitions
+# A SwapStep between two runs of passes can execute PIPELINED with its neighbours
+# (qsv_swap_pipelined, csrc/qsv.cu): the shard is cut into chunks by index bits that the neighbouring
+# passes do not have in their tiles, and chunk j of the exchange travels over NVLink while the passes
+# work on the other chunks.  This is the reference's reader / worker / writer overlap
+# (wenbo_engine/runner/pipeline.py:50-82) between HiSVSIM-style parts (hisvsim_repo/execute.hpp:665-685).
+XCHG_BW = 0.68e12        # measured, per direction: the TMA exchange kernel on 16 SMs (profiles/r02)
+PASS_BW = 5.2e12         # measured average of the pass kernel (profiles/r02)
+
+
+@dataclass
+class Transition:
+    """How one SwapStep is executed: the last `a_count` passes before it and the first `b_count` passes
+    after it run chunk by chunk around the exchange; chunk_bits are ascending local positions."""
+    a_count: int
+    b_count: int
+    chunk_bits: list
+
+
+def plan_transitions(prog: Program, max_chunk_bits: int = 4, min_chunk_pos: int = 10, max_side: int = 3,
+                     tile_bits: int = 11) -> dict:
+    """{index of a SwapStep in prog.steps: Transition}.  Greedy: passes are added on the side that costs
+    the fewest candidate chunk bits until the pipelined passes take as long as the exchange
+    (bytes / measured bandwidths), a side runs out of eligible passes, or fewer than one chunk bit of
+    position >= min_chunk_pos (runs of >= 16 KB for the TMA exchange kernel) would be left.  A pass is
+    eligible if it visits every tile and reads its input (no zero-support skipping, not the fused
+    initialisation); passes are never shared between two transitions."""
+    steps = prog.steps
+    amp = 16 if prog.dtype == "complex128" else 8
+    shard = amp * (1 << prog.n_local)
+    out: dict = {}
+    taken: set = set()
+
+    def eligible(k: int) -> bool:
+        if not 0 <= k < len(steps):
+            return False
+        s = steps[k]
+        return (isinstance(s, PassStep) and k not in taken and s.desc.n_active < 0
+                and not s.desc.zero_input and s.desc.n_tile == tile_bits)
+
+    for k, sw in enumerate(steps):
+        if not isinstance(sw, SwapStep):
+            continue
+        s_bits = len(sw.global_bits)
+        if s_bits > 3:
+            continue
+        avail = {p for p in range(min_chunk_pos, prog.n_local)} - set(sw.local_bits)
+        t_x = (1.0 - 0.5 ** s_bits) * shard / XCHG_BW
+        t_p = 2.0 * shard / PASS_BW / 0.89                 # a pass on sm_count - 16 SMs
+        want = max(2, min(2 * max_side, int(t_x / t_p + 0.999)))
+        a = b = 0
+        while a + b < want:
+            cands = []
+            if a < max_side and eligible(k - 1 - a):
+                cands.append(("a", k - 1 - a))
+            if b < max_side and eligible(k + 1 + b):
+                cands.append(("b", k + 1 + b))
+            best = None
+            for side, idx in cands:
+                d = steps[idx].desc
+                left = avail - set(d.load_bits[: d.n_tile])
+                if len(left) >= 1 and (best is None or len(left) > len(best[2])):
+                    best = (side, idx, left)
+            if best is None:
+                break
+            avail = best[2]
+            if best[0] == "a":
+                a += 1
+            else:
+                b += 1
+        if a + b == 0 or not avail:
+            continue
+        # chunks must stay large against the grid: >= 64 tiles per CTA of a chunked pass launch
+        c = min(max_chunk_bits, len(avail), max(0, prog.n_local - tile_bits - 13))
+        if prog.n_local - tile_bits - 13 < 1:
+            c = min(max_chunk_bits, len(avail), max(1, (prog.n_local - tile_bits) // 2))   # small (test) shards
+        if c < 1:
+            continue
+        bits = sorted(sorted(avail, reverse=True)[:c])
+        for i in range(a):
+            taken.add(k - 1 - i)
+        for i in range(b):
+            taken.add(k + 1 + i)
+        out[k] = Transition(a, b, bits)
+    return out

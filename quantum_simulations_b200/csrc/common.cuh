@@ -68,6 +68,10 @@ struct qsv_handle {
     size_t n_amps = 0;            // local amplitudes
     size_t amp_bytes = 16;
     void *d_state = nullptr;
+    // the shard allocation carries a small TAIL (flags of the exchange kernels, csrc/xchg.cuh) that the
+    // peers reach through the same mapping as the shard itself
+    void *alloc_base = nullptr;                 // what cudaMalloc returned (d_state, unless a scatter pass swapped roles)
+    unsigned long long *d_tail = nullptr;       // alloc_base + n_amps * amp_bytes
     // scatter passes write into a second buffer of the same size (allocated on demand); the two
     // exchange roles after every scatter pass.  scat_cur[r] / scat_other[r] = rank r's current and
     // second buffer as seen from this process (same-process pointers or CUDA IPC mappings).

@@ -62,10 +62,15 @@ struct Nccl {
 inline Nccl &nccl() { static Nccl n; return n; }
 
 struct Comm {
-    ncclComm_t comm = nullptr;
+    ncclComm_t comm = nullptr;   // null: shards of ONE process (qsv_comm_init_local), ordering by the flags alone
     // peer-memory path: the other shards of the box mapped into this process (CUDA IPC)
     std::vector<void *> peer;    // peer[r] = rank r's shard, nullptr if not mapped
+    std::vector<unsigned long long *> peer_tail;   // peer_tail[r] = flag words of rank r (xchg.cuh)
     bool peers_ready = false;
+    bool ipc_mapped = false;     // peer[] entries were opened with cudaIpcOpenMemHandle
+    unsigned long long seq = 0;  // sequence number of the exchange kernels (same on every rank)
+    std::vector<cudaEvent_t> ev_pool;   // events of pipelined transitions, reused
+    bool xchg_attr_set = false;
     void *bounce = nullptr;      // (peers) x chunk bytes, double buffered
     size_t bounce_bytes = 0;
     cudaStream_t copy_stream = nullptr;
@@ -78,8 +83,10 @@ struct Comm {
 static inline void qsv_comm_teardown(qsv_handle *h) {
     auto *c = (qsvx::Comm *)h->comm;
     if (!c) return;
-    for (size_t r = 0; r < c->peer.size(); ++r) if (c->peer[r] && (int)r != h->rank) cudaIpcCloseMemHandle(c->peer[r]);
+    if (c->ipc_mapped)
+        for (size_t r = 0; r < c->peer.size(); ++r) if (c->peer[r] && (int)r != h->rank) cudaIpcCloseMemHandle(c->peer[r]);
     if (c->comm) qsvx::nccl().CommDestroy(c->comm);
+    for (auto &e : c->ev_pool) cudaEventDestroy(e);
     if (c->bounce) cudaFree(c->bounce);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     for (auto &e : c->ev_xfer) if (e) cudaEventDestroy(e);
@@ -227,7 +234,113 @@ extern "C" int qsv_comm_set_peers(qsv_handle *h, const void *handles) {
             QSVX_FAIL(h, QSV_ECOMM, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
         }
     }
+    c->peer_tail.assign(h->world, nullptr);
+    for (int r = 0; r < h->world; ++r)
+        c->peer_tail[r] = r == h->rank ? h->d_tail : (unsigned long long *)((char *)c->peer[r] + h->n_amps * h->amp_bytes);
     c->peers_ready = true;
+    c->ipc_mapped = true;
+    return QSV_OK;
+}
+
+// Shards of ONE process (several handles on the devices this process can address directly — tests on a
+// single GPU, or one process driving a whole box): no NCCL communicator, no CUDA IPC; the exchange
+// kernels order themselves through the flag words of xchg.cuh.
+extern "C" int qsv_comm_init_local(qsv_handle *h) {
+    if (!h) return QSV_EINVAL;
+    if (h->comm) qsv_comm_teardown(h);
+    QSVX_CUDA(h, cudaSetDevice(h->device));
+    auto *c = new qsvx::Comm();
+    cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    for (auto &e : c->ev_xfer) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    for (auto &e : c->ev_copy) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    h->comm = c;
+    return QSV_OK;
+}
+
+// shards[r] = device pointer of rank r's shard (qsv_device_ptr of that handle), valid in this process
+extern "C" int qsv_comm_set_peers_local(qsv_handle *h, void *const *shards) {
+    if (!h || !shards) return QSV_EINVAL;
+    auto *c = (qsvx::Comm *)h->comm;
+    if (!c) QSVX_FAIL(h, QSV_ECOMM, "set_peers_local: qsv_comm_init_local was not called");
+    if (h->world > 8) QSVX_FAIL(h, QSV_EINVAL, "set_peers_local: world <= 8");
+    if (shards[h->rank] != h->d_state) QSVX_FAIL(h, QSV_EINVAL, "set_peers_local: entry %d must be this handle's shard", h->rank);
+    c->peer.assign(shards, shards + h->world);
+    c->peer_tail.assign(h->world, nullptr);
+    for (int r = 0; r < h->world; ++r) {
+        if (!shards[r]) QSVX_FAIL(h, QSV_EINVAL, "set_peers_local: null shard of rank %d", r);
+        c->peer_tail[r] = (unsigned long long *)((char *)shards[r] + h->n_amps * h->amp_bytes);
+    }
+    c->peers_ready = true;
+    c->ipc_mapped = false;
+    return QSV_OK;
+}
+
+// ---- exchange kernels of xchg.cuh: argument block of chunk `chunk_j` of a swap -------------------
+// chunk_bits: c local positions (none for a whole-shard exchange), disjoint from local_bits
+static int qsvx_xchg_args(qsv_handle *h, qsvx::Comm *c, int n_swap, const int *global_bits, const int *local_bits,
+                          int n_chunk, const int *chunk_bits, unsigned chunk_j, qsvx::XchgArgs &A, bool &tma_ok) {
+    memset(&A, 0, sizeof(A));
+    const int peers = 1 << n_swap;
+    int me = 0;
+    for (int i = 0; i < n_swap; ++i) me |= ((h->rank >> (global_bits[i] - h->n_local)) & 1) << i;
+    A.mine = (char *)h->d_state;
+    A.my_flags = h->d_tail;
+    A.my_rank = h->rank;
+    A.n_peers = peers;
+    A.me = me;
+    for (int d = 0; d < peers; ++d) {
+        int r = h->rank;
+        for (int i = 0; i < n_swap; ++i) {
+            const int rb = global_bits[i] - h->n_local;
+            r = (r & ~(1 << rb)) | (((d >> i) & 1) << rb);
+        }
+        A.peer[d] = (char *)c->peer[r];
+        A.peer_flags[d] = c->peer_tail[r];
+        A.rank_of[d] = r;
+        if (!A.peer[d] || !A.peer_flags[d]) QSVX_FAIL(h, QSV_ECOMM, "exchange: rank %d is not mapped", r);
+    }
+    int special[8], ns = 0;
+    for (int i = 0; i < n_swap; ++i) { special[ns++] = local_bits[i]; A.swap_pos[i] = local_bits[i]; }
+    for (int i = 0; i < n_chunk; ++i) {
+        special[ns++] = chunk_bits[i];
+        A.chunk_val |= (unsigned long long)((chunk_j >> i) & 1u) << chunk_bits[i];
+    }
+    std::sort(special, special + ns);
+    for (int i = 0; i + 1 < ns; ++i) if (special[i] == special[i + 1]) QSVX_FAIL(h, QSV_EINVAL, "exchange: repeated index bit %d", special[i]);
+    A.n_special = ns;
+    for (int i = 0; i < ns; ++i) A.pos[i] = special[i];
+    A.elem_log2 = h->amp_bytes == 16 ? 4u : 3u;
+    const int free_bits = h->n_local - ns;                 // compacted index bits of one pair
+    if (free_bits < 1) QSVX_FAIL(h, QSV_EINVAL, "exchange: shard too small for %d special bits", ns);
+    A.half_elems = 1ull << (free_bits - 1);
+    const unsigned half_log2 = (unsigned)(free_bits - 1) + A.elem_log2;          // log2(bytes of one half)
+    A.stage_log2 = std::min(14u, half_log2);
+    A.run_log2 = std::min(A.stage_log2, (unsigned)special[0] + A.elem_log2);
+    A.units_per_half = 1ull << (half_log2 - A.stage_log2);
+    A.seq = c->seq;
+    tma_ok = A.run_log2 >= 4 && A.stage_log2 >= 4 && (A.stage_log2 - A.run_log2) <= 6;   // <= 64 bulk copies per unit
+    if (A.run_log2 < 4) QSVX_FAIL(h, QSV_EINVAL, "exchange: runs of %u bytes (lowest swapped / chunk position %d) are below the 16-byte pieces the kernels move",
+                                  1u << A.run_log2, special[0]);
+    return QSV_OK;
+}
+
+// One exchange launch on `stream` with `sms` CTAs (one per SM: the TMA kernel claims the shared memory of its SM)
+static int qsvx_xchg_launch(qsv_handle *h, qsvx::Comm *c, cudaStream_t stream, const qsvx::XchgArgs &A, bool tma_ok, int sms) {
+    static const bool force_ldst = [] { const char *e = getenv("QSV_XCHG"); return e && !strcmp(e, "ldst"); }();
+    if (!c->xchg_attr_set) {
+        QSVX_CUDA(h, cudaFuncSetAttribute(qsvx::k_xchg_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsvx::xchg_smem_bytes(14)));
+        c->xchg_attr_set = true;
+    }
+    if (sms < 1) sms = 1;
+    if (tma_ok && !force_ldst) {
+        unsigned long long total = (unsigned long long)(A.n_peers - 1) * A.units_per_half;
+        const unsigned grid = (unsigned)std::min<unsigned long long>((unsigned long long)sms, std::max<unsigned long long>(total, 1ull));
+        // full-size stages claim the whole SM (no second CTA beside it); small test shards take what they need
+        qsvx::k_xchg_tma<<<grid, qsvx::kXchgThreads, qsvx::xchg_smem_bytes(A.stage_log2), stream>>>(A);
+    } else {
+        qsvx::k_xchg_ldst<4><<<(unsigned)sms, 1024, 0, stream>>>(A);
+    }
+    QSVX_CUDA(h, cudaGetLastError());
     return QSV_OK;
 }
 
@@ -311,6 +424,25 @@ extern "C" int qsv_swap_global_local(qsv_handle *h, int n_swap, const int *globa
         return r;
     };
     const size_t block_bytes = (h->n_amps >> n_swap) * h->amp_bytes;
+    static const bool xchg_default = [] { const char *e = getenv("QSV_SWAP_KERNEL"); return !(e && !strcmp(e, "pairs")); }();
+    if (c->peers_ready && h->use_peer_swap && (!c->comm || xchg_default)) {
+        // the whole exchange as ONE launch of the TMA kernel of xchg.cuh (its flag words are the barriers on
+        // both sides: no NCCL on this path); QSV_SWAP_KERNEL=pairs keeps the load/store kernel below
+        qsvx_timer_begin(h);
+        qsvx::XchgArgs A;
+        bool tma_ok = false;
+        ++c->seq;
+        int rc = qsvx_xchg_args(h, c, n_swap, global_bits, local_bits, 0, nullptr, 0u, A, tma_ok);
+        if (rc) return rc;
+        // one process per GPU: 32 SMs saturate NVLink twice over.  Shards of ONE process share a device, and
+        // a launch spins until its peers' launches are resident: all of them together must fit on it
+        const char *es = getenv("QSV_SWAP_SMS");
+        const int sms = es ? atoi(es) : (c->comm ? 32 : std::max(1, h->sm_count / (2 * h->world)));
+        rc = qsvx_xchg_launch(h, c, h->stream, A, tma_ok, sms);
+        if (rc) return rc;
+        qsvx_timer_end(h, 20 + n_swap);
+        return QSV_OK;
+    }
     if (c->peers_ready && h->use_peer_swap) {
         qsvx_timer_begin(h);
         PeerTable pt;

@@ -47,6 +47,16 @@ __device__ __forceinline__ uint32_t jit_slot(uint32_t x) { return tile_swizzle<3
 // of the rank whose swapped rank bits equal x, keep = this rank's swapped bits at the local positions
 struct JitDst { JV *p[8]; unsigned long long keep; };
 
+// index bits fixed from outside (a launch over ONE CHUNK of the shard: pipelined stage transitions run the
+// passes next to a swap chunk by chunk): the tile counter runs over the remaining non-tile bits; pos[] are
+// positions in TILE-INDEX space (tile bits removed), ascending; val = the fixed bits at those positions
+struct JitFix { unsigned n; unsigned pos[4]; unsigned long long val; };
+__device__ __forceinline__ unsigned long long jit_fix(unsigned long long t, const JitFix &F) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) if (i < (int)F.n) t = insert_zero_bit(t, (int)F.pos[i]);
+    return t | F.val;
+}
+
 struct JitRingSmem {
     JV buf[JIT_NBUF][2048];
     unsigned long long full[JIT_NBUF];

@@ -13,6 +13,7 @@
 #include "gate_kernels.cuh"
 #include "pass_kernel.cuh"
 #include "pass_ring.cuh"
+#include "xchg.cuh"
 #include "exchange.cuh"
 #include "jit.cuh"
 #include "sample.cuh"
@@ -153,8 +154,12 @@ int qsv_create(qsv_handle **out, int n_qubits, int dtype, int device, int rank, 
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) {
-        h->d_state = cache_take(device, h->n_amps * h->amp_bytes);
-        if (!h->d_state) e = cudaMalloc(&h->d_state, h->n_amps * h->amp_bytes);
+        const size_t bytes = h->n_amps * h->amp_bytes + qsvx::kTailBytes;
+        h->d_state = cache_take(device, bytes);
+        if (!h->d_state) e = cudaMalloc(&h->d_state, bytes);
+        h->alloc_base = h->d_state;
+        h->d_tail = (unsigned long long *)((char *)h->d_state + h->n_amps * h->amp_bytes);
+        if (e == cudaSuccess) e = cudaMemsetAsync(h->d_tail, 0, qsvx::kTailBytes, h->stream);
     }
     if (e == cudaSuccess) keep_pool_memory(device);
     if (e == cudaSuccess) { h->n_partials = kNormBlocks + 8; e = dev_alloc(h, (void **)&h->d_partials, h->n_partials * sizeof(double)); }
@@ -189,11 +194,12 @@ int qsv_destroy(qsv_handle *h) {
         if (h->comm) ((qsvx::Comm *)h->comm)->peer.clear();
     }
     qsv_comm_teardown(h);
+    if (h->d_state != h->alloc_base) std::swap(h->d_state, h->d_shadow);     // a scatter pass left the roles exchanged
     if (h->d_shadow) cudaFree(h->d_shadow);
     for (auto &t : h->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     if (h->t0) { cudaEventDestroy(h->t0); cudaEventDestroy(h->t1); }
     auto t2 = now();
-    if (h->n_amps * h->amp_bytes >= ((size_t)64 << 20)) cache_put(h->device, h->d_state, h->n_amps * h->amp_bytes);
+    if (h->n_amps * h->amp_bytes >= ((size_t)64 << 20)) cache_put(h->device, h->d_state, h->n_amps * h->amp_bytes + qsvx::kTailBytes);
     else cudaFree(h->d_state);
     auto t3 = now();
     dev_free(h, h->d_partials); dev_free(h, h->d_pass_scratch); dev_free(h, h->d_ops_scratch);
@@ -616,9 +622,15 @@ int qsv_program_create(qsv_handle *h, const qsv_pass *passes, int n_passes, cons
 }
 
 // tiles [tile_begin, tile_end) of pass i on `stream` (the whole pass: 0 .. n_amps >> 11)
-static int launch_pass_jit_range(qsv_handle *h, qsv_program *p, int i, uint32_t tile_begin, uint32_t tile_end, cudaStream_t stream) {
+struct JitFixArg { unsigned n; unsigned pos[4]; unsigned long long val; };   // = JitFix of jit_prelude.cuh
+
+static int launch_pass_jit_range(qsv_handle *h, qsv_program *p, int i, uint32_t tile_begin, uint32_t tile_end, cudaStream_t stream,
+                                 const JitFixArg *fix_in = nullptr, unsigned grid_cap = 0) {
     const uint32_t count = tile_end - tile_begin;
-    const unsigned grid = count < (uint32_t)h->sm_count ? count : (unsigned)h->sm_count;
+    const unsigned cap = grid_cap ? grid_cap : (unsigned)h->sm_count;
+    const unsigned grid = count < cap ? count : cap;
+    JitFixArg fix = {};
+    if (fix_in) fix = *fix_in;
     void *state = h->d_state;
     const double2 *tables = p->d_tables + p->fold_offset[i];
     unsigned long long rank_bits = (unsigned long long)h->rank << h->n_local;
@@ -626,9 +638,26 @@ static int launch_pass_jit_range(qsv_handle *h, qsv_program *p, int i, uint32_t 
     static const double zero = 0.0;
     void *coefs = p->jit_coefs[i].empty() ? (void *)&zero
                 : (h->dtype == QSV_C64 ? (void *)p->jit_coefs_f[i].data() : (void *)p->jit_coefs[i].data());
-    void *args[] = {&state, &tables, &rank_bits, &tb, &te, coefs};
+    void *args[] = {&state, &tables, &rank_bits, &tb, &te, coefs, &fix};
     QSV_CUDA(h, cudaLaunchKernel((const void *)p->jit[i], dim3(grid), dim3(128 * (qsvjit::groups() + 1)), args, qsvjit::kSmemBytes, stream));
     return QSV_OK;
+}
+
+// pass i restricted to the chunk whose index bits chunk_bits[] (local positions outside the tile) equal chunk_j
+static int launch_pass_jit_chunk(qsv_handle *h, qsv_program *p, int i, int n_chunk, const int *chunk_bits, unsigned chunk_j,
+                                 unsigned grid_cap, cudaStream_t stream) {
+    const qsv_pass &P = p->passes[i];
+    JitFixArg fix = {};
+    fix.n = (unsigned)n_chunk;
+    for (int k = 0; k < n_chunk; ++k) {
+        int below = 0;
+        for (int t = 0; t < P.n_tile; ++t) below += P.load_bits[t] < chunk_bits[k];
+        fix.pos[k] = (unsigned)(chunk_bits[k] - below);                  // position in tile-index space
+        fix.val |= (unsigned long long)((chunk_j >> k) & 1u) << fix.pos[k];
+    }
+    const uint32_t tiles = (uint32_t)((h->n_amps >> qsvjit::kT) >> n_chunk);
+    ScopedTimer t(h, 11, i);                                             // kind 11: one chunk of a pass
+    return launch_pass_jit_range(h, p, i, 0u, tiles, stream, &fix, grid_cap);
 }
 
 static int launch_pass_jit(qsv_handle *h, qsv_program *p, int i) {
@@ -673,69 +702,110 @@ int qsv_program_run_range(qsv_handle *h, qsv_program *p, int first, int count) {
     return QSV_OK;
 }
 
-// Pass `pass_index` of the program followed by the swap of the TOP n_swap local bits with rank bits
-// global_bits[], with the exchange OVERLAPPED with the pass: when the pass's tile does not contain
-// the swapped local bits, the shard splits into 2^n_swap blocks that the pass processes one by one,
-// in the order in which the swap needs them (phase k: block me ^ (k+1)); the peer-memory exchange
-// of a block pair runs on the copy stream as soon as both owners have finished that block, while
-// the compute stream continues with the next block.  Falls back to "pass, then swap" when the
-// conditions do not hold (pass not specialised, bits not on top, peers not mapped).
-int qsv_pass_swap_overlapped(qsv_handle *h, qsv_program *p, int pass_index, int n_swap, const int *global_bits,
-                             const int *local_bits, int *overlapped) {
+// ------------------------------------------------------- pipelined stage transition ----
+// A swap of rank bits with local bits, PIPELINED with the passes around it.  The shard is cut into
+// 2^n_chunk CHUNKS by index bits that none of those passes has in its tile (and that are not swapped):
+// a pass restricted to a chunk is an independent launch (tiles never cross chunks), and so is the
+// exchange of a chunk.  For chunk j:  passes a_first .. a_first+a_count-1 of `pa`  ->  exchange  ->
+// passes 0 .. b_count-1 of `pb`, with the pass launches on the handle's stream (sm_count - xchg_sms
+// CTAs) and the exchange kernels (csrc/xchg.cuh, xchg_sms CTAs of one SM each) on the copy stream, so
+// the NVLink transfer of chunk j runs beside the arithmetic of chunks j+1, j+2 (before the swap) and
+// j-1, j-2 (after it).  Cross-GPU ordering is inside the exchange kernels (flag words in peer memory);
+// nothing here blocks the host.  Every rank of the group must make the same call (same programs, same
+// bits): the CALLER agrees on that collectively (qsv_program_specialised over all ranks) — the library
+// never decides per rank.  Conditions that do not hold are an error, not a silent fallback.
+int qsv_program_specialised(qsv_handle *h, qsv_program *p, int *flags, int n) {
     QSV_CHECK_H(h);
-    if (overlapped) *overlapped = 0;
-    if (!p || pass_index < 0 || (size_t)pass_index >= p->passes.size()) QSV_FAIL(h, QSV_EINVAL, "pass_swap_overlapped: bad pass");
+    if (!p || !flags || n < (int)p->passes.size()) QSV_FAIL(h, QSV_EINVAL, "program_specialised: bad arguments");
+    for (size_t i = 0; i < p->passes.size(); ++i) flags[i] = p->jit[i] != nullptr;
+    return QSV_OK;
+}
+
+int qsv_swap_pipelined(qsv_handle *h, qsv_program *pa, int a_first, int a_count, qsv_program *pb, int b_count,
+                       int n_swap, const int *global_bits, const int *local_bits, int n_chunk, const int *chunk_bits,
+                       int xchg_sms) {
+    QSV_CHECK_H(h);
     auto *c = (qsvx::Comm *)h->comm;
-    bool ok = c && c->peers_ready && h->use_peer_swap && p->jit[pass_index] && n_swap >= 1 && n_swap <= 3 &&
-              global_bits && local_bits && (h->n_local - n_swap) >= qsvjit::kT + 1;
-    unsigned seen = 0;                                           // the TOP n_swap local positions, any order
-    for (int i = 0; ok && i < n_swap; ++i) {
-        const int rel = local_bits[i] - (h->n_local - n_swap);
-        ok = rel >= 0 && rel < n_swap && !((seen >> rel) & 1u);
-        if (ok) seen |= 1u << rel;
+    if (!c || !c->peers_ready || !h->use_peer_swap) QSV_FAIL(h, QSV_ECOMM, "swap_pipelined: peers are not mapped");
+    const int g = h->n_qubits - h->n_local;
+    if (n_swap < 1 || n_swap > 3 || n_swap > g || !global_bits || !local_bits) QSV_FAIL(h, QSV_EINVAL, "swap_pipelined: bad swap bits");
+    if (n_chunk < 1 || n_chunk > 4 || !chunk_bits) QSV_FAIL(h, QSV_EINVAL, "swap_pipelined: 1..4 chunk bits");
+    if (a_count < 0 || b_count < 0 || (a_count && !pa) || (b_count && !pb)) QSV_FAIL(h, QSV_EINVAL, "swap_pipelined: bad pass ranges");
+    if (a_count && (a_first < 0 || (size_t)(a_first + a_count) > pa->passes.size())) QSV_FAIL(h, QSV_EINVAL, "swap_pipelined: pass range A");
+    if (b_count && (size_t)b_count > pb->passes.size()) QSV_FAIL(h, QSV_EINVAL, "swap_pipelined: pass range B");
+    uint64_t special = 0;
+    for (int i = 0; i < n_swap; ++i) {
+        if (global_bits[i] < h->n_local || global_bits[i] >= h->n_qubits) QSV_FAIL(h, QSV_EINVAL, "swap_pipelined: global bit %d is not a rank bit", global_bits[i]);
+        if (local_bits[i] < 0 || local_bits[i] >= h->n_local || ((special >> local_bits[i]) & 1)) QSV_FAIL(h, QSV_EINVAL, "swap_pipelined: local bit %d", local_bits[i]);
+        for (int j = 0; j < i; ++j) if (global_bits[i] == global_bits[j]) QSV_FAIL(h, QSV_EINVAL, "swap_pipelined: repeated rank bit");
+        special |= 1ull << local_bits[i];
     }
-    const qsv_pass &P = p->passes[pass_index];
-    ok = ok && P.n_active < 0 && !P.zero_input;
-    for (int i = 0; ok && i < P.n_tile; ++i)
-        ok = P.load_bits[i] < h->n_local - n_swap && P.store_bits[i] < h->n_local - n_swap;
-    if (!ok) {
-        int rc = qsv_program_run_range(h, p, pass_index, 1);
-        if (rc) return rc;
-        return qsv_swap_global_local(h, n_swap, global_bits, local_bits);
+    uint64_t chunk_mask = 0;
+    for (int i = 0; i < n_chunk; ++i) {
+        if (chunk_bits[i] < 0 || chunk_bits[i] >= h->n_local || ((special >> chunk_bits[i]) & 1) || (i && chunk_bits[i] <= chunk_bits[i - 1]))
+            QSV_FAIL(h, QSV_EINVAL, "swap_pipelined: chunk bits must be ascending local positions that are not swapped (entry %d = %d)", i, chunk_bits[i]);
+        special |= 1ull << chunk_bits[i];
+        chunk_mask |= 1ull << chunk_bits[i];
     }
-    QSV_CUDA(h, cudaSetDevice(h->device));
-    const int peers = 1 << n_swap;
-    int me = 0;
-    for (int i = 0; i < n_swap; ++i) me |= ((h->rank >> (global_bits[i] - h->n_local)) & 1) << i;
-    const uint32_t n_tiles = (uint32_t)(h->n_amps >> qsvjit::kT);
-    const uint32_t per_block = n_tiles >> n_swap;            // the top local bits are the top tile-index bits
-    cudaStream_t S = h->stream, X = c->copy_stream;
-    ScopedTimer t(h, 30 + n_swap, pass_index);
-    cudaEvent_t ev;
-    QSV_CUDA(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    // block value d (bit i = local bit local_bits[i]) -> index of its contiguous range of tiles
-    auto tile_block = [&](int d) {
-        uint32_t b = 0;
-        for (int i = 0; i < n_swap; ++i) b |= (uint32_t)((d >> i) & 1) << (local_bits[i] - (h->n_local - n_swap));
-        return b;
+    auto check_pass = [&](qsv_program *p, int i) -> const char * {
+        if (!p->jit[i]) return "is not specialised";
+        const qsv_pass &P = p->passes[i];
+        if (P.n_active >= 0 || P.zero_input) return "skips tiles / creates the state itself";
+        for (int k = 0; k < P.n_tile; ++k) if ((chunk_mask >> P.load_bits[k]) & 1) return "has a chunk bit in its tile";
+        return nullptr;
     };
-    for (int k = 0; k < peers - 1; ++k) {
-        const int d = me ^ (k + 1);
-        int rc = launch_pass_jit_range(h, p, pass_index, tile_block(d) * per_block, (tile_block(d) + 1) * per_block, S);
-        if (rc) return rc;
-        QSV_CUDA(h, cudaEventRecord(ev, S));
-        QSV_CUDA(h, cudaStreamWaitEvent(X, ev, 0));
-        rc = qsvx_swap_phase(h, c, X, n_swap, global_bits, local_bits, k);       // barrier + one phase of the exchange
-        if (rc) return rc;
+    for (int i = 0; i < a_count; ++i) if (const char *why = check_pass(pa, a_first + i)) QSV_FAIL(h, QSV_EINVAL, "swap_pipelined: pass %d before the swap %s", a_first + i, why);
+    for (int i = 0; i < b_count; ++i) if (const char *why = check_pass(pb, i)) QSV_FAIL(h, QSV_EINVAL, "swap_pipelined: pass %d after the swap %s", i, why);
+    if (h->n_local - n_chunk < qsvjit::kT) QSV_FAIL(h, QSV_EINVAL, "swap_pipelined: chunks smaller than a tile");
+    QSV_CUDA(h, cudaSetDevice(h->device));
+    if (xchg_sms < 1) xchg_sms = 1;
+    if (xchg_sms > h->sm_count / 2) xchg_sms = h->sm_count / 2;
+    const unsigned pass_grid = (unsigned)(h->sm_count - xchg_sms);
+    const int J = 1 << n_chunk;
+    // a spinning exchange kernel must never wait for a kernel whose FIRST launch still has to load its
+    // module (lazy loading synchronises the context): touch every function of the pipeline now
+    {
+        cudaFuncAttributes fa;
+        for (int i = 0; i < a_count; ++i) QSV_CUDA(h, cudaFuncGetAttributes(&fa, (const void *)pa->jit[a_first + i]));
+        for (int i = 0; i < b_count; ++i) QSV_CUDA(h, cudaFuncGetAttributes(&fa, (const void *)pb->jit[i]));
+        QSV_CUDA(h, cudaFuncGetAttributes(&fa, (const void *)qsvx::k_xchg_tma));
+        QSV_CUDA(h, cudaFuncGetAttributes(&fa, (const void *)qsvx::k_xchg_ldst<4>));
     }
-    int rc = launch_pass_jit_range(h, p, pass_index, tile_block(me) * per_block, (tile_block(me) + 1) * per_block, S);
-    if (rc) return rc;
-    rc = qsvx_swap_barrier_on(h, c, X);                       // every exchange has landed everywhere
-    if (rc) return rc;
-    QSV_CUDA(h, cudaEventRecord(ev, X));
-    QSV_CUDA(h, cudaStreamWaitEvent(S, ev, 0));
-    QSV_CUDA(h, cudaEventDestroy(ev));
-    if (overlapped) *overlapped = 1;
+    while ((int)c->ev_pool.size() < 2 * J) {
+        cudaEvent_t e;
+        QSV_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->ev_pool.push_back(e);
+    }
+    cudaStream_t S = h->stream, X = c->copy_stream;
+    cudaEvent_t *evA = c->ev_pool.data(), *evX = c->ev_pool.data() + J;
+    ScopedTimer timer(h, 50 + n_swap, a_count * 16 + b_count);
+    const int lag = 2;
+    auto after = [&](int j) -> int {                     // passes after the swap on chunk j
+        QSV_CUDA(h, cudaStreamWaitEvent(S, evX[j], 0));
+        for (int i = 0; i < b_count; ++i) {
+            int rc = launch_pass_jit_chunk(h, pb, i, n_chunk, chunk_bits, (unsigned)j, pass_grid, S);
+            if (rc) return rc;
+        }
+        return QSV_OK;
+    };
+    for (int j = 0; j < J; ++j) {
+        for (int i = 0; i < a_count; ++i) {
+            int rc = launch_pass_jit_chunk(h, pa, a_first + i, n_chunk, chunk_bits, (unsigned)j, pass_grid, S);
+            if (rc) return rc;
+        }
+        QSV_CUDA(h, cudaEventRecord(evA[j], S));
+        QSV_CUDA(h, cudaStreamWaitEvent(X, evA[j], 0));
+        qsvx::XchgArgs A;
+        bool tma_ok = false;
+        ++c->seq;
+        int rc = qsvx_xchg_args(h, c, n_swap, global_bits, local_bits, n_chunk, chunk_bits, (unsigned)j, A, tma_ok);
+        if (rc) return rc;
+        rc = qsvx_xchg_launch(h, c, X, A, tma_ok, xchg_sms);
+        if (rc) return rc;
+        QSV_CUDA(h, cudaEventRecord(evX[j], X));
+        if (j >= lag) { rc = after(j - lag); if (rc) return rc; }
+    }
+    for (int j = J - lag < 0 ? 0 : J - lag; j < J; ++j) { int rc = after(j); if (rc) return rc; }
     return QSV_OK;
 }
 
@@ -891,7 +961,8 @@ int qsv_pass_scatter(qsv_handle *h, qsv_program *p, int pass_index, int n_swap, 
         static const double zero = 0.0;
         void *coefs = p->jit_coefs[pass_index].empty() ? (void *)&zero
                     : (h->dtype == QSV_C64 ? (void *)p->jit_coefs_f[pass_index].data() : (void *)p->jit_coefs[pass_index].data());
-        void *args[] = {&state, &tables, &rank_bits, &tb, &te, coefs, &dst};
+        JitFixArg fix = {};
+        void *args[] = {&state, &tables, &rank_bits, &tb, &te, coefs, &fix, &dst};
         QSV_CUDA(h, cudaLaunchKernel((const void *)fn, dim3(grid), dim3(128 * (qsvjit::groups() + 1)), args, qsvjit::kSmemBytes, h->stream));
         if (c && c->comm) {                          // all stores of all ranks have landed before anyone reads
             int rc = swap_barrier(h, c);

@@ -24,44 +24,97 @@ from quantum_simulations_b200.circuit.passes import PassStep, Program, SwapStep
 
 
 def execute(prog: Program, backend) -> None:
-    """Run `prog` on one shard.  `backend` provides run_passes(list[PassStep]) and
-    swap(global_bits, local_bits); consecutive passes are handed over together so that the
-    CUDA backend can specialise and replay them as one program."""
-    run: list = []
-    for step in list(prog.steps) + [None]:
-        if isinstance(step, PassStep):
-            run.append(step)
+    """Run `prog` on one shard.  `backend` provides run_passes(steps, first, count) over a maximal run of
+    consecutive passes and swap(global_bits, local_bits).  A backend that also has
+    ``transition(swap_step)`` / ``swap_pipelined(...)`` (CudaShard after prepare()) executes the swaps it
+    has a plan for PIPELINED with the passes next to them (sharding.plan_transitions); the passes a
+    transition consumed are skipped here."""
+    steps = list(prog.steps)
+    runs: list = []                      # (first index, [PassStep...]) maximal runs
+    k = 0
+    while k < len(steps):
+        if isinstance(steps[k], PassStep):
+            j = k
+            while j < len(steps) and isinstance(steps[j], PassStep):
+                j += 1
+            runs.append((k, steps[k:j]))
+            k = j
+        else:
+            if not isinstance(steps[k], SwapStep):
+                raise TypeError(f"sharded programs hold passes and swaps only, got {type(steps[k]).__name__}")
+            k += 1
+    run_at = {first: run for first, run in runs}
+    run_end = {first + len(run): (first, run) for first, run in runs}
+    plan_of = getattr(backend, "transition", lambda _s: None)
+    done_head: dict = {}                 # first index of a run -> passes already executed by a transition
+    k = 0
+    while k < len(steps):
+        st = steps[k]
+        if isinstance(st, PassStep):
+            run = run_at[k]
+            head = done_head.get(k, 0)
+            nxt = k + len(run)
+            tr = plan_of(steps[nxt]) if nxt < len(steps) else None
+            tail = tr.a_count if tr is not None else 0
+            scatter = tr is None and nxt < len(steps) and getattr(backend, "fused_exchange", False) and head < len(run)
+            if scatter:
+                tail = 1                 # scatter pass (opt-in): the last pass of the run is fused with the exchange
+            if len(run) - head - tail > 0:
+                if head == 0 and tail == 0:
+                    backend.run_passes(run)
+                else:
+                    backend.run_passes(run, head, len(run) - head - tail)
+            if scatter:
+                backend.scatter_swap(run, list(steps[nxt].global_bits), list(steps[nxt].local_bits))
+                nxt += 1
+            k = nxt
             continue
-        if run and isinstance(step, SwapStep) and hasattr(backend, "run_passes_then_swap"):
-            backend.run_passes_then_swap(run, list(step.global_bits), list(step.local_bits))
-            run = []
-            continue
-        if run:
-            backend.run_passes(run)
-            run = []
-        if isinstance(step, SwapStep):
-            backend.swap(list(step.global_bits), list(step.local_bits))
-        elif step is not None:
-            raise TypeError(f"sharded programs hold passes and swaps only, got {type(step).__name__}")
+        tr = plan_of(st)
+        if tr is None:
+            backend.swap(list(st.global_bits), list(st.local_bits))
+        else:
+            before = run_end.get(k)
+            after = run_at.get(k + 1)
+            backend.swap_pipelined(before[1] if before else None, tr.a_count, after if after else None, tr.b_count,
+                                   list(st.global_bits), list(st.local_bits), list(tr.chunk_bits))
+            if after is not None:
+                done_head[k + 1] = tr.b_count
+        k += 1
 
 
 class CudaShard:
     """backend of `execute` over libqsv: a DeviceState for (rank, world) with an NCCL communicator."""
 
     def __init__(self, n_qubits: int, rank: int, world: int, dtype="complex128", device: int | None = None,
-                 unique_id: bytes | None = None):
+                 unique_id: bytes | None = None, local: bool = False):
+        """local=True: this shard is one of several handles of ONE process (wire them with
+        ``CudaShard.wire_local``): no NCCL communicator, swaps run on the flag-ordered exchange kernels."""
         from quantum_simulations_b200.kernel.cuda import DeviceState
         self.state = DeviceState(n_qubits, dtype, rank if device is None else device, rank, world)
         self.rank, self.world = rank, world
         self._uploaded: dict = {}
         self.peer_swap, self.peer_error = False, None
         self.fused_exchange, self.fused_error = False, None
-        self.swaps = self.overlapped_swaps = self.fused_swaps = 0
-        if world > 1:
+        self.swaps = self.pipelined_swaps = self.fused_swaps = 0
+        self._transitions: dict = {}          # id(SwapStep) -> (SwapStep, Transition)
+        self.pipeline = os.environ.get("QSV_PIPELINE", "1") != "0"
+        self.xchg_sms = int(os.environ.get("QSV_XCHG_SMS", "16"))
+        if world > 1 and local:
+            self.state._ck(self.state.lib.qsv_comm_init_local(self.state._h))
+        elif world > 1:
             if unique_id is None or len(unique_id) != 128:
                 raise ValueError("world > 1 needs the 128-byte NCCL unique id of rank 0 (nccl_unique_id())")
             buf = C.create_string_buffer(unique_id, 128)
             self.state._ck(self.state.lib.qsv_comm_init(self.state._h, buf))
+
+    @staticmethod
+    def wire_local(shards) -> None:
+        """Shards of one process: hand every handle the device pointers of all of them."""
+        world = len(shards)
+        ptrs = (C.c_void_p * world)(*[s.state.device_ptr()[0] for s in shards])
+        for s in shards:
+            s.state._ck(s.state.lib.qsv_comm_set_peers_local(s.state._h, ptrs))
+            s.peer_swap = True
 
     def map_peers(self, dist) -> bool:
         """Exchange CUDA IPC handles of the shards (plumbing: an all-gather of 64 bytes per rank) so
@@ -113,32 +166,92 @@ class CudaShard:
         self.fused_exchange = all(flags)                 # all ranks must take the same path
         return self.fused_exchange
 
-    def prepare(self, prog: Program) -> None:
-        """Upload (and specialise) every run of passes once; execute() then only replays."""
+    def prepare(self, prog: Program, agree=None) -> None:
+        """Upload (and specialise) every run of passes once; execute() then only replays.  Swaps get a
+        pipelined transition (sharding.plan_transitions) when the peers are mapped and every pass it names
+        is specialised ON EVERY RANK: `agree(flag) -> bool` is the collective AND over the ranks
+        (ShardedSimulator passes an all-reduce; shards of one process are agreed by their driver)."""
+        steps = list(prog.steps)
+        handle_at: dict = {}
         run: list = []
-        for step in list(prog.steps) + [None]:
+        for k, step in enumerate(steps + [None]):
             if isinstance(step, PassStep):
                 run.append(step)
             elif run:
-                h = self._uploaded[id(run[0])] = self.state.upload_steps(run)
+                h = self.state.upload_steps(run)
+                self._uploaded[id(run[0])] = (run[0], h)       # the step object is kept alive: its id cannot be recycled
+                for i in range(len(run)):
+                    handle_at[k - len(run) + i] = (h, i)
                 if self.fused_exchange and isinstance(step, SwapStep):
                     l = (C.c_int * len(step.local_bits))(*step.local_bits)
                     self.state.lib.qsv_pass_scatter_prepare(self.state._h, h, len(run) - 1, len(step.local_bits), l)
                 run = []
+        if not (self.pipeline and self.peer_swap and not self.fused_exchange):
+            return
+        plans = sharding.plan_transitions(prog, min_chunk_pos=10 if prog.n_local >= 24 else 5)
+        for k in sorted(plans):
+            tr = plans[k]
+            ok = True
+            for idx in [k - 1 - i for i in range(tr.a_count)] + [k + 1 + i for i in range(tr.b_count)]:
+                h, i = handle_at[idx]
+                n = 64
+                flags = (C.c_int * n)()
+                # programs hold at most a few dozen passes; a longer one is simply not pipelined
+                ok = ok and i < n and self.state.lib.qsv_program_specialised(self.state._h, h, flags, n) == 0 and bool(flags[i])
+            if agree is not None:
+                ok = agree(bool(ok))
+            if ok:
+                self._transitions[id(steps[k])] = (steps[k], tr)
 
-    def run_passes(self, steps) -> None:
-        h = self._uploaded.get(id(steps[0]))
-        if h is None:
+    def transition(self, swap_step):
+        e = self._transitions.get(id(swap_step))
+        return e[1] if e is not None and e[0] is swap_step else None
+
+    def _handle_of(self, steps):
+        e = self._uploaded.get(id(steps[0]))
+        return e[1] if e is not None and e[0] is steps[0] else None
+
+    def release(self, prog: Program | None = None) -> None:
+        """Forget the device programs (and transitions) of `prog` (default: of every prepared program)."""
+        keep = {}
+        mine = None if prog is None else {id(s) for s in prog.steps}
+        for k, (step, h) in self._uploaded.items():
+            if mine is None or k in mine:
+                self.state.release_program(h)
+            else:
+                keep[k] = (step, h)
+        self._uploaded = keep
+        self._transitions = {k: v for k, v in self._transitions.items() if mine is not None and k not in mine}
+
+    def run_passes(self, steps, first: int = 0, count: int | None = None) -> None:
+        count = len(steps) - first if count is None else count
+        h = self._handle_of(steps)
+        temp = h is None
+        if temp:
             h = self.state.upload_steps(steps)
-            self.state.replay(h)
+        self.state._ck(self.state.lib.qsv_program_run_range(self.state._h, h, first, count))
+        if temp:
             self.state.release_program(h)
-        else:
-            self.state.replay(h)
 
-    def run_passes_then_swap(self, steps, global_bits, local_bits) -> None:
-        """All passes but the last as usual; the last one overlapped with the exchange
-        (qsv_pass_swap_overlapped) when its tile leaves the swapped bits alone."""
-        h = self._uploaded.get(id(steps[0]))
+    def swap_pipelined(self, before, a_count, after, b_count, global_bits, local_bits, chunk_bits) -> None:
+        """The swap together with the last a_count passes of `before` and the first b_count passes of
+        `after` (lists of PassStep prepared on this shard), chunk by chunk (qsv_swap_pipelined)."""
+        st, lib = self.state, self.state.lib
+        ha = self._handle_of(before) if a_count else None
+        hb = self._handle_of(after) if b_count else None
+        if (a_count and ha is None) or (b_count and hb is None):
+            raise RuntimeError("swap_pipelined: the neighbouring passes were not prepared on this shard")
+        s = len(global_bits)
+        g, l = (C.c_int * s)(*global_bits), (C.c_int * s)(*local_bits)
+        cb = (C.c_int * len(chunk_bits))(*chunk_bits)
+        st._ck(lib.qsv_swap_pipelined(st._h, ha, (len(before) - a_count) if a_count else 0, a_count, hb, b_count,
+                                      s, g, l, len(chunk_bits), cb, self.xchg_sms))
+        self.swaps += 1
+        self.pipelined_swaps += 1
+
+    def scatter_swap(self, steps, global_bits, local_bits) -> None:
+        """Scatter pass (opt-in, 2x memory): the LAST pass of `steps` fused with the exchange (qsv_pass_scatter)."""
+        h = self._handle_of(steps)
         temp = h is None
         if temp:
             h = self.state.upload_steps(steps)
@@ -147,14 +260,8 @@ class CudaShard:
         g = (C.c_int * s)(*global_bits)
         l = (C.c_int * s)(*local_bits)
         ov = C.c_int(0)
-        if len(steps) > 1:
-            st._ck(lib.qsv_program_run_range(st._h, h, 0, len(steps) - 1))
-        if self.fused_exchange:
-            st._ck(lib.qsv_pass_scatter(st._h, h, len(steps) - 1, s, g, l, C.byref(ov)))
-            self.fused_swaps += int(ov.value)
-        else:
-            st._ck(lib.qsv_pass_swap_overlapped(st._h, h, len(steps) - 1, s, g, l, C.byref(ov)))
-            self.overlapped_swaps += int(ov.value)
+        st._ck(lib.qsv_pass_scatter(st._h, h, len(steps) - 1, s, g, l, C.byref(ov)))
+        self.fused_swaps += int(ov.value)
         self.swaps += 1
         if temp:
             self.state.release_program(h)
@@ -167,6 +274,7 @@ class CudaShard:
         self.state._ck(self.state.lib.qsv_swap_global_local(self.state._h, s, g, l))
 
     def close(self) -> None:
+        self._uploaded = {}                   # the handle owns the device programs
         self.state.close()
 
 
@@ -222,6 +330,7 @@ class ShardedSimulator:
             fused_exchange = os.environ.get("QSV_FUSED_EXCHANGE", "0") == "1"
         self.fused_exchange = bool(fused_exchange) and self.peer_swap and self.shard.map_shadows(self.dist)
         self.logical_rank, self._flip_mask = self.rank, 0
+        self._prepared: dict = {}
 
     def plan(self, circuit_dict: dict, **compiler_kw) -> Program:
         from quantum_simulations_b200.kernel.cuda_dense import circuit_ops
@@ -258,10 +367,28 @@ class ShardedSimulator:
         self.run(prog)
         return self.shard.state.download(out)
 
+    def _agree(self, flag: bool) -> bool:
+        """Collective AND over the ranks (host plumbing): every rank takes the same execution path."""
+        if self.dist is None:
+            return bool(flag)
+        box = [None] * self.world
+        self.dist.all_gather_object(box, bool(flag))
+        return all(box)
+
+    def prepare(self, prog: Program) -> None:
+        """Upload and specialise the passes of `prog` and plan its pipelined transitions (collective)."""
+        self.shard.prepare(prog, self._agree)
+        self._prepared[id(prog)] = prog
+
     def run(self, prog: Program) -> None:
+        temp = self._prepared.get(id(prog)) is not prog
+        if temp:
+            self.shard.prepare(prog, self._agree)
         if not prog.fused_init:                # otherwise the first pass creates |0...0> itself
             self.shard.state.init_zero()
         execute(prog, self.shard)
+        if temp:
+            self.shard.release(prog)
         self.logical_rank = self.rank ^ prog.rank_flip_mask
         self._flip_mask = prog.rank_flip_mask
 

@@ -46,7 +46,8 @@ class FakeShard:
     def __init__(self, emu, state):
         self.emu, self.state = emu, state
 
-    def prepare(self, prog): pass
+    def prepare(self, prog, agree=None): pass
+    def release(self, prog=None): pass
 
     def run_passes(self, steps):
         t0 = time.perf_counter()
@@ -69,11 +70,14 @@ class FakeSim:
         emu = EmuShard(n, self.rank, self.world, self.dist)
         self.shard = FakeShard(emu, FakeState(emu))
         self.peer_swap, self.logical_rank, self._flip_mask = False, self.rank, 0
+        self._prepared = {}
 
     plan = MG.ShardedSimulator.plan
     plan_ops = MG.ShardedSimulator.plan_ops
     simulate_qasm = MG.ShardedSimulator.simulate_qasm
     run = MG.ShardedSimulator.run
+    prepare = MG.ShardedSimulator.prepare
+    _agree = MG.ShardedSimulator._agree
 
     def simulate(self, cd, out=None, **kw):
         self.run(self.plan(cd, **kw))

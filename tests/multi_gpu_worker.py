@@ -52,11 +52,11 @@ def main():
             got = np.concatenate([parts[l ^ mask].numpy().view(np.complex128) for l in range(world)])
             want = CO.simulate_c(cd)
             err = float(np.abs(got - want).max())
-            print(f"{name}: n={n} world={world} max|d|={err:.3e} swaps={sim.shard.swaps} overlapped={sim.shard.overlapped_swaps} "
+            print(f"{name}: n={n} world={world} max|d|={err:.3e} swaps={sim.shard.swaps} pipelined={sim.shard.pipelined_swaps} "
                   f"scatter_passes={sim.shard.fused_swaps}", flush=True)
             worst = max(worst, err)
             if name == "low_then_top":
-                overlapped_seen = sim.shard.overlapped_swaps + sim.shard.fused_swaps
+                overlapped_seen = sim.shard.pipelined_swaps + sim.shard.fused_swaps
             from oracle import ref_dense as O
             want_s = O.sample_indices(got, 7, 257)
             if not np.array_equal(samples, want_s):

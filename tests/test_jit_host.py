@@ -171,3 +171,29 @@ def test_warp_local_rounds_with_syncwarp(monkeypatch):
     assert local >= 2
     monkeypatch.delenv("QSV_JIT_WARP_SYNC")
     assert "__syncwarp();" not in kernel_source(prog.passes[0])          # the default kernels are unchanged
+
+
+def test_a_pass_launched_chunk_by_chunk_equals_the_whole_pass():
+    """Pipelined stage transitions launch a pass once per CHUNK: index bits outside the tile are fixed through
+    the kernel's JitFix argument (positions in tile-index space) and the tile counter runs over the rest.
+    The union of the chunk launches must be the pass."""
+    n = 14
+    prog = compile_circuit(W.random_1q_cz(n, 20, 1234), zero_init=False)
+    psi = _random_state(n, 5)
+    step = prog.passes[1]
+    tile = set(step.desc.load_bits[: step.desc.n_tile])
+    outside = [p for p in range(n) if p not in tile]
+    assert len(outside) == 3
+    for chunk_bits in ([outside[0]], [outside[2]], [outside[0], outside[2]], outside):
+        want, got = psi.copy(), psi.copy()
+        run_pass(want, step.desc, step.ops, n, 0, step.tables)
+        pos = [b - sum(t < b for t in tile) for b in chunk_bits]
+        tiles = (1 << (n - 11)) >> len(chunk_bits)
+        for j in range(1 << len(chunk_bits)):
+            val = sum(((j >> i) & 1) << pos[i] for i in range(len(chunk_bits)))
+            before = got.copy()
+            run_pass_on_host(step, got, n, grid=1, tile_range=(0, tiles), fix=(pos, val))
+            changed = np.nonzero(got != before)[0]
+            for i, b in enumerate(chunk_bits):                  # a chunk launch stays inside its chunk
+                assert np.all((changed >> b) & 1 == (j >> i) & 1)
+        assert np.abs(got - want).max() <= 1e-13

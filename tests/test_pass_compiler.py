@@ -224,3 +224,21 @@ def test_fused_initialisation_ignores_the_input():
         junk = np.concatenate([sh[r ^ prog.rank_flip_mask] for r in range(4)])
     assert np.abs(junk - want).max() <= 1e-12
     assert not PassCompiler(n, tile_bits=7, low_bits=2).compile(ops).fused_init          # plain compile: never
+
+
+def test_lowering_cache_follows_the_contents_of_the_op_list():
+    """One compiler, the SAME list object mutated in place between two compile() calls (a parameter sweep):
+    the second program must be the second circuit's (the cache used to be keyed on id() and length)."""
+    n = 9
+    a = ir_ops(W.random_1q_cz(n, 8, 5))
+    b = ir_ops(W.random_1q_cz(n, 8, 6))
+    assert len(a) == len(b)
+    comp = PassCompiler(n, tile_bits=6, low_bits=2)
+    ops = list(a)
+    for want_cd in (W.random_1q_cz(n, 8, 5), W.random_1q_cz(n, 8, 6)):
+        prog = comp.compile(ops)
+        psi = np.zeros(1 << n, dtype=np.complex128)
+        psi[0] = 1
+        run_program(prog, psi)
+        assert np.abs(psi - O.simulate(validate_circuit_dict(want_cd))).max() <= 1e-12
+        ops[:] = b
