@@ -394,59 +394,43 @@ def bench_single(args) -> None:
     print(json.dumps(line), flush=True)
 
 
-def bench_multi(args) -> None:
-    """N > 1: one process per GPU (torchrun).  Weak scaling: 2^30 amplitudes per GPU, i.e. the
-    same circuit family at n = 30 + log2(N) qubits, sharded by the top log2(N) qubits; stages
-    are connected by NCCL all-to-all qubit swaps over NVLink (csrc/exchange.cuh)."""
-    import math
-    import torch
-    from quantum_simulations_b200.runner.multi_gpu import ShardedSimulator, execute
-    from quantum_simulations_b200.circuit.passes import PassStep, SwapStep
-    from quantum_simulations_b200.storage.pinned import PinnedBuffer
+BASELINE_QUBITS = {2: 34, 4: 34, 8: 36}     # BASELINE.json configs[3] (34 qubits on 2/4 B200) and configs[4] (36 on 8)
 
-    dtype = args.dtype
-    amp_bytes = np.dtype(dtype).itemsize
-    world = int(os.environ["WORLD_SIZE"])
-    g = int(math.log2(world))
-    n = args.qubits if args.qubits is not None else 30 + g
-    cd, info = workload(n)
-    sim = ShardedSimulator(n, dtype, fused_exchange=True) if args.fused_exchange else ShardedSimulator(n, dtype)
-    rank, dist, st = sim.rank, sim.dist, sim.shard.state
-    ckw = dict(tile_bits=args.tile_bits, low_bits=args.low_bits, max_rounds=args.max_rounds)
-    if args.no_low_store_round:
-        ckw["low_store_round"] = False
+
+def _timed_sharded(sim, cd, args, steps, warmup, ckw, tol):
+    """Plan + prepare + warm-up + `steps` timed executions of `cd` on the sharded simulator.
+    Returns a dict with the device-timed step (max over ranks), per-launch timings of rank 0 and the plan."""
+    import torch
+    from quantum_simulations_b200.circuit.passes import SwapStep
+    dist, st = sim.dist, sim.shard.state
     t0 = time.perf_counter()
     prog = sim.plan(cd, **ckw)
     compile_s = time.perf_counter() - t0
     sim.prepare(prog)
-    updates_per_step = len(cd["gates"]) * (1 << n)
-
-    def step():
-        sim.run(prog)
 
     def global_norm() -> float:
         v = torch.tensor([st.norm2()], dtype=torch.float64)
         dist.all_reduce(v, op=dist.ReduceOp.SUM)
         return float(v.item())
 
-    tol = 1e-9 if dtype == "complex128" else 1e-4
-    step()
+    sim.run(prog)
     plan_note = "default planner options"
     if abs(global_norm() - 1.0) > tol:
         # insurance: a plan that does not even conserve the norm is replaced by the conservative planner
         # (swaps on the top positions after a relabel pass, no eager flips, no table phases) before timing
+        sim.shard.release(prog)
         prog = sim.plan(cd, swap_anywhere=False, rank_flips=False, eager_flips=False, table_phases=False, **ckw)
         sim.prepare(prog)
         plan_note = "FALLBACK: conservative planner options (the default plan failed the norm check)"
-        step()
-    for _ in range(max(args.warmup - 1, 0)):
-        step()
+        sim.run(prog)
+    for _ in range(max(warmup - 1, 0)):
+        sim.run(prog)
     st.sync(); dist.barrier()
-    clocks = ClockSampler(sim.local_rank).start() if rank == 0 else None
+    clocks = ClockSampler(sim.local_rank).start() if sim.rank == 0 else None
     st.timing(True)
     st.timer_start()
-    for _ in range(args.steps):
-        step()
+    for _ in range(steps):
+        sim.run(prog)
     total_ms = st.timer_stop()
     per_launch = st.take_timings()
     st.timing(False)
@@ -454,60 +438,189 @@ def bench_multi(args) -> None:
     clk = clocks.stop() if clocks else None
     tmax = torch.tensor([total_ms], dtype=torch.float64)
     dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    total_ms = float(tmax.item())
     nrm = global_norm()
     if abs(nrm - 1.0) > tol:
         raise SystemExit(f"bench: state norm {nrm} != 1 — result invalid")
+    seq = "".join(("S%d" % len(s_.global_bits)) if isinstance(s_, SwapStep) else ("P" if s_.n_micro_ops else "p") for s_ in prog.steps)
+    return {"prog": prog, "total_ms": float(tmax.item()), "per_launch": per_launch, "clocks": clk, "norm": nrm,
+            "compile_s": compile_s, "plan_note": plan_note, "sequence": seq}
 
-    # end to end through the public object: plan + (cached) specialisation + run + D2H of the shard
+
+def _cross_g_parity(args, world, rank, local_rank, dist, n_par: int = 30, samples: int = 1 << 20) -> dict:
+    """OUTSIDE the timed region: the same circuit family at n_par qubits, once sharded over all ranks (the path
+    that was timed: stage plan, pipelined swaps) and once on rank 0's GPU alone; 2^20 seeded amplitude indices
+    are compared.  (Full-vector parity against the CPU oracle is the test suite's job, n <= 26.)"""
+    from quantum_simulations_b200.runner.multi_gpu import ShardedSimulator
+    cd, _ = workload(n_par)
+    g = world.bit_length() - 1
+    sim = ShardedSimulator(n_par, args.dtype)
+    shard = sim.simulate(cd)
+    logical, pipelined = sim.logical_rank, sim.shard.pipelined_swaps
+    sim.close()
+    idx = np.random.default_rng(2026).integers(0, 1 << n_par, size=samples, dtype=np.int64)
+    n_loc = n_par - g
+    mine = (idx >> n_loc) == logical
+    box = [None] * world
+    dist.all_gather_object(box, (np.nonzero(mine)[0], shard[idx[mine] & ((1 << n_loc) - 1)]))
+    del shard
+    out = None
+    if rank == 0:
+        from quantum_simulations_b200.kernel.cuda_dense import simulate
+        got = np.zeros(samples, dtype=np.complex128)
+        seen = np.zeros(samples, dtype=bool)
+        for where, vals in box:
+            got[where] = vals
+            seen[where] = True
+        one = simulate(cd, dtype=args.dtype, device=local_rank)
+        err = float(np.abs(got - one[idx]).max())
+        tol = 1e-12 if args.dtype == "complex128" else 1e-5
+        out = {"what": f"{samples} seeded amplitude indices of the {n_par}-qubit circuit of the same family: sharded run on "
+                       f"{world} GPUs (same planner and swap path as the timed run) vs the single-GPU run on rank 0's GPU",
+               "n_qubits": n_par, "sampled_amplitudes": int(samples), "all_indices_covered": bool(seen.all()),
+               "pipelined_swaps_in_the_sharded_run": int(pipelined), "max_abs_diff": err, "tolerance": tol,
+               "ok": bool(seen.all() and err <= tol)}
+    dist.barrier()
+    return out
+
+
+def _one_gpu_rate(args, local_rank: int, n: int = 30, steps: int = 5, warmup: int = 3) -> dict:
+    """The 1-GPU rate of the same circuit family (BASELINE configs[2], n = 30) measured in THIS run on rank 0's GPU:
+    the denominator of SURVEY.md section 8d's parallel efficiency."""
+    from quantum_simulations_b200.circuit.sharding import plan_single
+    from quantum_simulations_b200.kernel.cuda import DeviceState
+    from quantum_simulations_b200.kernel.cuda_dense import circuit_ops
+    cd, info = workload(n)
+    prog = plan_single(circuit_ops(cd), n, args.dtype, True, False)
+    with DeviceState(n, args.dtype, local_rank) as st:
+        h = st.upload_program(prog)
+        for _ in range(warmup):
+            st.replay(h)
+        st.sync()
+        st.timer_start()
+        for _ in range(steps):
+            st.replay(h)
+        ms = st.timer_stop() / steps
+    return {"n_qubits": n, "ms_per_step": ms, "value": info["gates"] * (1 << n) / (ms * 1e-3), "unit": UNIT,
+            "steps": steps, "warmup": warmup}
+
+
+def bench_multi(args) -> None:
+    """N > 1: one process per GPU (torchrun).  Default workload = BASELINE.json configs[3] / configs[4]: the random
+    depth-20 circuit at 34 qubits on 2 and 4 GPUs and at 36 qubits (1 TiB) on 8, sharded by the top log2(N) qubits
+    (--qubits overrides).  Beside the headline the line carries the WEAK series (2^30 amplitudes per GPU,
+    n = 30 + log2 N), a cross-G parity check and the 1-GPU rate of this run for the parallel efficiency."""
+    import math
+    import torch
+    from quantum_simulations_b200 import _lib as L
+    from quantum_simulations_b200.runner.multi_gpu import ShardedSimulator
+
+    dtype = args.dtype
+    amp_bytes = np.dtype(dtype).itemsize
+    world = int(os.environ["WORLD_SIZE"])
+    g = int(math.log2(world))
+    n = args.qubits if args.qubits is not None else BASELINE_QUBITS.get(world, 30 + g)
+    cd, info = workload(n)
+    ckw = dict(tile_bits=args.tile_bits, low_bits=args.low_bits, max_rounds=args.max_rounds)
+    if args.no_low_store_round:
+        ckw["low_store_round"] = False
+    tol = 1e-9 if dtype == "complex128" else 1e-4
+    sim = ShardedSimulator(n, dtype, fused_exchange=True) if args.fused_exchange else ShardedSimulator(n, dtype)
+    rank, dist = sim.rank, sim.dist
+    updates_per_step = len(cd["gates"]) * (1 << n)
+    run = _timed_sharded(sim, cd, args, args.steps, args.warmup, ckw, tol)
+    prog, total_ms, per_launch, clk = run["prog"], run["total_ms"], run["per_launch"], run["clocks"]
+
+    # end to end through the public object: plan + (cached) specialisation + run + D2H of the WHOLE shard, streamed
+    # through two pinned staging buffers (the state does not fit in host memory at 34 / 36 qubits)
     n_loc = n - g
     shard_bytes = amp_bytes * (1 << n_loc)
-    e2e_s = None
+    e2e_s, e2e_sum = None, 0.0
     if not args.no_e2e:
-        host = PinnedBuffer((1 << n_loc) * amp_bytes)
-        out = host.array(dtype, 1 << n_loc)
-        sim.simulate(cd, out, **ckw)
+        acc = [0.0]
+
+        def sink(view, first):          # touch every piece on the host: first amplitude of each (a cheap witness)
+            acc[0] += float(abs(view[0]))
+
+        sim.simulate(cd, sink=sink, **ckw)
         dist.barrier()
-        reps = max(1, min(args.steps, 3))
+        reps = max(1, min(args.steps, 2 if n_loc > 31 else 3))
         t0 = time.perf_counter()
         for _ in range(reps):
-            sim.simulate(cd, out, **ckw)
+            sim.simulate(cd, sink=sink, **ckw)
         dist.barrier()
         e2e_t = torch.tensor([(time.perf_counter() - t0) / reps], dtype=torch.float64)
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-        e2e_s = float(e2e_t.item())
-        host.free()
+        e2e_s, e2e_sum = float(e2e_t.item()), acc[0]
+    peer_swap, peer_error, xchg_sms, pipeline_on = sim.peer_swap, sim.shard.peer_error, getattr(sim.shard, "xchg_sms", None), bool(getattr(sim.shard, "pipeline", False))
+    fused_flag = bool(getattr(sim, "fused_exchange", False))
+    sim.close()
+    L.load().qsv_release_cached()
+    dist.barrier()
+
+    # ---- beside the headline (all outside its timed region) ----
+    weak = None
+    if not args.no_weak and n != 30 + g:
+        wsim = ShardedSimulator(30 + g, dtype)
+        wcd, winfo = workload(30 + g)
+        w = _timed_sharded(wsim, wcd, args, min(args.steps, 5), min(args.warmup, 3), ckw, tol)
+        wsim.close()
+        L.load().qsv_release_cached()
+        w_ms = w["total_ms"] / min(args.steps, 5)
+        weak = {"n_qubits": 30 + g, "amps_per_gpu_log2": 30, "gates": winfo["gates"], "ms_per_step": w_ms,
+                "value": winfo["gates"] * (1 << (30 + g)) / (w_ms * 1e-3), "unit": UNIT, "step_sequence": w["sequence"],
+                "what": "weak-scaling series: 2^30 amplitudes per GPU, same circuit family"}
+    parity = None if args.no_parity else _cross_g_parity(args, world, rank, sim.local_rank, dist, min(30, n))
+    one = _one_gpu_rate(args, sim.local_rank) if (rank == 0 and not args.no_parity) else None
 
     if rank == 0:
         ms_per_step = total_ms / args.steps
-        pass_ms, init_ms = split_init_pass(per_launch, args.steps, prog.fused_init)
+        value = updates_per_step / (ms_per_step * 1e-3)
+        pass_ms, init_ms = split_init_pass([x for x in per_launch if x[1] != 11], args.steps, prog.fused_init)
         swap_ms = [(ms, kind - 20) for ms, kind, _ in per_launch if 20 <= kind < 30]
-        fused_ms = [(ms, kind - 30) for ms, kind, _ in per_launch if 30 <= kind < 40]
         scatter_ms = [(ms, kind - 40) for ms, kind, _ in per_launch if 40 <= kind < 50]
         piped = [(ms, kind - 50, pi) for ms, kind, pi in per_launch if 50 <= kind < 60]
-        avg_pass_ms = float(np.mean(pass_ms))
+        avg_pass_ms = float(np.mean(pass_ms)) if pass_ms else float("nan")
         alg_bytes = 2 * amp_bytes * (1 << n_loc)
         peak, peak_src = _peaks()
         achieved = alg_bytes / (avg_pass_ms * 1e-3) / 1e9
+        per_step = lambda xs: xs[-max(1, len(xs) // max(args.steps, 1)):] if xs else []      # noqa: E731
         nv = [{"bits": b, "ms": round(ms, 3),
                "sent_gb_per_gpu": round((1 - 0.5 ** b) * shard_bytes / 1e9, 3),
                "gbs_per_direction": round((1 - 0.5 ** b) * shard_bytes / (ms * 1e-3) / 1e9, 1),
-               "frac_of_900": round((1 - 0.5 ** b) * shard_bytes / (ms * 1e-3) / 900e9, 3)}
-              for ms, b in swap_ms[-prog.stats["swaps"]:]] if swap_ms else []
+               "frac_of_900": round((1 - 0.5 ** b) * shard_bytes / (ms * 1e-3) / 900e9, 3)} for ms, b in per_step(swap_ms)]
+        # a pipelined region = its passes + the exchange beside them; what the exchange ADDS to the step is the
+        # region minus what its passes take on their own (the average streaming pass of this run)
+        regions = []
+        for ms, b, pi in per_step(piped):
+            n_p = pi // 16 + pi % 16
+            sent = (1 - 0.5 ** b) * shard_bytes
+            regions.append({"bits": b, "ms": round(ms, 3), "passes_before": pi // 16, "passes_after": pi % 16,
+                            "sent_gb_per_gpu": round(sent / 1e9, 3),
+                            "exchange_alone_at_900_ms": round(sent / 900e9 * 1e3, 3),
+                            "exposed_ms": round(ms - n_p * avg_pass_ms, 3),
+                            "nvlink_gbs_per_direction_over_region": round(sent / (ms * 1e-3) / 1e9, 1)})
+        exposed = sum(r_["exposed_ms"] for r_ in regions) + sum(ms for ms, _ in per_step(swap_ms)) + 0.0
         import ctypes
-        from quantum_simulations_b200 import _lib as L
         prog_bytes = len(prog.passes) * ctypes.sizeof(L.QsvPass) + prog.stats["micro_ops"] * ctypes.sizeof(L.QsvOp)
+        eff = None
+        if one is not None:
+            eff = {"definition": "SURVEY.md 8d: amp-updates/s at G GPUs / (G x amp-updates/s of the 1-GPU n=30 run of the same "
+                                 "circuit family), the 1-GPU rate measured in this run on rank 0's GPU",
+                   "value": value / (world * one["value"]), "one_gpu": one,
+                   "weak_series_value": None if weak is None else weak["value"] / (world * one["value"])}
         line = {
-            "metric": METRIC, "value": updates_per_step / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
             "config": {**info, "amps_per_gpu_log2": n_loc, "sharding": f"top {g} qubits = rank bits",
+                       "baseline_config": "BASELINE.json configs[3]/[4]" if n == BASELINE_QUBITS.get(world) else "--qubits override",
                        "passes_per_step": len(prog.passes), "swaps_per_step": prog.stats["swaps"],
                        "swap_bits_per_step": prog.stats["swap_bits"], "ops_per_step": prog.stats["micro_ops"],
-                       "step_sequence": "".join(("S%d" % len(s_.global_bits)) if isinstance(s_, SwapStep)
-                                                else ("P" if s_.n_micro_ops else "p") for s_ in prog.steps),
+                       "step_sequence": run["sequence"],
                        "l2_hygiene": f"shard {(1 << n_loc) * amp_bytes / 2**30:.0f} GiB >> 126 MB L2",
-                       "host_compile_s": compile_s, "plan": plan_note,
+                       "host_compile_s": run["compile_s"], "plan": run["plan_note"],
+                       "scaling_note": "amplitudes per GPU: 2^30 at N=1 (configs[2]), 2^33 / 2^32 / 2^33 at N=2 / 4 / 8 "
+                                       "(configs[3], [4]); the weak series with 2^30 per GPU is under weak_series",
                        "timing": "CUDA events on each rank's stream, max over ranks"},
             "gate_layers_per_s": info["levels"] / (ms_per_step * 1e-3),
             "hbm_gbs_per_gate_layer_per_gpu": info["levels"] * alg_bytes / (ms_per_step * 1e-3) / 1e9,
@@ -515,39 +628,34 @@ def bench_multi(args) -> None:
                          "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
                          "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_pass_ms,
                          "launches_timed": len(pass_ms), "share_of_step": sum(pass_ms) / total_ms,
-                         "launches": "every pass that reads and writes the shard once (the write-only init pass, "
-                                     f"{round(float(np.mean(init_ms)), 3) if init_ms else None} ms, is excluded)"},
-            "overlapped_pass_swap": {"count_per_step": len(fused_ms) // max(args.steps, 1),
-                                     "ms": [round(ms, 3) for ms, _ in fused_ms[-max(1, len(fused_ms) // max(args.steps, 1)):]] if fused_ms else [],
-                                     "what": "last pass of a stage split into 2^s blocks, exchange of each block pair on a second "
-                                             "stream while the next block is computed (qsv_pass_swap_overlapped)"},
-            "pipelined_swap": {"count_per_step": len(piped) // max(args.steps, 1),
-                               "regions": [{"bits": b, "ms": round(ms, 3), "passes_before": pi // 16, "passes_after": pi % 16}
-                                           for ms, b, pi in piped[-max(1, len(piped) // max(args.steps, 1)):]] if piped else [],
-                               "xchg_sms": getattr(sim.shard, "xchg_sms", None), "enabled": bool(getattr(sim.shard, "pipeline", False)),
+                         "launches": "every whole-shard pass launch that reads and writes the shard once (the write-only init "
+                                     f"pass, {round(float(np.mean(init_ms)), 3) if init_ms else None} ms, and the chunked "
+                                     "launches inside pipelined regions are excluded)"},
+            "pipelined_swap": {"enabled": pipeline_on, "count_per_step": len(piped) // max(args.steps, 1), "regions": regions,
+                               "xchg_sms": xchg_sms,
                                "what": "stage transition executed chunk by chunk (qsv_swap_pipelined): the TMA exchange kernel of "
                                        "chunk j on xchg_sms SMs beside the pass kernels of the neighbouring chunks on the other SMs; "
                                        "ms = the whole region (its passes included)"},
-            "scatter_pass": {"enabled": bool(getattr(sim, "fused_exchange", False)),
-                             "count_per_step": len(scatter_ms) // max(args.steps, 1),
-                             "ms": [round(ms, 3) for ms, _ in scatter_ms[-max(1, len(scatter_ms) // max(args.steps, 1)):]] if scatter_ms else [],
-                             "what": "last pass of a stage fused with the exchange: its stores go straight into the second "
-                                     "buffers of the peers over NVLink (qsv_pass_scatter, --fused-exchange; 2x shard memory)"},
-            "nvlink": {"path": "peer-memory kernel (CUDA IPC, loads/stores over NVLink)" if sim.peer_swap
-                       else f"chunked ncclSend/ncclRecv ({sim.shard.peer_error or 'QSV_SWAP=nccl'})", "swaps": nv, "share_of_step": (sum(ms for ms, _ in swap_ms) + sum(ms for ms, _ in fused_ms) + sum(ms for ms, _ in scatter_ms)) / total_ms,
-                       "pipelined_regions_share_of_step": sum(ms for ms, _, _ in piped) / total_ms,
+            "scatter_pass": {"enabled": fused_flag, "count_per_step": len(scatter_ms) // max(args.steps, 1),
+                             "ms": [round(ms, 3) for ms, _ in per_step(scatter_ms)]},
+            "nvlink": {"path": "peer memory over CUDA IPC: TMA bulk-copy exchange kernel, flag-word ordering (csrc/xchg.cuh)" if peer_swap
+                       else f"chunked ncclSend/ncclRecv ({peer_error or 'QSV_SWAP=nccl'})", "swaps": nv,
+                       "exposed_ms_per_step": round(exposed, 3), "share_of_step": exposed / ms_per_step,
+                       "pipelined_regions_share_of_step": sum(ms for ms, _, _ in per_step(piped)) / ms_per_step,
                        "peak_gbs_per_direction": 900.0},
+            "parallel_efficiency": eff, "weak_series": weak, "parity": parity,
             "gpu_launches": len(per_launch) + (0 if prog.fused_init else 2 * args.steps),
             "clocks": clk,
             "e2e": None if e2e_s is None else
                    {"value": updates_per_step / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3,
                     "h2d_bytes_per_step": int(prog_bytes) * world, "d2h_bytes_per_step": int(shard_bytes) * world,
-                    "what": "ShardedSimulator.simulate(circuit, out=pinned host shard) on every rank: validate + "
-                            "stage planning + (cached) kernel specialisation + |0> + passes + swaps + D2H of the "
-                            "shard; host perf_counter, max over ranks"},
+                    "d2h_gbs_per_gpu": shard_bytes / max(e2e_s - ms_per_step * 1e-3, 1e-9) / 1e9, "host_witness": e2e_sum,
+                    "what": "ShardedSimulator.simulate(circuit, sink=...) on every rank: validate + stage planning + (cached) "
+                            "kernel specialisation + |0> + passes + swaps + D2H of the WHOLE shard, streamed through two "
+                            "pinned staging buffers of 256 MiB to a host sink (the state is larger than host memory at "
+                            "34 / 36 qubits); host perf_counter, max over ranks"},
         }
         print(json.dumps(line), flush=True)
-    sim.close()
     dist.barrier()
     dist.destroy_process_group()
 
@@ -577,6 +685,8 @@ def main() -> None:
                     help="experiment (N = 1): warp-local round exchanges with __syncwarp() instead of the group barrier")
     ap.add_argument("--streaming-stores", action="store_true",
                     help="experiment (N = 1): st.global.cs (evict-first) for the final stores of a pass")
+    ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the weak-series run beside the headline")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the cross-G parity check and the 1-GPU rate")
     ap.add_argument("--fused-exchange", action="store_true",
                     help="N > 1: second buffer per shard, the pass before a swap stores straight into the peers (qsv_pass_scatter)")
     args = ap.parse_args()

@@ -318,6 +318,19 @@ static int qsvx_xchg_args(qsv_handle *h, qsvx::Comm *c, int n_swap, const int *g
     A.run_log2 = std::min(A.stage_log2, (unsigned)special[0] + A.elem_log2);
     A.units_per_half = 1ull << (half_log2 - A.stage_log2);
     A.seq = c->seq;
+    A.stage_log2 = std::min(12u, half_log2);                          // 4 KB units (small units complete sooner)
+    if (const char *e = getenv("QSV_XCHG_STAGE_LOG2")) {             // experiment
+        const unsigned v = (unsigned)atoi(e);
+        if (v >= 10 && v <= 15 && v <= half_log2) A.stage_log2 = v;
+    }
+    A.run_log2 = std::min(A.stage_log2, (unsigned)special[0] + A.elem_log2);
+    A.units_per_half = 1ull << (half_log2 - A.stage_log2);
+    qsvx::xchg_ring_shape(A.stage_log2, A.n_warps, A.n_remote, A.n_local);
+    if (const char *e = getenv("QSV_XCHG_RING")) {                   // "<issuing warps>,<remote slots>,<local slots>"
+        unsigned w = 0, r = 0, l = 0;
+        if (sscanf(e, "%u,%u,%u", &w, &r, &l) == 3 && w >= 1 && w <= 4 && r >= 2 && l >= 2 && r >= l &&
+            qsvx::xchg_smem_bytes(A.stage_log2, w, r, l) <= qsvx::kXchgMaxSmem) { A.n_warps = w; A.n_remote = r; A.n_local = l; }
+    }
     tma_ok = A.run_log2 >= 4 && A.stage_log2 >= 4 && (A.stage_log2 - A.run_log2) <= 6;   // <= 64 bulk copies per unit
     if (A.run_log2 < 4) QSVX_FAIL(h, QSV_EINVAL, "exchange: runs of %u bytes (lowest swapped / chunk position %d) are below the 16-byte pieces the kernels move",
                                   1u << A.run_log2, special[0]);
@@ -328,7 +341,7 @@ static int qsvx_xchg_args(qsv_handle *h, qsvx::Comm *c, int n_swap, const int *g
 static int qsvx_xchg_launch(qsv_handle *h, qsvx::Comm *c, cudaStream_t stream, const qsvx::XchgArgs &A, bool tma_ok, int sms) {
     static const bool force_ldst = [] { const char *e = getenv("QSV_XCHG"); return e && !strcmp(e, "ldst"); }();
     if (!c->xchg_attr_set) {
-        QSVX_CUDA(h, cudaFuncSetAttribute(qsvx::k_xchg_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsvx::xchg_smem_bytes(14)));
+        QSVX_CUDA(h, cudaFuncSetAttribute(qsvx::k_xchg_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsvx::kXchgMaxSmem));
         c->xchg_attr_set = true;
     }
     if (sms < 1) sms = 1;
@@ -336,7 +349,7 @@ static int qsvx_xchg_launch(qsv_handle *h, qsvx::Comm *c, cudaStream_t stream, c
         unsigned long long total = (unsigned long long)(A.n_peers - 1) * A.units_per_half;
         const unsigned grid = (unsigned)std::min<unsigned long long>((unsigned long long)sms, std::max<unsigned long long>(total, 1ull));
         // full-size stages claim the whole SM (no second CTA beside it); small test shards take what they need
-        qsvx::k_xchg_tma<<<grid, qsvx::kXchgThreads, qsvx::xchg_smem_bytes(A.stage_log2), stream>>>(A);
+        qsvx::k_xchg_tma<<<grid, qsvx::kXchgThreads, qsvx::xchg_smem_bytes(A.stage_log2, A.n_warps, A.n_remote, A.n_local), stream>>>(A);
     } else {
         qsvx::k_xchg_ldst<4><<<(unsigned)sms, 1024, 0, stream>>>(A);
     }

@@ -12,10 +12,12 @@
 // other rank the second half, so each element is moved by exactly one GPU.  A unit of work is 16 KB of
 // the pair (one or more contiguous runs; a run is 2^lowest special position elements): one elected
 // thread per CTA pulls the local and the remote unit into shared memory with cp.async.bulk (TMA, no
-// registers, no L1), then pushes them back crosswise with cp.async.bulk shared -> global; a ring of NS
-// stages keeps (NS-1) * 16 KB of remote reads in flight per SM.  Measured on 2 B200 (tools/xchg_bench.cu,
-// profiles/r02/xchg_bench_2gpu.jsonl): throughput is in-flight bound, 43 GB/s per SM, and 16 SMs reach
-// the same 686 GB/s per direction that the load/store kernel needs all 148 SMs for.
+// registers, no L1), then pushes them back crosswise with cp.async.bulk shared -> global.  Two rings of
+// 16 KB slots: a deep one for the remote halves (NVLink round trip) and a shallow one for the local
+// halves.  Measured on 2 B200 (tools/xchg_bench.cu, profiles/r02/xchg_bench_2gpu.jsonl): throughput is
+// in-flight bound (a 16 KB remote bulk read takes ~3.7 us alone, ~6 us beside the pass kernels); with
+// 80 KB of remote reads in flight per SM 16 SMs reach the 686 GB/s per direction that the load/store
+// kernel needs all 148 SMs for.
 //
 // Cross-GPU ordering without NCCL: two monotone 64-bit flags per source rank in the (peer-mapped)
 // tail of every shard allocation.
@@ -31,7 +33,6 @@
 
 namespace qsvx {
 
-constexpr int kXchgStages = 6;
 constexpr int kXchgThreads = 128;
 constexpr int kFlagSlots = 8;                 // world <= 8 on one box
 constexpr size_t kTailBytes = 4096;           // flags + counters at the end of every shard allocation
@@ -53,7 +54,8 @@ struct XchgArgs {
     unsigned long long chunk_val;             // the chunk bits of this launch, already at their positions
     unsigned elem_log2;                       // log2(bytes per amplitude)
     unsigned run_log2;                        // log2(bytes of one contiguous run) <= stage_log2
-    unsigned stage_log2;                      // log2(bytes of one unit of work = one ring stage per direction)
+    unsigned stage_log2;                      // log2(bytes of one unit of work = one ring slot)
+    unsigned n_warps, n_remote, n_local;      // TMA kernel: issuing threads per CTA, slots of each one's remote / local ring
     unsigned long long units_per_half;        // units in one half of a pair
     unsigned long long half_elems;            // elements in one half of a pair (compacted index space)
     unsigned long long seq;                   // flag value of this launch
@@ -86,16 +88,28 @@ __device__ __forceinline__ unsigned long long xs_addr(const XchgArgs &A, unsigne
     return e << A.elem_log2;
 }
 
+// W issuing threads per CTA (lane 0 of warps 0..W-1), each with its own interleaved share of the CTA's units
+// and its own two rings of R-byte slots: NR slots for the REMOTE halves (NVLink round trip, ~3.3 us alone and
+// more beside the pass kernels: the deep ring) and NL slots for the local halves (HBM latency only; loaded
+// just in time).  What was measured on 2 B200 (profiles/r02/xchg_bench_2gpu*.jsonl): throughput is bound by
+// the remote bytes in flight and small units complete sooner than large ones; the issue loop of one thread is
+// instruction-latency bound (a version with 64-bit divisions in it ran at half the rate), hence several
+// issuing threads, a division-free loop (cursors advance by precomputed steps) and the addresses of a unit
+// computed once, at its remote load, and cached in shared memory for its local load and its stores.
+struct XchgUnit { unsigned long long la, ra, e0; int d; int pad; };   // cached per remote slot
+
 __global__ void __launch_bounds__(kXchgThreads, 1) k_xchg_tma(const __grid_constant__ XchgArgs A) {
     extern __shared__ __align__(128) unsigned char xs_smem[];
     const unsigned R = 1u << A.stage_log2;                  // bytes per unit and direction
     const unsigned run = 1u << A.run_log2;                  // contiguous bytes per bulk copy
     const unsigned pieces = R >> A.run_log2;
-    unsigned long long *bar = reinterpret_cast<unsigned long long *>(xs_smem + (size_t)kXchgStages * 2 * R);
+    const unsigned W = A.n_warps, NR = A.n_remote, NL = A.n_local;
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(xs_smem + (size_t)W * (NR + NL) * R);
+    XchgUnit *cache = reinterpret_cast<XchgUnit *>(bars + W * (NR + NL));
     const int tid = threadIdx.x;
     if (tid == 0) {
-        for (int s = 0; s < kXchgStages; ++s)
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(xs_u32(&bar[s])));
+        for (unsigned s = 0; s < W * (NR + NL); ++s)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(xs_u32(&bars[s])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // ---- barrier in: my passes of this chunk are done (stream order); wait for the peers' passes
@@ -105,74 +119,116 @@ __global__ void __launch_bounds__(kXchgThreads, 1) k_xchg_tma(const __grid_const
         xs_wait(A.my_flags + A.rank_of[d], A.seq);
     }
     __syncthreads();
-    if (tid != 0) return;
+    const unsigned warp = (unsigned)tid >> 5;
+    if ((tid & 31) != 0 || warp >= W) return;
 
-    const unsigned long long total = (unsigned long long)(A.n_peers - 1) * A.units_per_half;
-    const unsigned long long grid = gridDim.x, bid = blockIdx.x;
-    const unsigned long long n_my = total > bid ? (total - bid + grid - 1) / grid : 0;
+    unsigned char *rbuf = xs_smem + (size_t)warp * (NR + NL) * R, *lbuf = rbuf + (size_t)NR * R;
+    unsigned long long *rbar = bars + warp * (NR + NL), *lbar = rbar + NR;
+    XchgUnit *cch = cache + warp * NR;
+    const unsigned P1 = (unsigned)A.n_peers - 1u;
+    const unsigned long long total = (unsigned long long)P1 * A.units_per_half;
+    const unsigned long long first = (unsigned long long)blockIdx.x + (unsigned long long)warp * gridDim.x;
+    const unsigned long long step = (unsigned long long)W * gridDim.x;
+    const unsigned long long n_my = total > first ? (total - first + step - 1) / step : 0;
     const unsigned unit_elems = R >> A.elem_log2, run_elems = run >> A.elem_log2;
+    // remote-load cursor: unit index gi = first + i * step  ->  peer slot ck = gi % P1, unit in the pair cu = gi / P1
+    unsigned ck = (unsigned)(first % P1);
+    unsigned long long cu = first / P1;
+    const unsigned dk = (unsigned)(step % P1);
+    const unsigned long long du = step / P1;
+    unsigned rs_load = 0;                                    // remote slot the next remote load goes into
+    unsigned ls_load = 0, ls_unit = 0;                       // local slot of the next local load; remote slot of ITS unit
+    unsigned long long issued_r = 0, issued_l = 0;
 
-    auto issue_loads = [&](unsigned long long i) {
-        const unsigned long long gi = bid + i * grid;
-        const int k = (int)(gi % (unsigned long long)(A.n_peers - 1));
-        const unsigned long long u = gi / (unsigned long long)(A.n_peers - 1);
-        const int d = A.me ^ (k + 1);
-        const unsigned long long e0 = (A.me < d ? 0ull : A.half_elems) + u * unit_elems;
-        const int st = (int)(i % kXchgStages);
-        unsigned char *sl = xs_smem + (size_t)st * 2 * R;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(xs_u32(&bar[st])), "r"(2u * R) : "memory");
-        for (unsigned q = 0; q < pieces; ++q) {            // remote first: longest latency
-            const char *gr = A.peer[d] + xs_addr(A, e0 + (unsigned long long)q * run_elems, A.me);
+    auto load_remote = [&]() {
+        XchgUnit u;
+        u.d = A.me ^ (int)(ck + 1);
+        u.e0 = (A.me < u.d ? 0ull : A.half_elems) + cu * unit_elems;
+        u.la = (unsigned long long)A.mine + xs_addr(A, u.e0, u.d);
+        u.ra = (unsigned long long)A.peer[u.d] + xs_addr(A, u.e0, A.me);
+        u.pad = 0;
+        cch[rs_load] = u;
+        unsigned char *sl = rbuf + (size_t)rs_load * R;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(xs_u32(&rbar[rs_load])), "r"(R) : "memory");
+        if (pieces == 1) {
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(xs_u32(sl + R + q * run)), "l"(gr), "r"(run), "r"(xs_u32(&bar[st])) : "memory");
+                         ::"r"(xs_u32(sl)), "l"(u.ra), "r"(R), "r"(xs_u32(&rbar[rs_load])) : "memory");
+        } else {
+            for (unsigned q = 0; q < pieces; ++q) {
+                const char *gr = A.peer[u.d] + xs_addr(A, u.e0 + (unsigned long long)q * run_elems, A.me);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(xs_u32(sl + q * run)), "l"(gr), "r"(run), "r"(xs_u32(&rbar[rs_load])) : "memory");
+            }
         }
-        for (unsigned q = 0; q < pieces; ++q) {
-            const char *gl = A.mine + xs_addr(A, e0 + (unsigned long long)q * run_elems, d);
+        ck += dk; cu += du;
+        if (ck >= P1) { ck -= P1; ++cu; }
+        if (++rs_load == NR) rs_load = 0;
+        ++issued_r;
+    };
+    auto load_local = [&]() {                                // the unit's remote load was issued earlier: its addresses are cached
+        const XchgUnit u = cch[ls_unit];
+        unsigned char *sl = lbuf + (size_t)ls_load * R;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(xs_u32(&lbar[ls_load])), "r"(R) : "memory");
+        if (pieces == 1) {
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(xs_u32(sl + q * run)), "l"(gl), "r"(run), "r"(xs_u32(&bar[st])) : "memory");
+                         ::"r"(xs_u32(sl)), "l"(u.la), "r"(R), "r"(xs_u32(&lbar[ls_load])) : "memory");
+        } else {
+            for (unsigned q = 0; q < pieces; ++q) {
+                const char *gl = A.mine + xs_addr(A, u.e0 + (unsigned long long)q * run_elems, u.d);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(xs_u32(sl + q * run)), "l"(gl), "r"(run), "r"(xs_u32(&lbar[ls_load])) : "memory");
+            }
         }
+        if (++ls_load == NL) ls_load = 0;
+        if (++ls_unit == NR) ls_unit = 0;
+        ++issued_l;
     };
-    auto issue_stores = [&](unsigned long long i) {
-        const unsigned long long gi = bid + i * grid;
-        const int k = (int)(gi % (unsigned long long)(A.n_peers - 1));
-        const unsigned long long u = gi / (unsigned long long)(A.n_peers - 1);
-        const int d = A.me ^ (k + 1);
-        const unsigned long long e0 = (A.me < d ? 0ull : A.half_elems) + u * unit_elems;
-        const int st = (int)(i % kXchgStages);
-        unsigned char *sl = xs_smem + (size_t)st * 2 * R;
-        for (unsigned q = 0; q < pieces; ++q) {
-            char *gr = A.peer[d] + xs_addr(A, e0 + (unsigned long long)q * run_elems, A.me);
-            char *gl = A.mine + xs_addr(A, e0 + (unsigned long long)q * run_elems, d);
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gr), "r"(xs_u32(sl + q * run)), "r"(run) : "memory");
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gl), "r"(xs_u32(sl + R + q * run)), "r"(run) : "memory");
-        }
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    };
-
-    for (unsigned long long i = 0; i < n_my && i < (unsigned long long)(kXchgStages - 1); ++i) issue_loads(i);
-    for (unsigned long long k = 0; k < n_my; ++k) {
-        const int st = (int)(k % kXchgStages);
-        const uint32_t parity = (uint32_t)((k / kXchgStages) & 1ull);
+    auto wait_bar = [&](unsigned long long *bar, uint32_t parity) {
         uint32_t done = 0;
         while (!done) {
             asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                         : "=r"(done) : "r"(xs_u32(&bar[st])), "r"(parity) : "memory");
+                         : "=r"(done) : "r"(xs_u32(bar)), "r"(parity) : "memory");
         }
-        issue_stores(k);
-        const unsigned long long nxt = k + kXchgStages - 1;
-        if (nxt < n_my) {
-            // every store group but the newest has finished READING its stage: the stage of unit k-1 is free
+    };
+
+    while (issued_r < n_my && issued_r + 1 < NR) load_remote();
+    while (issued_l < n_my && issued_l + 1 < NL) load_local();
+    unsigned rs = 0, ls = 0, rpar = 0, lpar = 0;             // slots and phases of the unit whose stores are next
+    for (unsigned long long k = 0; k < n_my; ++k) {
+        wait_bar(&lbar[ls], lpar);
+        wait_bar(&rbar[rs], rpar);
+        const XchgUnit u = cch[rs];
+        unsigned char *sr = rbuf + (size_t)rs * R, *sl = lbuf + (size_t)ls * R;
+        if (pieces == 1) {                                   // crosswise: local half -> peer, remote half -> here
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(u.ra), "r"(xs_u32(sl)), "r"(R) : "memory");
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(u.la), "r"(xs_u32(sr)), "r"(R) : "memory");
+        } else {
+            for (unsigned q = 0; q < pieces; ++q) {
+                char *gr = A.peer[u.d] + xs_addr(A, u.e0 + (unsigned long long)q * run_elems, A.me);
+                char *gl = A.mine + xs_addr(A, u.e0 + (unsigned long long)q * run_elems, u.d);
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gr), "r"(xs_u32(sl + q * run)), "r"(run) : "memory");
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gl), "r"(xs_u32(sr + q * run)), "r"(run) : "memory");
+            }
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        if (++rs == NR) { rs = 0; rpar ^= 1u; }
+        if (++ls == NL) { ls = 0; lpar ^= 1u; }
+        if (issued_r < n_my || issued_l < n_my) {
+            // every store group but the newest has finished READING shared memory: the slots of unit k-1 (for
+            // k = 0: the one slot of each ring that has not been used yet) are free — rs_load / ls_load point at them
             asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            issue_loads(nxt);
+            if (issued_r < n_my) load_remote();
+            if (issued_l < n_my) load_local();
         }
     }
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // all my writes (local and remote) are complete
     asm volatile("fence.proxy.async;" ::: "memory");
     __threadfence_system();
-    // ---- barrier out: the last CTA of this launch tells the peers and waits for them
+    // ---- barrier out: the last issuing thread of this launch tells the peers and waits for them
     unsigned *ctr = reinterpret_cast<unsigned *>(A.my_flags + kTailCounterWord);
-    const unsigned old = atomicInc(ctr, gridDim.x - 1);
-    if (old == gridDim.x - 1) {
+    const unsigned n_issuers = gridDim.x * W;
+    const unsigned old = atomicInc(ctr, n_issuers - 1);
+    if (old == n_issuers - 1) {
         __threadfence_system();
         for (int k = 0; k < A.n_peers - 1; ++k) xs_signal(A.peer_flags[A.me ^ (k + 1)] + kFlagSlots + A.my_rank, A.seq);
         for (int k = 0; k < A.n_peers - 1; ++k) xs_wait(A.my_flags + kFlagSlots + A.rank_of[A.me ^ (k + 1)], A.seq);
@@ -226,6 +282,20 @@ __global__ void __launch_bounds__(1024, 1) k_xchg_ldst(const __grid_constant__ X
     }
 }
 
-inline size_t xchg_smem_bytes(unsigned stage_log2) { return (size_t)kXchgStages * 2 * ((size_t)1 << stage_log2) + 8 * kXchgStages + 64; }
+inline size_t xchg_smem_bytes(unsigned stage_log2, unsigned n_warps, unsigned n_remote, unsigned n_local) {
+    return (size_t)n_warps * ((size_t)(n_remote + n_local) * (((size_t)1 << stage_log2) + 8) + (size_t)n_remote * 32) + 64;
+}
+constexpr size_t kXchgMaxSmem = 227 * 1024;
+// default shape: 4 issuing threads, the slots that fit split 10 : 4 between the remote and the local ring
+// (4 KB slots: 4 x 14 x 4 KB = 224 KB, 144 KB of remote reads in flight per SM)
+inline void xchg_ring_shape(unsigned stage_log2, unsigned &n_warps, unsigned &n_remote, unsigned &n_local) {
+    n_warps = 4;
+    unsigned slots = (unsigned)((kXchgMaxSmem - 4096) / ((size_t)n_warps << stage_log2));
+    while (slots < 4 && n_warps > 1) { n_warps >>= 1; slots = (unsigned)((kXchgMaxSmem - 4096) / ((size_t)n_warps << stage_log2)); }
+    if (slots > 14) slots = 14;
+    if (slots < 4) slots = 4;
+    n_local = slots >= 12 ? 4 : (slots >= 7 ? 3 : 2);
+    n_remote = slots - n_local;
+}
 
 }  // namespace qsvx

@@ -102,6 +102,30 @@ class DeviceState:
         self._ck(self.lib.qsv_download(self._h, out.ctypes.data, offset, count))
         return out
 
+    def stream_to_host(self, sink, chunk_amps: int = 1 << 24, offset: int = 0, count: int | None = None) -> int:
+        """Hand the shard to `sink(view, first_amp)` piece by piece through TWO pinned staging buffers (the copy
+        of piece c+1 runs while the sink works on piece c) — the way a state that does not fit in host memory
+        leaves the device (checkpoint writers, reductions).  Views are only valid inside the call.  Returns
+        the bytes copied."""
+        from quantum_simulations_b200.storage.pinned import PinnedBuffer
+        count = self.n_amps - offset if count is None else count
+        chunk_amps = max(1, min(chunk_amps, count))
+        bufs = [PinnedBuffer(chunk_amps * self.dtype.itemsize) for _ in range(2)]
+        try:
+            pieces = [(o, min(chunk_amps, offset + count - o)) for o in range(offset, offset + count, chunk_amps)]
+            if pieces:
+                self._ck(self.lib.qsv_download_async(self._h, bufs[0].ptr, pieces[0][0], pieces[0][1]))
+            for c, (o, m) in enumerate(pieces):
+                self.sync()
+                if c + 1 < len(pieces):
+                    self._ck(self.lib.qsv_download_async(self._h, bufs[(c + 1) & 1].ptr, pieces[c + 1][0], pieces[c + 1][1]))
+                sink(bufs[c & 1].array(self.dtype, m), o)
+            self.sync()
+        finally:
+            for b in bufs:
+                b.free()
+        return count * self.dtype.itemsize
+
     def device_ptr(self) -> tuple[int, int, int]:
         p, n, s = C.c_void_p(), C.c_size_t(), C.c_void_p()
         self._ck(self.lib.qsv_device_ptr(self._h, C.byref(p), C.byref(n), C.byref(s)))

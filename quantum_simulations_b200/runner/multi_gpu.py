@@ -359,12 +359,17 @@ class ShardedSimulator:
         self.run(self.plan_ops(fuse_2q_blocks(ops, tol=1e-14), **compiler_kw))
         return self.shard.state.download(out)
 
-    def simulate(self, circuit_dict: dict, out: np.ndarray | None = None, **compiler_kw) -> np.ndarray:
+    def simulate(self, circuit_dict: dict, out: np.ndarray | None = None, sink=None, chunk_amps: int = 1 << 24,
+                 **compiler_kw):
         """Returns the amplitudes of LOGICAL shard ``self.logical_rank`` (= rank ^ the program's
         rank_flip_mask: an X gate left pending on a rank bit is a renaming of the shards, not a
-        data movement); index of amplitude i of the result = (logical_rank << n_local) | i."""
+        data movement); index of amplitude i of the result = (logical_rank << n_local) | i.
+        With ``sink(view, first_amp)`` the shard is not returned but streamed to the sink through two pinned
+        staging buffers of chunk_amps amplitudes (states larger than host memory: 36 qubits = 128 GiB per GPU)."""
         prog = self.plan(circuit_dict, **compiler_kw)
         self.run(prog)
+        if sink is not None:
+            return self.shard.state.stream_to_host(sink, chunk_amps)
         return self.shard.state.download(out)
 
     def _agree(self, flag: bool) -> bool:

@@ -79,8 +79,11 @@ class FakeSim:
     prepare = MG.ShardedSimulator.prepare
     _agree = MG.ShardedSimulator._agree
 
-    def simulate(self, cd, out=None, **kw):
+    def simulate(self, cd, out=None, sink=None, chunk_amps=1 << 24, **kw):
         self.run(self.plan(cd, **kw))
+        if sink is not None:
+            sink(self.shard.emu.psi, 0)
+            return self.shard.emu.psi.nbytes
         return self.shard.state.download(out)
 
     def close(self): pass
@@ -98,5 +101,5 @@ PIN.PinnedBuffer = FakePinned
 if __name__ == "__main__":
     import bench
     sys.argv = ["bench.py", "--gpus", sys.argv[1], "--qubits", "12", "--steps", "2", "--warmup", "3",
-                "--tile-bits", "6", "--low-bits", "2"]
+                "--tile-bits", "6", "--low-bits", "2", "--no-weak", "--no-parity"]
     bench.main()

@@ -57,7 +57,7 @@ int main(int argc, char **argv) {
     }
     unsigned long long seq = 0;
     const int top = n_local - 1;
-    auto run = [&](int sms, int run_log2, int mode /*0 tma 1 ldst*/, bool beside, bool verify) {
+    auto run = [&](int sms, int run_log2, int mode /*0 tma 1 ldst*/, bool beside, bool verify, unsigned nw = 4, unsigned nr = 10, unsigned nl = 4, unsigned sl2 = 12) {
         ++seq;
         for (int r = 0; r < 2; ++r) {
             CK(cudaSetDevice(r));
@@ -74,10 +74,10 @@ int main(int argc, char **argv) {
             A.elem_log2 = 4; A.run_log2 = run_log2; A.stage_log2 = 14;
             A.half_elems = n >> 2;                                   // pair = 2^(n_local-1) elements, half of it
             A.units_per_half = (A.half_elems * 16) >> A.stage_log2;
-            A.seq = seq;
+            A.seq = seq; A.n_warps = nw; A.n_remote = nr; A.n_local = nl; A.stage_log2 = sl2; A.units_per_half = (A.half_elems * 16) >> A.stage_log2; if (A.run_log2 > A.stage_log2) A.run_log2 = A.stage_log2;
             if (beside) { CK(cudaEventRecord(c0[r], sc[r])); k_stream<<<148 - sms, 512, 200 * 1024, sc[r]>>>(side[r], n, 2); CK(cudaEventRecord(c1[r], sc[r])); }
             CK(cudaEventRecord(e0[r], sx[r]));
-            if (mode == 0) qsvx::k_xchg_tma<<<sms, qsvx::kXchgThreads, qsvx::xchg_smem_bytes(14), sx[r]>>>(A);
+            if (mode == 0) qsvx::k_xchg_tma<<<sms, qsvx::kXchgThreads, qsvx::xchg_smem_bytes(sl2, nw, nr, nl), sx[r]>>>(A);
             else qsvx::k_xchg_ldst<4><<<sms, 1024, 0, sx[r]>>>(A);
             CK(cudaGetLastError());
             CK(cudaEventRecord(e1[r], sx[r]));
@@ -96,17 +96,23 @@ int main(int argc, char **argv) {
         }
         const double sent = (double)(n / 2) * 16;                    // bytes leaving each GPU
         printf("{\"kernel\": \"%s\", \"sms\": %d, \"run_bytes\": %d, \"beside_stream\": %d, \"ms\": %.3f, \"gbs_per_direction\": %.1f, "
-               "\"stream_ms\": %.3f, \"stream_gbs\": %.1f, \"verified\": %d, \"bad\": %llu}\n",
+               "\"stream_ms\": %.3f, \"stream_gbs\": %.1f, \"verified\": %d, \"bad\": %llu, \"warps_remote_local\": [%u, %u, %u], \"stage_bytes\": %u}\n",
                mode == 0 ? "tma" : "ldst", sms, 1 << run_log2, (int)beside, ms, sent / ms / 1e6, cms,
-               beside ? 2.0 * 2 * n * 16 / cms / 1e6 : 0.0, (int)verify, nbad);
+               beside ? 2.0 * 2 * n * 16 / cms / 1e6 : 0.0, (int)verify, nbad, nw, nr, nl, 1u << sl2);
         fflush(stdout);
     };
     run(16, 14, 0, false, true);                                     // correctness first
+    run(16, 9, 0, false, true);                                      // 512-byte runs: 32 bulk copies per half
     run(16, 12, 1, false, true);
-    for (int rl : {9, 11, 12, 14})
-        for (int sms : {8, 12, 16, 20}) run(sms, rl, 0, false, false);
-    for (int sms : {8, 16, 32, 64, 148}) run(sms, 12, 1, false, false);
-    for (int sms : {8, 12, 16, 24}) run(sms, 14, 0, true, false);
-    for (int sms : {16, 32}) run(sms, 12, 1, true, false);
+    for (int sms : {6, 8, 12, 16}) {
+        run(sms, 14, 0, false, false, 4, 10, 4, 12);
+        run(sms, 14, 0, false, false, 4, 11, 3, 12);
+        run(sms, 14, 0, false, false, 4, 7, 7, 12);
+        run(sms, 14, 0, false, false, 2, 10, 4, 13);
+        run(sms, 14, 0, false, false, 2, 21, 7, 12);
+        run(sms, 14, 0, false, false, 1, 10, 4, 14);
+    }
+    for (int sms : {8, 12, 16}) { run(sms, 14, 0, true, false, 4, 10, 4, 12); run(sms, 14, 0, true, false, 2, 10, 4, 13); }
+    for (int sms : {16, 32}) run(sms, 12, 1, false, false);
     return 0;
 }
