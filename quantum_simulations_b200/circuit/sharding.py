@@ -191,7 +191,7 @@ def plan(ir_ops, n_qubits: int, n_local: int, dtype: str = "complex128", zero_in
 # passes do not have in their tiles, and chunk j of the exchange travels over NVLink while the passes
 # work on the other chunks.  This is the reference's reader / worker / writer overlap
 # (wenbo_engine/runner/pipeline.py:50-82) between HiSVSIM-style parts (hisvsim_repo/execute.hpp:665-685).
-XCHG_BW = 0.68e12        # measured, per direction: the TMA exchange kernel on 16 SMs (profiles/r02)
+XCHG_BW = 0.45e12        # measured, per direction: the TMA exchange kernel BESIDE the pass kernels (0.69e12 alone; profiles/r02)
 PASS_BW = 5.2e12         # measured average of the pass kernel (profiles/r02)
 
 
@@ -205,7 +205,7 @@ class Transition:
 
 
 def plan_transitions(prog: Program, max_chunk_bits: int = 4, min_chunk_pos: int = 10, max_side: int = 3,
-                     tile_bits: int = 11) -> dict:
+                     tile_bits: int = 11, min_chunk_bits: int | None = None) -> dict:
     """{index of a SwapStep in prog.steps: Transition}.  Greedy: passes are added on the side that costs
     the fewest candidate chunk bits until the pipelined passes take as long as the exchange
     (bytes / measured bandwidths), a side runs out of eligible passes, or fewer than one chunk bit of
@@ -217,6 +217,8 @@ def plan_transitions(prog: Program, max_chunk_bits: int = 4, min_chunk_pos: int 
     shard = amp * (1 << prog.n_local)
     out: dict = {}
     taken: set = set()
+    if min_chunk_bits is None:               # >= 8 chunks for the overlap to be fine-grained; test-sized shards take what there is
+        min_chunk_bits = 3 if prog.n_local - tile_bits - 13 >= 3 else 1
 
     def eligible(k: int) -> bool:
         if not 0 <= k < len(steps):
@@ -233,7 +235,7 @@ def plan_transitions(prog: Program, max_chunk_bits: int = 4, min_chunk_pos: int 
             continue
         avail = {p for p in range(min_chunk_pos, prog.n_local)} - set(sw.local_bits)
         t_x = (1.0 - 0.5 ** s_bits) * shard / XCHG_BW
-        t_p = 2.0 * shard / PASS_BW / 0.89                 # a pass on sm_count - 16 SMs
+        t_p = 2.0 * shard / PASS_BW / 0.87                 # a pass on sm_count - 20 SMs
         want = max(2, min(2 * max_side, int(t_x / t_p + 0.999)))
         a = b = 0
         while a + b < want:
@@ -246,7 +248,7 @@ def plan_transitions(prog: Program, max_chunk_bits: int = 4, min_chunk_pos: int 
             for side, idx in cands:
                 d = steps[idx].desc
                 left = avail - set(d.load_bits[: d.n_tile])
-                if len(left) >= 1 and (best is None or len(left) > len(best[2])):
+                if len(left) >= min_chunk_bits and (best is None or len(left) > len(best[2])):
                     best = (side, idx, left)
             if best is None:
                 break

@@ -98,7 +98,7 @@ class CudaShard:
         self.swaps = self.pipelined_swaps = self.fused_swaps = 0
         self._transitions: dict = {}          # id(SwapStep) -> (SwapStep, Transition)
         self.pipeline = os.environ.get("QSV_PIPELINE", "1") != "0"
-        self.xchg_sms = int(os.environ.get("QSV_XCHG_SMS", "16"))
+        self.xchg_sms = int(os.environ.get("QSV_XCHG_SMS", "20"))
         if world > 1 and local:
             self.state._ck(self.state.lib.qsv_comm_init_local(self.state._h))
         elif world > 1:
