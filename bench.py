@@ -117,14 +117,36 @@ def workload(n: int) -> tuple[dict, dict]:
 
 
 # ----------------------------------------------------------------------- CPU arms
-def _cpu_numpy_rate(cd: dict) -> tuple[float, float]:
-    """The reference's formulation (index arrays + gather/scatter, ref_dense.py:13-41)
-    restated in oracle/ref_dense.py; returns (amp-updates/s, seconds)."""
-    from oracle import ref_dense as O
+def _reference_simulate():
+    """wenbo_engine.kernel.ref_dense.simulate of the UNMODIFIED reference (oracle/_ref/, placed there by
+    __graft_entry__.build() from /root/reference; git-ignored, travels with the built files), or None."""
+    ref = ROOT / "oracle" / "_ref"
+    if not (ref / "wenbo_engine" / "kernel" / "ref_dense.py").is_file():
+        return None
+    if str(ref) not in sys.path:
+        sys.path.insert(0, str(ref))
+    try:
+        from wenbo_engine.kernel.ref_dense import simulate as ref_simulate
+        return ref_simulate
+    except Exception:
+        return None
+
+
+def _cpu_rate(cd: dict) -> tuple[float, float, str]:
+    """(amp-updates/s, seconds, kind) of the reference's CPU statevector path on `cd`: the reference's own
+    ref_dense.simulate when oracle/_ref holds it (kind "reference"), else its restatement oracle/ref_dense.py
+    simulate(indexed=True) (kind "port": the same NumPy index-array formulation, ref_dense.py:13-41)."""
+    ref = _reference_simulate()
     t0 = time.perf_counter()
-    O.simulate(cd, indexed=True)
+    if ref is not None:
+        ref(cd)
+        kind = "reference"
+    else:
+        from oracle import ref_dense as O
+        O.simulate(cd, indexed=True)
+        kind = "port"
     dt = time.perf_counter() - t0
-    return len(cd["gates"]) * (1 << cd["number_of_qubits"]) / dt, dt
+    return len(cd["gates"]) * (1 << cd["number_of_qubits"]) / dt, dt, kind
 
 
 def _cpu_c_rate(cd: dict) -> tuple[float, float, int]:
@@ -136,13 +158,16 @@ def _cpu_c_rate(cd: dict) -> tuple[float, float, int]:
     return len(cd["gates"]) * (1 << cd["number_of_qubits"]) / dt, dt, CO.n_threads()
 
 
+_WHAT = {"reference": "wenbo_engine.kernel.ref_dense.simulate of the unmodified reference (oracle/_ref)",
+         "port": "oracle/ref_dense.py simulate(indexed=True) = the reference's NumPy gather/scatter formulation restated"}
+
+
 def cpu_baseline(n_sample: int = 20) -> dict:
     cd, _ = workload(n_sample)
-    rate, dt = _cpu_numpy_rate(cd)
-    out = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
+    rate, dt, kind = _cpu_rate(cd)
+    out = {"value": rate, "unit": UNIT, "cores": 1, "kind": kind,
            "sample": f"same circuit family at n={n_sample} (random_1q_cz depth 20, {len(cd['gates'])} gates), "
-                     f"oracle/ref_dense.py simulate(indexed=True) = the reference's NumPy gather/scatter "
-                     f"formulation, complex128, {dt:.1f} s",
+                     f"{_WHAT[kind]}, complex128, single-threaded NumPy like the reference, {dt:.1f} s",
            "host_cores_available": os.cpu_count()}
     try:
         cdc, _ = workload(min(n_sample + 4, 24))
@@ -159,33 +184,29 @@ def reference_arm(args) -> None:
     if rank != 0:
         return
     budget = 150.0 / max(args.steps + args.warmup, 1)          # seconds per step
-    from oracle import ref_dense as O
-    probe = np.zeros(1 << 18, dtype=np.complex128); probe[0] = 1
-    t0 = time.perf_counter()
-    for q in (0, 9, 17):
-        O.apply_1q_indexed(probe, q, O.gate_matrix("H"))
-    rate_guess = 3 * (1 << 18) / (time.perf_counter() - t0)
-    n_sample = 16
-    for n in range(16, 25):
+    probe_cd, _ = workload(14)
+    rate_guess, _, kind = _cpu_rate(probe_cd)
+    rate_guess *= 0.6                                          # the probe is cache resident, the sample is not
+    n_sample = 14
+    for n in range(14, 25):
         cd, _ = workload(n)
         if len(cd["gates"]) * (1 << n) / rate_guess <= budget:
             n_sample = n
     cd, info = workload(n_sample)
     for _ in range(args.warmup):
-        _cpu_numpy_rate(cd)
+        _cpu_rate(cd)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        _cpu_numpy_rate(cd)
+        _cpu_rate(cd)
     dt = time.perf_counter() - t0
     value = args.steps * len(cd["gates"]) * (1 << n_sample) / dt
     sample = (f"bounded sample: same circuit family at n={n_sample} ({len(cd['gates'])} gates, complex128), "
-              "oracle/ref_dense.py simulate(indexed=True): the reference's NumPy index-array formulation; "
-              "NumPy elementwise kernels are single-threaded")
+              f"{_WHAT[kind]}; NumPy elementwise kernels are single-threaded")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "complex128",
             "data": "synthetic", "config": {**info, "note": "CPU arm runs a bounded sample of the GPU arm's workload"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample,
                              "host_cores_available": os.cpu_count()},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -213,6 +234,43 @@ def jit_stats() -> dict:
 
 
 # ----------------------------------------------------------------------- GPU arm
+def _other_workload(args, wl: str, n: int, dtype: str, steps: int = 5, warmup: int = 3) -> dict:
+    """A short device-timed run of another BASELINE workload (configs[1] QFT-28, GHZ, complex64) with the same
+    accounting as the headline: value = gates * 2^n / time, roofline fraction of its streaming pass launches."""
+    global WORKLOAD
+    from quantum_simulations_b200.circuit.sharding import plan_single
+    from quantum_simulations_b200.kernel.cuda import DeviceState
+    from quantum_simulations_b200.kernel.cuda_dense import circuit_ops
+    keep, WORKLOAD = WORKLOAD, wl
+    try:
+        cd, info = workload(n)
+    finally:
+        WORKLOAD = keep
+    prog = plan_single(circuit_ops(cd), n, dtype, True, False)
+    amp_bytes = np.dtype(dtype).itemsize
+    with DeviceState(n, dtype, args.device) as st:
+        h = st.upload_program(prog)
+        for _ in range(warmup):
+            st.replay(h)
+        st.sync()
+        st.timing(True)
+        st.timer_start()
+        for _ in range(steps):
+            st.replay(h)
+        ms = st.timer_stop() / steps
+        per_launch = st.take_timings()
+        st.timing(False)
+        norm = st.norm2()
+    streamed, _ = split_init_pass(per_launch, steps, prog.fused_init)
+    peak, _ = _peaks()
+    avg = float(np.mean(streamed)) if streamed else None
+    return {"workload": info["workload"], "n_qubits": n, "dtype": dtype, "gates": info["gates"], "levels": info["levels"],
+            "passes_per_step": len(prog.passes), "ms_per_step": ms, "value": info["gates"] * (1 << n) / (ms * 1e-3), "unit": UNIT,
+            "gate_layers_per_s": info["levels"] / (ms * 1e-3), "norm": norm,
+            "roofline_frac": None if not avg else 2 * amp_bytes * (1 << n) / (avg * 1e-3) / 1e9 / peak,
+            "avg_pass_ms": avg, "steps": steps, "warmup": warmup}
+
+
 def bench_single(args) -> None:
     from quantum_simulations_b200.kernel.cuda import DeviceState
     from quantum_simulations_b200.kernel.cuda_dense import circuit_ops, simulate
@@ -322,6 +380,12 @@ def bench_single(args) -> None:
         t_ = json.loads(tf.read_text())
         traffic, traffic_src = t_["dram_bytes_per_launch"], t_["source"]
 
+    # ---- the other BASELINE workloads on this GPU (short runs, beside the headline) ----
+    others = None
+    if not args.no_others and WORKLOAD == "random" and n == 30 and dtype == "complex128":
+        others = [_other_workload(args, wl, n_, dt_) for wl, n_, dt_ in
+                  (("qft", 28, "complex128"), ("ghz", 30, "complex128"), ("ghz", 20, "complex128"), ("random", 30, "complex64"))]
+
     # ---- end to end through the public API, result in pinned HOST memory ----
     e2e = None
     if not args.no_e2e:
@@ -352,6 +416,18 @@ def bench_single(args) -> None:
         e2e["d2h_only_ms"] = d2h_s * 1e3
         e2e["d2h_gbs"] = (1 << n) * amp_bytes / d2h_s / 1e9
         host.free()
+        # the same call in a FRESH process with the on-disk kernel cache switched off: a circuit structure
+        # never seen before pays NVRTC for each of its passes (in parallel) on top of the warm number
+        try:
+            r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--e2e-cold-child", "--qubits", str(n), "--dtype", dtype,
+                                "--device", str(args.device), "--workload", WORKLOAD],
+                               capture_output=True, text=True, timeout=300, env=dict(os.environ, QSV_JIT_CACHE="0"))
+            cold = json.loads(r.stdout.strip().splitlines()[-1])
+            e2e["cold"] = {"ms_per_step": cold["ms"], "value": updates_per_step / (cold["ms"] * 1e-3), "unit": UNIT,
+                           "jit": cold["jit"], "what": "first simulate() of a fresh process with QSV_JIT_CACHE=0 (every pass kernel "
+                                                       "compiled by NVRTC), pinned host output, host perf_counter"}
+        except Exception as e:      # context only
+            e2e["cold"] = {"error": str(e)[:200]}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
@@ -382,6 +458,7 @@ def bench_single(args) -> None:
                      "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_pass_ms,
                      "launches_timed": len(streamed_ms), "share_of_step": pass_share,
                      "launches": "every pass that reads and writes the state once (the write-only init pass is excluded)"},
+        "other_workloads": others,
         "zero_support_skipping": zs,
         "full_first_pass": full_first,
         "jit": jit_stats(),
@@ -679,6 +756,8 @@ def main() -> None:
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-zero-support", action="store_true")
+    ap.add_argument("--e2e-cold-child", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--no-others", action="store_true", help="N = 1: skip the short runs of the other BASELINE workloads")
     ap.add_argument("--no-low-store-round", action="store_true",
                     help="experiment: no idle round before stores whose registers hold a low (row) position")
     ap.add_argument("--warp-local-rounds", action="store_true",
@@ -695,6 +774,17 @@ def main() -> None:
     WORKLOAD = args.workload
     if args.impl == "reference":
         reference_arm(args)
+        return
+    if args.e2e_cold_child:
+        from quantum_simulations_b200.kernel.cuda_dense import simulate
+        from quantum_simulations_b200.storage.pinned import PinnedBuffer
+        n_ = args.qubits or 30
+        cd_, _ = workload(n_)
+        host_ = PinnedBuffer((1 << n_) * np.dtype(args.dtype).itemsize)
+        out_ = host_.array(args.dtype, 1 << n_)
+        t0_ = time.perf_counter()
+        simulate(cd_, dtype=args.dtype, device=args.device, out=out_)
+        print(json.dumps({"ms": (time.perf_counter() - t0_) * 1e3, "jit": jit_stats()}), flush=True)
         return
     world = int(os.environ.get("WORLD_SIZE", args.gpus))
     if world == 1:

@@ -512,8 +512,6 @@ def test_runner_errors():
             run({"gates": []}, td)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("QSV_TEST_SCATTER") != "1",
-                    reason="planner switch added after the round's last GPU minute: opt-in until it has run on hardware")
 @pytest.mark.parametrize("jit", [True, False])
 @pytest.mark.parametrize("workload", ["random_1q_cz", "random_mixed", "qft"])
 def test_low_position_register_stores(workload, jit):
@@ -530,8 +528,6 @@ def test_low_position_register_stores(workload, jit):
         assert np.abs(got - want).max() <= TOL[dtype]
 
 
-@pytest.mark.skipif(__import__("os").environ.get("QSV_TEST_SCATTER") != "1",
-                    reason="generator switch added after the round's last GPU minute: opt-in until it has run on hardware")
 def test_warp_local_rounds_on_the_device(monkeypatch):
     """warp_local_rounds + QSV_JIT_WARP_SYNC=1: __syncwarp() instead of the group barrier between rounds
     whose exchange stays inside each warp (tests/test_jit_host.py checks the same kernels on the CPU)."""

@@ -27,15 +27,9 @@ def test_sharded_gpus_match_oracle(world):
     print(r.stdout[-1500:])
 
 
-# Scatter passes (ABI v6: the pass before a swap stores straight into the peers' second buffers) were
-# written after this round's GPU budget was spent: they build, their addressing is checked on the CPU
-# (tests/test_jit_build.py), but they have not run on hardware yet, so the tests are opt-in.
-scatter_opt_in = pytest.mark.skipif(os.environ.get("QSV_TEST_SCATTER") != "1",
-                                    reason="scatter passes: opt-in until validated on hardware (QSV_TEST_SCATTER=1)")
-
-
+# Scatter passes (the pass before a swap stores straight into the peers' second buffers; opt-in at run time
+# because it needs 2x the shard in HBM): validated on hardware in round 2 (profiles/r02), always tested.
 @pytest.mark.gpu
-@scatter_opt_in
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_sharded_gpus_with_scatter_passes_match_oracle(world):
     if _gpus() < world:
@@ -51,7 +45,6 @@ def test_sharded_gpus_with_scatter_passes_match_oracle(world):
 
 
 @pytest.mark.gpu
-@scatter_opt_in
 @pytest.mark.parametrize("dtype,world", [("complex128", 2), ("complex128", 4), ("complex64", 2)])
 def test_scatter_pass_shards_of_one_process_on_one_device(dtype, world):
     """All shards as handles of THIS process on device 0 (qsv_scatter_set_targets wires raw pointers):
