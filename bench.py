@@ -477,7 +477,6 @@ BASELINE_QUBITS = {2: 34, 4: 34, 8: 36}     # BASELINE.json configs[3] (34 qubit
 def _timed_sharded(sim, cd, args, steps, warmup, ckw, tol):
     """Plan + prepare + warm-up + `steps` timed executions of `cd` on the sharded simulator.
     Returns a dict with the device-timed step (max over ranks), per-launch timings of rank 0 and the plan."""
-    import torch
     from quantum_simulations_b200.circuit.passes import SwapStep
     dist, st = sim.dist, sim.shard.state
     t0 = time.perf_counter()
@@ -486,9 +485,7 @@ def _timed_sharded(sim, cd, args, steps, warmup, ckw, tol):
     sim.prepare(prog)
 
     def global_norm() -> float:
-        v = torch.tensor([st.norm2()], dtype=torch.float64)
-        dist.all_reduce(v, op=dist.ReduceOp.SUM)
-        return float(v.item())
+        return dist.allreduce(float(st.norm2()), "sum")
 
     sim.run(prog)
     plan_note = "default planner options"
@@ -513,13 +510,12 @@ def _timed_sharded(sim, cd, args, steps, warmup, ckw, tol):
     st.timing(False)
     dist.barrier()
     clk = clocks.stop() if clocks else None
-    tmax = torch.tensor([total_ms], dtype=torch.float64)
-    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms = dist.allreduce(float(total_ms), "max")
     nrm = global_norm()
     if abs(nrm - 1.0) > tol:
         raise SystemExit(f"bench: state norm {nrm} != 1 — result invalid")
     seq = "".join(("S%d" % len(s_.global_bits)) if isinstance(s_, SwapStep) else ("P" if s_.n_micro_ops else "p") for s_ in prog.steps)
-    return {"prog": prog, "total_ms": float(tmax.item()), "per_launch": per_launch, "clocks": clk, "norm": nrm,
+    return {"prog": prog, "total_ms": total_ms, "per_launch": per_launch, "clocks": clk, "norm": nrm,
             "compile_s": compile_s, "plan_note": plan_note, "sequence": seq}
 
 
@@ -537,8 +533,7 @@ def _cross_g_parity(args, world, rank, local_rank, dist, n_par: int = 30, sample
     idx = np.random.default_rng(2026).integers(0, 1 << n_par, size=samples, dtype=np.int64)
     n_loc = n_par - g
     mine = (idx >> n_loc) == logical
-    box = [None] * world
-    dist.all_gather_object(box, (np.nonzero(mine)[0], shard[idx[mine] & ((1 << n_loc) - 1)]))
+    box = dist.all_gather_object((np.nonzero(mine)[0], shard[idx[mine] & ((1 << n_loc) - 1)]))
     del shard
     out = None
     if rank == 0:
@@ -582,12 +577,11 @@ def _one_gpu_rate(args, local_rank: int, n: int = 30, steps: int = 5, warmup: in
 
 
 def bench_multi(args) -> None:
-    """N > 1: one process per GPU (torchrun).  Default workload = BASELINE.json configs[3] / configs[4]: the random
+    """N > 1: one process per GPU (launched by torchrun; the processes talk over runner/plumbing.py and NVLink).  Default workload = BASELINE.json configs[3] / configs[4]: the random
     depth-20 circuit at 34 qubits on 2 and 4 GPUs and at 36 qubits (1 TiB) on 8, sharded by the top log2(N) qubits
     (--qubits overrides).  Beside the headline the line carries the WEAK series (2^30 amplitudes per GPU,
     n = 30 + log2 N), a cross-G parity check and the 1-GPU rate of this run for the parallel efficiency."""
     import math
-    import torch
     from quantum_simulations_b200 import _lib as L
     from quantum_simulations_b200.runner.multi_gpu import ShardedSimulator
 
@@ -625,9 +619,7 @@ def bench_multi(args) -> None:
         for _ in range(reps):
             sim.simulate(cd, sink=sink, **ckw)
         dist.barrier()
-        e2e_t = torch.tensor([(time.perf_counter() - t0) / reps], dtype=torch.float64)
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-        e2e_s, e2e_sum = float(e2e_t.item()), acc[0]
+        e2e_s, e2e_sum = dist.allreduce((time.perf_counter() - t0) / reps, "max"), acc[0]
     peer_swap, peer_error, xchg_sms, pipeline_on = sim.peer_swap, sim.shard.peer_error, getattr(sim.shard, "xchg_sms", None), bool(getattr(sim.shard, "pipeline", False))
     fused_flag = bool(getattr(sim, "fused_exchange", False))
     sim.close()
@@ -734,7 +726,7 @@ def bench_multi(args) -> None:
         }
         print(json.dumps(line), flush=True)
     dist.barrier()
-    dist.destroy_process_group()
+    dist.close()
 
 
 def main() -> None:

@@ -6,8 +6,9 @@ Here every rank keeps its 2^n_local amplitudes in HBM for the whole run; stages 
 qubits (zero communication, rank bits enter as constants) and are connected by
 ``SwapStep``s = one NCCL all-to-all of the swapped blocks over NVLink (csrc/exchange.cuh).
 
-``torch.distributed`` is used for PLUMBING only (rendezvous: broadcast of the NCCL unique id,
-barriers, max-reduction of timings); no tensor of the state ever passes through it.
+The host side needs only a rendezvous and a few tiny collectives (NCCL unique id, CUDA IPC handles,
+"do all ranks agree", sums of marginals): runner/plumbing.py does that over plain TCP (stdlib);
+no amplitude ever passes through it, and the product imports no tensor library.
 """
 from __future__ import annotations
 
@@ -126,8 +127,7 @@ class CudaShard:
         lib, h = self.state.lib, self.state._h
         mine = C.create_string_buffer(64)
         ok = lib.qsv_comm_ipc_handle(h, mine) == 0
-        box = [None] * self.world
-        dist.all_gather_object(box, mine.raw if ok else None)
+        box = dist.all_gather_object(mine.raw if ok else None)
         if any(b is None for b in box):
             self.peer_error = "cudaIpcGetMemHandle failed on some rank"
             mapped = False
@@ -135,9 +135,7 @@ class CudaShard:
             mapped = lib.qsv_comm_set_peers(h, C.create_string_buffer(b"".join(box), 64 * self.world)) == 0
             if not mapped:
                 self.peer_error = (lib.qsv_last_error(h) or b"?").decode(errors="replace")
-        flags = [None] * self.world
-        dist.all_gather_object(flags, bool(mapped))
-        self.peer_swap = all(flags)
+        self.peer_swap = dist.all(bool(mapped))
         lib.qsv_set_option(h, L.OPT_PEER_SWAP, int(self.peer_swap))     # all ranks must take the same path
         return self.peer_swap
 
@@ -154,16 +152,13 @@ class CudaShard:
         ok = lib.qsv_comm_shadow_ipc_handle(h, mine) == 0
         if not ok:
             self.fused_error = (lib.qsv_last_error(h) or b"?").decode(errors="replace")
-        box = [None] * self.world
-        dist.all_gather_object(box, mine.raw if ok else None)
+        box = dist.all_gather_object(mine.raw if ok else None)
         mapped = False
         if all(b is not None for b in box):
             mapped = lib.qsv_comm_set_shadow_peers(h, C.create_string_buffer(b"".join(box), 64 * self.world)) == 0
             if not mapped:
                 self.fused_error = (lib.qsv_last_error(h) or b"?").decode(errors="replace")
-        flags = [None] * self.world
-        dist.all_gather_object(flags, bool(mapped))
-        self.fused_exchange = all(flags)                 # all ranks must take the same path
+        self.fused_exchange = dist.all(bool(mapped))     # all ranks must take the same path
         return self.fused_exchange
 
     def prepare(self, prog: Program, agree=None) -> None:
@@ -286,26 +281,20 @@ def nccl_unique_id() -> bytes:
     return buf.raw
 
 
-# ------------------------------------------------------------------ torch.distributed plumbing
+# ------------------------------------------------------------------ host plumbing (runner/plumbing.py)
 def dist_env() -> tuple[int, int, int]:
     return (int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")),
             int(os.environ.get("WORLD_SIZE", "1")))
 
 
 def init_plumbing():
-    """gloo process group over MASTER_ADDR/MASTER_PORT (set by torchrun); returns torch.distributed."""
-    import torch.distributed as dist
-    if not dist.is_initialized():
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("MASTER_PORT", "29531")
-        dist.init_process_group(backend="gloo")
-    return dist
+    """The process-wide HostPlumbing over MASTER_ADDR / MASTER_PORT (set by torchrun)."""
+    from quantum_simulations_b200.runner.plumbing import init_plumbing as _init
+    return _init()
 
 
 def share_unique_id(dist, rank: int) -> bytes:
-    box = [nccl_unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(box, src=0)
-    return box[0]
+    return dist.broadcast_object(nccl_unique_id() if rank == 0 else None, src=0)
 
 
 class ShardedSimulator:
@@ -374,11 +363,7 @@ class ShardedSimulator:
 
     def _agree(self, flag: bool) -> bool:
         """Collective AND over the ranks (host plumbing): every rank takes the same execution path."""
-        if self.dist is None:
-            return bool(flag)
-        box = [None] * self.world
-        self.dist.all_gather_object(box, bool(flag))
-        return all(box)
+        return bool(flag) if self.dist is None else self.dist.all(flag)
 
     def prepare(self, prog: Program) -> None:
         """Upload and specialise the passes of `prog` and plan its pipelined transitions (collective)."""
@@ -400,20 +385,14 @@ class ShardedSimulator:
     def probabilities(self, qubits) -> np.ndarray:
         """Marginal distribution over logical `qubits` of the whole sharded state (identical on every
         rank): per-shard marginals (qsv_probabilities, rank bits allowed) summed over the shards."""
-        import torch
         p = self.shard.state.probabilities(self._physical(qubits))
         if self.world > 1:
-            t = torch.from_numpy(p)
-            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
-            p = t.numpy()
+            p = self.dist.allreduce(p, "sum")
         return p
 
     def expect_z(self, qubits) -> float:
-        import torch
-        v = torch.tensor([self.shard.state.expect_z(self._physical(qubits))], dtype=torch.float64)
-        if self.world > 1:
-            self.dist.all_reduce(v, op=self.dist.ReduceOp.SUM)
-        return float(v.item())
+        v = float(self.shard.state.expect_z(self._physical(qubits)))
+        return self.dist.allreduce(v, "sum") if self.world > 1 else v
 
     def _physical(self, qubits) -> list:
         """After a run the layout is the identity except for the shard renaming of rank_flip_mask: a
@@ -430,7 +409,6 @@ class ShardedSimulator:
         chain over all shards (rank order = index order), evaluated redundantly on every rank
         from the all-gathered leaf sums (8 bytes per 1024 amplitudes); every rank then walks the
         leaves of the shots that fall into its shard."""
-        import torch
         st, lib = self.shard.state, self.shard.state.lib
         n_loc = self.n - self.g
         leaf_log2 = min(10, n_loc)
@@ -438,9 +416,8 @@ class ShardedSimulator:
         mine = np.empty(n_leaves, dtype=np.float64)
         st._ck(lib.qsv_leaf_sums(st._h, mine.ctypes.data_as(C.POINTER(C.c_double))))
         if self.world > 1:
-            parts = [torch.empty(n_leaves, dtype=torch.float64) for _ in range(self.world)]
-            self.dist.all_gather(parts, torch.from_numpy(mine))
-            sums = np.concatenate([parts[l ^ self._flip_mask].numpy() for l in range(self.world)])   # logical order
+            parts = self.dist.all_gather_object(mine)
+            sums = np.concatenate([parts[l ^ self._flip_mask] for l in range(self.world)])   # logical order
         else:
             sums = mine
         offs = np.empty(len(sums) + 1)
@@ -465,11 +442,10 @@ class ShardedSimulator:
                                             got.ctypes.data_as(C.POINTER(C.c_uint64))))
             out[sel] = got.astype(np.int64) + (self.logical_rank << n_loc)
         if self.world > 1:
-            t = torch.from_numpy(out)
             if self.rank != 0:
-                t[over] = 0                           # the clamp is contributed once (rank 0)
-            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
-            out = t.numpy()
+                out[over] = 0                         # the clamp is contributed once (rank 0)
+            parts = self.dist.all_gather_object(out)  # integer sum (indices exceed float64's exact range at n > 53)
+            out = np.sum(np.stack(parts), axis=0, dtype=np.int64)
         return out.astype(np.uint64)
 
     def close(self) -> None:
@@ -514,9 +490,7 @@ def run(circuit_dict: dict, work_dir, chunk_size: int = 1 << 20, dtype: str = "c
         wal = WAL(work / "wal.json", circuit_dict=cd) if (use_wal and sim.rank == 0) else None
         current = wal.committed_buf if wal else "a"
         if sim.dist is not None:
-            box = [current]
-            sim.dist.broadcast_object_list(box, src=0)
-            current = box[0]
+            current = sim.dist.broadcast_object(current, src=0)
         dst = _buf_dir(work, _other(current))
         if sim.rank == 0:
             _wipe_buf(dst)

@@ -14,7 +14,7 @@ sys.path.insert(0, str(ROOT / "tests"))
 
 import quantum_simulations_b200.runner.multi_gpu as MG          # noqa: E402
 import quantum_simulations_b200.storage.pinned as PIN            # noqa: E402
-from gloo_worker import EmuShard                                 # noqa: E402
+from multi_process_worker import EmuShard                                 # noqa: E402
 
 
 class FakeState:

@@ -1,5 +1,5 @@
 """Worker of tests/test_multi_gpu.py (run under torchrun on a multi-GPU box): real libqsv
-shards + NCCL swaps, gathered over gloo on rank 0 and compared with the C oracle."""
+shards + NVLink swaps, gathered over the host plumbing on rank 0 and compared with the C oracle."""
 from __future__ import annotations
 
 import sys
@@ -12,7 +12,6 @@ sys.path.insert(0, str(ROOT))
 
 
 def main():
-    import torch
     from oracle import c_oracle as CO
     from quantum_simulations_b200 import workloads as W
     from quantum_simulations_b200.circuit.io import validate_circuit_dict
@@ -45,11 +44,10 @@ def main():
         else:
             shard = sim.simulate(cd)
         samples = sim.sample(seed=7, shots=257)
-        parts = [torch.empty(shard.size * 2, dtype=torch.float64) for _ in range(world)] if rank == 0 else None
-        dist.gather(torch.from_numpy(shard.view(np.float64).copy()), parts, dst=0)
+        parts = dist.all_gather_object(shard)
         if rank == 0:
             mask = sim.logical_rank ^ sim.rank           # physical shard r holds logical shard r ^ mask
-            got = np.concatenate([parts[l ^ mask].numpy().view(np.complex128) for l in range(world)])
+            got = np.concatenate([parts[l ^ mask] for l in range(world)])
             want = CO.simulate_c(cd)
             err = float(np.abs(got - want).max())
             print(f"{name}: n={n} world={world} max|d|={err:.3e} swaps={sim.shard.swaps} pipelined={sim.shard.pipelined_swaps} "
@@ -69,8 +67,7 @@ def main():
     import tempfile, os
     from quantum_simulations_b200.runner import multi_gpu as MG
     from quantum_simulations_b200.runner.single_node import collect_state
-    box = [tempfile.mkdtemp(prefix="qsv_mg_") if rank == 0 else None]
-    dist.broadcast_object_list(box, src=0)
+    box = [dist.broadcast_object(tempfile.mkdtemp(prefix="qsv_mg_") if rank == 0 else None, src=0)]
     cd = validate_circuit_dict(W.random_1q_cz(n, 10, 21))
     buf = MG.run(cd, box[0], chunk_size=1 << (n - 5), dtype="complex128")
     if rank == 0:
@@ -79,7 +76,7 @@ def main():
         print(f"runner.multi_gpu.run: {len(os.listdir(buf / 'chunks'))} chunk files, max|d|={err:.3e}", flush=True)
         worst = max(worst, err)
     dist.barrier()
-    dist.destroy_process_group()
+    dist.close()
     if rank == 0 and worst > 1e-12:
         raise SystemExit(f"multi-GPU parity failed: {worst}")
     if rank == 0 and sim.peer_swap and overlapped_seen < 1:

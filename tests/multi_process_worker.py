@@ -1,4 +1,5 @@
-"""Worker of tests/test_multi_process_gloo.py: one PROCESS per shard, gloo for the exchange.
+"""Worker of tests/test_multi_process_host.py: one PROCESS per shard, the host plumbing (runner/plumbing.py,
+plain TCP) for the exchange.
 
 Runs the product-side multi-GPU logic (sharding.plan + runner.multi_gpu.execute) with the NumPy
 pass emulator standing in for libqsv (there is no GPU here); the SwapStep is a real
@@ -31,14 +32,13 @@ class EmuShard:
             run_pass(self.psi, s.desc, s.ops, self.n_local, self.rank, s.tables)
 
     def swap(self, global_bits, local_bits):
-        import torch
         s = len(global_bits)
         assert list(local_bits) == [self.n_local - s + i for i in range(s)]
         me = 0
         for i, gb in enumerate(global_bits):
             me |= ((self.rank >> (gb - self.n_local)) & 1) << i
         blocks = self.psi.reshape(1 << s, -1)
-        reqs, recv = [], {}
+        out = {}
         for d in range(1 << s):
             if d == me:
                 continue
@@ -46,19 +46,20 @@ class EmuShard:
             for i, gb in enumerate(global_bits):
                 rb = gb - self.n_local
                 peer = (peer & ~(1 << rb)) | (((d >> i) & 1) << rb)
-            out = torch.from_numpy(np.ascontiguousarray(blocks[d]).view(np.float64).copy())
-            recv[d] = torch.empty_like(out)
-            reqs.append(self.dist.isend(out, dst=peer))
-            reqs.append(self.dist.irecv(recv[d], src=peer))
-        for r in reqs:
-            r.wait()
-        for d, t in recv.items():
-            blocks[d] = t.numpy().view(np.complex128)
+            out[peer] = (d, blocks[d].copy())
+        box = self.dist.all_gather_object(out)          # every rank: {destination rank: (block index there... , data)}
+        for src, sent in enumerate(box):
+            if self.rank in sent:
+                _, data = sent[self.rank]
+                # the block I receive from `src` replaces my block with the index of src's swapped bits
+                d_src = 0
+                for i, gb in enumerate(global_bits):
+                    d_src |= ((src >> (gb - self.n_local)) & 1) << i
+                blocks[d_src] = data
         self.swaps += 1
 
 
 def main():
-    import torch.distributed as dist
     from quantum_simulations_b200 import workloads as W
     from quantum_simulations_b200.circuit import sharding
     from quantum_simulations_b200.circuit.io import validate_circuit_dict
@@ -89,7 +90,7 @@ def main():
     execute(prog, shard)
     np.save(out_dir / f"qasm_rank{rank ^ prog.rank_flip_mask}.npy", shard.psi)
     dist.barrier()
-    dist.destroy_process_group()
+    dist.close()
 
 
 def qasm_text(n: int) -> str:

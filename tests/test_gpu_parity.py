@@ -441,6 +441,35 @@ def test_n26_matches_c_oracle_sampled():
     assert np.abs(got - want).max() <= 1e-12
 
 
+def _full_vector_vs_c_oracle(n, dtype="complex128"):
+    """Every amplitude of the BASELINE random depth-20 circuit at n qubits against oracle/ref_dense_c.c on the
+    box's host cores (the reference's own kernels-vs-oracle test at its full size,
+    wenbo_engine/tests/test_kernel_vs_ref.py:26-32; tolerance = BASELINE.json's)."""
+    from quantum_simulations_b200.kernel.cuda_dense import simulate
+    cd = W.random_1q_cz(n, 20, 1234)
+    got = simulate(cd, dtype=dtype)
+    want = CO.simulate_c(validate_circuit_dict(cd))
+    worst = 0.0
+    step = 1 << 24                                   # blockwise: no third full-size temporary on the host
+    for o in range(0, 1 << n, step):
+        worst = max(worst, float(np.abs(got[o:o + step] - want[o:o + step]).max()))
+    print(f"full-vector parity n={n} {dtype}: max|d| = {worst:.3e} over 2^{n} amplitudes")
+    assert worst <= TOL[dtype]
+
+
+@pytest.mark.gpu
+def test_n28_full_vector_matches_c_oracle():
+    _full_vector_vs_c_oracle(28)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(__import__("os").environ.get("QSV_TEST_FULL") != "1",
+                    reason="BASELINE configs[2] at full size: 2 x 16 GiB on the host and ~2 min of the C oracle on 16 "
+                           "cores — run with QSV_TEST_FULL=1 (log: profiles/r02/parity_n30_full_vector.log)")
+def test_n30_full_vector_matches_c_oracle():
+    _full_vector_vs_c_oracle(30)
+
+
 # ----------------------------------------------------------------------- runner
 @pytest.mark.parametrize("spec,chunk_size,kw", RUNNER_SPECS)
 def test_runner_matches_reference_runner_golden(golden_runner, spec, chunk_size, kw):

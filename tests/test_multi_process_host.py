@@ -22,7 +22,7 @@ def test_sharded_run_across_processes(tmp_path, world):
     for rank in range(world):
         env = dict(os.environ, RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world),
                    MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1")
-        procs.append(subprocess.Popen([sys.executable, str(ROOT / "tests" / "gloo_worker.py"), str(tmp_path), str(n)],
+        procs.append(subprocess.Popen([sys.executable, str(ROOT / "tests" / "multi_process_worker.py"), str(tmp_path), str(n)],
                                       env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     outs = [p.communicate(timeout=240)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), "\n".join(outs)
@@ -36,7 +36,7 @@ def test_sharded_run_across_processes(tmp_path, world):
 
 def _check_qasm(tmp_path, world, n):
     sys.path.insert(0, str(ROOT / "tests"))
-    from gloo_worker import qasm_text
+    from multi_process_worker import qasm_text
     from quantum_simulations_b200.circuit.qasm import qasm_to_ops
     _, ops = qasm_to_ops(qasm_text(n))
     want = np.zeros(1 << n, dtype=np.complex128)
@@ -65,3 +65,45 @@ def test_bench_multi_control_flow_on_cpu(tmp_path):
     assert line["config"]["swaps_per_step"] >= 1 and line["config"]["plan"] == "default planner options"
     assert line["e2e"]["value"] > 0 and line["roofline"]["bound"] == "hbm" and "nvlink" in line
     assert outs[1][0].strip() == ""                                  # only rank 0 prints
+
+
+def test_host_plumbing_collectives(tmp_path):
+    """runner/plumbing.py over three real processes: gather, broadcast, AND, barrier, rank-ordered reductions."""
+    world = 3
+    port = 30100 + (os.getpid() % 200)
+    code = (
+        "import sys, json, numpy as np\n"
+        f"sys.path.insert(0, {str(ROOT)!r})\n"
+        "from quantum_simulations_b200.runner.plumbing import init_plumbing, shutdown_plumbing\n"
+        "p = init_plumbing(); r = p.rank\n"
+        "out = {'gather': p.all_gather_object({'r': r, 'b': bytes([r]) * 4}), 'bcast': p.broadcast_object('x' * (r + 1), src=1),\n"
+        "       'all_t': p.all(True), 'all_f': p.all(r != 2), 'sum': p.allreduce(0.1 * (r + 1), 'sum'), 'max': p.allreduce(float(r), 'max'),\n"
+        "       'vec': p.allreduce(np.arange(4.0) * (r + 1), 'sum').tolist(), 'big': int(p.allreduce(np.ones(1 << 20), 'sum')[-1])}\n"
+        "p.barrier(); shutdown_plumbing()\n"
+        "out['gather'] = [[g['r'], g['b'].hex()] for g in out['gather']]\n"
+        "print(json.dumps(out))\n")
+    procs = []
+    for rank in range(world):
+        env = dict(os.environ, RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=120) for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(o[1][-1500:] for o in outs)
+    import json
+    res = [json.loads(o[0].strip().splitlines()[-1]) for o in outs]
+    assert all(r == res[0] for r in res)                     # every rank sees the same results, bit for bit
+    r0 = res[0]
+    assert r0["gather"] == [[0, "00000000"], [1, "01010101"], [2, "02020202"]] and r0["bcast"] == "xx"
+    assert r0["all_t"] is True and r0["all_f"] is False and r0["max"] == 2.0 and r0["big"] == 3
+    assert r0["sum"] == (0.1 + 0.2) + 0.30000000000000004 and r0["vec"] == [0.0, 6.0, 12.0, 18.0]
+
+
+def test_the_product_imports_no_tensor_library():
+    """North star: host side = Python + ctypes over the C ABI; torch may launch the processes (torchrun) but
+    nothing under quantum_simulations_b200/ imports it."""
+    import re
+    bad = []
+    for f in (ROOT / "quantum_simulations_b200").rglob("*.py"):
+        for i, line in enumerate(f.read_text().splitlines(), 1):
+            if re.match(r"\s*(import|from)\s+(torch|triton|jax|cupy)\b", line):
+                bad.append(f"{f.relative_to(ROOT)}:{i}: {line.strip()}")
+    assert not bad, bad
