@@ -375,7 +375,7 @@ def bench_single(args) -> None:
     achieved = alg_bytes / (avg_pass_ms * 1e-3) / 1e9
     pass_share = sum(streamed_ms) / total_ms if total_ms else None
     traffic, traffic_src = None, None
-    tf = ROOT / "profiles" / "r01" / "traffic_k_pass_jit_n30.json"
+    tf = ROOT / "profiles" / "r02" / "traffic_k_pass_jit_n30.json"
     if tf.exists() and n == 30 and dtype == "complex128" and WORKLOAD == "random":
         t_ = json.loads(tf.read_text())
         traffic, traffic_src = t_["dram_bytes_per_launch"], t_["source"]

@@ -51,6 +51,7 @@ struct qsv_program {
     cudaGraphExec_t graph = nullptr;
     // run-time specialised kernels (jit.cuh): one per pass, null = interpret the pass
     std::vector<cudaKernel_t> jit;
+    std::vector<uint64_t> jit_keys;                   // entries of the kernel cache this program pins (jit.cuh)
     std::vector<std::vector<double>> jit_coefs;
     std::vector<std::vector<float>> jit_coefs_f;      // the same values for complex64 kernels
     // scatter passes (pass fused with the exchange after it): host copy of the ops for their

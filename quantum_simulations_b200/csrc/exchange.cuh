@@ -318,6 +318,11 @@ static int qsvx_xchg_args(qsv_handle *h, qsvx::Comm *c, int n_swap, const int *g
     A.run_log2 = std::min(A.stage_log2, (unsigned)special[0] + A.elem_log2);
     A.units_per_half = 1ull << (half_log2 - A.stage_log2);
     A.seq = c->seq;
+    {   // seconds a launch waits for a peer before it gives up (QSV_XCHG_TIMEOUT_S; shards of one process: short)
+        const char *e = getenv("QSV_XCHG_TIMEOUT_S");
+        const double sec = e ? atof(e) : (c->comm ? 60.0 : 10.0);
+        A.timeout_ns = (unsigned long long)((sec > 0.01 ? sec : 0.01) * 1e9);
+    }
     A.stage_log2 = std::min(12u, half_log2);                          // 4 KB units (small units complete sooner)
     if (const char *e = getenv("QSV_XCHG_STAGE_LOG2")) {             // experiment
         const unsigned v = (unsigned)atoi(e);
@@ -334,6 +339,16 @@ static int qsvx_xchg_args(qsv_handle *h, qsvx::Comm *c, int n_swap, const int *g
     tma_ok = A.run_log2 >= 4 && A.stage_log2 >= 4 && (A.stage_log2 - A.run_log2) <= 6;   // <= 64 bulk copies per unit
     if (A.run_log2 < 4) QSVX_FAIL(h, QSV_EINVAL, "exchange: runs of %u bytes (lowest swapped / chunk position %d) are below the 16-byte pieces the kernels move",
                                   1u << A.run_log2, special[0]);
+    return QSV_OK;
+}
+
+// The sticky error word of this rank's tail: non-zero = an exchange kernel gave up waiting for a peer.
+static int qsvx_check_peers_alive(qsv_handle *h) {
+    auto *c = (qsvx::Comm *)h->comm;
+    if (!c || !c->peers_ready || c->seq == 0) return QSV_OK;
+    unsigned long long w = 0;
+    QSVX_CUDA(h, cudaMemcpy(&w, h->d_tail + qsvx::kTailErrorWord, sizeof(w), cudaMemcpyDeviceToHost));
+    if (w) QSVX_FAIL(h, QSV_ECOMM, "exchange %llu: a peer did not arrive within the time limit (QSV_XCHG_TIMEOUT_S); the state of this shard is undefined", w);
     return QSV_OK;
 }
 

@@ -226,7 +226,7 @@ int qsv_sync(qsv_handle *h) {
     QSV_CHECK_H(h);
     QSV_CUDA(h, cudaSetDevice(h->device));
     QSV_CUDA(h, cudaStreamSynchronize(h->stream));
-    return QSV_OK;
+    return qsvx_check_peers_alive(h);
 }
 
 int qsv_device_ptr(qsv_handle *h, void **ptr, size_t *n_amps_local, void **stream) {
@@ -614,7 +614,7 @@ int qsv_program_create(qsv_handle *h, const qsv_pass *passes, int n_passes, cons
         std::vector<qsvjit::Kernel> ks;
         std::string err;
         qsvjit::resolve(h->device, srcs, ks, err);
-        for (int i = 0; i < n_passes; ++i) p->jit[i] = ks[i].fn;
+        for (int i = 0; i < n_passes; ++i) { p->jit[i] = ks[i].fn; if (ks[i].key) p->jit_keys.push_back(ks[i].key); }
         if (!err.empty()) h->err = "jit (falling back to the interpreting kernel): " + err;
     }
     *out = p;
@@ -901,6 +901,7 @@ static cudaKernel_t scatter_kernel(qsv_handle *h, qsv_program *p, int i, int n_s
     std::string err;
     qsvjit::resolve(h->device, srcs, ks, err);
     if (!err.empty()) h->err = "jit (scatter pass): " + err;
+    if (ks[0].key) p->jit_keys.push_back(ks[0].key);
     qsv_program::ScatterKernel e{i, n_swap, {0, 0, 0}, ks[0].fn};
     for (int k = 0; k < n_swap; ++k) e.bits[k] = local_bits[k];
     p->scatter.push_back(e);                        // a failed build is remembered as well (fn == nullptr)
@@ -1033,7 +1034,7 @@ int qsv_jit_build_pass(const qsv_pass *pass, const qsv_op *ops, int dtype, size_
             mkdir(dir.c_str(), 0755);
             char name[64];
             snprintf(name, sizeof(name), "/%016llx.cubin", (unsigned long long)qsvjit::source_key(src));
-            qsvjit::write_file_atomic(dir + name, cubin);
+            qsvjit::write_file_atomic(dir + name, qsvjit::cache_pack(src, cubin));
         }
     }
     if (cubin_bytes) *cubin_bytes = cubin.size();
@@ -1077,6 +1078,10 @@ int qsv_program_destroy(qsv_handle *h, qsv_program *p) {
     cudaSetDevice(h->device);
     if (p->graph) cudaGraphExecDestroy(p->graph);
     dev_free(h, p->d_passes); dev_free(h, p->d_ops); dev_free(h, p->d_tables);   // stream-ordered after the last run
+    if (!p->jit_keys.empty()) {
+        cudaStreamSynchronize(h->stream);                 // its kernels may be unloaded once nobody holds them
+        qsvjit::release(p->jit_keys);
+    }
     delete p;
     return QSV_OK;
 }

@@ -38,6 +38,7 @@ constexpr int kFlagSlots = 8;                 // world <= 8 on one box
 constexpr size_t kTailBytes = 4096;           // flags + counters at the end of every shard allocation
 // tail layout (uint64 words): [0..7] kind 0 by source rank, [8..15] kind 1 by source rank, [16] CTA counter
 constexpr int kTailCounterWord = 16;
+constexpr int kTailErrorWord = 17;            // sticky: an exchange kernel gave up waiting for a peer (value = seq)
 
 struct XchgArgs {
     char *mine;                               // this rank's shard
@@ -59,6 +60,7 @@ struct XchgArgs {
     unsigned long long units_per_half;        // units in one half of a pair
     unsigned long long half_elems;            // elements in one half of a pair (compacted index space)
     unsigned long long seq;                   // flag value of this launch
+    unsigned long long timeout_ns;            // a wait for a peer's flag gives up after this long (sticky error word)
 };
 
 __device__ __forceinline__ uint32_t xs_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -74,8 +76,26 @@ __device__ __forceinline__ unsigned long long xs_peek(const unsigned long long *
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
     return v;
 }
-__device__ __forceinline__ void xs_wait(const unsigned long long *flag, unsigned long long v) {
-    while (xs_peek(flag) < v) __nanosleep(64);
+__device__ __forceinline__ unsigned long long xs_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// Wait until *flag >= v.  Nothing guarantees that the peer's kernel is running (a crashed rank, shards of one
+// process that the device could not co-schedule): after timeout_ns the wait gives up, records the launch in the
+// sticky error word of this rank's tail and returns false — the host reports it at the next synchronisation.
+__device__ __forceinline__ bool xs_wait(const XchgArgs &A, const unsigned long long *flag, unsigned long long v) {
+    if (xs_peek(A.my_flags + kTailErrorWord) != 0ull) return false;
+    const unsigned long long t0 = xs_now();
+    unsigned spins = 0;
+    while (xs_peek(flag) < v) {
+        __nanosleep(64);
+        if ((++spins & 1023u) == 0u && xs_now() - t0 > A.timeout_ns) {
+            xs_signal(A.my_flags + kTailErrorWord, A.seq);
+            return false;
+        }
+    }
+    return true;
 }
 
 // byte offset inside a shard of compacted element offset e with the swapped bits set to `blk`
@@ -113,12 +133,16 @@ __global__ void __launch_bounds__(kXchgThreads, 1) k_xchg_tma(const __grid_const
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // ---- barrier in: my passes of this chunk are done (stream order); wait for the peers' passes
+    __shared__ int xs_ok;
+    if (tid == 0) xs_ok = 1;
+    __syncthreads();
     if (tid < A.n_peers - 1) {
         const int d = A.me ^ (tid + 1);
         if (blockIdx.x == 0) xs_signal(A.peer_flags[d] + A.my_rank, A.seq);
-        xs_wait(A.my_flags + A.rank_of[d], A.seq);
+        if (!xs_wait(A, A.my_flags + A.rank_of[d], A.seq)) xs_ok = 0;
     }
     __syncthreads();
+    if (!xs_ok) return;                                      // a peer never arrived: move nothing
     const unsigned warp = (unsigned)tid >> 5;
     if ((tid & 31) != 0 || warp >= W) return;
 
@@ -231,7 +255,7 @@ __global__ void __launch_bounds__(kXchgThreads, 1) k_xchg_tma(const __grid_const
     if (old == n_issuers - 1) {
         __threadfence_system();
         for (int k = 0; k < A.n_peers - 1; ++k) xs_signal(A.peer_flags[A.me ^ (k + 1)] + kFlagSlots + A.my_rank, A.seq);
-        for (int k = 0; k < A.n_peers - 1; ++k) xs_wait(A.my_flags + kFlagSlots + A.rank_of[A.me ^ (k + 1)], A.seq);
+        for (int k = 0; k < A.n_peers - 1; ++k) xs_wait(A, A.my_flags + kFlagSlots + A.rank_of[A.me ^ (k + 1)], A.seq);
     }
 }
 
@@ -240,12 +264,16 @@ __global__ void __launch_bounds__(kXchgThreads, 1) k_xchg_tma(const __grid_const
 template <int U>
 __global__ void __launch_bounds__(1024, 1) k_xchg_ldst(const __grid_constant__ XchgArgs A) {
     const int tid = threadIdx.x;
+    __shared__ int xs_ok;
+    if (tid == 0) xs_ok = 1;
+    __syncthreads();
     if (tid < A.n_peers - 1) {
         const int d = A.me ^ (tid + 1);
         if (blockIdx.x == 0) xs_signal(A.peer_flags[d] + A.my_rank, A.seq);
-        xs_wait(A.my_flags + A.rank_of[d], A.seq);
+        if (!xs_wait(A, A.my_flags + A.rank_of[d], A.seq)) xs_ok = 0;
     }
     __syncthreads();
+    if (!xs_ok) return;
     const unsigned long long half16 = (A.half_elems << A.elem_log2) >> 4;          // 16-byte pieces in one half
     const unsigned long long total = (unsigned long long)(A.n_peers - 1) * half16;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
@@ -278,14 +306,14 @@ __global__ void __launch_bounds__(1024, 1) k_xchg_ldst(const __grid_constant__ X
     if (old == gridDim.x - 1) {
         __threadfence_system();
         for (int k = 0; k < A.n_peers - 1; ++k) xs_signal(A.peer_flags[A.me ^ (k + 1)] + kFlagSlots + A.my_rank, A.seq);
-        for (int k = 0; k < A.n_peers - 1; ++k) xs_wait(A.my_flags + kFlagSlots + A.rank_of[A.me ^ (k + 1)], A.seq);
+        for (int k = 0; k < A.n_peers - 1; ++k) xs_wait(A, A.my_flags + kFlagSlots + A.rank_of[A.me ^ (k + 1)], A.seq);
     }
 }
 
 inline size_t xchg_smem_bytes(unsigned stage_log2, unsigned n_warps, unsigned n_remote, unsigned n_local) {
     return (size_t)n_warps * ((size_t)(n_remote + n_local) * (((size_t)1 << stage_log2) + 8) + (size_t)n_remote * 32) + 64;
 }
-constexpr size_t kXchgMaxSmem = 227 * 1024;
+constexpr size_t kXchgMaxSmem = 227 * 1024 - 1024;     // dynamic part: the kernels also hold a few static words
 // default shape: 4 issuing threads, the slots that fit split 10 : 4 between the remote and the local ring
 // (4 KB slots: 4 x 14 x 4 KB = 224 KB, 144 KB of remote reads in flight per SM)
 inline void xchg_ring_shape(unsigned stage_log2, unsigned &n_warps, unsigned &n_remote, unsigned &n_local) {

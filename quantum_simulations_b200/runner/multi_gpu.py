@@ -370,11 +370,12 @@ class ShardedSimulator:
         self.shard.prepare(prog, self._agree)
         self._prepared[id(prog)] = prog
 
-    def run(self, prog: Program) -> None:
+    def run(self, prog: Program, init: bool = True) -> None:
+        """init=False: the program continues from what the shards hold (a resumed / segmented run)."""
         temp = self._prepared.get(id(prog)) is not prog
         if temp:
             self.shard.prepare(prog, self._agree)
-        if not prog.fused_init:                # otherwise the first pass creates |0...0> itself
+        if init and not prog.fused_init:       # otherwise the first pass creates |0...0> itself
             self.shard.state.init_zero()
         execute(prog, self.shard)
         if temp:
@@ -463,18 +464,22 @@ def simulate_sharded(circuit_dict: dict, dtype="complex128", out: np.ndarray | N
 
 
 def run(circuit_dict: dict, work_dir, chunk_size: int = 1 << 20, dtype: str = "complex128",
-        use_wal: bool = True, **compiler_kw):
-    """Multi-GPU form of ``runner.single_node.run`` (reference single_node.py:78-138), launched
-    with one process per GPU: simulate from |0...0>, then every rank writes the chunk files of
-    its (logical) shard through two pinned staging buffers; rank 0 publishes the manifest and
-    commits the WAL after all chunks are durable.  Returns the buffer path (``collect_state``
-    reads it exactly like a single-device run).  A restart re-runs the circuit: intermediate
-    states are laid out stage by stage, only the final one is in logical order."""
+        use_wal: bool = True, checkpoint_every: int = 0, stop_after_checkpoints: int | None = None, **compiler_kw):
+    """Multi-GPU form of ``runner.single_node.run`` (reference single_node.py:78-176), launched with one process per
+    GPU.  The circuit is cut into SEGMENTS of `checkpoint_every` levels (0 = one segment); each segment is planned
+    and executed as a sharded program that starts and ends in the identity layout, and after each segment every
+    rank writes the chunk files of its shard through two pinned staging buffers; rank 0 publishes the manifest and
+    commits the WAL (done_steps = levels completed — the same count the single-device runner and the reference
+    commit, so a work directory is resumable by either) once all chunks are durable.  A restart loads the
+    committed buffer into the shards and continues with the next segment (reference resume:
+    single_node.py:143-176, wal/wal.py:85-89); a directory whose WAL already covers the circuit returns at once.
+    stop_after_checkpoints (tests): return after that many checkpoints, as a crash would.
+    Returns the committed buffer path (``collect_state`` reads it exactly like a single-device run)."""
     from pathlib import Path
 
-    from quantum_simulations_b200.runner.single_node import _buf_dir, _other, _wipe_buf
-    from quantum_simulations_b200.storage.block_store import chunk_filename, write_chunk_atomic
-    from quantum_simulations_b200.storage.manifest import Manifest, write_manifest_atomic
+    from quantum_simulations_b200.runner.single_node import _buf_dir, _other, _wipe_buf, build_steps
+    from quantum_simulations_b200.storage.block_store import chunk_filename, read_chunk, write_chunk_atomic
+    from quantum_simulations_b200.storage.manifest import Manifest, read_manifest, write_manifest_atomic
     from quantum_simulations_b200.storage.pinned import PinnedBuffer
     from quantum_simulations_b200.wal.wal import WAL
 
@@ -487,42 +492,75 @@ def run(circuit_dict: dict, work_dir, chunk_size: int = 1 << 20, dtype: str = "c
         if (1 << n_loc) % chunk_size:
             raise ValueError("2^n must be divisible by chunk_size")
         work = Path(work_dir)
+        levels = [st_["local_ops"] + st_["nonlocal_ops"] for st_ in build_steps(cd, n, False)]   # one entry per level
         wal = WAL(work / "wal.json", circuit_dict=cd) if (use_wal and sim.rank == 0) else None
-        current = wal.committed_buf if wal else "a"
+        current, start = (wal.committed_buf, wal.done_steps) if wal else ("a", 0)
         if sim.dist is not None:
-            current = sim.dist.broadcast_object(current, src=0)
-        dst = _buf_dir(work, _other(current))
-        if sim.rank == 0:
-            _wipe_buf(dst)
-        if sim.dist is not None:
-            sim.dist.barrier()
-        sim.run(sim.plan(cd, **compiler_kw))
+            current, start = sim.dist.broadcast_object((current, start), src=0)
         per_rank = (1 << n_loc) // chunk_size
-        first = sim.logical_rank * per_rank                     # logical shard order = index order
         st, np_dtype = sim.shard.state, sim.dtype
-        bufs = [PinnedBuffer(chunk_size * np_dtype.itemsize), PinnedBuffer(chunk_size * np_dtype.itemsize)]
-        try:
-            st._ck(st.lib.qsv_download_async(st._h, bufs[0].ptr, 0, chunk_size))
-            for c in range(per_rank):
+        if start >= len(levels) and (start > 0 or not levels):
+            if (_buf_dir(work, current) / "manifest.json").exists():
+                return _buf_dir(work, current)                  # the committed buffer already holds the final state
+            start = 0
+        if start > 0:                                           # resume: committed chunks -> shards (identity layout)
+            src = _buf_dir(work, current)
+            m = read_manifest(src)
+            if m.n_qubits != n or m.n_chunks * m.chunk_size != (1 << n):
+                raise ValueError("the committed checkpoint does not belong to this circuit size")
+            per_src = (1 << n_loc) // m.chunk_size
+            for c in range(per_src):
+                data = read_chunk(src / "chunks" / m.chunks[sim.rank * per_src + c], np.dtype(m.dtype))
+                st.upload(data.astype(np_dtype, copy=False), c * m.chunk_size)
+        every = checkpoint_every if checkpoint_every > 0 else max(len(levels) - start, 1)
+        n_ckpt = 0
+        lo = start
+        while True:
+            hi = min(lo + every, len(levels))
+            final = hi >= len(levels)
+            ops = [op for lv in levels[lo:hi] for op in lv]
+            from_zero = lo == 0
+            # only the LAST segment may leave an X pending on a rank bit as a renaming of the shards; a segment
+            # that is continued must end with every amplitude where the identity layout puts it
+            prog = sim.plan_ops(ops, zero_init=from_zero, **dict(compiler_kw, rank_flips=bool(final and compiler_kw.get("rank_flips", True))))
+            if from_zero or ops:
+                sim.run(prog, init=from_zero)
+            logical = sim.rank ^ prog.rank_flip_mask
+            dst = _buf_dir(work, _other(current))
+            if sim.rank == 0:
+                _wipe_buf(dst)
+            if sim.dist is not None:
+                sim.dist.barrier()
+            first = logical * per_rank                          # logical shard order = index order
+            bufs = [PinnedBuffer(chunk_size * np_dtype.itemsize), PinnedBuffer(chunk_size * np_dtype.itemsize)]
+            try:
+                st._ck(st.lib.qsv_download_async(st._h, bufs[0].ptr, 0, chunk_size))
+                for c in range(per_rank):
+                    st.sync()
+                    if c + 1 < per_rank:
+                        st._ck(st.lib.qsv_download_async(st._h, bufs[(c + 1) & 1].ptr, (c + 1) * chunk_size, chunk_size))
+                    write_chunk_atomic(dst / "chunks" / chunk_filename(first + c), bufs[c & 1].array(np_dtype, chunk_size), np_dtype)
                 st.sync()
-                if c + 1 < per_rank:
-                    st._ck(st.lib.qsv_download_async(st._h, bufs[(c + 1) & 1].ptr, (c + 1) * chunk_size, chunk_size))
-                write_chunk_atomic(dst / "chunks" / chunk_filename(first + c), bufs[c & 1].array(np_dtype, chunk_size), np_dtype)
-            st.sync()
-        finally:
-            for b in bufs:
-                b.free()
-        if sim.dist is not None:
-            sim.dist.barrier()
-        if sim.rank == 0:
-            total = per_rank * sim.world
-            write_manifest_atomic(dst, Manifest(n_qubits=n, chunk_size=chunk_size, n_chunks=total, dtype=np_dtype.name,
-                                                chunks=[chunk_filename(i) for i in range(total)]))
-            if wal:
-                wal.commit_step(len(cd["gates"]) - 1 if cd["gates"] else 0, _other(current))
-                wal.close()
-        if sim.dist is not None:
-            sim.dist.barrier()
-        return dst
+            finally:
+                for b in bufs:
+                    b.free()
+            if sim.dist is not None:
+                sim.dist.barrier()                              # every chunk of every rank is durable
+            if sim.rank == 0:
+                total = per_rank * sim.world
+                write_manifest_atomic(dst, Manifest(n_qubits=n, chunk_size=chunk_size, n_chunks=total, dtype=np_dtype.name,
+                                                    chunks=[chunk_filename(i) for i in range(total)]))
+                if wal:
+                    wal.commit_step(max(hi - 1, 0), _other(current))
+            current = _other(current)
+            n_ckpt += 1
+            if sim.dist is not None:
+                sim.dist.barrier()
+            if final or (stop_after_checkpoints is not None and n_ckpt >= stop_after_checkpoints):
+                break
+            lo = hi
+        if wal:
+            wal.close()
+        return _buf_dir(work, current)
     finally:
         sim.close()

@@ -76,6 +76,24 @@ def main():
         print(f"runner.multi_gpu.run: {len(os.listdir(buf / 'chunks'))} chunk files, max|d|={err:.3e}", flush=True)
         worst = max(worst, err)
     dist.barrier()
+    # resumable checkpoints: segments of 4 levels; the first call stops after ONE checkpoint (as a crash would),
+    # the second resumes from the WAL's done_steps and finishes; a third call on the finished directory returns at once
+    box = [dist.broadcast_object(tempfile.mkdtemp(prefix="qsv_mg_ck_") if rank == 0 else None, src=0)]
+    cd = validate_circuit_dict(W.random_1q_cz(n, 12, 33))
+    import json as _json
+    MG.run(cd, box[0], chunk_size=1 << (n - 5), checkpoint_every=4, stop_after_checkpoints=1)
+    done_first = _json.loads((Path(box[0]) / "wal.json").read_text())["done_steps"] if rank == 0 else None
+    buf = MG.run(cd, box[0], chunk_size=1 << (n - 5), checkpoint_every=4)
+    buf_again = MG.run(cd, box[0], chunk_size=1 << (n - 5), checkpoint_every=4)
+    if rank == 0:
+        wal = _json.loads((Path(box[0]) / "wal.json").read_text())
+        got = collect_state(buf)
+        err = float(np.abs(got - CO.simulate_c(cd)).max())
+        print(f"runner.multi_gpu.run resumed: done_steps {done_first} -> {wal['done_steps']} of 12 levels, max|d|={err:.3e}", flush=True)
+        if done_first != 4 or wal["done_steps"] != 12 or str(buf_again) != str(buf):
+            raise SystemExit(f"resume bookkeeping wrong: first={done_first} wal={wal} again={buf_again} vs {buf}")
+        worst = max(worst, err)
+    dist.barrier()
     dist.close()
     if rank == 0 and worst > 1e-12:
         raise SystemExit(f"multi-GPU parity failed: {worst}")

@@ -52,7 +52,7 @@ int main(int argc, char **argv) {
         CK(cudaStreamCreateWithFlags(&sx[r], cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&sc[r], cudaStreamNonBlocking));
         CK(cudaEventCreate(&e0[r])); CK(cudaEventCreate(&e1[r])); CK(cudaEventCreate(&c0[r])); CK(cudaEventCreate(&c1[r]));
-        CK(cudaFuncSetAttribute(qsvx::k_xchg_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CK(cudaFuncSetAttribute(qsvx::k_xchg_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsvx::kXchgMaxSmem));
         CK(cudaFuncSetAttribute(k_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     }
     unsigned long long seq = 0;
@@ -74,7 +74,7 @@ int main(int argc, char **argv) {
             A.elem_log2 = 4; A.run_log2 = run_log2; A.stage_log2 = 14;
             A.half_elems = n >> 2;                                   // pair = 2^(n_local-1) elements, half of it
             A.units_per_half = (A.half_elems * 16) >> A.stage_log2;
-            A.seq = seq; A.n_warps = nw; A.n_remote = nr; A.n_local = nl; A.stage_log2 = sl2; A.units_per_half = (A.half_elems * 16) >> A.stage_log2; if (A.run_log2 > A.stage_log2) A.run_log2 = A.stage_log2;
+            A.seq = seq; A.timeout_ns = 5000000000ull; A.n_warps = nw; A.n_remote = nr; A.n_local = nl; A.stage_log2 = sl2; A.units_per_half = (A.half_elems * 16) >> A.stage_log2; if (A.run_log2 > A.stage_log2) A.run_log2 = A.stage_log2;
             if (beside) { CK(cudaEventRecord(c0[r], sc[r])); k_stream<<<148 - sms, 512, 200 * 1024, sc[r]>>>(side[r], n, 2); CK(cudaEventRecord(c1[r], sc[r])); }
             CK(cudaEventRecord(e0[r], sx[r]));
             if (mode == 0) qsvx::k_xchg_tma<<<sms, qsvx::kXchgThreads, qsvx::xchg_smem_bytes(sl2, nw, nr, nl), sx[r]>>>(A);
