@@ -285,6 +285,8 @@ def bench_single(args) -> None:
                defer_diagonals=args.defer_diagonals, fold_tables=not args.no_fold_tables)
     if args.no_low_store_round:
         ckw["low_store_round"] = False
+    if args.low_store_bits is not None:
+        ckw["low_store_bits"] = args.low_store_bits
     if args.warp_local_rounds:
         ckw["warp_local_rounds"] = True
         os.environ["QSV_JIT_WARP_SYNC"] = "1"
@@ -752,6 +754,8 @@ def main() -> None:
     ap.add_argument("--no-others", action="store_true", help="N = 1: skip the short runs of the other BASELINE workloads")
     ap.add_argument("--no-low-store-round", action="store_true",
                     help="experiment: no idle round before stores whose registers hold a low (row) position")
+    ap.add_argument("--low-store-bits", type=int, default=None,
+                    help="experiment: idle round before the stores only if a store position below this is in registers")
     ap.add_argument("--warp-local-rounds", action="store_true",
                     help="experiment (N = 1): warp-local round exchanges with __syncwarp() instead of the group barrier")
     ap.add_argument("--streaming-stores", action="store_true",

@@ -492,6 +492,7 @@ class PassCompiler:
                  defer_diagonals: bool = False, absorb: bool = True, allow_swaps: bool = True,
                  swap_anywhere: bool = False, rank_flips: bool = False, park_off_last_round: bool = True,
                  table_phases: bool = True, eager_flips: bool = True, low_store_round: bool = True,
+                 low_store_bits: int | None = None,
                  warp_local_rounds: bool = False):
         self.n = n_qubits
         self.n_local = n_qubits if n_local is None else n_local
@@ -536,6 +537,10 @@ class PassCompiler:
         # lanes cover whole rows.  False (experiment): store as is — half-row stores that L2 merges,
         # against one shared-memory round trip less.
         self.low_store_round = low_store_round
+        # the idle round before the stores is added only if the last round holds a store position BELOW this in
+        # registers (default: any of the W row positions; 1 = only position 0, i.e. only if a thread would write
+        # half sectors; 2 = positions 0 and 1)
+        self.low_store_bits = low_store_bits
         # experiment: keep the two tile positions that select the WARP inside a consumer group (thread
         # bits 5, 6) the same from one round to the next wherever both rounds leave them out of the
         # registers.  The shared-memory exchange between such rounds stays inside each warp, and the
@@ -884,6 +889,7 @@ class PassCompiler:
 
         lo_load = {i for i in range(t) if load_bits[i] < W}
         lo_store = {i for i in range(t) if store[i] < W}
+        lo_force = lo_store if self.low_store_bits is None else {i for i in range(t) if store[i] < self.low_store_bits}
 
         # register tile-indices of every round, padded to 4 with idle indices
         plan = []
@@ -899,7 +905,7 @@ class PassCompiler:
             plan.append((self._idle_regs(lo_store if self.ring else lo_load | lo_store), []))
         if set(plan[0][0]) & lo_load and not self.ring:
             plan.insert(0, (self._idle_regs(lo_load), []))
-        if set(plan[-1][0]) & lo_store and self.low_store_round:
+        if set(plan[-1][0]) & lo_force and self.low_store_round:
             plan.append((self._idle_regs(lo_store), []))
         if len(plan) == 1:
             # one round = same thread mapping for load and store: only coalesced on both

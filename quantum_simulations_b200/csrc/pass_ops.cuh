@@ -92,6 +92,46 @@ __device__ __forceinline__ void op_rot(V (&v)[kRegAmps], const R t, const R s, c
     }
 }
 
+// ---- sign-deferring forms (used by the run-time specialised kernels, csrc/jit.cuh) --------------------------
+// The specialised kernels do not execute sign flips where the circuit has them (a quarter of the instructions
+// of a pass were LOP3 on sign bits): the generator carries them as PENDING signs — per register a compile-time
+// bit (NEG), per register slot a per-thread mask (the parity of CZ partners) — and folds them into the next
+// mixing op of that slot, where they are free: operand negation, or a +-1 / sign-carrying coefficient.
+__device__ __forceinline__ double sign_factor(double, int m) { return __hiloint2double(0x3ff00000 ^ m, 0); }   // +-1.0
+__device__ __forceinline__ float sign_factor(float, int m) { return __int_as_float(0x3f800000 ^ m); }
+
+// HAD on (A, sg * B) with A = +-a, B = +-b (compile-time signs NEG, bit j = register j); sg = +-1 per thread.
+// Outputs carry no pending sign:  b <- A - sg B ;  a <- 2A - b
+template <typename V, typename R, int TB, unsigned NEG>
+__device__ __forceinline__ void op_had_sg(V (&v)[kRegAmps], const R sg) {
+#pragma unroll
+    for (int j = 0; j < kRegAmps; ++j) if (!(j & (1 << TB))) {
+        V &a = v[j], &b = v[j | (1 << TB)];
+        const bool na = (NEG >> j) & 1u, nb = (NEG >> (j | (1 << TB))) & 1u;
+        b.x = fma(nb ? sg : -sg, b.x, na ? -a.x : a.x); a.x = fma(na ? (R)-2 : (R)2, a.x, -b.x);
+        b.y = fma(nb ? sg : -sg, b.y, na ? -a.y : a.y); a.y = fma(na ? (R)-2 : (R)2, a.y, -b.y);
+    }
+}
+// ROT on (A, sigma * B), ts = t * sigma, ss = s * sigma (sigma = +-1 per thread, folded into the coefficients by
+// the caller).  The a outputs are clean; the b registers hold sigma * (true b): sigma STAYS PENDING on the b half.
+template <typename V, typename R, int TB, unsigned NEG>
+__device__ __forceinline__ void op_rot_sg(V (&v)[kRegAmps], const R ts, const R ss) {
+#pragma unroll
+    for (int j = 0; j < kRegAmps; ++j) if (!(j & (1 << TB))) {
+        V &a = v[j], &b = v[j | (1 << TB)];
+        const bool na = (NEG >> j) & 1u, nb = (NEG >> (j | (1 << TB))) & 1u;
+        a.x = fma(nb ? ts : -ts, b.x, na ? -a.x : a.x); a.y = fma(nb ? ts : -ts, b.y, na ? -a.y : a.y);
+        b.x = fma(ss, a.x, nb ? -b.x : b.x);            b.y = fma(ss, a.y, nb ? -b.y : b.y);
+        a.x = fma(-ts, b.x, a.x);                       a.y = fma(-ts, b.y, a.y);
+    }
+}
+// SCALE that also settles the compile-time pending signs
+template <typename V, typename R, unsigned NEG>
+__device__ __forceinline__ void op_scale_neg(V (&v)[kRegAmps], const R s) {
+#pragma unroll
+    for (int j = 0; j < kRegAmps; ++j) { const R f = ((NEG >> j) & 1u) ? -s : s; v[j].x *= f; v[j].y *= f; }
+}
+
 template <typename V, int TB, bool CHECK>
 __device__ __forceinline__ void op_xswap(V (&v)[kRegAmps], const uint32_t rc) {
     QSV_PAIR_LOOP(TB, CHECK, rc) {
