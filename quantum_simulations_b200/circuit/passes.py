@@ -492,7 +492,7 @@ class PassCompiler:
                  defer_diagonals: bool = False, absorb: bool = True, allow_swaps: bool = True,
                  swap_anywhere: bool = False, rank_flips: bool = False, park_off_last_round: bool = True,
                  table_phases: bool = True, eager_flips: bool = True, low_store_round: bool = True,
-                 low_store_bits: int | None = None,
+                 low_store_bits: int | None = 2,
                  warp_local_rounds: bool = False):
         self.n = n_qubits
         self.n_local = n_qubits if n_local is None else n_local
@@ -538,8 +538,9 @@ class PassCompiler:
         # against one shared-memory round trip less.
         self.low_store_round = low_store_round
         # the idle round before the stores is added only if the last round holds a store position BELOW this in
-        # registers (default: any of the W row positions; 1 = only position 0, i.e. only if a thread would write
-        # half sectors; 2 = positions 0 and 1)
+        # registers.  Default 2 (positions 0 and 1: a thread would otherwise write 16- or 32-byte pieces of a row);
+        # position 2 in registers means 64-byte pieces, which cost nothing measurable, while the saved round does
+        # (profiles/r02/bench_ab_signs_deferred_lsb2.json: 41.9 -> 40.7 ms).  None = any of the W row positions.
         self.low_store_bits = low_store_bits
         # experiment: keep the two tile positions that select the WARP inside a consumer group (thread
         # bits 5, 6) the same from one round to the next wherever both rounds leave them out of the
