@@ -204,12 +204,12 @@ class Transition:
     chunk_bits: list
 
 
-def plan_transitions(prog: Program, max_chunk_bits: int = 4, min_chunk_pos: int = 10, max_side: int = 3,
+def plan_transitions(prog: Program, max_chunk_bits: int = 4, min_chunk_pos: int = 8, max_side: int = 3,
                      tile_bits: int = 11, min_chunk_bits: int | None = None) -> dict:
     """{index of a SwapStep in prog.steps: Transition}.  Greedy: passes are added on the side that costs
     the fewest candidate chunk bits until the pipelined passes take as long as the exchange
     (bytes / measured bandwidths), a side runs out of eligible passes, or fewer than one chunk bit of
-    position >= min_chunk_pos (runs of >= 16 KB for the TMA exchange kernel) would be left.  A pass is
+    position >= min_chunk_pos (runs of >= 4 KB = one unit of the TMA exchange kernel) would be left.  A pass is
     eligible if it visits every tile and reads its input (no zero-support skipping, not the fused
     initialisation); passes are never shared between two transitions."""
     steps = prog.steps

@@ -183,7 +183,7 @@ class CudaShard:
                 run = []
         if not (self.pipeline and self.peer_swap and not self.fused_exchange):
             return
-        plans = sharding.plan_transitions(prog, min_chunk_pos=10 if prog.n_local >= 24 else 5)
+        plans = sharding.plan_transitions(prog, min_chunk_pos=8 if prog.n_local >= 24 else 5)   # >= 4 KB runs = one exchange unit
         for k in sorted(plans):
             tr = plans[k]
             ok = True

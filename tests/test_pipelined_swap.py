@@ -53,7 +53,7 @@ def test_transition_plans_are_valid():
                      (36, 3, W.random_1q_cz(36, 20, 1234)), (34, 2, W.random_1q_cz(34, 20, 1234)),
                      (20, 2, W.qft(20)), (21, 3, W.random_mixed(21, 300, 8)), (20, 1, W.ghz(20))]:
         prog = sharding.plan(circuit_ops(validate_circuit_dict(cd)), n, n - g, "complex128", swap_anywhere=True, rank_flips=True)
-        plans = sharding.plan_transitions(prog, min_chunk_pos=10 if n - g >= 24 else 5)
+        plans = sharding.plan_transitions(prog, min_chunk_pos=8 if n - g >= 24 else 5)
         used = set()
         for k, tr in plans.items():
             seen_any = True
