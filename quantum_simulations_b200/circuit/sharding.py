@@ -23,8 +23,9 @@ from dataclasses import dataclass
 
 from quantum_simulations_b200.circuit.passes import PassCompiler, PassStep, Program, SwapStep
 
-HBM_BW = 5.8e12          # achieved by a pass kernel, B/s (profiles/r01)
-NVLINK_BW = 0.55e12      # achieved by the chunked in-place exchange, B/s per direction
+HBM_BW = 5.3e12          # achieved by a pass kernel, B/s (profiles/r02: 6.5 ms per 34.4 GB sweep)
+NVLINK_BW = 0.68e12      # achieved by the exchange kernel alone, B/s per direction (profiles/r02)
+PIPELINED_EXPOSED = 0.35 # fraction of a swap's stand-alone time that a pipelined transition leaves exposed (measured 0.1-0.45)
 
 
 def fuse_init(prog: Program) -> Program:
@@ -38,9 +39,10 @@ def fuse_init(prog: Program) -> Program:
     return prog
 
 
-def estimate_seconds(prog: Program, fused_exchange: bool = False) -> float:
+def estimate_seconds(prog: Program, fused_exchange: bool = False, pipelined: bool = False) -> float:
     """fused_exchange: a swap right after a pass runs inside that pass (scatter pass, qsv_pass_scatter):
-    the pair costs the longer of the two instead of their sum."""
+    the pair costs the longer of the two instead of their sum.  pipelined: swaps run as pipelined transitions
+    (qsv_swap_pipelined) and cost only their exposed part."""
     amp = 16 if prog.dtype == "complex128" else 8
     shard = amp * (1 << prog.n_local)
     t = 0.0
@@ -53,6 +55,8 @@ def estimate_seconds(prog: Program, fused_exchange: bool = False) -> float:
             x = (1.0 - 0.5 ** len(s.global_bits)) * shard / NVLINK_BW
             if fused_exchange and last_pass is not None:
                 x = max(0.0, x - last_pass)
+            elif pipelined:
+                x *= PIPELINED_EXPOSED
             t += x
             last_pass = None
     return t

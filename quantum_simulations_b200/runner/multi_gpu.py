@@ -179,7 +179,11 @@ class CudaShard:
                     handle_at[k - len(run) + i] = (h, i)
                 if self.fused_exchange and isinstance(step, SwapStep):
                     l = (C.c_int * len(step.local_bits))(*step.local_bits)
-                    self.state.lib.qsv_pass_scatter_prepare(self.state._h, h, len(run) - 1, len(step.local_bits), l)
+                    ok = self.state.lib.qsv_pass_scatter_prepare(self.state._h, h, len(run) - 1, len(step.local_bits), l) == 0
+                    # the library falls back to "pass, then swap" when it has no scatter kernel: every rank must
+                    # take the same branch, so one rank without the kernel switches the scatter path off everywhere
+                    if agree is not None and not agree(bool(ok)):
+                        self.fused_exchange = False
                 run = []
         if not (self.pipeline and self.peer_swap and not self.fused_exchange):
             return
