@@ -286,3 +286,46 @@ def expectation_z(psi: np.ndarray, qubits) -> float:
     for q in qubits:
         par ^= (idx >> q) & 1
     return float(np.sum(np.where(par == 1, -p, p)))
+
+
+def run_qasm_steps(n: int, steps, cregs: dict, seed: int = 0):
+    """ONE TRAJECTORY of an OpenQASM 2.0 program with mid-circuit measure / reset / classical if
+    (steps of quantum_simulations_b200.circuit.qasm.qasm_to_steps).  "Parity unpinned": the reference has no
+    such path (its Qiskit converter drops measurements; HiSVSIM's collapse is state_vector.hpp:829-893), so the
+    definition is frozen HERE and the CUDA path (kernel.cuda_dense.run_qasm) restates it:
+        rng = np.random.default_rng(seed); every measure / reset draws ONE u = rng.random(), in program order;
+        p0 = sum of |amp|^2 over the indices whose bit q is 0 (float64);  outcome = 0 if u < p0 else 1;
+        the other half is zeroed and the state divided by sqrt(p_outcome);  reset applies X after outcome 1;
+        if(creg == value): creg read as an integer, bit 0 = least significant.
+    Returns (state, {creg: int})."""
+    rng = np.random.default_rng(seed)
+    psi = np.zeros(1 << n, dtype=np.complex128)
+    psi[0] = 1.0
+    bits = {name: 0 for name in cregs}
+    idx = np.arange(1 << n, dtype=np.int64)
+
+    def measure(q: int) -> int:
+        u = rng.random()
+        p = marginal_probabilities(psi, [q])
+        out = 0 if u < p[0] else 1
+        psi[((idx >> q) & 1) != out] = 0.0
+        psi[:] = psi / np.sqrt(p[out])
+        return out
+
+    for st in steps:
+        if st[0] == "ops":
+            apply_ops(psi, st[1])
+        elif st[0] == "measure":
+            _, q, creg, bit = st
+            out = measure(q)
+            bits[creg] = (bits[creg] & ~(1 << bit)) | (out << bit)
+        elif st[0] == "reset":
+            if measure(st[1]) == 1:
+                apply_1q(psi, st[1], np.array([[0, 1], [1, 0]], dtype=np.complex128))
+        elif st[0] == "if":
+            _, creg, value, ops = st
+            if bits[creg] == value:
+                apply_ops(psi, ops)
+        else:
+            raise ValueError(f"unknown step {st[0]!r}")
+    return psi, bits

@@ -127,11 +127,12 @@ def _split_args(s: str) -> list[str]:
     return [a.strip() for a in out]
 
 
-def qasm_to_ops(text: str, with_statement_index: bool = False):
+def qasm_to_ops(text: str, with_statement_index: bool = False, _events: list | None = None, _cregs: dict | None = None):
     """Parse an OpenQASM 2.0 program -> (n_qubits, [(qubits, U)]) in program order.
     with_statement_index=True adds a third value: for every op the 0-based index of the gate
     STATEMENT it came from (a broadcast or a ccx yields several ops of one statement; barrier /
-    measure / declarations are not counted) — what HiSVSIM's part files number."""
+    measure / declarations are not counted) — what HiSVSIM's part files number.
+    (_events / _cregs: used by qasm_to_steps, which keeps measure / reset / if instead of refusing them.)"""
     text = re.sub(r"//[^\n]*", "", text)
     regs: dict[str, tuple[int, int]] = {}           # name -> (offset, size)
     gates: dict[str, tuple[list, list, list]] = {}  # name -> (params, qargs, body statements)
@@ -217,6 +218,42 @@ def qasm_to_ops(text: str, with_statement_index: bool = False):
             regs[m.group(1)] = (n, int(m.group(2)))
             n += int(m.group(2))
             continue
+        if _events is not None:                    # classical mode: keep the non-unitary statements as events
+            m = re.fullmatch(r"creg\s+(\w+)\s*\[\s*(\d+)\s*\]", st)
+            if m:
+                _cregs[m.group(1)] = int(m.group(2))
+                continue
+            m = re.fullmatch(r"measure\s+(\w+)\s*(?:\[\s*(\d+)\s*\])?\s*->\s*(\w+)\s*(?:\[\s*(\d+)\s*\])?", st)
+            if m:
+                if m.group(1) not in regs or m.group(3) not in _cregs:
+                    raise QasmError(f"measure: unknown register in {st!r}")
+                off, size = regs[m.group(1)]
+                qs_ = range(off, off + size) if m.group(2) is None else [off + int(m.group(2))]
+                bs_ = range(_cregs[m.group(3)]) if m.group(4) is None else [int(m.group(4))]
+                if len(qs_) != len(bs_) or any(b >= _cregs[m.group(3)] for b in bs_):
+                    raise QasmError(f"measure: register sizes do not match in {st!r}")
+                for q_, b_ in zip(qs_, bs_):
+                    _events.append((len(ops), "measure", q_, m.group(3), b_))
+                continue
+            m = re.fullmatch(r"reset\s+(\w+)\s*(?:\[\s*(\d+)\s*\])?", st)
+            if m and m.group(1) in regs:
+                off, size = regs[m.group(1)]
+                for q_ in (range(off, off + size) if m.group(2) is None else [off + int(m.group(2))]):
+                    _events.append((len(ops), "reset", q_))
+                continue
+            m = re.fullmatch(r"if\s*\(\s*(\w+)\s*==\s*(\d+)\s*\)\s*(.*)", st, re.S)
+            if m:
+                if m.group(1) not in _cregs:
+                    raise QasmError(f"if: unknown classical register {m.group(1)!r}")
+                if re.match(r"(measure|reset|if)\b", m.group(3)):
+                    raise QasmError("if: only gate statements can be conditional")
+                before_if = len(ops)
+                conditional = ("if", m.group(1), int(m.group(2)))
+                st = m.group(3).strip()                     # falls through: the gate statement is parsed below
+            else:
+                conditional = None
+        else:
+            conditional = None
         if re.match(r"(creg|barrier|measure)\b", st):
             continue
         m = re.fullmatch(r"reset\s+(\w+)\s*(?:\[\s*(\d+)\s*\])?", st)
@@ -255,9 +292,55 @@ def qasm_to_ops(text: str, with_statement_index: bool = False):
             emit(m.group(1), params, [a[i] if len(a) > 1 else a[0] for a in args])
         stmt_of += [n_stmt] * (len(ops) - before)
         n_stmt += 1
+        if conditional is not None:                 # the ops of this statement leave the unconditional stream
+            cond_ops = ops[before_if:]
+            del ops[before_if:]
+            del stmt_of[before_if:]
+            _events.append((len(ops), conditional[0], conditional[1], conditional[2], cond_ops))
     if n == 0:
         raise QasmError("no qreg declared")
     return (n, ops, stmt_of) if with_statement_index else (n, ops)
+
+
+def qasm_to_steps(text: str):
+    """OpenQASM 2.0 WITH its non-unitary statements: mid-circuit `measure`, `reset`, and classically controlled
+    gates `if(c==k) gate ...;` (six of the QASMBench circuits vendored with the reference use them).
+    Returns (n_qubits, steps, cregs): cregs = {name: size}; steps is a list of
+        ("ops", [(qubits, U), ...])            a unitary segment (as qasm_to_ops)
+        ("measure", qubit, creg, bit)          projective Z measurement, outcome -> creg[bit]
+        ("reset", qubit)                       measure, then X if the outcome was 1
+        ("if", creg, value, [(qubits, U)...])  the ops run iff the integer value of creg (bit 0 = LSB) == value
+    Execution semantics (one TRAJECTORY under a seed) are frozen in oracle/ref_dense.py::run_qasm_steps; the
+    reference has no such path (its converter drops measurements), HiSVSIM's collapse primitive is
+    state_vector.hpp:829-893."""
+    events: list = []
+    cregs: dict = {}
+    n, ops = qasm_to_ops(text, _events=events, _cregs=cregs)
+    steps: list = []
+    at = 0
+    for ev in events:
+        pos = ev[0]
+        if pos > at:
+            steps.append(("ops", ops[at:pos]))
+            at = pos
+        steps.append(tuple(ev[1:]))
+    if at < len(ops):
+        steps.append(("ops", ops[at:]))
+    return n, steps, cregs
+
+
+def is_unitary_program(steps) -> bool:
+    """True if the steps can run as ONE unitary circuit with the measurements read at the end: no reset, no if,
+    and no gate on a qubit after that qubit was measured."""
+    measured: set = set()
+    for st in steps:
+        if st[0] in ("reset", "if"):
+            return False
+        if st[0] == "measure":
+            measured.add(st[1])
+        elif st[0] == "ops" and any(q in measured for qs, _ in st[1] for q in qs):
+            return False
+    return True
 
 
 def qasm_to_dict(text: str) -> dict:

@@ -77,9 +77,62 @@ def simulate(circuit_dict: dict, dtype="complex128", device: int = 0, out: np.nd
     return res
 
 
+def run_qasm(text: str, seed: int = 0, dtype="complex128", device: int = 0, **compiler_kw):
+    """ONE TRAJECTORY of an OpenQASM 2.0 program with mid-circuit `measure`, `reset` and `if(c==k)` on the GPU:
+    unitary segments run as fused programs on the resident state, every measurement is a marginal
+    (qsv_probabilities) + a seeded draw + a projection sweep (DeviceState.project; HiSVSIM
+    state_vector.hpp:829-893).  Semantics, draw order and the outcome rule are those of
+    oracle/ref_dense.py::run_qasm_steps.  Returns (final state, {creg: int})."""
+    from quantum_simulations_b200.circuit.fusion import fuse_2q_blocks
+    from quantum_simulations_b200.circuit.qasm import qasm_to_steps
+    from quantum_simulations_b200.circuit.sharding import plan_single
+    from quantum_simulations_b200.kernel.cuda import DeviceState
+
+    n, steps, cregs = qasm_to_steps(text)
+    rng = np.random.default_rng(seed)
+    bits = {name: 0 for name in cregs}
+    X = np.array([[0, 1], [1, 0]], dtype=np.complex128)
+    with DeviceState(n, dtype, device) as st:
+        st.init_zero()
+
+        def run_ops(ops) -> None:
+            ops = fuse_2q_blocks(ops, tol=1e-14)
+            if not ops:
+                return
+            if n >= REG_BITS:
+                st.run_program(plan_single(ops, n, st.dtype.name, False, False, **compiler_kw))   # from the state as it is
+            else:
+                for qs, U in ops:
+                    st.apply_op(qs, U)
+
+        def measure(q: int) -> int:
+            u = rng.random()
+            p = st.probabilities([q])
+            outcome = 0 if u < p[0] else 1
+            st.project(q, outcome)
+            return outcome
+
+        for step in steps:
+            if step[0] == "ops":
+                run_ops(step[1])
+            elif step[0] == "measure":
+                _, q, creg, bit = step
+                bits[creg] = (bits[creg] & ~(1 << bit)) | (measure(q) << bit)
+            elif step[0] == "reset":
+                if measure(step[1]) == 1:
+                    st.apply_1q(step[1], X)
+            elif step[0] == "if":
+                if bits[step[1]] == step[2]:
+                    run_ops(step[3])
+            else:
+                raise ValueError(f"unknown step {step[0]!r}")
+        return st.download(), bits
+
+
 def simulate_qasm(text: str, dtype="complex128", device: int = 0, out: np.ndarray | None = None, **compiler_kw) -> np.ndarray:
     """OpenQASM 2.0 program -> final state on the GPU (circuit/qasm.py front end; CNOT-ladder
-    decompositions of controlled phases are fused back into diagonal blocks first)."""
+    decompositions of controlled phases are fused back into diagonal blocks first).  Programs with
+    mid-circuit measure / reset / if are not unitary: use run_qasm (one seeded trajectory)."""
     from quantum_simulations_b200.circuit.fusion import fuse_2q_blocks
     from quantum_simulations_b200.circuit.qasm import qasm_to_ops
     from quantum_simulations_b200.kernel.cuda import DeviceState

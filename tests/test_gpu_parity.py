@@ -568,3 +568,32 @@ def test_warp_local_rounds_on_the_device(monkeypatch):
         for dtype in ("complex128", "complex64"):
             got = simulate(cd, dtype=dtype, warp_local_rounds=True, low_store_round=False)
             assert np.abs(got - want).max() <= TOL[dtype]
+
+
+def test_qasm_trajectories_with_measure_reset_if_on_the_device():
+    """run_qasm (mid-circuit measure / reset / classical if, one seeded trajectory) against the oracle's
+    definition: same outcomes, same classical registers, same final state."""
+    import math
+    from oracle import ref_dense as O
+    from quantum_simulations_b200.circuit.qasm import qasm_to_steps
+    from quantum_simulations_b200.kernel.cuda_dense import run_qasm
+    head = 'OPENQASM 2.0;\ninclude "qelib1.inc";\n'
+    teleport = head + ("qreg q[3]; creg c0[1]; creg c1[1]; ry(0.9) q[0]; t q[0]; h q[1]; cx q[1],q[2]; cx q[0],q[1]; h q[0];"
+                       "measure q[0] -> c0[0]; measure q[1] -> c1[0]; if(c1==1) x q[2]; if(c0==1) z q[2]; reset q[0]; reset q[1];")
+    n = 14
+    big = head + f"qreg q[{n}]; creg c[3];" + "".join(f"h q[{i}];" for i in range(n)) + \
+        "".join(f"cx q[{i}],q[{i + 1}]; rz({0.1 * (i + 1)}) q[{i + 1}];" for i in range(n - 1)) + \
+        "measure q[3] -> c[0]; measure q[9] -> c[1]; if(c==3) ry(0.4) q[0]; if(c==1) h q[5]; reset q[9];" + \
+        "".join(f"ry({0.05 * (i + 1)}) q[{i}];" for i in range(n)) + "measure q[0] -> c[2]; if(c==5) x q[13];"
+    for text in (teleport, big):
+        nq, steps, cregs = qasm_to_steps(text)
+        for seed in range(4):
+            want, wbits = O.run_qasm_steps(nq, steps, cregs, seed)
+            got, gbits = run_qasm(text, seed=seed)
+            assert gbits == wbits
+            assert np.abs(got - want).max() <= 1e-12
+    a, b = math.cos(0.45), math.sin(0.45) * np.exp(0.25j * math.pi)
+    got, _ = run_qasm(teleport, seed=11)
+    want = np.zeros(8, dtype=np.complex128)
+    want[0], want[4] = a, b
+    assert abs(abs(np.vdot(want, got)) - 1) < 1e-12

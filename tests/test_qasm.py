@@ -241,3 +241,49 @@ def test_random_programs_through_fusion_and_the_planner():
         psi = run_program(prog, psi)
         assert np.abs(psi - want).max() <= 1e-11, seed
     assert fused_away > 1000
+
+
+TELEPORT = HEAD + """qreg q[3]; creg c0[1]; creg c1[1];
+ry(0.9) q[0]; t q[0];
+h q[1]; cx q[1],q[2];
+cx q[0],q[1]; h q[0];
+measure q[0] -> c0[0]; measure q[1] -> c1[0];
+if(c1==1) x q[2];
+if(c0==1) z q[2];
+reset q[0]; reset q[1];
+"""
+
+
+def test_steps_keep_measure_reset_and_if():
+    from quantum_simulations_b200.circuit.qasm import qasm_to_steps, is_unitary_program
+    n, steps, cregs = qasm_to_steps(TELEPORT)
+    assert n == 3 and cregs == {"c0": 1, "c1": 1}
+    kinds = [s[0] for s in steps]
+    assert kinds == ["ops", "measure", "measure", "if", "if", "reset", "reset"]
+    assert steps[1][1:] == (0, "c0", 0) and steps[3][1:3] == ("c1", 1) and [qs for qs, _ in steps[3][3]] == [[2]]
+    assert not is_unitary_program(steps)
+    # a program whose measurements are only read at the end stays one unitary circuit
+    _, s2, _ = qasm_to_steps(HEAD + "qreg q[2]; creg c[2]; h q[0]; cx q[0],q[1]; measure q -> c;")
+    assert [s[0] for s in s2] == ["ops", "measure", "measure"] and is_unitary_program(s2)
+    _, s3, _ = qasm_to_steps(HEAD + "qreg q[2]; creg c[2]; h q[0]; measure q[0] -> c[0]; h q[0];")
+    assert not is_unitary_program(s3)
+    with pytest.raises(QasmError, match="unknown classical register"):
+        qasm_to_steps(HEAD + "qreg q[1]; if(c==1) x q[0];")
+    with pytest.raises(QasmError, match="only gate statements"):
+        qasm_to_steps(HEAD + "qreg q[1]; creg c[1]; if(c==1) reset q[0];")
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_teleportation_trajectory_known_answer(seed):
+    """Whatever the two measurement outcomes are, qubit 2 ends in T RY(0.9)|0> and qubits 0, 1 in |00>
+    (oracle definition of one trajectory, oracle/ref_dense.py::run_qasm_steps)."""
+    import math
+    from quantum_simulations_b200.circuit.qasm import qasm_to_steps
+    n, steps, cregs = qasm_to_steps(TELEPORT)
+    psi, bits = O.run_qasm_steps(n, steps, cregs, seed)
+    a, b = math.cos(0.45), math.sin(0.45) * np.exp(0.25j * math.pi)
+    want = np.zeros(8, dtype=np.complex128)
+    want[0], want[4] = a, b
+    assert abs(np.vdot(psi, psi).real - 1) < 1e-12
+    assert abs(abs(np.vdot(want, psi)) - 1) < 1e-12          # equal up to a global phase
+    assert set(bits) == {"c0", "c1"} and all(v in (0, 1) for v in bits.values())
