@@ -59,3 +59,33 @@ def test_single_gpu_control_flow_on_cpu():
     assert r["roofline"]["launches_timed"] == (r["config"]["passes_per_step"] - 1) * r["steps"]
     assert r["zero_support_skipping"]["ms_per_step"] > 0
     assert r["full_first_pass"]["ms_per_step"] > 0 and r["config"]["planner_switches"]["low_store_round"] is True
+
+
+def _line2(name):
+    return json.loads((ROOT / "profiles" / "r02" / name).read_text().strip().splitlines()[-1])
+
+
+def test_round2_single_gpu_line():
+    r = _line2("bench_n30_default.json")
+    assert r["n_gpus"] == 1 and r["config"]["n_qubits"] == 30 and r["dtype"] == "complex128"
+    assert r["cpu_baseline"]["kind"] == "reference"                     # the unmodified reference, from oracle/_ref
+    rf = r["roofline"]
+    assert 0.8 < rf["frac"] <= 1.0 and abs(rf["traffic"] / rf["algorithmic_bytes_per_launch"] - 1) < 0.01
+    assert r["e2e"]["cold"]["jit"]["kernels_compiled"] >= 1 and r["e2e"]["cold"]["ms_per_step"] > r["e2e"]["ms_per_step"]
+    names = [(o["n_qubits"], o["dtype"]) for o in r["other_workloads"]]
+    assert (28, "complex128") in names and (30, "complex64") in names and (20, "complex128") in names
+    assert all(abs(o["norm"] - 1) < 1e-6 for o in r["other_workloads"])
+
+
+def test_round2_multi_gpu_lines_are_the_baseline_configs():
+    """bench.py --gpus N runs BASELINE configs[3] / [4] by default and carries parity, efficiency and the weak series."""
+    for name, n_gpus, n in (("bench_n34_2gpu_final.json", 2, 34), ("bench_n34_4gpu_final.json", 4, 34),
+                            ("bench_n36_8gpu_1TiB_final.json", 8, 36)):
+        r = _line2(name)
+        assert r["n_gpus"] == n_gpus and r["config"]["n_qubits"] == n and r["metric"] == "amplitude-updates/s"
+        assert r["parity"]["ok"] and r["parity"]["sampled_amplitudes"] >= 1 << 20 and r["parity"]["max_abs_diff"] <= 1e-12
+        assert r["pipelined_swap"]["count_per_step"] >= 1 and r["nvlink"]["share_of_step"] < 0.15
+        pe = r["parallel_efficiency"]
+        assert abs(pe["value"] - r["value"] / (n_gpus * pe["one_gpu"]["value"])) < 1e-9 and pe["value"] >= 0.60
+        assert r["weak_series"]["n_qubits"] == 30 + n_gpus.bit_length() - 1
+        assert r["e2e"]["d2h_bytes_per_step"] == 16 * 2 ** n
