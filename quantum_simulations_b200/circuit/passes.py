@@ -492,7 +492,7 @@ class PassCompiler:
                  defer_diagonals: bool = False, absorb: bool = True, allow_swaps: bool = True,
                  swap_anywhere: bool = False, rank_flips: bool = False, park_off_last_round: bool = True,
                  table_phases: bool = True, eager_flips: bool = True, low_store_round: bool = True,
-                 low_store_bits: int | None = 2,
+                 low_store_bits: int | None = 2, park_reorder: bool = True,
                  warp_local_rounds: bool = False):
         self.n = n_qubits
         self.n_local = n_qubits if n_local is None else n_local
@@ -542,6 +542,7 @@ class PassCompiler:
         # position 2 in registers means 64-byte pieces, which cost nothing measurable, while the saved round does
         # (profiles/r02/bench_ab_signs_deferred_lsb2.json: 41.9 -> 40.7 ms).  None = any of the W row positions.
         self.low_store_bits = low_store_bits
+        self.park_reorder = park_reorder
         # experiment: keep the two tile positions that select the WARP inside a consumer group (thread
         # bits 5, 6) the same from one round to the next wherever both rounds leave them out of the
         # registers.  The shared-memory exchange between such rounds stays inside each warp, and the
@@ -887,16 +888,32 @@ class PassCompiler:
             store = [explicit_store[c] for c in content]
         else:
             store = self._choose_store(content, load_bits, home, park, final, finished)   # per tile index
+            if rounds and not final and self.park_reorder and self.low_store_bits is not None:
+                # Which parked content sits on which of the low (row) positions is free: the next pass loads all of
+                # them.  Give the LOWEST positions to contents that are NOT in the registers of the last compute
+                # round, so that this pass can store straight from that round (no idle store round: a register-held
+                # content on position 0 / 1 would make every thread write 16- / 32-byte pieces of a row).
+                last_regs = set(rounds[-1][0])
+                movable = [i for i in range(t) if store[i] < W and not (content[i] in finished and store[i] == home[content[i]])]
+                slots = sorted(store[i] for i in movable)
+                for i, p_ in zip(sorted(movable, key=lambda i: (content[i] in last_regs, store[i])), slots):
+                    store[i] = p_
 
         lo_load = {i for i in range(t) if load_bits[i] < W}
         lo_store = {i for i in range(t) if store[i] < W}
         lo_force = lo_store if self.low_store_bits is None else {i for i in range(t) if store[i] < self.low_store_bits}
+        lo_force_pos = {store[i] for i in lo_force}
 
         # register tile-indices of every round, padded to 4 with idle indices
         plan = []
-        for regs_c, rops in rounds:
+        for k_, (regs_c, rops) in enumerate(rounds):
             regs = [idx_of[c] for c in regs_c]
-            for i in range(t - 1, -1, -1):
+            idle = list(range(t - 1, -1, -1))
+            if k_ == len(rounds) - 1 and self.park_reorder:
+                # the last compute round stores from its registers: pad it with indices that are NOT stored to a
+                # low (row) position, or the padding alone would force the idle store round
+                idle.sort(key=lambda i: store[i] in lo_force_pos)
+            for i in idle:
                 if len(regs) >= REG_BITS:
                     break
                 if i not in regs:

@@ -49,7 +49,7 @@ def estimate_seconds(prog: Program, fused_exchange: bool = False, pipelined: boo
     last_pass = None
     for s in prog.steps:
         if isinstance(s, PassStep):
-            last_pass = 2 * shard / HBM_BW * (1.0 + 0.012 * s.n_micro_ops)
+            last_pass = 2 * shard / HBM_BW * (1.0 + 0.006 * s.n_micro_ops + 0.06 * max(0, s.desc.n_rounds - 2))
             t += last_pass
         elif isinstance(s, SwapStep):
             x = (1.0 - 0.5 ** len(s.global_bits)) * shard / NVLINK_BW
@@ -118,6 +118,17 @@ def candidate_placements(n: int, g: int, direct: bool = False) -> list[list[int]
 
 def plan_single(ir_ops, n_qubits: int, dtype: str = "complex128", zero_init: bool = True,
                 skip_zero_support: bool = False, **compiler_kw) -> Program:
+    """One device: `_plan_single_one` under both rules for the low positions of parked qubits (PassCompiler
+    park_reorder) unless the caller fixes the rule; fewer passes, then fewer shared-memory rounds, wins."""
+    if "park_reorder" in compiler_kw:
+        return _plan_single_one(ir_ops, n_qubits, dtype, zero_init, skip_zero_support, **compiler_kw)
+    cands = [_plan_single_one(ir_ops, n_qubits, dtype, zero_init, skip_zero_support, **dict(compiler_kw, park_reorder=pr))
+             for pr in (True, False)]
+    return min(cands, key=lambda p: (p.stats["passes"], p.stats["rounds"]))
+
+
+def _plan_single_one(ir_ops, n_qubits: int, dtype: str = "complex128", zero_init: bool = True,
+                     skip_zero_support: bool = False, **compiler_kw) -> Program:
     """One device.  From |0...0> the initial placement is free, which removes the layout-restoring
     pass at the end: plan once without restoration, read off where every qubit ended up, and start
     the qubits there instead (the plan is driven by qubit contents, so it repeats itself up to the
@@ -170,19 +181,28 @@ def plan(ir_ops, n_qubits: int, n_local: int, dtype: str = "complex128", zero_in
     ident = list(range(n_qubits))
     if not zero_init:
         return comp.compile(ir_ops)
+    # which parked qubit takes which low position changes every later pass: both rules are planned and the
+    # cost model picks (the reordering saves idle store rounds but now and then costs a pass)
+    comps = [comp]
+    if "park_reorder" not in compiler_kw:
+        comps.append(PassCompiler(n_qubits, n_local, dtype, **dict(compiler_kw, park_reorder=False)))
     best, best_t = None, None
     base = candidate_placements(n_qubits, g)
     for init in candidate_placements(n_qubits, g, direct=bool(compiler_kw.get("swap_anywhere"))):
-        try:
-            prog = comp.compile(ir_ops, init_pos=init, home_pos=ident)
-        except (NotImplementedError, RuntimeError):
-            continue
-        t = estimate_seconds(prog, fused_exchange)
-        # the exchange placements must win clearly (a pass saved, not model noise): the block
-        # placements are the ones whose swaps overlap with the pass before them
-        if best is None or t < best_t * (1.0 if init in base else 0.97):
-            best, best_t = prog, t
-            best.stats["init_pos"] = init
+        for cmp_ in comps:
+            if getattr(comp, "_lowered", None) is not None:
+                cmp_._lowered = comp._lowered                   # same op list: lowered once
+            try:
+                prog = cmp_.compile(ir_ops, init_pos=init, home_pos=ident)
+            except (NotImplementedError, RuntimeError):
+                continue
+            t = estimate_seconds(prog, fused_exchange)
+            # the exchange placements must win clearly (a pass saved, not model noise): the block
+            # placements are the ones whose swaps overlap with the pass before them
+            if best is None or t < best_t * (1.0 if init in base else 0.97):
+                best, best_t = prog, t
+                best.stats["init_pos"] = init
+                best.stats["park_reorder"] = cmp_.park_reorder
     if best is None:
         return fuse_init(comp.compile(ir_ops))
     best.stats["estimated_s"] = best_t
