@@ -492,7 +492,7 @@ class PassCompiler:
                  defer_diagonals: bool = False, absorb: bool = True, allow_swaps: bool = True,
                  swap_anywhere: bool = False, rank_flips: bool = False, park_off_last_round: bool = True,
                  table_phases: bool = True, eager_flips: bool = True, low_store_round: bool = True,
-                 low_store_bits: int | None = 2, park_reorder: bool = True,
+                 low_store_bits: int | None = 2, park_reorder: bool = False,
                  warp_local_rounds: bool = False):
         self.n = n_qubits
         self.n_local = n_qubits if n_local is None else n_local
@@ -542,6 +542,9 @@ class PassCompiler:
         # position 2 in registers means 64-byte pieces, which cost nothing measurable, while the saved round does
         # (profiles/r02/bench_ab_signs_deferred_lsb2.json: 41.9 -> 40.7 ms).  None = any of the W row positions.
         self.low_store_bits = low_store_bits
+        # experiment (off): parked qubits / the padding of the last compute round avoid low store positions, which
+        # removes the idle store round of more passes — measured on the headline plan: one pass -0.45 ms, another
+        # +0.84 ms (profiles/r02/bench_ab_park_reorder.json), so it is not the default
         self.park_reorder = park_reorder
         # experiment: keep the two tile positions that select the WARP inside a consumer group (thread
         # bits 5, 6) the same from one round to the next wherever both rounds leave them out of the

@@ -118,13 +118,8 @@ def candidate_placements(n: int, g: int, direct: bool = False) -> list[list[int]
 
 def plan_single(ir_ops, n_qubits: int, dtype: str = "complex128", zero_init: bool = True,
                 skip_zero_support: bool = False, **compiler_kw) -> Program:
-    """One device: `_plan_single_one` under both rules for the low positions of parked qubits (PassCompiler
-    park_reorder) unless the caller fixes the rule; fewer passes, then fewer shared-memory rounds, wins."""
-    if "park_reorder" in compiler_kw:
-        return _plan_single_one(ir_ops, n_qubits, dtype, zero_init, skip_zero_support, **compiler_kw)
-    cands = [_plan_single_one(ir_ops, n_qubits, dtype, zero_init, skip_zero_support, **dict(compiler_kw, park_reorder=pr))
-             for pr in (True, False)]
-    return min(cands, key=lambda p: (p.stats["passes"], p.stats["rounds"]))
+    """One device (see _plan_single_one)."""
+    return _plan_single_one(ir_ops, n_qubits, dtype, zero_init, skip_zero_support, **compiler_kw)
 
 
 def _plan_single_one(ir_ops, n_qubits: int, dtype: str = "complex128", zero_init: bool = True,
@@ -181,11 +176,7 @@ def plan(ir_ops, n_qubits: int, n_local: int, dtype: str = "complex128", zero_in
     ident = list(range(n_qubits))
     if not zero_init:
         return comp.compile(ir_ops)
-    # which parked qubit takes which low position changes every later pass: both rules are planned and the
-    # cost model picks (the reordering saves idle store rounds but now and then costs a pass)
     comps = [comp]
-    if "park_reorder" not in compiler_kw:
-        comps.append(PassCompiler(n_qubits, n_local, dtype, **dict(compiler_kw, park_reorder=False)))
     best, best_t = None, None
     base = candidate_placements(n_qubits, g)
     for init in candidate_placements(n_qubits, g, direct=bool(compiler_kw.get("swap_anywhere"))):
