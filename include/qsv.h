@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define QSV_ABI_VERSION 7
+#define QSV_ABI_VERSION 8
 
 /* dtypes (wenbo_engine/storage/block_store.py:11 fixes complex64; the oracle is complex128) */
 #define QSV_C64  0
@@ -84,6 +84,14 @@ int qsv_download(qsv_handle *h, void *host, size_t off_amps, size_t n_amps);
 /* Async variants for pinned host buffers (checkpoint path); complete at qsv_sync(). */
 int qsv_upload_async(qsv_handle *h, const void *pinned_host, size_t off_amps, size_t n_amps);
 int qsv_download_async(qsv_handle *h, void *pinned_host, size_t off_amps, size_t n_amps);
+/* ASYNCHRONOUS CHECKPOINTS — the GPU form of the reference's reader / worker / writer pipeline
+ * (wenbo_engine/runner/pipeline.py:50-82, 162-171): qsv_snapshot copies the shard into a second device buffer
+ * (stream ordered, HBM speed); qsv_snapshot_download_async pulls ranges of that SNAPSHOT to pinned host memory
+ * on a second stream (callable from a writer thread) while the handle's stream already runs the next passes;
+ * qsv_snapshot_sync waits for those copies.  A new snapshot waits for the previous one to be drained. */
+int qsv_snapshot(qsv_handle *h);
+int qsv_snapshot_download_async(qsv_handle *h, void *host, size_t offset_amps, size_t n_amps);
+int qsv_snapshot_sync(qsv_handle *h);
 int qsv_host_alloc(void **ptr, size_t bytes);          /* cudaHostAlloc: pinned staging */
 int qsv_host_free(void *ptr);
 

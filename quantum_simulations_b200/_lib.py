@@ -70,6 +70,9 @@ SIGNATURES = {
     "qsv_download": (C.c_int, [_H, C.c_void_p, C.c_size_t, C.c_size_t]),
     "qsv_upload_async": (C.c_int, [_H, C.c_void_p, C.c_size_t, C.c_size_t]),
     "qsv_download_async": (C.c_int, [_H, C.c_void_p, C.c_size_t, C.c_size_t]),
+    "qsv_snapshot": (C.c_int, [_H]),
+    "qsv_snapshot_download_async": (C.c_int, [_H, C.c_void_p, C.c_size_t, C.c_size_t]),
+    "qsv_snapshot_sync": (C.c_int, [_H]),
     "qsv_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "qsv_host_free": (C.c_int, [C.c_void_p]),
     "qsv_apply_1q": (C.c_int, [_H, C.c_int, _dp]),

@@ -80,6 +80,10 @@ struct qsv_handle {
     std::vector<void *> scat_cur, scat_other;
     bool scat_ready = false, scat_ipc = false;
     cudaStream_t stream = nullptr;
+    // asynchronous checkpoints (qsv_snapshot*): a device-side copy of the shard drained on a second stream
+    cudaStream_t io_stream = nullptr;
+    cudaEvent_t ev_snap = nullptr, ev_io = nullptr;
+    bool io_pending = false;
     // scratch for reductions / one-shot passes
     double *d_partials = nullptr; size_t n_partials = 0;
     qsv_op *d_ops_scratch = nullptr; size_t ops_scratch_cap = 0;

@@ -1,22 +1,144 @@
-"""``runner.pipeline.run`` — same surface as the reference's pipelined runner
-(wenbo_engine/runner/pipeline.py:85-160: reader thread -> compute -> writer thread with bounded
-queues of ``buffer_depth`` chunks).
+"""``runner.pipeline.run`` — the reference's pipelined runner (wenbo_engine/runner/pipeline.py:85-171:
+reader thread -> worker -> writer thread with bounded queues of ``buffer_depth`` chunks) on a GPU.
 
-What that pipeline overlaps — chunk reads, gate application, fsynced chunk writes — collapses on a
-GPU with the state resident in HBM: there is nothing to read between steps, gate application is the
-fused passes, and the only I/O left is the checkpoint, which ``runner.single_node`` already
-overlaps (the device-to-host copy of chunk c+1 runs while chunk c is written and fsynced, two
-pinned staging buffers).  ``buffer_depth`` is therefore accepted for compatibility and unused."""
+What that pipeline overlaps is chunk I/O with gate application.  With the state resident in HBM nothing is
+read between steps, so the I/O that is left is the checkpoint — and that is what overlaps here:
+
+    compute stream   steps ... | snapshot (device copy, ~10 ms / 16 GiB) | next steps ...
+    writer thread                         | D2H of the SNAPSHOT through a ring of ``buffer_depth`` pinned
+                                            buffers -> chunk files (fsync) -> manifest -> WAL commit |
+
+``runner.single_node.run`` stops the device while a checkpoint is written (only the copy of chunk c+1 overlaps the
+write of chunk c); here the gates of the next steps run while the previous checkpoint drains.  Same arguments,
+files, WAL schema and crash behaviour (a checkpoint is committed only after all its chunks and the manifest are
+durable; WE_CRASH_AFTER_CHUNK / WE_CRASH_AT_CHECKPOINT as in single_node).  Costs a second state-sized buffer in
+HBM (n <= 32 complex128 on one B200)."""
 from __future__ import annotations
 
+import os
+import threading
 from pathlib import Path
 
-from quantum_simulations_b200.runner import single_node
+import numpy as np
+
+from quantum_simulations_b200.circuit.io import validate_circuit_dict
+from quantum_simulations_b200.circuit.passes import PassCompiler
+from quantum_simulations_b200.runner import single_node as SN
+from quantum_simulations_b200.storage.block_store import chunk_filename, write_chunk_atomic
+from quantum_simulations_b200.storage.manifest import Manifest, write_manifest_atomic
+from quantum_simulations_b200.wal.wal import WAL
+
+REG_BITS = 4
+
+
+class _Writer:
+    """One checkpoint in flight: drains the device snapshot to `dst_dir` on its own thread."""
+
+    def __init__(self, st, dst_dir: Path, man: Manifest, np_dtype, buffer_depth: int, on_durable, inject: bool):
+        self.error: BaseException | None = None
+        self._t = threading.Thread(target=self._run, args=(st, dst_dir, man, np_dtype, buffer_depth, on_durable, inject), daemon=True)
+        self._t.start()
+
+    def _run(self, st, dst_dir, man, np_dtype, depth, on_durable, inject) -> None:
+        from quantum_simulations_b200.storage.pinned import PinnedBuffer
+        try:
+            SN._wipe_buf(dst_dir)
+            crash_after = SN._crash_after() if inject else None
+            cs = man.chunk_size
+            depth = max(2, min(depth, man.n_chunks + 1))
+            bufs = [PinnedBuffer(cs * np_dtype.itemsize) for _ in range(depth)]
+            try:
+                # keep depth-1 copies queued on the I/O stream; a buffer is reused only after its chunk is on disk
+                issued = 0
+                while issued < min(depth - 1, man.n_chunks):
+                    st._ck(st.lib.qsv_snapshot_download_async(st._h, bufs[issued % depth].ptr, issued * cs, cs))
+                    issued += 1
+                for c in range(man.n_chunks):
+                    st._ck(st.lib.qsv_snapshot_sync(st._h))          # (waits for every queued copy: chunk c is among them)
+                    if issued < man.n_chunks:
+                        st._ck(st.lib.qsv_snapshot_download_async(st._h, bufs[issued % depth].ptr, issued * cs, cs))
+                        issued += 1
+                    write_chunk_atomic(dst_dir / "chunks" / man.chunks[c], bufs[c % depth].array(np_dtype, cs), np_dtype)
+                    if crash_after is not None and c + 1 >= crash_after:
+                        os._exit(1)
+                st._ck(st.lib.qsv_snapshot_sync(st._h))
+            finally:
+                for b in bufs:
+                    b.free()
+            write_manifest_atomic(dst_dir, man)
+            on_durable()
+        except BaseException as e:                      # surfaced by join()
+            self.error = e
+
+    def join(self) -> None:
+        self._t.join()
+        if self.error is not None:
+            raise self.error
 
 
 def run(circuit_dict: dict, work_dir: str | Path, chunk_size: int = 1 << 20, buffer_depth: int = 4,
-        use_wal: bool = True, use_fusion: bool = False, **kw) -> Path:
+        use_wal: bool = True, use_fusion: bool = False, dtype: str = "complex128", device: int = 0,
+        checkpoint_every: int = 0, tile_bits: int | None = None, low_bits: int | None = None) -> Path:
+    """Run the circuit on the GPU with ASYNCHRONOUS checkpoints; returns the path of the final state buffer."""
+    from quantum_simulations_b200.kernel.cuda import DeviceState
+
     if buffer_depth < 1:
         raise ValueError("buffer_depth must be >= 1")
-    return single_node.run(circuit_dict, work_dir, chunk_size=chunk_size, use_wal=use_wal,
-                           use_fusion=use_fusion, **kw)
+    cd = validate_circuit_dict(circuit_dict)
+    n = cd["number_of_qubits"]
+    N = 1 << n
+    chunk_size = min(chunk_size, N)
+    if N % chunk_size != 0:
+        raise ValueError("2^n must be divisible by chunk_size")
+    np_dtype = np.dtype(dtype)
+    work = Path(work_dir)
+    steps = SN.build_steps(cd, n, use_fusion)
+    wal = WAL(work / "wal.json", circuit_dict=cd) if use_wal else None
+    start = wal.done_steps if wal else 0
+    current = wal.committed_buf if wal else "a"
+    man = Manifest(n_qubits=n, chunk_size=chunk_size, n_chunks=N // chunk_size, dtype=np_dtype.name,
+                   chunks=[chunk_filename(i) for i in range(N // chunk_size)])
+    compiler = PassCompiler(n, dtype=np_dtype.name, tile_bits=tile_bits, low_bits=low_bits) if n >= REG_BITS else None
+
+    with DeviceState(n, np_dtype, device) as st:
+        if start > 0:
+            SN._load_checkpoint(st, SN._buf_dir(work, current), np_dtype)
+        else:
+            st.init_zero()
+        writer: _Writer | None = None
+        last_ckpt, n_ckpt = start, 0
+        try:
+            for idx in range(start, len(steps)):
+                step = steps[idx]
+                if step["nonlocal_ops"]:
+                    raise NotImplementedError("non-local gate on a single-device run")
+                SN.execute_ops(st, step["local_ops"], compiler)
+                final = idx == len(steps) - 1
+                if final or (checkpoint_every and (idx + 1 - last_ckpt) >= checkpoint_every):
+                    if writer is not None:
+                        writer.join()                       # one checkpoint in flight: its commit comes first
+                    dst = SN._other(current)
+                    st._ck(st.lib.qsv_snapshot(st._h))      # stream ordered after the step; the device goes on
+
+                    def committed(idx=idx, dst=dst):
+                        if wal:
+                            wal.commit_step(idx, dst)
+
+                    writer = _Writer(st, SN._buf_dir(work, dst), man, np_dtype, buffer_depth, committed,
+                                     inject=(n_ckpt == SN._crash_at_checkpoint()))
+                    n_ckpt += 1
+                    current, last_ckpt = dst, idx + 1
+            if writer is not None:
+                writer.join()
+                writer = None
+            if not (SN._buf_dir(work, current) / "manifest.json").exists():      # empty circuit
+                SN._write_checkpoint(st, SN._buf_dir(work, current), man, np_dtype)
+        finally:
+            if writer is not None:                              # an error in the main thread: let the copy finish
+                try:
+                    writer.join()
+                except BaseException:
+                    pass
+    if wal:
+        wal.close()
+    return SN._buf_dir(work, current)

@@ -75,20 +75,20 @@ def test_qiskit_import_mirror():
 _SCRIPT = """
 import sys, json
 sys.path.insert(0, {root!r})
-from quantum_simulations_b200.runner.single_node import run
+from quantum_simulations_b200.runner.{runner} import run
 cd = json.loads({cd!r})
 run(cd, {work!r}, chunk_size={cs}, use_wal=True, checkpoint_every=1)
 """
 
 
-def _run_sub(cd, work, cs, crash_after=None, at_checkpoint=0):
+def _run_sub(cd, work, cs, crash_after=None, at_checkpoint=0, runner="single_node"):
     env = os.environ.copy()
     env["WE_CRASH_AT_CHECKPOINT"] = str(at_checkpoint)
     if crash_after is not None:
         env["WE_CRASH_AFTER_CHUNK"] = str(crash_after)
     else:
         env.pop("WE_CRASH_AFTER_CHUNK", None)
-    script = _SCRIPT.format(root=str(ROOT), cd=json.dumps(cd), work=str(work), cs=cs)
+    script = _SCRIPT.format(root=str(ROOT), cd=json.dumps(cd), work=str(work), cs=cs, runner=runner)
     return subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, timeout=300)
 
 
@@ -138,3 +138,30 @@ def test_resume_from_a_committed_checkpoint(tmp_path):
     assert wal.done_steps == 2 and wal.committed_buf == "a"
     final = recover(cd, tmp_path, chunk_size=cs, checkpoint_every=1)
     assert np.abs(collect_state(final) - O.simulate(validate_circuit_dict(cd))).max() <= 1e-12
+
+
+@pytest.mark.gpu
+def test_pipeline_runner_checkpoints_asynchronously_and_is_recoverable(tmp_path):
+    """runner.pipeline.run: checkpoints drain from a device snapshot on a writer thread while the next steps run.
+    Same files, WAL and crash behaviour as single_node: (1) a full run equals the oracle and commits every step;
+    (2) a crash inside the third checkpoint leaves two committed steps, and single_node's recover() finishes the
+    directory the pipeline runner wrote."""
+    from quantum_simulations_b200.runner import pipeline
+    from quantum_simulations_b200.runner.single_node import collect_state
+    n = 12
+    cd = W.random_1q_cz(n, 6, 9)
+    cs = 1 << (n - 3)
+    want = O.simulate(validate_circuit_dict(cd))
+    final = pipeline.run(cd, tmp_path / "full", chunk_size=cs, buffer_depth=3, use_wal=True, checkpoint_every=1)
+    wal = WAL(tmp_path / "full" / "wal.json", circuit_dict=cd)
+    assert wal.done_steps == 6 and np.abs(collect_state(final) - want).max() <= 1e-12
+    final = pipeline.run(cd, tmp_path / "sparse", chunk_size=cs, buffer_depth=2, use_wal=True, checkpoint_every=4, use_fusion=False)
+    assert WAL(tmp_path / "sparse" / "wal.json", circuit_dict=cd).done_steps == 6
+    assert np.abs(collect_state(final) - want).max() <= 1e-12
+    work = tmp_path / "crash"
+    r = _run_sub(cd, work, cs, crash_after=2, at_checkpoint=2, runner="pipeline")
+    assert r.returncode != 0, r.stderr.decode()[-500:]
+    wal = WAL(work / "wal.json", circuit_dict=cd)
+    assert wal.done_steps == 2 and wal.committed_buf == "a"
+    final = recover(cd, work, chunk_size=cs, checkpoint_every=1)
+    assert np.abs(collect_state(final) - want).max() <= 1e-12
