@@ -83,3 +83,24 @@ def qasm_with_parts(qasm_text: str, part_text: str):
         raise ValueError(f"the part file labels {len(parts)} gates, the program has {max(stmt) + 1}")
     new_ops, qsets, _ = reorder_by_parts(ops, [parts[s_] for s_ in stmt])
     return n, new_ops, qsets
+
+
+def qasm_parts(qasm_text: str, part_text: str):
+    """(n_qubits, [ops of part 0, ops of part 1, ...]) in execution order — the input of
+    circuit.sharding.plan_parts, which runs every part as ONE STAGE with a single gather of the qubits it mixes
+    in front of it (HiSVSIM's execution model, hisvsim_repo/execute.hpp:665-685)."""
+    from quantum_simulations_b200.circuit.qasm import qasm_to_ops
+    n, ops, stmt = qasm_to_ops(qasm_text, with_statement_index=True)
+    parts = read_part_file(part_text)
+    if stmt and max(stmt) >= len(parts):
+        raise ValueError(f"the part file labels {len(parts)} gates, the program has {max(stmt) + 1}")
+    labels = [parts[s_] for s_ in stmt]
+    new_ops, _, order = reorder_by_parts(ops, labels)
+    count = {p: 0 for p in order}
+    for lb in labels:
+        count[lb] += 1
+    out, at = [], 0
+    for p in order:
+        out.append(new_ops[at:at + count[p]])
+        at += count[p]
+    return n, out

@@ -287,3 +287,106 @@ def plan_transitions(prog: Program, max_chunk_bits: int = 4, min_chunk_pos: int 
             taken.add(k + 1 + i)
         out[k] = Transition(a, b, bits)
     return out
+
+
+# ------------------------------------------------------------------ parts as stages (HiSVSIM)
+def mixed_qubits(qs, U, tol: float = 0.0) -> set:
+    """The qubits of an op that the op MIXES (everything else it only inspects: controls, diagonal factors):
+    qubit k of `qs` is inspect-only iff U has no entry between row and column indices that differ in its bit
+    (row order of the reference: qs[0] is the most significant bit of the matrix index)."""
+    import numpy as np
+    U = np.asarray(U)
+    k = len(qs)
+    out = set()
+    for j, q in enumerate(qs):
+        bit = 1 << (k - 1 - j)
+        r, c = np.nonzero(np.abs(U) > tol)
+        if np.any((r & bit) != (c & bit)):
+            out.add(q)
+    return out
+
+
+def plan_parts(parts_ops, n_qubits: int, n_local: int, dtype: str = "complex128", zero_init: bool = True,
+               **compiler_kw) -> Program:
+    """HiSVSIM execution model on this engine (hisvsim_repo/execute.hpp:542-728, svsim-mpi.hpp:123-173): the
+    circuit arrives as PARTS (circuit/hisvsim_parts.qasm_with_parts: the acyclic partition HiSVSIM's partitioner
+    wrote next to a .qasm file); every part is ONE STAGE — before it, the qubits it mixes are gathered onto local
+    index bits by a single swap (HiSVSIM's gather_qubits, execute.hpp:665-685), then its gates run as fused passes
+    without communication.  parts_ops = [[(qubits, U), ...], ...] in execution order.
+    Which local qubits leave at a boundary: the ones whose next mixing use is farthest away (Belady).  Raises
+    ValueError if a part mixes more than n_local qubits (it cannot be one stage on these shards)."""
+    g = n_qubits - n_local
+    parts_ops = [list(p) for p in parts_ops if p]
+    if g == 0 or not parts_ops:
+        return plan_single([op for p in parts_ops for op in p], n_qubits, dtype, zero_init, **compiler_kw)
+    mixes = [set().union(*[mixed_qubits(qs, U) for qs, U in p]) if p else set() for p in parts_ops]
+    for k, m in enumerate(mixes):
+        if len(m) > n_local:
+            raise ValueError(f"part {k} mixes {len(m)} qubits but a shard holds {n_local}: it cannot run as one stage")
+    kw = dict(compiler_kw)
+    kw["rank_flips"] = False                                # every stage ends with its amplitudes in place
+    comp = PassCompiler(n_qubits, n_local, dtype, **kw)
+
+    def next_use(q: int, k: int) -> int:
+        for j in range(k, len(mixes)):
+            if q in mixes[j]:
+                return j
+        return len(mixes) + (0 if q >= n_local else 1)      # never again: qubits whose HOME is a rank bit leave first
+
+    def layout_for(pos: list, k: int) -> list:
+        """pos with the mixed qubits of part k made local: each one on a rank bit trades places with the local
+        qubit that is mixed again last."""
+        pos = list(pos)
+        at = {p: q for q, p in enumerate(pos)}
+        for q in sorted(mixes[k]):
+            if pos[q] < n_local:
+                continue
+            cands = [c for c in range(n_qubits) if pos[c] < n_local and c not in mixes[k]]
+            out = max(cands, key=lambda c: (next_use(c, k + 1), pos[c]))
+            pos[q], pos[out] = pos[out], pos[q]
+            at[pos[q]], at[pos[out]] = q, out
+        return pos
+
+    ident = list(range(n_qubits))
+    layouts = []
+    cur = ident
+    for k in range(len(parts_ops)):
+        cur = layout_for(cur, k)
+        layouts.append(cur)
+    layouts.append(ident)                                   # the run ends in the identity layout
+    total = Program(n_qubits, n_local, dtype)
+    flips = None
+    if not zero_init and layouts[0] != ident:               # a state that is already there: gather for the first part
+        pre = comp.compile([], init_pos=ident, home_pos=layouts[0])
+        total.steps += pre.steps
+        flips = pre.final_flips
+    stats = {"passes": 0, "rounds": 0, "micro_ops": 0, "swaps": 0, "swap_bits": 0}
+    for k, ops in enumerate(parts_ops):
+        prog = comp.compile(ops, init_pos=layouts[k], home_pos=layouts[k + 1], init_flips=flips)
+        flips = prog.final_flips if any(prog.final_flips) else None
+        total.steps += prog.steps
+        for key in stats:
+            stats[key] += prog.stats.get(key, 0)
+    if flips is not None:
+        raise RuntimeError("plan_parts: a pending X frame survived the last part")
+    total.final_pos = ident
+    total.final_flips = [0] * n_qubits
+    total.stats = dict(stats, parts=len(parts_ops), init_pos=layouts[0],
+                       tile_bits=prog.stats.get("tile_bits"), low_bits=prog.stats.get("low_bits"))
+    return fuse_init(total) if zero_init else total
+
+
+def split_into_parts(ir_ops, max_mixed: int) -> list:
+    """A partition for plan_parts when no part file exists: consecutive gates form a part until the set of qubits
+    the part MIXES would exceed max_mixed (HiSVSIM's 'nat' strategy: parts in natural gate order)."""
+    parts, cur, mixed = [], [], set()
+    for qs, U in ir_ops:
+        m = mixed_qubits(qs, U)
+        if cur and len(mixed | m) > max_mixed:
+            parts.append(cur)
+            cur, mixed = [], set()
+        cur.append((qs, U))
+        mixed |= m
+    if cur:
+        parts.append(cur)
+    return parts

@@ -341,6 +341,13 @@ class ShardedSimulator:
             compiler_kw.setdefault("fused_exchange", True)                # cost model: a swap hides the pass before it
         return sharding.plan(ops, self.n, self.n - self.g, self.dtype.name, **compiler_kw)
 
+    def plan_parts(self, parts_ops: list, **compiler_kw) -> Program:
+        """Stage plan that follows a given PARTITION of the circuit (HiSVSIM part files,
+        circuit/hisvsim_parts.qasm_parts): one stage per part, one gather of the qubits it mixes in front of it
+        (sharding.plan_parts)."""
+        compiler_kw.setdefault("swap_anywhere", bool(self.peer_swap))
+        return sharding.plan_parts(parts_ops, self.n, self.n - self.g, self.dtype.name, **compiler_kw)
+
     def simulate_qasm(self, text: str, out: np.ndarray | None = None, **compiler_kw) -> np.ndarray:
         """OpenQASM 2.0 program from |0...0> on the sharded state (front end as in
         kernel.cuda_dense.simulate_qasm); returns this rank's logical shard like ``simulate``."""

@@ -62,3 +62,46 @@ def test_cyclic_partition_is_rejected():
         reorder_by_parts(ops, [0, 1])
     with pytest.raises(ValueError, match="1..G"):
         read_part_file("1 h_0 0\n3 h_2 0\n")
+
+
+def test_parts_run_as_stages():
+    """sharding.plan_parts: every part of a partition is ONE stage of the sharded program — a single gather of the
+    qubits it mixes in front of it, then passes without communication (HiSVSIM execute.hpp:665-685).  Checked
+    through the pass emulator on 2/4/8 shards against the oracle, for the part file above and for partitions
+    cut by the engine's own 'nat' splitter."""
+    from quantum_simulations_b200 import workloads as W
+    from quantum_simulations_b200.circuit import sharding
+    from quantum_simulations_b200.circuit.hisvsim_parts import qasm_parts
+    from quantum_simulations_b200.circuit.io import validate_circuit_dict
+    from quantum_simulations_b200.circuit.passes import PassStep, SwapStep
+    from quantum_simulations_b200.kernel import gates as G
+    from tests.pass_emulator import run_program_sharded
+
+    def run(prog, n):
+        psi = np.random.default_rng(1).standard_normal(1 << n) + 0j          # fused init ignores what is there
+        if not prog.fused_init:
+            psi = np.zeros(1 << n, dtype=np.complex128)
+            psi[0] = 1
+        return run_program_sharded(prog, psi)
+
+    # the QASMBench-style file with its part file, padded to 9 qubits so that it can be sharded 2 ways
+    qasm9 = QASM.replace("qreg q[4];", "qreg q[4]; qreg pad[5];").replace("creg c[4];", "creg c[4]; creg d[5];") \
+                .replace("measure q -> c;", "h pad[4]; cx pad[4],q[0]; measure q -> c;")
+    parts9 = PARTS.replace("7 h_16 2\n", "7 h_16 2\n8 h_17 3\n9 cx_18 3\n")
+    n, parts = qasm_parts(qasm9, parts9)
+    assert n == 9 and [len(p) for p in parts] == [3, 2, 16, 2]               # ccx expands to 15 ops
+    prog = sharding.plan_parts(parts, n, n - 1, tile_bits=6, low_bits=2, swap_anywhere=True)
+    want = state(n, [op for p in parts for op in p])
+    assert np.abs(run(prog, n) - want).max() <= 1e-12
+    for n, g, cd in ((10, 2, W.random_mixed(10, 150, 3)), (11, 1, W.qft(11)), (12, 3, W.random_1q_cz(12, 12, 7))):
+        cd = validate_circuit_dict(cd)
+        ops = [(q["qubits"], G.gate_matrix(q["gate"], q["params"])) for q in cd["gates"]]
+        parts = sharding.split_into_parts(ops, n - g - 1)
+        assert all(len(set().union(*[sharding.mixed_qubits(qs, U) for qs, U in p])) <= n - g - 1 for p in parts)
+        prog = sharding.plan_parts(parts, n, n - g, tile_bits=6, low_bits=2, swap_anywhere=True)
+        assert prog.final_pos == list(range(n)) and prog.stats["parts"] == len(parts)
+        # at most one swap step in front of every part and one to restore the identity layout at the end
+        assert sum(isinstance(s_, SwapStep) for s_ in prog.steps) <= len(parts) + 1
+        assert np.abs(run(prog, n) - O.simulate(cd)).max() <= 1e-12
+    with pytest.raises(ValueError, match="cannot run as one stage"):
+        sharding.plan_parts([ops], 12, 9)
