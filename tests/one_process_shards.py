@@ -16,7 +16,7 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
 
-def run_case(n, world, dtype, cd, pipeline, xchg_sms=3, planner_kw=None):
+def run_case(n, world, dtype, cd, pipeline, xchg_sms=3, planner_kw=None, parts=False):
     from quantum_simulations_b200.circuit import sharding
     from quantum_simulations_b200.circuit.io import validate_circuit_dict
     from quantum_simulations_b200.kernel.cuda_dense import circuit_ops
@@ -24,7 +24,11 @@ def run_case(n, world, dtype, cd, pipeline, xchg_sms=3, planner_kw=None):
 
     g = world.bit_length() - 1
     cd = validate_circuit_dict(cd)
-    prog = sharding.plan(circuit_ops(cd), n, n - g, dtype, swap_anywhere=True, rank_flips=True, **(planner_kw or {}))
+    if parts:     # HiSVSIM execution model: the circuit cut into parts, every part one stage (sharding.plan_parts)
+        ops = circuit_ops(cd)
+        prog = sharding.plan_parts(sharding.split_into_parts(ops, n - g - 2), n, n - g, dtype, swap_anywhere=True)
+    else:
+        prog = sharding.plan(circuit_ops(cd), n, n - g, dtype, swap_anywhere=True, rank_flips=True, **(planner_kw or {}))
     shards = [CudaShard(n, r, world, dtype, device=0, local=True) for r in range(world)]
     try:
         CudaShard.wire_local(shards)
@@ -63,7 +67,7 @@ def main():
               "mixed": lambda: W.random_mixed(n, 300, 8)}[name]()
         want = O.simulate(validate_circuit_dict(cd))
         for pipeline in (True, False):
-            got, info = run_case(n, world, dtype, cd, pipeline, case.get("xchg_sms", 3))
+            got, info = run_case(n, world, dtype, cd, pipeline, case.get("xchg_sms", 3), parts=case.get("parts", False))
             err = float(np.abs(got - want.astype(got.dtype)).max())
             print(json.dumps({"case": case, "pipeline": pipeline, "max_abs_err": err, **info}), flush=True)
             tol = 1e-12 if dtype == "complex128" else 2e-5

@@ -39,6 +39,14 @@ def test_pipelined_transitions_match_oracle_c64():
     assert all(l["max_abs_err"] <= 2e-5 for l in out)
 
 
+@pytest.mark.gpu
+def test_parts_as_stages_on_the_device():
+    """sharding.plan_parts (HiSVSIM: one stage per part, one gather in front of it) executed on 4 shards."""
+    out = _run([{"n": 20, "world": 4, "dtype": "complex128", "circuit": c, "parts": True, "expect_pipelined": False}
+                for c in ("random", "mixed")])
+    assert all(l["max_abs_err"] <= 1e-12 and l["swaps"] >= 2 for l in out)
+
+
 def test_transition_plans_are_valid():
     """CPU: every planned transition names chunk bits outside the tiles of its passes and the swapped bits,
     never shares a pass between two swaps, and skips the fused-initialisation pass."""
