@@ -390,3 +390,33 @@ def split_into_parts(ir_ops, max_mixed: int) -> list:
     if cur:
         parts.append(cur)
     return parts
+
+
+def plan_atlas(circuit_dict: dict, n_local: int, dtype: str = "complex128", method: str = "heuristic",
+               zero_init: bool = True, **compiler_kw):
+    """The reference's staging (``atlas_stages``, circuit/staging.py: heuristic / greedy / ILP choice of the local
+    qubit set per stage, SWAP steps between stages, final ``log_to_phys``) as the stage structure of a sharded GPU
+    run: consecutive all-local steps form one PART, a SWAP step closes it, and sharding.plan_parts turns the parts
+    into stages.  The SWAP gates themselves cost nothing here (a swap of two qubits is a relabelling in the pass
+    compiler), so the state ends in atlas's PHYSICAL layout: returns (Program, log_to_phys), and
+    ``permute_state`` / ``collect_state(apply_permutation=True)`` map it back (reference staging.py:639-658)."""
+    from quantum_simulations_b200.circuit.io import validate_circuit_dict
+    from quantum_simulations_b200.circuit.staging import atlas_stages
+    cd = validate_circuit_dict(circuit_dict)
+    n = cd["number_of_qubits"]
+    steps, log_to_phys = atlas_stages(cd, n_local, method=method)
+    parts, cur = [], []
+    for st in steps:
+        if st["nonlocal_ops"] and not st["local_ops"]:          # a SWAP step (or an unlocalisable gate): stage boundary
+            if cur:
+                parts.append(cur)
+            cur = list(st["nonlocal_ops"])
+        else:
+            cur += list(st["local_ops"]) + list(st["nonlocal_ops"])
+    if cur:
+        parts.append(cur)
+    # a part may still mix more qubits than a shard holds once its leading SWAPs are counted: cut it further
+    fine = []
+    for p in parts:
+        fine += split_into_parts(p, n_local)
+    return plan_parts(fine, n, n_local, dtype, zero_init, **compiler_kw), log_to_phys

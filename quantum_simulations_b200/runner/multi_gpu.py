@@ -475,7 +475,8 @@ def simulate_sharded(circuit_dict: dict, dtype="complex128", out: np.ndarray | N
 
 
 def run(circuit_dict: dict, work_dir, chunk_size: int = 1 << 20, dtype: str = "complex128",
-        use_wal: bool = True, checkpoint_every: int = 0, stop_after_checkpoints: int | None = None, **compiler_kw):
+        use_wal: bool = True, checkpoint_every: int = 0, stop_after_checkpoints: int | None = None,
+        use_staging: bool = False, staging_method: str = "heuristic", **compiler_kw):
     """Multi-GPU form of ``runner.single_node.run`` (reference single_node.py:78-176), launched with one process per
     GPU.  The circuit is cut into SEGMENTS of `checkpoint_every` levels (0 = one segment); each segment is planned
     and executed as a sharded program that starts and ends in the identity layout, and after each segment every
@@ -485,6 +486,11 @@ def run(circuit_dict: dict, work_dir, chunk_size: int = 1 << 20, dtype: str = "c
     committed buffer into the shards and continues with the next segment (reference resume:
     single_node.py:143-176, wal/wal.py:85-89); a directory whose WAL already covers the circuit returns at once.
     stop_after_checkpoints (tests): return after that many checkpoints, as a crash would.
+    use_staging=True (reference single_node.py:108-134): the stage structure comes from the reference's
+    ``atlas_stages`` (staging_method "heuristic" | "greedy" | "ilp") instead of the engine's own planner
+    (sharding.plan_atlas: each atlas stage = one stage here); the run is then one segment, the chunks are written
+    in atlas's PHYSICAL layout and ``qubit_mapping.json`` holds log_to_phys, exactly as the reference does, so
+    ``collect_state(buf, apply_permutation=True, work_dir=...)`` returns the logical state.
     Returns the committed buffer path (``collect_state`` reads it exactly like a single-device run)."""
     from pathlib import Path
 
@@ -524,6 +530,11 @@ def run(circuit_dict: dict, work_dir, chunk_size: int = 1 << 20, dtype: str = "c
                 data = read_chunk(src / "chunks" / m.chunks[sim.rank * per_src + c], np.dtype(m.dtype))
                 st.upload(data.astype(np_dtype, copy=False), c * m.chunk_size)
         every = checkpoint_every if checkpoint_every > 0 else max(len(levels) - start, 1)
+        log_to_phys = None
+        if use_staging:
+            if staging_method not in ("heuristic", "greedy", "ilp"):
+                raise ValueError(f"unknown staging method: {staging_method!r}")
+            start, every = 0, max(len(levels), 1)               # one segment, planned by atlas_stages
         n_ckpt = 0
         lo = start
         while True:
@@ -533,7 +544,12 @@ def run(circuit_dict: dict, work_dir, chunk_size: int = 1 << 20, dtype: str = "c
             from_zero = lo == 0
             # only the LAST segment may leave an X pending on a rank bit as a renaming of the shards; a segment
             # that is continued must end with every amplitude where the identity layout puts it
-            prog = sim.plan_ops(ops, zero_init=from_zero, **dict(compiler_kw, rank_flips=bool(final and compiler_kw.get("rank_flips", True))))
+            if use_staging:
+                kw_ = dict(compiler_kw)
+                kw_.setdefault("swap_anywhere", bool(sim.peer_swap))
+                prog, log_to_phys = sharding.plan_atlas(cd, n_loc, sim.dtype.name, staging_method, True, **kw_)
+            else:
+                prog = sim.plan_ops(ops, zero_init=from_zero, **dict(compiler_kw, rank_flips=bool(final and compiler_kw.get("rank_flips", True))))
             if from_zero or ops:
                 sim.run(prog, init=from_zero)
             logical = sim.rank ^ prog.rank_flip_mask
@@ -561,6 +577,10 @@ def run(circuit_dict: dict, work_dir, chunk_size: int = 1 << 20, dtype: str = "c
                 total = per_rank * sim.world
                 write_manifest_atomic(dst, Manifest(n_qubits=n, chunk_size=chunk_size, n_chunks=total, dtype=np_dtype.name,
                                                     chunks=[chunk_filename(i) for i in range(total)]))
+                if log_to_phys is not None:
+                    import json as _json
+                    from quantum_simulations_b200.storage._atomic import publish_text
+                    publish_text(work / "qubit_mapping.json", _json.dumps(list(log_to_phys)))
                 if wal:
                     wal.commit_step(max(hi - 1, 0), _other(current))
             current = _other(current)

@@ -94,6 +94,19 @@ def main():
             raise SystemExit(f"resume bookkeeping wrong: first={done_first} wal={wal} again={buf_again} vs {buf}")
         worst = max(worst, err)
     dist.barrier()
+    # use_staging=True: the reference's atlas_stages supplies the stages; chunks in the physical layout +
+    # qubit_mapping.json, un-permuted by collect_state exactly like a reference work directory
+    box = [dist.broadcast_object(tempfile.mkdtemp(prefix="qsv_mg_st_") if rank == 0 else None, src=0)]
+    cd = validate_circuit_dict(W.random_mixed(n, 200, 17))
+    for method in ("heuristic", "ilp"):
+        buf = MG.run(cd, str(Path(box[0]) / method), chunk_size=1 << (n - 5), use_staging=True, staging_method=method)
+        if rank == 0:
+            got = collect_state(buf, apply_permutation=True, work_dir=str(Path(box[0]) / method))
+            err = float(np.abs(got - CO.simulate_c(cd)).max())
+            l2p = _json.loads((Path(box[0]) / method / "qubit_mapping.json").read_text())
+            print(f"runner.multi_gpu.run use_staging={method}: mapping identity={l2p == list(range(n))} max|d|={err:.3e}", flush=True)
+            worst = max(worst, err)
+        dist.barrier()
     dist.close()
     if rank == 0 and worst > 1e-12:
         raise SystemExit(f"multi-GPU parity failed: {worst}")

@@ -123,3 +123,22 @@ def test_planned_placements_incl_exchange_candidates_match_oracle(workload, g):
             shards = psi.reshape(1 << g, -1)
             psi = np.concatenate([shards[r ^ prog.rank_flip_mask] for r in range(1 << g)])
         assert np.abs(psi - O.simulate(validate_circuit_dict(cd))).max() <= 1e-12
+
+
+@pytest.mark.parametrize("method", ["heuristic", "greedy", "ilp"])
+def test_atlas_stages_drive_the_sharded_plan(method):
+    """sharding.plan_atlas: the reference's staging (atlas_stages: local sets per stage, SWAP steps, log_to_phys)
+    supplies the stage boundaries of the sharded program; the state comes out in atlas's physical layout and
+    permute_state maps it back (reference staging.py:587-658)."""
+    from quantum_simulations_b200.circuit import sharding
+    from quantum_simulations_b200.circuit.staging import permute_state
+    for n, g, cd in ((10, 2, W.random_mixed(10, 120, 3)), (11, 1, W.qft(11)), (12, 3, W.random_1q_cz(12, 12, 7))):
+        cd = validate_circuit_dict(cd)
+        prog, l2p = sharding.plan_atlas(cd, n - g, method=method, tile_bits=6, low_bits=2, swap_anywhere=True)
+        assert sorted(l2p) == list(range(n)) and prog.stats["parts"] >= 1
+        psi = np.random.default_rng(1).standard_normal(1 << n) + 0j      # the fused first pass ignores what is there
+        if not prog.fused_init:
+            psi = np.zeros(1 << n, dtype=np.complex128)
+            psi[0] = 1
+        got = permute_state(run_program_sharded(prog, psi), l2p)
+        assert np.abs(got - O.simulate(cd)).max() <= 1e-12
