@@ -15,7 +15,9 @@ kwargs keep the reference's names and meaning:
   kernel          only "cuda" exists here ("scalar"/"batched" are the reference's CPU kernels)
   use_fusion      False: one compiled program per circuit level (the reference's one I/O pass
                   per level); True: levels are batched and compiled together (batch_levels)
-  use_staging     accepted; on one GPU every qubit is local so it is the identity mapping
+  use_staging     on one GPU every qubit is local: atlas_stages(cd, k=n) is the batched circuit with the identity
+                  mapping, which is written to qubit_mapping.json as the reference does (single_node.py:130-134);
+                  sharded runs take their stages from atlas_stages in runner.multi_gpu.run(use_staging=True)
 new kwargs: dtype ("complex128" default | "complex64"), device, checkpoint_every (steps
 between durable checkpoints; 0 = only the final state), tile_bits / low_bits (pass compiler).
 """
@@ -120,6 +122,12 @@ def run(
     np_dtype = np.dtype(dtype)
     work = Path(work_dir)
     steps = build_steps(cd, n, use_fusion)          # one device: k = n, every op is local
+    if use_staging:                                 # reference single_node.py:108-134 with k = n: nothing to stage
+        from quantum_simulations_b200.circuit.staging import atlas_stages
+        from quantum_simulations_b200.storage._atomic import publish_text
+        steps, log_to_phys = atlas_stages(cd, n, method=staging_method)
+        work.mkdir(parents=True, exist_ok=True)
+        publish_text(work / "qubit_mapping.json", json.dumps(list(log_to_phys)))
 
     fence = FencingLock(work) if use_fencing else None
     if fence:
