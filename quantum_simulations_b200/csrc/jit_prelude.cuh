@@ -50,11 +50,18 @@ struct JitDst { JV *p[8]; unsigned long long keep; };
 // index bits fixed from outside (a launch over ONE CHUNK of the shard: pipelined stage transitions run the
 // passes next to a swap chunk by chunk): the tile counter runs over the remaining non-tile bits; pos[] are
 // positions in TILE-INDEX space (tile bits removed), ascending; val = the fixed bits at those positions
-struct JitFix { unsigned n; unsigned pos[4]; unsigned long long val; };
+// blk: the CTAs are dealt blocks of 2^blk CONSECUTIVE tiles round-robin (0 = tile by tile), see jit_seq
+struct JitFix { unsigned n; unsigned pos[4]; unsigned blk; unsigned long long val; };
 __device__ __forceinline__ unsigned long long jit_fix(unsigned long long t, const JitFix &F) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) if (i < (int)F.n) t = insert_zero_bit(t, (int)F.pos[i]);
     return t | F.val;
+}
+// the s-th tile (relative to tile_begin) of this CTA.  Strictly increasing in s for every CTA, and (cta, s) -> tile is
+// a bijection onto 0, 1, 2, ...: producers and consumer groups of a CTA walk the same sequence and stop at the
+// first tile beyond the range.
+__device__ __forceinline__ unsigned jit_seq(unsigned s, unsigned blk) {
+    return ((((s >> blk) * gridDim.x) + blockIdx.x) << blk) + (s & ((1u << blk) - 1u));
 }
 
 struct JitRingSmem {

@@ -670,7 +670,16 @@ int qsv_program_create(qsv_handle *h, const qsv_pass *passes, int n_passes, cons
 }
 
 // tiles [tile_begin, tile_end) of pass i on `stream` (the whole pass: 0 .. n_amps >> 11)
-struct JitFixArg { unsigned n; unsigned pos[4]; unsigned long long val; };   // = JitFix of jit_prelude.cuh
+struct JitFixArg { unsigned n; unsigned pos[4]; unsigned blk; unsigned long long val; };   // = JitFix of jit_prelude.cuh
+
+// QSV_JIT_TILE_BLOCK=k (experiment, default 0): a CTA is dealt 2^k consecutive tiles at a time instead of every
+// grid-th tile (jit_seq in jit_prelude.cuh).  Clipped so that every CTA still gets several blocks.
+static unsigned tile_block_log2(uint32_t count, unsigned grid) {
+    static const int want = [] { const char *e = getenv("QSV_JIT_TILE_BLOCK"); int k = e ? atoi(e) : 0; return k < 0 ? 0 : (k > 8 ? 8 : k); }();
+    unsigned k = (unsigned)want;
+    while (k > 0 && (((uint64_t)grid << k) * 4u) > count) --k;
+    return k;
+}
 
 static int launch_pass_jit_range(qsv_handle *h, qsv_program *p, int i, uint32_t tile_begin, uint32_t tile_end, cudaStream_t stream,
                                  const JitFixArg *fix_in = nullptr, unsigned grid_cap = 0) {
@@ -679,6 +688,7 @@ static int launch_pass_jit_range(qsv_handle *h, qsv_program *p, int i, uint32_t 
     const unsigned grid = count < cap ? count : cap;
     JitFixArg fix = {};
     if (fix_in) fix = *fix_in;
+    fix.blk = tile_block_log2(count, grid);
     void *state = h->d_state;
     const double2 *tables = p->d_tables + p->fold_offset[i];
     unsigned long long rank_bits = (unsigned long long)h->rank << h->n_local;

@@ -85,10 +85,13 @@ static inline uint32_t jit_slot(uint32_t x) { return tile_swizzle<3>(x); }
 #endif
 
 struct JitDst { JV *p[8]; unsigned long long keep; };
-struct JitFix { unsigned n; unsigned pos[4]; unsigned long long val; };
+struct JitFix { unsigned n; unsigned pos[4]; unsigned blk; unsigned long long val; };
 static inline unsigned long long jit_fix(unsigned long long t, const JitFix &F) {
     for (int i = 0; i < 4; ++i) if (i < (int)F.n) t = insert_zero_bit(t, (int)F.pos[i]);
     return t | F.val;
+}
+static inline unsigned jit_seq(unsigned s, unsigned blk) {
+    return ((((s >> blk) * gridDim.x) + blockIdx.x) << blk) + (s & ((1u << blk) - 1u));
 }
 
 // ---- mbarrier: `count` arrivals complete a phase; wait(parity) returns once the phase of that parity is over

@@ -78,7 +78,7 @@ def host_kernel(step, dtype="complex128", scatter_bits=None):
         fn = lib.jit_host_run
         fn.restype = C.c_int
         fn.argtypes = [C.c_void_p, C.c_void_p, C.c_ulonglong, C.c_uint, C.c_uint, C.c_void_p, C.POINTER(C.c_void_p),
-                       C.c_ulonglong, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint), C.c_ulonglong]
+                       C.c_ulonglong, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint), C.c_ulonglong, C.c_uint]
         import re
         nt = int(re.search(r"__launch_bounds__\((\d+), 1\)", src).group(1))
         _cache[key] = (fn, nt)
@@ -86,7 +86,7 @@ def host_kernel(step, dtype="complex128", scatter_bits=None):
 
 
 def run_pass_on_host(step, shard: np.ndarray, n_local: int, rank: int = 0, grid: int = 2, tile_range=None,
-                     scatter=None, fix=None) -> None:
+                     scatter=None, fix=None, tile_block: int = 0) -> None:
     """Apply the pass to `shard` (in place) with the host build of its specialised kernel.
     scatter = (local_bits, targets, keep): the scatter variant; targets[x] = array that receives the
     amplitudes whose swapped local bits equal x (the shard itself is only read)."""
@@ -103,5 +103,5 @@ def run_pass_on_host(step, shard: np.ndarray, n_local: int, rank: int = 0, grid:
         dst = (C.c_void_p * 8)(*([t.ctypes.data for t in targets] + [None] * (8 - len(targets))))
     fpos, fval = fix if fix is not None else ((), 0)             # fix = (positions in tile-index space, value there)
     rc = fn(shard.ctypes.data, tables.ctypes.data, rank << n_local, tb, te, coefs.ctypes.data, dst, keep, grid, nt,
-            len(fpos), (C.c_uint * 4)(*(list(fpos) + [0] * (4 - len(fpos)))), fval)
+            len(fpos), (C.c_uint * 4)(*(list(fpos) + [0] * (4 - len(fpos)))), fval, tile_block)
     assert rc == 0

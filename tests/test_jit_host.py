@@ -173,11 +173,13 @@ def test_warp_local_rounds_with_syncwarp(monkeypatch):
     assert "__syncwarp();" not in kernel_source(prog.passes[0])          # the default kernels are unchanged
 
 
-def test_a_pass_launched_chunk_by_chunk_equals_the_whole_pass():
+@pytest.mark.parametrize("pair,blk", [("0", 0), ("1", 1), ("2", 2)])
+def test_a_pass_launched_chunk_by_chunk_equals_the_whole_pass(monkeypatch, pair, blk):
     """Pipelined stage transitions launch a pass once per CHUNK: index bits outside the tile are fixed through
     the kernel's JitFix argument (positions in tile-index space) and the tile counter runs over the rest.
     The union of the chunk launches must be the pass."""
     n = 14
+    monkeypatch.setenv("QSV_JIT_PAIR", pair)
     prog = compile_circuit(W.random_1q_cz(n, 20, 1234), zero_init=False)
     psi = _random_state(n, 5)
     step = prog.passes[1]
@@ -192,8 +194,55 @@ def test_a_pass_launched_chunk_by_chunk_equals_the_whole_pass():
         for j in range(1 << len(chunk_bits)):
             val = sum(((j >> i) & 1) << pos[i] for i in range(len(chunk_bits)))
             before = got.copy()
-            run_pass_on_host(step, got, n, grid=1, tile_range=(0, tiles), fix=(pos, val))
+            run_pass_on_host(step, got, n, grid=1 + blk, tile_range=(0, tiles), fix=(pos, val), tile_block=blk)
             changed = np.nonzero(got != before)[0]
             for i, b in enumerate(chunk_bits):                  # a chunk launch stays inside its chunk
                 assert np.all((changed >> b) & 1 == (j >> i) & 1)
         assert np.abs(got - want).max() <= 1e-13
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+def test_tile_blocks_and_paired_loads(monkeypatch, dtype):
+    """QSV_JIT_TILE_BLOCK (a CTA is dealt 2^k consecutive tiles at a time: JitFix.blk / jit_seq) and QSV_JIT_PAIR=1
+    (the producers fill two ring buffers at once) change which CTA moves which tile and how the tile reaches shared
+    memory — never the result.  Grids that do not divide the tile count, a single tile, an odd tile range and a
+    chunked launch (JitFix positions) are all walked."""
+    n = 15                                                  # 16 tiles
+    tol = 1e-13 if dtype == "complex128" else 2e-6
+    prog = compile_circuit(W.random_1q_cz(n, 20, 1234), dtype=dtype, zero_init=False)
+    steps = prog.passes[:2]
+    psi = _random_state(n, 6)
+    for pair in ("0", "1", "2"):
+        monkeypatch.setenv("QSV_JIT_PAIR", pair)
+        for step in steps:
+            want = psi.copy()
+            run_pass(want, step.desc, step.ops, n, 0, step.tables)
+            for grid, blk in ((1, 0), (3, 0), (3, 1), (2, 2), (5, 1), (3, 4)):
+                got = psi.astype(dtype)
+                run_pass_on_host(step, got, n, grid=grid, tile_block=blk)
+                assert np.abs(got - want).max() <= tol, (pair, grid, blk)
+            # an odd range of tiles: only those tiles change, whatever the mapping
+            part = psi.astype(dtype)
+            run_pass_on_host(step, part, n, grid=2, tile_range=(3, 10), tile_block=1)
+            full = psi.astype(dtype)
+            run_pass_on_host(step, full, n, grid=2, tile_block=0)
+            changed = np.flatnonzero(np.abs(part - psi.astype(dtype)) > 0)
+            assert len(changed) and np.abs(part[changed] - full[changed]).max() <= tol
+            same = np.flatnonzero(part == psi.astype(dtype))
+            assert len(changed) + len(same) == 1 << n and len(changed) <= 7 * 2048
+
+
+def test_paired_loads_leave_zero_input_and_scatter_kernels_alone(monkeypatch):
+    from tests.jit_host_run import kernel_source
+    prog = compile_circuit(W.random_1q_cz(14, 20, 1234))
+    assert prog.passes[0].desc.zero_input == 1
+    monkeypatch.setenv("QSV_JIT_PAIR", "0")
+    plain0, plain1 = kernel_source(prog.passes[0]), kernel_source(prog.passes[1])
+    monkeypatch.setenv("QSV_JIT_PAIR", "1")
+    assert kernel_source(prog.passes[0]) == plain0          # nothing is read: nothing to pair
+    paired = kernel_source(prog.passes[1])
+    assert paired != plain1 and "tile1" in paired and "jit_seq(s + 1, F.blk)" in paired and "tile3" not in paired
+    monkeypatch.setenv("QSV_JIT_PAIR", "2")
+    assert "jit_seq(s + 3, F.blk)" in kernel_source(prog.passes[1])
+    assert kernel_source(prog.passes[1], scatter_bits=[12]) == \
+        (monkeypatch.setenv("QSV_JIT_PAIR", "0") or kernel_source(prog.passes[1], scatter_bits=[12]))

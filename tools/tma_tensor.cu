@@ -79,6 +79,7 @@ struct Params {
     unsigned long long n_tiles;
     unsigned long long index_bits;           // amplitude-index bits that select the tile (the tile id is spread over them)
     int n, a, nbuf, load_mode, store_mode;
+    int blk, pair;                           // CTA owns 2^blk consecutive tiles at a time; cp.async loads two tiles at once
     int ops;                                 // TMA instructions per tile
     unsigned long long split_bits;           // the bits the ops of one tile differ in (excess runs), 0 if ops == 1
     unsigned long long dim_mask[5];          // coordinate k = (base & dim_mask[k]) >> dim_shift[k]
@@ -91,6 +92,53 @@ __device__ __forceinline__ unsigned long long deposit(unsigned long long v, unsi
     for (int b = 0; mask; ++b, mask >>= 1)
         if (mask & 1) { out |= (v & 1ull) << b; v >>= 1; }
     return out;
+}
+
+// s-th tile of this CTA: blocks of 2^blk consecutive tiles are dealt to the CTAs round-robin (blk = 0: tile s * grid + cta)
+__device__ __forceinline__ unsigned long long seq_tile(unsigned long long s, int blk) {
+    return ((((s >> blk) * gridDim.x) + blockIdx.x) << blk) + (s & ((1ull << blk) - 1));
+}
+
+// 2^PM tiles at once: lanes 0-7 copy a row of tile s, lanes 8-15 the same row of tile s + 1, ... (the next 2^ib
+// amplitudes when the CTA owns consecutive tiles), so one warp instruction covers 2^PM x 128 contiguous bytes
+template <int PM>
+__device__ __forceinline__ void load_multi(const Params &P, double2 *bufs, uint64_t *full, uint64_t *empty, int gt) {
+    constexpr int M = 1 << PM, TB = 4 - PM, KB = 4 + PM;
+    const int sel = (gt >> 3) & (M - 1);
+    unsigned long long po = 0;
+    unsigned xlo = gt & 7;
+    for (int k = 0; k < 3; ++k) po |= (unsigned long long)((gt >> k) & 1) << P.tile_bit[k];
+    for (int k = 0; k < TB; ++k) {
+        po |= (unsigned long long)((gt >> (3 + PM + k)) & 1) << P.tile_bit[3 + k];
+        xlo |= ((gt >> (3 + PM + k)) & 1) << (3 + k);
+    }
+    for (unsigned long long s = 0;; s += M) {
+        unsigned long long t[M];
+#pragma unroll
+        for (int j = 0; j < M; ++j) t[j] = seq_tile(s + j, P.blk);
+        if (t[0] >= P.n_tiles) break;
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+            const uint32_t use = (uint32_t)((s + j) / P.nbuf);
+            if (t[j] < P.n_tiles && use > 0) mbar_wait(&empty[(s + j) % P.nbuf], (use - 1) & 1);
+        }
+        unsigned long long mine = t[0];
+#pragma unroll
+        for (int j = 1; j < M; ++j) if (sel == j) mine = t[j];
+        if (mine < P.n_tiles) {
+            const double2 *g = P.src + deposit(mine, P.index_bits) + po;
+            double2 *d = bufs + (size_t)((s + sel) % P.nbuf) * (1u << kT);
+#pragma unroll
+            for (int i = 0; i < (1 << KB); ++i) {
+                unsigned long long o = 0;
+#pragma unroll
+                for (int k = 0; k < KB; ++k) if ((i >> k) & 1) o |= 1ull << P.tile_bit[3 + TB + k];
+                cp_async_16(d + (i << (3 + TB)) + xlo, g + o);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < M; ++j) if (t[j] < P.n_tiles) cp_async_arrive(&full[(s + j) % P.nbuf]);
+    }
 }
 
 __global__ void __launch_bounds__(2 * kGroup, 1)
@@ -108,7 +156,6 @@ k_copy(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUte
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const unsigned long long first = blockIdx.x, stride = gridDim.x;
     const bool loader = tid >= kGroup;
     const int gt = tid & (kGroup - 1);
     // tile-local element x = i * 128 + gt  ->  offset inside the state (amplitudes)
@@ -122,8 +169,11 @@ k_copy(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUte
 
     if (loader) {
         if (P.load_mode == 0 && gt != 0) return;
-        unsigned long long s = 0;
-        for (unsigned long long tile = first; tile < P.n_tiles; tile += stride, ++s) {
+        if (P.load_mode == 1 && P.pair == 1) { load_multi<1>(P, bufs, full, empty, gt); return; }
+        if (P.load_mode == 1 && P.pair == 2) { load_multi<2>(P, bufs, full, empty, gt); return; }
+        for (unsigned long long s = 0;; ++s) {
+            const unsigned long long tile = seq_tile(s, P.blk);
+            if (tile >= P.n_tiles) break;
             const int b = (int)(s % P.nbuf);
             const uint32_t use = (uint32_t)(s / P.nbuf);
             if (use > 0) mbar_wait(&empty[b], (use - 1) & 1);
@@ -149,9 +199,10 @@ k_copy(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUte
     }
     // ---- store group ----
     if (P.store_mode == 0 && gt != 0) return;
-    unsigned long long s = 0;
     int prev_b = -1;
-    for (unsigned long long tile = first; tile < P.n_tiles; tile += stride, ++s) {
+    for (unsigned long long s = 0;; ++s) {
+        const unsigned long long tile = seq_tile(s, P.blk);
+        if (tile >= P.n_tiles) break;
         const int b = (int)(s % P.nbuf);
         const uint32_t use = (uint32_t)(s / P.nbuf);
         mbar_wait(&full[b], use & 1);
@@ -269,6 +320,20 @@ static int build_shape(int n, int a, const std::vector<int> &free_bits, Params &
     return k == kT ? P.ops : 0;
 }
 
+static std::vector<int> env_list(const char *name) {
+    std::vector<int> out;
+    const char *e = getenv(name);
+    if (e) {
+        char tmp[128];
+        strncpy(tmp, e, 127);
+        tmp[127] = 0;
+        char *save = nullptr;
+        for (char *tok = strtok_r(tmp, ",", &save); tok; tok = strtok_r(nullptr, ",", &save)) out.push_back(atoi(tok));
+    }
+    if (out.empty()) out.push_back(0);
+    return out;
+}
+
 int main(int argc, char **argv) {
     if (argc < 5) { fprintf(stderr, "usage: tma_tensor n a nbuf bits[,bits...] ...\n"); return 2; }
     const int n = atoi(argv[1]), a = atoi(argv[2]), nbuf = atoi(argv[3]);
@@ -338,14 +403,21 @@ int main(int argc, char **argv) {
         for (int k = 0; k < 5; ++k)
             sprintf(dimtxt + strlen(dimtxt), "%s[%llu, %llu, %u]", k ? ", " : "", (unsigned long long)dims[k].extent,
                     (unsigned long long)dims[k].stride_bytes, dims[k].box);
-        for (int lm = 0; lm < 2; ++lm)
-            for (int sm = 0; sm < 2; ++sm) {
+        // variants: TMA_ONLY=cp keeps only cp.async + STG (what the pass kernel does); TMA_BLK="0,2,4": tile-to-CTA
+        // mappings (blocks of 2^blk consecutive tiles per CTA); TMA_PAIR="0,1": cp.async loads two tiles at once
+        const bool only_cp = getenv("TMA_ONLY") && !strcmp(getenv("TMA_ONLY"), "cp");
+        std::vector<int> blks = env_list("TMA_BLK"), pairs = env_list("TMA_PAIR");
+        for (int lm = only_cp ? 1 : 0; lm < 2; ++lm)
+            for (int sm = only_cp ? 1 : 0; sm < 2; ++sm)
+                for (int blk : blks)
+                    for (int pair : pairs) {
+                if (pair && lm != 1) continue;
                 if ((lm == 0 || sm == 0) && res != CUDA_SUCCESS) {
                     printf("{\"free_bits\": [%s], \"load\": %d, \"store\": %d, \"error\": \"cuTensorMapEncodeTiled = %d\", "
                            "\"dims_extent_stride_box\": [%s]}\n", shape, lm, sm, (int)res, dimtxt);
                     continue;
                 }
-                P.load_mode = lm; P.store_mode = sm;
+                P.load_mode = lm; P.store_mode = sm; P.blk = blk; P.pair = pair;
                 cudaMemsetAsync(dst, 0, amps * 16);
                 cudaMemsetAsync(bad, 0, 8);
                 k_copy<<<sms, 2 * kGroup, smem>>>(maps[0], maps[1], P);
@@ -354,7 +426,7 @@ int main(int argc, char **argv) {
                 cudaError_t err = cudaMemcpy(&hbad, bad, 8, cudaMemcpyDeviceToHost);
                 if (err != cudaSuccess) { printf("{\"free_bits\": [%s], \"error\": \"%s\"}\n", shape, cudaGetErrorString(err)); return 1; }
                 float best = 1e9f, sum = 0;
-                const int reps = 5;
+                const int reps = 4;
                 for (int rep = 0; rep < reps; ++rep) {
                     cudaEventRecord(e0);
                     k_copy<<<sms, 2 * kGroup, smem>>>(maps[0], maps[1], P);
@@ -366,10 +438,10 @@ int main(int argc, char **argv) {
                     sum += ms;
                 }
                 printf("{\"n\": %d, \"a\": %d, \"nbuf\": %d, \"free_bits\": [%s], \"load\": \"%s\", \"store\": \"%s\", "
-                       "\"tma_ops_per_tile\": %d, \"aliased_index_dim\": %d, \"dims_extent_stride_box\": [%s], "
+                       "\"blk\": %d, \"pair\": %d, \"tma_ops_per_tile\": %d, \"aliased_index_dim\": %d, \"dims_extent_stride_box\": [%s], "
                        "\"ms_best\": %.3f, \"ms_mean\": %.3f, \"gbs\": %.0f, \"mismatches\": %llu}\n",
-                       n, a, nbuf, shape, lm ? "cp.async" : "tma_tensor", sm ? "stg" : "tma_tensor", ops, (int)aliased, dimtxt,
-                       best, sum / reps, 2.0 * amps * 16 / (sum / reps) / 1e6, hbad);
+                       n, a, nbuf, shape, lm ? "cp.async" : "tma_tensor", sm ? "stg" : "tma_tensor", blk, pair, ops, (int)aliased,
+                       only_cp ? "" : dimtxt, best, sum / reps, 2.0 * amps * 16 / (sum / reps) / 1e6, hbad);
                 fflush(stdout);
             }
     }
