@@ -303,6 +303,8 @@ def bench_single(args) -> None:
             st_.init_zero()
         st_.replay(handle_)
 
+    fingerprints: list = []
+
     def timed_run():
         with DeviceState(n, dtype, args.device) as st:
             handle = st.upload_program(prog)
@@ -317,7 +319,16 @@ def bench_single(args) -> None:
             total_ms_ = st.timer_stop()
             per_launch_ = st.take_timings()
             st.timing(False)
-            return total_ms_, per_launch_, clocks.stop(), st.norm2()
+            clk_ = clocks.stop()
+            norm_ = st.norm2()
+            # fingerprint of the final state: the data-movement switches of the pass kernel (tile-to-CTA mapping,
+            # paired loads) must not change a single bit of it
+            import hashlib
+            cnt = min(1 << 14, 1 << n)
+            fp_ = hashlib.sha1(st.download(count=cnt).tobytes()
+                               + st.download(offset=((1 << n) // 3) & ~(cnt - 1), count=cnt).tobytes()).hexdigest()[:16]
+            fingerprints.append(fp_)
+            return total_ms_, per_launch_, clk_, norm_
 
     norm_tol = 1e-9 if dtype == "complex128" else 1e-4
     total_ms, per_launch, clk, norm = timed_run()
@@ -448,9 +459,12 @@ def bench_single(args) -> None:
                    "planner_switches": {"low_store_round": not args.no_low_store_round,
                                         "warp_local_rounds": bool(args.warp_local_rounds),
                                         "streaming_stores": os.environ.get("QSV_JIT_STCS") == "1",
-                                        "init_pass_full": "QSV_INIT_PASS_FULL" in os.environ},
+                                        "init_pass_full": "QSV_INIT_PASS_FULL" in os.environ,
+                                        "tile_block_log2": os.environ.get("QSV_JIT_TILE_BLOCK", "default"),
+                                        "pair_loads": os.environ.get("QSV_JIT_PAIR", "default")},
                    "l2_hygiene": f"state {(1 << n) * amp_bytes / 2**30:.0f} GiB >> 126 MB L2: every pass streams from HBM",
-                   "host_compile_s": compile_s},
+                   "host_compile_s": compile_s,
+                   "state_fingerprint": fingerprints[0] if fingerprints else None},
         "gate_layers_per_s": info["levels"] / (ms_per_step * 1e-3),
         "hbm_gbs_per_gate_layer": info["levels"] * alg_bytes / (ms_per_step * 1e-3) / 1e9,
         "roofline": {"bound": "hbm", "kernel": "k_pass_jit (run-time specialised ring kernel; k_pass_ring / k_pass interpret "

@@ -674,8 +674,9 @@ struct JitFixArg { unsigned n; unsigned pos[4]; unsigned blk; unsigned long long
 
 // QSV_JIT_TILE_BLOCK=k (experiment, default 0): a CTA is dealt 2^k consecutive tiles at a time instead of every
 // grid-th tile (jit_seq in jit_prelude.cuh).  Clipped so that every CTA still gets several blocks.
+constexpr int kDefaultTileBlock = 0;
 static unsigned tile_block_log2(uint32_t count, unsigned grid) {
-    static const int want = [] { const char *e = getenv("QSV_JIT_TILE_BLOCK"); int k = e ? atoi(e) : 0; return k < 0 ? 0 : (k > 8 ? 8 : k); }();
+    static const int want = [] { const char *e = getenv("QSV_JIT_TILE_BLOCK"); int k = (e && e[0]) ? atoi(e) : kDefaultTileBlock; return k < 0 ? 0 : (k > 8 ? 8 : k); }();
     unsigned k = (unsigned)want;
     while (k > 0 && (((uint64_t)grid << k) * 4u) > count) --k;
     return k;

@@ -44,9 +44,9 @@ class FakeState:
             k = len(prog.passes)
             self._timed += [((time.perf_counter() - t0) * 1e3 / k, 10, i) for i in range(k)]
 
-    def download(self, out=None):
+    def download(self, out=None, offset=0, count=None):
         if out is None:
-            return self.psi.copy()
+            return self.psi[offset: None if count is None else offset + count].copy()
         out[:] = self.psi
         return out
 
