@@ -32,6 +32,22 @@ def _mat(U, dim: int):
     return u, u.ctypes.data_as(C.POINTER(C.c_double))
 
 
+_MARGINAL_BITS = 10          # bins of a marginal live in shared memory up to 2^10 (csrc/sample.cuh k_marginal)
+
+
+def pad_marginal_qubits(qubits: list, n_local: int, bits: int = _MARGINAL_BITS) -> list:
+    """`qubits` followed by the lowest local qubits not among them, up to `bits` in total (never fewer than asked)."""
+    have = set(qubits)
+    extra = [q for q in range(n_local) if q not in have][: max(0, bits - len(qubits))]
+    return list(qubits) + extra
+
+
+def fold_marginal(wide: np.ndarray, asked: int) -> np.ndarray:
+    """sum a marginal over the padding bits: outcome bit k of `wide` is qubit k of the widened list, the first
+    `asked` of which are the caller's"""
+    return np.ascontiguousarray(wide.reshape(-1, 1 << asked).sum(axis=0))
+
+
 class DeviceState:
     """2^n_local amplitudes of an n-qubit state in HBM (shard `rank` of `world`)."""
 
@@ -260,11 +276,19 @@ class DeviceState:
         return out.value
 
     def probabilities(self, qubits) -> np.ndarray:
-        """Marginal distribution of this shard over `qubits` (bit k of the outcome = qubits[k])."""
-        qs = (C.c_int * max(len(qubits), 1))(*qubits)
-        out = np.zeros(1 << len(qubits), dtype=np.float64)
-        self._ck(self.lib.qsv_probabilities(self._h, len(qubits), qs, out.ctypes.data_as(C.POINTER(C.c_double))))
-        return out
+        """Marginal distribution of this shard over `qubits` (bit k of the outcome = qubits[k]).
+
+        A marginal over FEW qubits is a histogram with few bins, and every thread of the kernel adds to one of them:
+        2 bins cost 43-87 ms at 30 qubits where 1024 bins cost 5.7 ms (profiles/r02/kernel_table_n30_c128.txt).  So
+        the request is widened with the lowest local qubits that are not in it (neighbouring lanes then hit
+        different bins) up to 10 qubits = 1024 bins in shared memory, and the extra bits are summed away here."""
+        qubits = list(qubits)
+        asked = len(qubits)
+        wide = pad_marginal_qubits(qubits, self.n_local)
+        qs = (C.c_int * max(len(wide), 1))(*wide)
+        out = np.zeros(1 << len(wide), dtype=np.float64)
+        self._ck(self.lib.qsv_probabilities(self._h, len(wide), qs, out.ctypes.data_as(C.POINTER(C.c_double))))
+        return fold_marginal(out, asked)
 
     def expect_z(self, qubits) -> float:
         """<Z_q1 Z_q2 ...> contribution of this shard."""

@@ -81,7 +81,12 @@ lines += ["", "FP64 / amplitude = FP64 instructions of the consumer code / 16 am
           "FP64-pipe bound, below it HBM bound.  No DMMA: DFMA and DMMA share one pipe (profiles/r02/fp64_peak_mixed.json: "
           "34.2 alone, 37.0 alone, 34.1 together).  No UTMA/UBLKCP in the pass kernel: its tile fill is 256 separate 128-byte "
           "rows per tile, measured faster with cp.async (LDGSTS) than with one bulk copy per row (profiles/r01/tma_ring_microbench_n30.jsonl); "
-          "the TMA engine is used where the runs are long: the exchange kernel below.", ""]
+          "the TENSOR-MAP form (cp.async.bulk.tensor.5d, one instruction per tile; tools/tma_tensor.cu, "
+          "profiles/r02/tma_tensor_variants_n30.jsonl) matches or beats cp.async only for tiles with at most 3 runs of free bits "
+          "(6.57 vs 6.08 TB/s contiguous, 4.6 vs 4.6 TB/s for 8 top bits) and collapses where a tile needs several instructions "
+          "(2 per tile: 2.7 TB/s, 8: 1.3, 32: 0.26 against 4.4-6.3 for cp.async) — 5 of the 6 planned tile shapes.  The 32 LDGSTS per "
+          "kernel are the paired loads: two tiles at once, 256 contiguous bytes per request.  The TMA engine is used where the runs "
+          "are long: the exchange kernel below.", ""]
 so = ROOT / "quantum_simulations_b200" / "csrc" / "libqsv.so"
 names = subprocess.run(["cuobjdump", "-sass", str(so)], capture_output=True, text=True).stdout
 funs = re.findall(r"Function : (\S+)", names)
