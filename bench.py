@@ -399,6 +399,19 @@ def bench_single(args) -> None:
         others = [_other_workload(args, wl, n_, dt_) for wl, n_, dt_ in
                   (("qft", 28, "complex128"), ("ghz", 30, "complex128"), ("ghz", 20, "complex128"), ("random", 30, "complex64"))]
 
+    # ---- the per-gate ABI (a1/a2 operator face) and the observables against the same roofline ----
+    per_gate = None
+    if not args.no_others and n >= 20:
+        try:
+            import io as _io
+            from quantum_simulations_b200.bench.kernel import bench_kernel
+            rows = bench_kernel(n, dtype, reps=3, device=args.device, out=_io.StringIO(), quick=True)
+            per_gate = {"what": "quantum_simulations_b200.bench.kernel (quick): one launch per gate, CUDA events, algorithmic "
+                                "bytes (2 x state per gate, half for a controlled gate, 1 x for an observable) / time / measured HBM peak",
+                        "rows": [{k: r[k] for k in ("kernel", "what", "ms", "gbs", "frac")} for r in rows]}
+        except Exception as e:                       # secondary table: never costs the headline line
+            per_gate = {"error": f"{type(e).__name__}: {e}"[:200]}
+
     # ---- end to end through the public API, result in pinned HOST memory ----
     e2e = None
     if not args.no_e2e:
@@ -475,6 +488,7 @@ def bench_single(args) -> None:
                      "launches_timed": len(streamed_ms), "share_of_step": pass_share,
                      "launches": "every pass that reads and writes the state once (the write-only init pass is excluded)"},
         "other_workloads": others,
+        "per_gate_kernels": per_gate,
         "zero_support_skipping": zs,
         "full_first_pass": full_first,
         "jit": jit_stats(),

@@ -72,7 +72,8 @@ def _spread(n: int) -> list[int]:
 
 
 def bench_kernel(n_qubits: int = 30, dtype: str = "complex128", reps: int = 5, device: int = 0,
-                 observables: bool = True, out=sys.stdout) -> list[dict]:
+                 observables: bool = True, out=sys.stdout, quick: bool = False) -> list[dict]:
+    """quick=True: one representative case per kernel (what `bench.py` puts into its line as `per_gate_kernels`)."""
     peak, peak_src = hbm_peak_gbs()
     rows: list[dict] = []
     n = n_qubits
@@ -91,22 +92,23 @@ def bench_kernel(n_qubits: int = 30, dtype: str = "complex128", reps: int = 5, d
 
         print(f"n = {n} ({st.dtype.name}, {st.n_amps * st.dtype.itemsize / 2**30:.2f} GiB), HBM peak {peak:.1f} GB/s: {peak_src}", file=out)
         print(f"{'kernel':<16} {'what':<34} {'time':>11} {'traffic':>13}  {'frac':>6}", file=out)
-        for q in _spread(n):
+        for q in ((0, n // 2, n - 1) if quick else _spread(n)):
             add("k_apply_1q", f"H on qubit {q}", 1.0, True, _bench_1q(st, q, "H", reps))
-        for g in ("X", "T"):                      # the reference's other two 1-qubit cases (bench/kernel.py:46)
+        for g in (() if quick else ("X", "T")):   # the reference's other two 1-qubit cases (bench/kernel.py:46)
             add("k_apply_1q", f"{g} on qubit 0 (dense 2x2 path)", 1.0, True, _bench_1q(st, 0, g, reps))
-        pairs = [(0, 1), (1, 0), (0, n - 1), (n // 2, n // 2 + 1), (n - 2, n - 1)]
+        pairs = [(0, 1), (n - 2, n - 1)] if quick else [(0, 1), (1, 0), (0, n - 1), (n // 2, n // 2 + 1), (n - 2, n - 1)]
         for qa, qb in pairs:
             add("k_apply_2q", f"CNOT on ({qa},{qb}) dense 4x4", 1.0, True, _bench_2q(st, qa, qb, "CNOT", reps))
         ry = gmod.gate_matrix("RY", {"theta": 0.37})
-        for c, t in ((1, 0), (0, n - 1), (n - 1, 0), (n // 2, n // 2 + 1)):
+        for c, t in (((0, n - 1), (n - 1, 0)) if quick else ((1, 0), (0, n - 1), (n - 1, 0), (n // 2, n // 2 + 1))):
             add("k_apply_ctrl_1q", f"controlled RY, ctrl {c} tgt {t}", 0.5, True,
                 _time(st, lambda c=c, t=t: st.apply_ctrl_1q(c, t, ry), reps))
-        for qs in ((0,), (n - 1,), (0, 1), (0, n - 1), (0, 1, 2, n // 2, n - 2, n - 1)):
+        for qs in (((0, n - 1),) if quick else ((0,), (n - 1,), (0, 1), (0, n - 1), (0, 1, 2, n // 2, n - 2, n - 1))):
             ph = np.exp(1j * rng.uniform(0, 2 * np.pi, 1 << len(qs)))
             add("k_apply_diag", f"diagonal on {len(qs)} qubit(s) {list(qs)}"[:34], 1.0, True,
                 _time(st, lambda qs=qs, ph=ph: st.apply_diag(list(qs), ph), reps))
-        for qs in ((0, 1, 2), (n - 3, n - 2, n - 1), (0, 1, 2, 3, 4), (1, 5, n // 2, n - 4, n - 1)):
+        for qs in (((n - 3, n - 2, n - 1), (1, 5, n // 2, n - 4, n - 1)) if quick else
+                   ((0, 1, 2), (n - 3, n - 2, n - 1), (0, 1, 2, 3, 4), (1, 5, n // 2, n - 4, n - 1))):
             k = len(qs)
             m = rng.normal(size=(1 << k, 1 << k)) + 1j * rng.normal(size=(1 << k, 1 << k))
             U, _ = np.linalg.qr(m)
@@ -114,11 +116,11 @@ def bench_kernel(n_qubits: int = 30, dtype: str = "complex128", reps: int = 5, d
                 _time(st, lambda qs=qs, U=U: st.apply_kq(list(qs), U), reps))
         if observables:
             add("k_norm2_partial", "sum |amp|^2", 1.0, False, _time(st, st.norm2, reps))
-            for qs in ((0,), (n - 1,), tuple(range(min(10, n)))):
+            for qs in (((0,),) if quick else ((0,), (n - 1,), tuple(range(min(10, n))))):
                 add("probabilities", f"marginal over {len(qs)} qubit(s) from {qs[0]}", 1.0, False,
                     _time(st, lambda qs=qs: st.probabilities(list(qs)), reps))
             add("expect_z", f"<Z_0 Z_{n - 1}>", 1.0, False, _time(st, lambda: st.expect_z([0, n - 1]), reps))
-            for shots in (1, 4096):
+            for shots in ((4096,) if quick else (1, 4096)):
                 add("sample", f"{shots} shot(s), seeded", 1.0, False, _time(st, lambda s=shots: st.sample(11, s), reps))
         norm = st.norm2()
     for r in rows:

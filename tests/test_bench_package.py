@@ -115,6 +115,8 @@ def test_kernel_table_control_flow_and_accounting(monkeypatch):
         assert r["algorithmic_bytes"] == int((2 if writes else 1) * 16 * touched * 4096)
         assert r["frac"] == pytest.approx(r["gbs"] / peak, abs=1e-3)
     assert "H on qubit 0" in out.getvalue() and "norm^2" in out.getvalue()
+    quick = KB.bench_kernel(12, "complex128", reps=1, out=io.StringIO(), quick=True)      # what bench.py embeds in its line
+    assert {r["kernel"] for r in quick} == kinds and len(quick) < len(rows) // 2
     rows64 = KB.bench_kernel(12, "complex64", reps=1, observables=False, out=io.StringIO())
     assert all(r["dtype"] == "complex64" and not r["kernel"].startswith(("prob", "expect", "sample")) for r in rows64)
 
