@@ -121,6 +121,29 @@ def test_kernel_table_control_flow_and_accounting(monkeypatch):
     assert all(r["dtype"] == "complex64" and not r["kernel"].startswith(("prob", "expect", "sample")) for r in rows64)
 
 
+def test_io_table_runs_on_the_chunk_store():
+    from quantum_simulations_b200.bench import io as BIO
+    r = BIO.bench_io(1 << 12, 3, out=io.StringIO())
+    assert r["write_MBs"] > 0 and r["read_MBs"] > 0
+
+
+def test_hyperparam_sweep_table(monkeypatch):
+    """the reference's sweep (bench/hyperparam_sweep.py:33-118): every (chunk, fusion) for the single-node runner and
+    every buffer depth for the pipeline runner, without WAL"""
+    from quantum_simulations_b200.bench import hyperparam_sweep as HS
+    from quantum_simulations_b200 import workloads as W
+    calls = []
+    monkeypatch.setattr(HS, "sn_run", lambda cd, td, **kw: calls.append(("sn", kw)))
+    monkeypatch.setattr(HS, "pl_run", lambda cd, td, **kw: calls.append(("pl", kw)))
+    out = io.StringIO()
+    res = HS.sweep(lambda: W.qft(6), "QFT-6", chunk_exponents=[4, 8], buffer_depths=[1, 4], reps=2, out=out)
+    assert len(res) == 2 * 2 * (1 + 2) and len(calls) == 2 * len(res)
+    assert all(kw["use_wal"] is False for _, kw in calls)
+    assert {kw["chunk_size"] for _, kw in calls} == {16, 64}            # 2^8 is clipped to the state (2^6)
+    assert {kw.get("buffer_depth") for k, kw in calls if k == "pl"} == {1, 4}
+    assert "HYPERPARAMETER SWEEP: QFT-6" in out.getvalue() and "best:" in out.getvalue()
+
+
 # ------------------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
 @pytest.mark.parametrize("family", MQ.NATIVE_FAMILIES)

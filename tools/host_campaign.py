@@ -1,0 +1,70 @@
+"""Seeded campaign of the CPU execution of generated kernels (tests/jit_host_run.py) over random circuits, planner
+switches, dtypes, grid sizes, tile-to-CTA mappings and load forms: every specialised pass kernel of every plan against
+the NumPy pass emulator.  CPU only; a slice of this runs in the suite (tests/test_jit_host.py).
+    python tools/host_campaign.py [first_seed] [n_seeds] [workers]"""
+import os
+import sys
+from concurrent.futures import ProcessPoolExecutor
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+
+def one(seed: int):
+    import numpy as np
+    from quantum_simulations_b200 import workloads as W
+    from quantum_simulations_b200.kernel.cuda_dense import compile_circuit
+    from tests.jit_host_run import run_pass_on_host
+    from tests.pass_emulator import run_pass
+
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(12, 16))
+    dtype = "complex64" if rng.random() < 0.3 else "complex128"
+    pair = str(int(rng.integers(0, 3)))
+    os.environ["QSV_JIT_PAIR"] = pair
+    kind = int(rng.integers(0, 3))
+    cd = (W.random_1q_cz(n, int(rng.integers(6, 22)), seed) if kind == 0 else
+          W.random_mixed(n, int(rng.integers(60, 260)), seed) if kind == 1 else W.qft(n))
+    kw = {}
+    if rng.random() < 0.3:
+        kw["low_store_round"] = False
+    if rng.random() < 0.3:
+        kw["low_store_bits"] = [None, 1, 3][int(rng.integers(0, 3))]
+    if rng.random() < 0.3:
+        kw["park_reorder"] = True
+    prog = compile_circuit(cd, dtype=dtype, zero_init=bool(rng.random() < 0.5), **kw)
+    psi = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
+    psi /= np.linalg.norm(psi)
+    tol = 1e-13 if dtype == "complex128" else 3e-6
+    checked = 0
+    for k, step in enumerate(prog.passes[:3]):
+        want = psi.copy()
+        if step.desc.zero_input:
+            want[:] = 0
+            want[0] = 1
+        run_pass(want, step.desc, step.ops, n, 0, step.tables)
+        got = psi.astype(dtype)
+        grid, blk = int(rng.integers(1, 6)), int(rng.integers(0, 4))
+        run_pass_on_host(step, got, n, grid=grid, tile_block=blk)
+        err = float(np.abs(got - want).max())
+        if not err <= tol:
+            return seed, f"FAIL n={n} {dtype} pair={pair} pass={k} grid={grid} blk={blk} kw={kw} err={err}"
+        psi = want
+        checked += 1
+    return seed, f"ok {checked} kernels n={n} {dtype} pair={pair}"
+
+
+if __name__ == "__main__":
+    first = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+    count = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+    workers = int(sys.argv[3]) if len(sys.argv) > 3 else max(1, (os.cpu_count() or 2) - 2)
+    bad = 0
+    total = 0
+    with ProcessPoolExecutor(max_workers=workers) as ex:
+        for seed, msg in ex.map(one, range(first, first + count)):
+            print(seed, msg, flush=True)
+            bad += msg.startswith("FAIL")
+            total += int(msg.split()[1]) if msg.startswith("ok") else 0
+    print(f"campaign: {count} plans, {total} kernels checked, {bad} failures")
+    sys.exit(1 if bad else 0)
