@@ -718,6 +718,7 @@ def bench_multi(args) -> None:
                        "step_sequence": run["sequence"],
                        "l2_hygiene": f"shard {(1 << n_loc) * amp_bytes / 2**30:.0f} GiB >> 126 MB L2",
                        "host_compile_s": run["compile_s"], "plan": run["plan_note"],
+                       "plan_search": prog.stats.get("search"),
                        "scaling_note": "amplitudes per GPU: 2^30 at N=1 (configs[2]), 2^33 / 2^32 / 2^33 at N=2 / 4 / 8 "
                                        "(configs[3], [4]); the weak series with 2^30 per GPU is under weak_series",
                        "timing": "CUDA events on each rank's stream, max over ranks"},

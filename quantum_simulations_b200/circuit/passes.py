@@ -493,7 +493,14 @@ class PassCompiler:
                  swap_anywhere: bool = False, rank_flips: bool = False, park_off_last_round: bool = True,
                  table_phases: bool = True, eager_flips: bool = True, low_store_round: bool = True,
                  low_store_bits: int | None = 2, park_reorder: bool = False,
-                 warp_local_rounds: bool = False):
+                 warp_local_rounds: bool = False, explore_seed: int | None = None, explore_p: float = 0.4,
+                 explore_k: int = 3):
+        # explore_seed (circuit/sharding.plan's search): the tile of a pass normally follows the pending targets in
+        # program order; with a seed, each slot is instead drawn (probability explore_p) among the first explore_k
+        # distinct candidates.  Every such plan is as valid as the greedy one (the dependency scan is the same);
+        # a few hundred of them sometimes contain one with a pass less.
+        self.explore_seed, self.explore_p, self.explore_k = explore_seed, explore_p, explore_k
+        self._rng = None
         self.n = n_qubits
         self.n_local = n_qubits if n_local is None else n_local
         self.dtype = np.dtype(dtype).name
@@ -566,6 +573,8 @@ class PassCompiler:
         index bits of qubits no pass has had in its tile yet are still 0 everywhere.
         fuse_init=True: the program STARTS from |0...0> whatever the shard holds: its first pass does not
         read its input (qsv_pass.zero_input), so neither a memset nor the read half of that pass is paid."""
+        import random
+        self._rng = None if self.explore_seed is None else random.Random(self.explore_seed)   # same plan for the same seed
         # positions whose index bit may be 1 somewhere in the stored state; None = all (no skipping)
         self._support = set() if (zero_state and self.n_local == self.n) else None
         n = self.n
@@ -800,17 +809,26 @@ class PassCompiler:
         in_tile = set(tile)
         outside_cap = self.t - self.a if pool is not None else self.t
         n_outside = 0
+        rng = self._rng
         while len(tile) < self.t:
             _, missing = _scan(remaining, in_tile, self.lookahead)
             pick = None
+            cands: list = []
             for i in missing:
                 c = remaining[i].target
                 if pos[c] >= self.n_local:
                     continue                       # rank bit: cannot be mixed in this stage
                 if pool is not None and c not in pool and n_outside >= outside_cap:
                     continue
-                pick = c
-                break
+                if rng is None:
+                    pick = c
+                    break
+                if c not in cands:
+                    cands.append(c)
+                    if len(cands) >= self.explore_k:
+                        break
+            if rng is not None and cands:
+                pick = cands[0] if rng.random() >= self.explore_p else rng.choice(cands)
             if pick is None:
                 break
             if pool is not None and pick not in pool:

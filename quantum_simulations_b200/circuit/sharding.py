@@ -21,7 +21,7 @@ from __future__ import annotations
 
 from dataclasses import dataclass
 
-from quantum_simulations_b200.circuit.passes import PassCompiler, PassStep, Program, SwapStep
+from quantum_simulations_b200.circuit.passes import PassCompiler, PassStep, Program, SwapStep, _ops_fingerprint
 
 HBM_BW = 5.3e12          # achieved by a pass kernel, B/s (profiles/r02: 6.5 ms per 34.4 GB sweep)
 NVLINK_BW = 0.68e12      # achieved by the exchange kernel alone, B/s per direction (profiles/r02)
@@ -164,7 +164,7 @@ def _plan_single_one(ir_ops, n_qubits: int, dtype: str = "complex128", zero_init
 
 
 def plan(ir_ops, n_qubits: int, n_local: int, dtype: str = "complex128", zero_init: bool = True,
-         **compiler_kw) -> Program:
+         search: int | None = None, **compiler_kw) -> Program:
     """Compile `ir_ops` for shards of 2^n_local amplitudes.  With zero_init the initial
     placement is chosen among a few candidates by the cost model; the final layout is always
     the identity (logical qubit q on physical bit q)."""
@@ -197,7 +197,146 @@ def plan(ir_ops, n_qubits: int, n_local: int, dtype: str = "complex128", zero_in
     if best is None:
         return fuse_init(comp.compile(ir_ops))
     best.stats["estimated_s"] = best_t
+    trials = search_trials(n_local, g) if search is None else int(search)
+    if trials > 0:
+        key = (_ops_fingerprint(ir_ops), n_qubits, n_local, dtype, trials, repr(sorted(compiler_kw.items())))
+        hit = _SEARCHED.get(key)
+        if hit is None:
+            placements = [best.stats["init_pos"]] + [p for p in candidate_placements(n_qubits, g, direct=bool(compiler_kw.get("swap_anywhere")))
+                                                      if p != best.stats["init_pos"]]
+            hit = _search(ir_ops, n_qubits, n_local, dtype, best, placements, compiler_kw, trials, getattr(comp, "_lowered", None))
+            if len(_SEARCHED) >= 8:
+                _SEARCHED.pop(next(iter(_SEARCHED)))
+            _SEARCHED[key] = hit
+        seed, init, stats = hit
+        if seed is not None:                                # re-plan the winner: a Program holds ctypes arrays, not cached
+            c = PassCompiler(n_qubits, n_local, dtype, **dict(compiler_kw, explore_seed=seed))
+            c._lowered = getattr(comp, "_lowered", None)
+            found = c.compile(ir_ops, init_pos=init, home_pos=ident)
+            found.stats.update(stats, init_pos=init, park_reorder=c.park_reorder)
+            best = found
+        else:
+            best.stats.update(stats)
     return fuse_init(best)
+
+
+# ------------------------------------------------------------------ randomised restarts of the pass planner
+# The pass planner is greedy: the tile of a pass follows the pending targets in program order.  On the sharded
+# BASELINE circuits a few of several hundred seeded variations of that order (PassCompiler(explore_seed=...)) need
+# one pass less (36 qubits on 8 shards, 34 on 4: 9 -> 8 passes of 51 / 25 ms each; tools/plan_search.py), and a plan
+# takes ~17 ms.  plan() therefore searches when a pass is expensive: shards of >= 2^28 amplitudes, sharded runs
+# only (on one device no variation with fewer passes exists for these circuits, and the greedy plan is the one
+# measured on hardware).  Deterministic (fixed seeds): every rank finds the same plan.
+SEARCH_TRIALS = 768
+_SEARCHED: dict = {}
+
+
+def search_trials(n_local: int, g: int) -> int:
+    import os
+    e = os.environ.get("QSV_PLAN_SEARCH")
+    if e is not None and e.strip() != "":
+        return max(0, int(e))
+    return SEARCH_TRIALS if (g > 0 and n_local >= 28) else 0
+
+
+def shape_factor(step: PassStep, dtype: str) -> float:
+    """Time of the copy skeleton on this pass's tile shape relative to the streaming floor — the measured cost of
+    the access pattern (profiles/r02/tma_tensor_sweep_n30.jsonl): what counts is how many of the
+    four positions right above the 128-byte row are in the tile."""
+    w = 3 if dtype == "complex128" else 4
+    lb = set(step.desc.load_bits[: step.desc.n_tile])
+    low = [p for p in range(w, w + 4) if p in lb]
+    if w in lb and len(low) >= 2:
+        return 1.02
+    if len(low) >= 2:
+        return 1.17
+    if w in lb:
+        return 1.19
+    return 1.30                                             # 128-byte pieces, with paired loads (1.39 without)
+
+
+def pass_factor(step: PassStep, dtype: str) -> float:
+    """pass time / streaming floor: the slower of the access pattern and the shared-memory rounds
+    (3 rounds: 5.3-5.4 ms at 30 qubits whatever the op count, 4 rounds: 7.0-7.5; floor 5.24)"""
+    r = step.desc.n_rounds
+    rounds = 1.03 if r <= 3 else 1.35 + 0.2 * (r - 4)
+    return max(shape_factor(step, dtype), rounds)
+
+
+def estimate_seconds_v2(prog: Program, transitions: dict | None = None) -> float:
+    """Shape- and round-aware estimate used to compare PLANS OF THE SAME CIRCUIT (the search below): passes at
+    the measured copy peak times pass_factor, swaps at what their pipelined transition leaves exposed."""
+    amp = 16 if prog.dtype == "complex128" else 8
+    shard = amp * (1 << prog.n_local)
+    floor = 2 * shard / 6.555e12
+    if transitions is None:
+        transitions = plan_transitions(prog, min_chunk_pos=8 if prog.n_local >= 24 else 5)
+    t = 0.0
+    for k, s in enumerate(prog.steps):
+        if isinstance(s, PassStep):
+            t += floor * (pass_factor(s, prog.dtype) if not s.desc.zero_input else 0.45)
+        elif isinstance(s, SwapStep):
+            frac = 1.0 - 0.5 ** len(s.global_bits)
+            tr = transitions.get(k)
+            if tr is None:
+                t += frac * shard / NVLINK_BW
+            else:
+                t_x = frac * shard / XCHG_BW
+                hidden = (tr.a_count + tr.b_count) * (2.0 * shard / PASS_BW / 0.87) * (1.0 - 0.5 ** len(tr.chunk_bits))
+                t += max(0.0, t_x - hidden) + t_x * 0.5 ** len(tr.chunk_bits)
+    return t
+
+
+def _plan_key(prog: Program, transitions: dict) -> tuple:
+    swaps = [s for s in prog.steps if isinstance(s, SwapStep)]
+    covered = sum(tr.a_count + tr.b_count for tr in transitions.values())
+    chunk = min((len(tr.chunk_bits) for tr in transitions.values()), default=0)
+    return (prog.stats["passes"], len(swaps), sum(len(s.global_bits) for s in swaps), len(swaps) - len(transitions), covered, chunk)
+
+
+def _search(ir_ops, n_qubits: int, n_local: int, dtype: str, base: Program, placements: list, compiler_kw: dict,
+            trials: int, lowered):
+    """(seed or None, placement, stats): the best of `trials` seeded variations of the greedy plan `base` (seeds
+    outermost, the candidate initial placements inside: the budget counts plans), if it saves at least one pass
+    without more / larger / less overlapped swaps and its estimate is >= 4 % better; else (None, None, stats).
+    The search stops early once four acceptable plans have been seen."""
+    mcp = 8 if n_local >= 24 else 5
+    tr0 = plan_transitions(base, min_chunk_pos=mcp)
+    k0 = _plan_key(base, tr0)
+    t0 = estimate_seconds_v2(base, tr0)
+    ident = list(range(n_qubits))
+    best_seed, best_init, best_t, best_passes = None, None, t0, k0[0]
+    done = accepted = 0
+    # half of the budget varies the greedy plan on ITS placement (placements[0]), the rest goes round the others
+    order = [(seed, placements[0]) for seed in range(trials // 2 if len(placements) > 1 else trials)]
+    seed = 0
+    while len(order) < trials and len(placements) > 1:
+        order += [(seed, p_) for p_ in placements[1:]]
+        seed += 1
+    for seed, init in order[:trials]:
+        if accepted >= 4:
+            break
+        done += 1
+        c = PassCompiler(n_qubits, n_local, dtype, **dict(compiler_kw, explore_seed=seed))
+        c._lowered = lowered
+        try:
+            prog = c.compile(ir_ops, init_pos=init, home_pos=ident)
+        except (NotImplementedError, RuntimeError):
+            continue
+        if prog.stats["passes"] >= k0[0]:
+            continue
+        tr = plan_transitions(prog, min_chunk_pos=mcp)
+        k = _plan_key(prog, tr)
+        if k[1] > k0[1] or k[2] > k0[2] or k[3] > k0[3] or k[4] < min(k0[4], 2 * (k[1] - k[3])) or (k0[5] and k[5] < min(k0[5], 3)):
+            continue
+        t = estimate_seconds_v2(prog, tr)
+        if t <= 0.96 * t0:
+            accepted += 1
+            if t < best_t:
+                best_seed, best_init, best_t, best_passes = seed, init, t, prog.stats["passes"]
+    stats = {"search": {"plans_tried": done, "seed": best_seed, "passes_before": k0[0], "passes_after": best_passes,
+                        "estimate_v2_before_s": t0, "estimate_v2_after_s": best_t}}
+    return best_seed, best_init, stats
 
 
 # ------------------------------------------------------------------ pipelined stage transitions

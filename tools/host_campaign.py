@@ -33,6 +33,8 @@ def one(seed: int):
         kw["low_store_bits"] = [None, 1, 3][int(rng.integers(0, 3))]
     if rng.random() < 0.3:
         kw["park_reorder"] = True
+    if rng.random() < 0.4:                                  # a seeded variation of the greedy plan (sharding.plan's search)
+        kw.update(explore_seed=int(rng.integers(0, 1000)), explore_p=float(rng.choice([0.2, 0.4, 0.7])))
     prog = compile_circuit(cd, dtype=dtype, zero_init=bool(rng.random() < 0.5), **kw)
     psi = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
     psi /= np.linalg.norm(psi)
