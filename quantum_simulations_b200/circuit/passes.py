@@ -456,6 +456,40 @@ class Program:
         return [s for s in self.steps if isinstance(s, PassStep)]
 
 
+# ---------------------------------------------------------------- what a specialised kernel can hold
+# csrc/jit.cuh (kMaxOps, kMaxCoefs): a pass of 2^11 amplitudes is emitted as straight-line code only if it has at
+# most 256 micro-ops and reads at most 448 doubles from its kernel-parameter constant bank; a larger pass runs on
+# the interpreting kernels at 0.17-0.36 of the HBM roofline instead of ~0.8 (profiles/r01).  The planner therefore
+# keeps every such pass inside both limits (PassCompiler(fit_jit=True), the default): two specialised passes beat
+# one interpreted pass.
+JIT_MAX_OPS, JIT_MAX_COEFS = 256, 448
+
+
+def jit_coefs(step: "PassStep") -> int:
+    """Doubles the specialised kernel of `step` reads as C.c[i] — the count qsvjit::generate() makes (csrc/jit.cuh):
+    ROT 2 (sine and tangent of the three shears), a PREPHASE pre-op 2 more, PHASE 2, SCALE 1."""
+    n = 0
+    for k in range(step.desc.n_ops):
+        op = step.ops[k]
+        if op.kind == L.OP_ROT:
+            n += 2
+        elif op.kind == L.OP_PHASE:
+            n += 2
+        elif op.kind == L.OP_SCALE:
+            n += 1
+        if op.kind in (L.OP_HAD, L.OP_ROT) and (op.flags & L.OPF_PREPHASE):
+            n += 2
+    return n
+
+
+def fits_jit(step: "PassStep") -> bool:
+    """True if the pass is within the limits of a run-time specialised kernel (or is not a 2^11-amplitude pass at
+    all: those are executed by the simple interpreting kernel whatever their size)."""
+    if step.desc.n_tile != RING_TILE_BITS:
+        return True
+    return step.desc.n_ops <= JIT_MAX_OPS and jit_coefs(step) <= JIT_MAX_COEFS
+
+
 # -------------------------------------------------------------------- dependency scan
 def _scan(ops, mixable, lookahead: int | None = None):
     """(run, missing): ops that can execute, in order, when exactly the contents in `mixable`
@@ -494,12 +528,15 @@ class PassCompiler:
                  table_phases: bool = True, eager_flips: bool = True, low_store_round: bool = True,
                  low_store_bits: int | None = 2, park_reorder: bool = False,
                  warp_local_rounds: bool = False, explore_seed: int | None = None, explore_p: float = 0.4,
-                 explore_k: int = 3):
+                 explore_k: int = 3, fit_jit: bool = True):
         # explore_seed (circuit/sharding.plan's search): the tile of a pass normally follows the pending targets in
         # program order; with a seed, each slot is instead drawn (probability explore_p) among the first explore_k
         # distinct candidates.  Every such plan is as valid as the greedy one (the dependency scan is the same);
         # a few hundred of them sometimes contain one with a pass less.
         self.explore_seed, self.explore_p, self.explore_k = explore_seed, explore_p, explore_k
+        # True: no pass of 2^11 amplitudes exceeds what a specialised kernel holds (JIT_MAX_OPS micro-ops,
+        # JIT_MAX_COEFS coefficients): compile() re-plans with a smaller per-pass op budget until all of them fit
+        self.fit_jit = fit_jit
         self._rng = None
         self.n = n_qubits
         self.n_local = n_qubits if n_local is None else n_local
@@ -566,6 +603,31 @@ class PassCompiler:
     # ---- public -----------------------------------------------------------------------
     def compile(self, ir_ops, init_pos=None, init_flips=None, home_pos=None, zero_state: bool = False,
                 fuse_init: bool = False) -> Program:
+        """_compile_once, re-planned with a smaller per-pass op budget while a pass of 2^11 amplitudes exceeds what a
+        run-time specialised kernel holds (fit_jit; jit_coefs / fits_jit above).  The budgets tried are fixed, so
+        every rank of a sharded run arrives at the same plan; circuits whose passes fit (all BASELINE workloads) are
+        planned exactly once, as before."""
+        prog = self._compile_once(ir_ops, init_pos, init_flips, home_pos, zero_state, fuse_init)
+        if not self.fit_jit or all(fits_jit(s) for s in prog.passes):
+            return prog
+        keep = self.max_ops
+        try:
+            for cap in (224, 160, 112, 80, 56):
+                if cap >= keep:
+                    continue
+                self.max_ops = cap
+                cand = self._compile_once(ir_ops, init_pos, init_flips, home_pos, zero_state, fuse_init)
+                cand.stats["fit_jit_max_ops"] = cap
+                prog = cand
+                if all(fits_jit(s) for s in prog.passes):
+                    break
+        finally:
+            self.max_ops = keep
+        prog.stats["passes_beyond_jit"] = sum(not fits_jit(s) for s in prog.passes)
+        return prog
+
+    def _compile_once(self, ir_ops, init_pos=None, init_flips=None, home_pos=None, zero_state: bool = False,
+                      fuse_init: bool = False) -> Program:
         """init_pos[q]: physical position of IR qubit q before the first op (default q);
         home_pos[q]: position it must have after the last one (default: init_pos[q]).
         zero_state=True: the caller guarantees the state is |0...0> when the program starts (rank 0
