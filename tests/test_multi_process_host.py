@@ -107,3 +107,30 @@ def test_the_product_imports_no_tensor_library():
             if re.match(r"\s*(import|from)\s+(torch|triton|jax|cupy)\b", line):
                 bad.append(f"{f.relative_to(ROOT)}:{i}: {line.strip()}")
     assert not bad, bad
+
+
+def test_plumbing_codec_is_closed_and_round_trips():
+    """The collectives carry a closed set of types (runner/plumbing.py encode / decode): no pickle on the wire, so a
+    process that reaches rank 0's port cannot make it execute anything; malformed messages are refused."""
+    from quantum_simulations_b200.runner import plumbing as P
+    assert "pickle" not in Path(P.__file__).read_text().split('"""', 2)[2]          # (the docstring explains why)
+    vals = [None, True, False, 0, -1, 2 ** 70, -(2 ** 65), 1.5, float("inf"), "héllo", b"\x00\x01", [1, [2, (3, None)]], (), {},
+            {1: (2, b"x"), "a": [1.0]}, np.arange(6.0).reshape(2, 3), np.array(3.0), np.zeros((0,), dtype=np.int64),
+            np.arange(4) * 1j, np.float64(2.5), np.int64(7), np.bool_(True), np.uint64(2 ** 63)]
+    for v in vals:
+        w = P.decode(bytes(P.encode(v)))
+        if isinstance(v, np.ndarray):
+            assert w.dtype == v.dtype and w.shape == v.shape and np.array_equal(w, v)
+        else:
+            assert w == v and not isinstance(w, np.generic)
+    both = P.decode(bytes(P.encode((np.arange(3), np.arange(3) * 1j))))
+    assert isinstance(both, tuple) and np.array_equal(both[1], np.arange(3) * 1j)
+    for bad in (b"", b"Z", b"I\x05\x00\x00\x00ab", b"L" + b"\xff" * 8, b"NN", b"S\x02" + b"\x00" * 7 + b"a",
+                b"A\x03\x01<f8" + b"\x02" + b"\x00" * 7 + b"\x08" + b"\x00" * 7 + b"\x00" * 8,        # shape (2,) but 8 bytes
+                b"A\x02\x00|O" + b"\x08" + b"\x00" * 7 + b"\x00" * 8,                                  # object dtype
+                b"A\x03\x00xyz" + b"\x00" * 8):                                                        # no such dtype
+        with pytest.raises(ValueError):
+            P.decode(bad)
+    for refused in (object(), np.array([object()]), {object(): 1}, lambda: 0):
+        with pytest.raises(TypeError):
+            P.encode(refused)
