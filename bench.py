@@ -625,6 +625,28 @@ def bench_multi(args) -> None:
     if args.no_low_store_round:
         ckw["low_store_round"] = False
     tol = 1e-9 if dtype == "complex128" else 1e-4
+
+    # ---- parity FIRST: the sharded path (stage plan, pipelined swaps, the data-movement switches of the pass kernels)
+    # against the single-GPU run, before anything is timed.  If it fails under the default switches, the paired loads /
+    # tile blocks of the pass kernels are switched off — the setting every multi-GPU line of profiles/r02 was measured
+    # with — checked again, and the run is timed under that; the line says so (config.preflight).
+    parity, preflight = None, None
+    if not args.no_parity:
+        from quantum_simulations_b200.runner.multi_gpu import dist_env
+        from quantum_simulations_b200.runner.plumbing import init_plumbing
+        rank_, local_rank_, _ = dist_env()
+        dist_ = init_plumbing()
+        parity = _cross_g_parity(args, world, rank_, local_rank_, dist_, min(30, n))
+        ok = dist_.broadcast_object(None if parity is None else bool(parity["ok"]), src=0)
+        if not ok and "QSV_JIT_PAIR" not in os.environ and "QSV_JIT_TILE_BLOCK" not in os.environ:
+            os.environ["QSV_JIT_PAIR"] = "0"
+            os.environ["QSV_JIT_TILE_BLOCK"] = "0"
+            L.load().qsv_release_cached()
+            first = parity
+            parity = _cross_g_parity(args, world, rank_, local_rank_, dist_, min(30, n))
+            preflight = {"what": "FALLBACK: the parity check failed under the default pass-kernel switches; timed with "
+                                 "QSV_JIT_PAIR=0 QSV_JIT_TILE_BLOCK=0", "first_check": first}
+        L.load().qsv_release_cached()
     sim = ShardedSimulator(n, dtype, fused_exchange=True) if args.fused_exchange else ShardedSimulator(n, dtype)
     rank, dist = sim.rank, sim.dist
     updates_per_step = len(cd["gates"]) * (1 << n)
@@ -668,7 +690,6 @@ def bench_multi(args) -> None:
         weak = {"n_qubits": 30 + g, "amps_per_gpu_log2": 30, "gates": winfo["gates"], "ms_per_step": w_ms,
                 "value": winfo["gates"] * (1 << (30 + g)) / (w_ms * 1e-3), "unit": UNIT, "step_sequence": w["sequence"],
                 "what": "weak-scaling series: 2^30 amplitudes per GPU, same circuit family"}
-    parity = None if args.no_parity else _cross_g_parity(args, world, rank, sim.local_rank, dist, min(30, n))
     one = _one_gpu_rate(args, sim.local_rank) if (rank == 0 and not args.no_parity) else None
 
     if rank == 0:
@@ -718,7 +739,7 @@ def bench_multi(args) -> None:
                        "step_sequence": run["sequence"],
                        "l2_hygiene": f"shard {(1 << n_loc) * amp_bytes / 2**30:.0f} GiB >> 126 MB L2",
                        "host_compile_s": run["compile_s"], "plan": run["plan_note"],
-                       "plan_search": prog.stats.get("search"),
+                       "plan_search": prog.stats.get("search"), "preflight": preflight,
                        "scaling_note": "amplitudes per GPU: 2^30 at N=1 (configs[2]), 2^33 / 2^32 / 2^33 at N=2 / 4 / 8 "
                                        "(configs[3], [4]); the weak series with 2^30 per GPU is under weak_series",
                        "timing": "CUDA events on each rank's stream, max over ranks"},

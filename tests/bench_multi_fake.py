@@ -2,6 +2,7 @@
 (test infrastructure), the process group is real gloo.  Checks that the JSON line is assembled."""
 from __future__ import annotations
 
+import os
 import sys
 import time
 from pathlib import Path
@@ -42,6 +43,7 @@ class FakeState:
 
 class FakeShard:
     peer_error = "emulated"
+    pipelined_swaps = 0
 
     def __init__(self, emu, state):
         self.emu, self.state = emu, state
@@ -84,7 +86,10 @@ class FakeSim:
         if sink is not None:
             sink(self.shard.emu.psi, 0)
             return self.shard.emu.psi.nbytes
-        return self.shard.state.download(out)
+        got = self.shard.state.download(out)
+        if os.environ.get("FAKE_BREAK_PAIRED_LOADS") == "1" and os.environ.get("QSV_JIT_PAIR") != "0":
+            got[3] += 1e-3               # stands for a data-movement switch that misbehaves on the sharded path
+        return got
 
     def close(self): pass
 
@@ -98,8 +103,20 @@ class FakePinned:
 MG.ShardedSimulator = FakeSim
 PIN.PinnedBuffer = FakePinned
 
+
+def _fake_single_gpu_simulate(cd, dtype="complex128", device=0, **kw):
+    """stands for kernel.cuda_dense.simulate on rank 0's GPU in the cross-G parity check (test infrastructure)"""
+    from oracle import ref_dense as O
+    return O.simulate(cd).astype(dtype)
+
+
+import quantum_simulations_b200.kernel.cuda_dense as CD         # noqa: E402
+CD.simulate = _fake_single_gpu_simulate
+
 if __name__ == "__main__":
     import bench
     sys.argv = ["bench.py", "--gpus", sys.argv[1], "--qubits", "12", "--steps", "2", "--warmup", "3",
-                "--tile-bits", "6", "--low-bits", "2", "--no-weak", "--no-parity"]
+                "--tile-bits", "6", "--low-bits", "2", "--no-weak"] + (["--no-parity"] if len(sys.argv) < 3 else [])
+    if len(sys.argv) >= 3:               # "parity": the parity-first path; the 1-GPU rate needs a device, so it is stubbed
+        bench._one_gpu_rate = lambda *a, **k: {"n_qubits": 12, "ms_per_step": 1.0, "value": 1.0, "unit": bench.UNIT, "steps": 1, "warmup": 0}
     bench.main()

@@ -67,6 +67,37 @@ def test_bench_multi_control_flow_on_cpu(tmp_path):
     assert outs[1][0].strip() == ""                                  # only rank 0 prints
 
 
+@pytest.mark.parametrize("broken", [False, True])
+def test_bench_multi_checks_parity_before_it_times(broken):
+    """bench.py --gpus 2: the cross-G parity check runs BEFORE the timed region; when it fails under the default
+    data-movement switches of the pass kernels the run falls back to QSV_JIT_PAIR=0 / QSV_JIT_TILE_BLOCK=0 on every
+    rank, checks again and says so in config.preflight (emulator fakes, real plumbing)."""
+    import json
+    world = 2
+    port = 30400 + (os.getpid() % 150) + (37 if broken else 0)
+    procs = []
+    for rank in range(world):
+        env = dict(os.environ, RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world),
+                   MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1")
+        env.pop("QSV_JIT_PAIR", None)
+        env.pop("QSV_JIT_TILE_BLOCK", None)
+        if broken:
+            env["FAKE_BREAK_PAIRED_LOADS"] = "1"
+        procs.append(subprocess.Popen([sys.executable, str(ROOT / "tests" / "bench_multi_fake.py"), str(world), "parity"],
+                                      env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=300) for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(o[1][-2000:] for o in outs)
+    line = json.loads(outs[0][0].strip().splitlines()[-1])
+    assert line["parity"]["ok"] is True and line["parity"]["all_indices_covered"] is True
+    assert line["parallel_efficiency"]["one_gpu"]["n_qubits"] == 12
+    if broken:
+        pre = line["config"]["preflight"]
+        assert pre["what"].startswith("FALLBACK") and pre["first_check"]["ok"] is False
+        assert pre["first_check"]["max_abs_diff"] > 1e-4
+    else:
+        assert line["config"]["preflight"] is None
+
+
 def test_host_plumbing_collectives(tmp_path):
     """runner/plumbing.py over three real processes: gather, broadcast, AND, barrier, rank-ordered reductions."""
     world = 3
