@@ -402,14 +402,14 @@ def bench_single(args) -> None:
     # ---- the per-gate ABI (a1/a2 operator face) and the observables against the same roofline ----
     per_gate = None
     if not args.no_others and n >= 20:
-        try:
-            import io as _io
-            from quantum_simulations_b200.bench.kernel import bench_kernel
-            rows = bench_kernel(n, dtype, reps=3, device=args.device, out=_io.StringIO(), quick=True)
+        try:                                         # in a child process: a secondary table never costs the headline line
+            r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--per-gate-child", "--qubits", str(n), "--dtype", dtype,
+                                "--device", str(args.device)], capture_output=True, text=True, timeout=240)
+            rows = json.loads(r.stdout.strip().splitlines()[-1])
             per_gate = {"what": "quantum_simulations_b200.bench.kernel (quick): one launch per gate, CUDA events, algorithmic "
                                 "bytes (2 x state per gate, half for a controlled gate, 1 x for an observable) / time / measured HBM peak",
-                        "rows": [{k: r[k] for k in ("kernel", "what", "ms", "gbs", "frac")} for r in rows]}
-        except Exception as e:                       # secondary table: never costs the headline line
+                        "rows": [{k: r_[k] for k in ("kernel", "what", "ms", "gbs", "frac")} for r_ in rows]}
+        except Exception as e:
             per_gate = {"error": f"{type(e).__name__}: {e}"[:200]}
 
     # ---- end to end through the public API, result in pinned HOST memory ----
@@ -801,6 +801,7 @@ def main() -> None:
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-zero-support", action="store_true")
     ap.add_argument("--e2e-cold-child", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--per-gate-child", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-others", action="store_true", help="N = 1: skip the short runs of the other BASELINE workloads")
     ap.add_argument("--no-low-store-round", action="store_true",
                     help="experiment: no idle round before stores whose registers hold a low (row) position")
@@ -820,6 +821,12 @@ def main() -> None:
     WORKLOAD = args.workload
     if args.impl == "reference":
         reference_arm(args)
+        return
+    if args.per_gate_child:
+        import io as _io
+        from quantum_simulations_b200.bench.kernel import bench_kernel
+        rows_ = bench_kernel(args.qubits or 30, args.dtype, reps=3, device=args.device, out=_io.StringIO(), quick=True)
+        print(json.dumps(rows_), flush=True)
         return
     if args.e2e_cold_child:
         from quantum_simulations_b200.kernel.cuda_dense import simulate
