@@ -158,6 +158,16 @@ def _cpu_c_rate(cd: dict) -> tuple[float, float, int]:
     return len(cd["gates"]) * (1 << cd["number_of_qubits"]) / dt, dt, CO.n_threads()
 
 
+def _blas_threads() -> int:
+    """threads NumPy's BLAS uses here: the reference's 2-qubit gates are a (4 x 4) @ (4 x M) product per gate
+    (ref_dense.py:41), which OpenBLAS runs on its thread pool; everything else is single-threaded NumPy"""
+    try:
+        from threadpoolctl import threadpool_info
+        return max([int(i.get("num_threads", 1)) for i in threadpool_info() if i.get("user_api") == "blas"] or [1])
+    except Exception:
+        return 1
+
+
 _WHAT = {"reference": "wenbo_engine.kernel.ref_dense.simulate of the unmodified reference (oracle/_ref)",
          "port": "oracle/ref_dense.py simulate(indexed=True) = the reference's NumPy gather/scatter formulation restated"}
 
@@ -165,9 +175,10 @@ _WHAT = {"reference": "wenbo_engine.kernel.ref_dense.simulate of the unmodified 
 def cpu_baseline(n_sample: int = 20) -> dict:
     cd, _ = workload(n_sample)
     rate, dt, kind = _cpu_rate(cd)
-    out = {"value": rate, "unit": UNIT, "cores": 1, "kind": kind,
+    out = {"value": rate, "unit": UNIT, "cores": _blas_threads(), "kind": kind,
            "sample": f"same circuit family at n={n_sample} (random_1q_cz depth 20, {len(cd['gates'])} gates), "
-                     f"{_WHAT[kind]}, complex128, single-threaded NumPy like the reference, {dt:.1f} s",
+                     f"{_WHAT[kind]}, complex128; cores = the BLAS threads its 2-qubit (4 x 4) @ (4 x M) products may use, "
+                     f"the gather / scatter and 1-qubit arithmetic are single-threaded NumPy; {dt:.1f} s",
            "host_cores_available": os.cpu_count()}
     try:
         cdc, _ = workload(min(n_sample + 4, 24))
@@ -201,12 +212,13 @@ def reference_arm(args) -> None:
     dt = time.perf_counter() - t0
     value = args.steps * len(cd["gates"]) * (1 << n_sample) / dt
     sample = (f"bounded sample: same circuit family at n={n_sample} ({len(cd['gates'])} gates, complex128), "
-              f"{_WHAT[kind]}; NumPy elementwise kernels are single-threaded")
+              f"{_WHAT[kind]}; cores = the BLAS threads its 2-qubit (4 x 4) @ (4 x M) products may use, the gather / scatter "
+              f"and 1-qubit arithmetic are single-threaded NumPy")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "complex128",
             "data": "synthetic", "config": {**info, "note": "CPU arm runs a bounded sample of the GPU arm's workload"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": _blas_threads(), "kind": kind, "sample": sample,
                              "host_cores_available": os.cpu_count()},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
