@@ -204,13 +204,13 @@ def plan(ir_ops, n_qubits: int, n_local: int, dtype: str = "complex128", zero_in
         if hit is None:
             placements = [best.stats["init_pos"]] + [p for p in candidate_placements(n_qubits, g, direct=bool(compiler_kw.get("swap_anywhere")))
                                                       if p != best.stats["init_pos"]]
-            hit = _search(ir_ops, n_qubits, n_local, dtype, best, placements, compiler_kw, trials, getattr(comp, "_lowered", None))
+            hit = _search_staged(ir_ops, n_qubits, n_local, dtype, best, placements, compiler_kw, trials, getattr(comp, "_lowered", None))
             if len(_SEARCHED) >= 8:
                 _SEARCHED.pop(next(iter(_SEARCHED)))
             _SEARCHED[key] = hit
         seed, init, stats = hit
         if seed is not None:                                # re-plan the winner: a Program holds ctypes arrays, not cached
-            c = PassCompiler(n_qubits, n_local, dtype, **dict(compiler_kw, explore_seed=seed))
+            c = PassCompiler(n_qubits, n_local, dtype, **dict(compiler_kw, explore_seed=seed, **stats["search"].get("explore", {})))
             c._lowered = getattr(comp, "_lowered", None)
             found = c.compile(ir_ops, init_pos=init, home_pos=ident)
             found.stats.update(stats, init_pos=init, park_reorder=c.park_reorder)
@@ -295,7 +295,7 @@ def _plan_key(prog: Program, transitions: dict) -> tuple:
 
 
 def _search(ir_ops, n_qubits: int, n_local: int, dtype: str, base: Program, placements: list, compiler_kw: dict,
-            trials: int, lowered):
+            trials: int, lowered, explore: dict | None = None):
     """(seed or None, placement, stats): the best of `trials` seeded variations of the greedy plan `base` (seeds
     outermost, the candidate initial placements inside: the budget counts plans), if it saves at least one pass
     without more / larger / less overlapped swaps and its estimate is >= 4 % better; else (None, None, stats).
@@ -317,7 +317,7 @@ def _search(ir_ops, n_qubits: int, n_local: int, dtype: str, base: Program, plac
         if accepted >= 4:
             break
         done += 1
-        c = PassCompiler(n_qubits, n_local, dtype, **dict(compiler_kw, explore_seed=seed))
+        c = PassCompiler(n_qubits, n_local, dtype, **dict(compiler_kw, explore_seed=seed, **(explore or {})))
         c._lowered = lowered
         try:
             prog = c.compile(ir_ops, init_pos=init, home_pos=ident)
@@ -335,8 +335,28 @@ def _search(ir_ops, n_qubits: int, n_local: int, dtype: str, base: Program, plac
             if t < best_t:
                 best_seed, best_init, best_t, best_passes = seed, init, t, prog.stats["passes"]
     stats = {"search": {"plans_tried": done, "seed": best_seed, "passes_before": k0[0], "passes_after": best_passes,
-                        "estimate_v2_before_s": t0, "estimate_v2_after_s": best_t}}
+                        "estimate_v2_before_s": t0, "estimate_v2_after_s": best_t, "explore": explore or {}}}
     return best_seed, best_init, stats
+
+
+# The search runs in stages: the planner's default exploration first (each tile slot drawn among the first 3 candidates),
+# and only if that finds nothing acceptable a wider one (first 5 candidates).  34 qubits on 2 shards: no acceptable plan
+# in the first stage, in the second seed 10 needs 8 passes instead of 9 with the same single 1-bit swap and the same
+# pipelined transition (estimate 471 -> 435 ms; tools/plan_search.py).  Fixed order: every rank finds the same plan.
+SEARCH_STAGES = ({}, {"explore_p": 0.4, "explore_k": 5})
+
+
+def _search_staged(ir_ops, n_qubits, n_local, dtype, base, placements, compiler_kw, trials, lowered):
+    tried = 0
+    out = (None, None, {"search": {"plans_tried": 0, "seed": None}})
+    for stage in SEARCH_STAGES:
+        seed, init, stats = _search(ir_ops, n_qubits, n_local, dtype, base, placements, compiler_kw, trials, lowered, dict(stage))
+        tried += stats["search"]["plans_tried"]
+        stats["search"]["plans_tried"] = tried
+        out = (seed, init, stats)
+        if seed is not None:
+            break
+    return out
 
 
 # ------------------------------------------------------------------ pipelined stage transitions

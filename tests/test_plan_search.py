@@ -71,7 +71,8 @@ def test_search_in_plan_keeps_or_improves_and_stays_correct(n, g):
     assert "search" not in greedy.stats
     found = sharding.plan(ops, n, n - g, search=96, **kw)
     info = found.stats["search"]
-    assert info["plans_tried"] <= 96 and info["passes_before"] == greedy.stats["passes"]
+    assert info["plans_tried"] <= 96 * len(sharding.SEARCH_STAGES) and info["passes_before"] == greedy.stats["passes"]
+    assert info["explore"] in [dict(st) for st in sharding.SEARCH_STAGES]
     if info["seed"] is None:
         assert signature(found) == signature(greedy)
     else:
@@ -106,3 +107,39 @@ def test_shape_and_round_factors_follow_the_measurements():
     assert four.desc.n_rounds == 4 and sharding.pass_factor(four, "complex128") == 1.35
     est = sharding.estimate_seconds_v2(prog)
     assert 0.036 < est < 0.044                              # measured: 39.9 ms
+
+
+def test_second_stage_explores_wider_only_when_the_first_finds_nothing(monkeypatch):
+    """The staged search (sharding.SEARCH_STAGES): stage 2 (first five candidates per slot) runs only if stage 1 found no
+    acceptable plan; the winner is re-planned with the exploration parameters of ITS stage and equals the oracle."""
+    calls = []
+    real = sharding._search
+
+    def spy(*a, **k):
+        out = real(*a, **k)
+        calls.append((dict(a[9]) if len(a) > 9 else dict(k.get("explore") or {}), out[0]))
+        return out
+
+    monkeypatch.setattr(sharding, "_search", spy)
+    n, g = 13, 1
+    cd = W.random_1q_cz(n, 20, 1234)
+    kw = dict(tile_bits=7, low_bits=2, swap_anywhere=True, rank_flips=True)
+    sharding._SEARCHED.clear()
+    found = sharding.plan(ir_ops(cd), n, n - g, search=48, **kw)
+    assert calls and calls[0][0] == {}
+    if calls[0][1] is not None:
+        assert len(calls) == 1                                   # stage 1 found a plan: stage 2 never ran
+    else:
+        assert len(calls) == 2 and calls[1][0] == {"explore_p": 0.4, "explore_k": 5}
+    assert found.stats["search"]["explore"] == calls[-1][0]
+    assert np.abs(run_sharded(found, n, g) - O.simulate(validate_circuit_dict(cd))).max() <= 1e-12
+    # a forced second-stage winner is re-planned with the wider exploration
+    sharding._SEARCHED.clear()
+    monkeypatch.setattr(sharding, "SEARCH_STAGES", ({"explore_p": 0.4, "explore_k": 5},))
+    wide = sharding.plan(ir_ops(cd), n, n - g, search=96, **kw)
+    assert wide.stats["search"]["explore"] == {"explore_p": 0.4, "explore_k": 5}
+    assert np.abs(run_sharded(wide, n, g) - O.simulate(validate_circuit_dict(cd))).max() <= 1e-12
+    if wide.stats["search"]["seed"] is not None:
+        again = PassCompiler(n, n - g, explore_seed=wide.stats["search"]["seed"], explore_p=0.4, explore_k=5, **kw).compile(
+            ir_ops(cd), init_pos=wide.stats["init_pos"], home_pos=list(range(n)))
+        assert signature(again)[1:] == signature(wide)[1:] or signature(again) == signature(wide)
