@@ -35,6 +35,8 @@ def one(seed: int):
         kw["park_reorder"] = True
     if rng.random() < 0.4:                                  # a seeded variation of the greedy plan (sharding.plan's search)
         kw.update(explore_seed=int(rng.integers(0, 1000)), explore_p=float(rng.choice([0.2, 0.4, 0.7])))
+        if seed >= 5000:                                    # (drawn for later seeds only: earlier seeds keep their cases)
+            kw["explore_k"] = int(rng.choice([3, 5]))       # the second stage of sharding.plan's search
     prog = compile_circuit(cd, dtype=dtype, zero_init=bool(rng.random() < 0.5), **kw)
     psi = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
     psi /= np.linalg.norm(psi)
