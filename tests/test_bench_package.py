@@ -144,6 +144,25 @@ def test_hyperparam_sweep_table(monkeypatch):
     assert "HYPERPARAMETER SWEEP: QFT-6" in out.getvalue() and "best:" in out.getvalue()
 
 
+def test_matmul_vs_io_table():
+    """the reference's side-by-side table (bench/matmul_vs_io.py:84-141) with the device tier stubbed: files tier real"""
+    from quantum_simulations_b200.bench import matmul_vs_io as MV
+    seen = []
+
+    def fake_tiers(cs, dtype, device):
+        seen.append(cs)
+        return {"1q_GBs": 4000.0, "2q_GBs": 6000.0, "ms_per_gate": 0.01, "pcie_GBs": 50.0, "pcie_ms_per_chunk": 1.0}
+
+    out = io.StringIO()
+    rows = MV.bench_compare([1 << 10, 1 << 12], out=out, tiers=fake_tiers)
+    assert seen == [1 << 10, 1 << 12] and len(rows) == 2
+    assert all(r["kernel_over_pcie"] == 100.0 and r["gates_to_match_pcie"] == 100 and r["files_MBs"] > 0 for r in rows)
+    assert "I/O bound (fuse!)" in out.getvalue() and "gates to match" in out.getvalue()
+    assert [MV.verdict(x) for x in (11, 5, 1)] == ["I/O bound (fuse!)", "I/O leaning", "balanced"]
+    with pytest.raises(ValueError):
+        MV.device_tiers(3000)
+
+
 # ------------------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
 @pytest.mark.parametrize("family", MQ.NATIVE_FAMILIES)

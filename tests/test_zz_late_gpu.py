@@ -31,3 +31,10 @@ def test_deep_circuit_runs_on_specialised_kernels_only():
     assert all(fits_jit(s) for s in prog.passes) and prog.stats.get("fit_jit_max_ops")
     got = simulate(cd)
     assert np.abs(got - O.simulate(cd)).max() <= 1e-11
+
+
+@pytest.mark.gpu
+def test_matmul_vs_io_on_the_device():
+    from quantum_simulations_b200.bench import matmul_vs_io as MV
+    rows = MV.bench_compare([1 << 16, 1 << 20], out=io.StringIO())
+    assert len(rows) == 2 and all(r["1q_GBs"] > 0 and r["2q_GBs"] > 0 and r["pcie_GBs"] > 0 and r["files_MBs"] > 0 for r in rows)
