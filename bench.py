@@ -649,15 +649,23 @@ def bench_multi(args) -> None:
         rank_, local_rank_, _ = dist_env()
         dist_ = init_plumbing()
         parity = _cross_g_parity(args, world, rank_, local_rank_, dist_, min(30, n))
-        ok = dist_.broadcast_object(None if parity is None else bool(parity["ok"]), src=0)
-        if not ok and "QSV_JIT_PAIR" not in os.environ and "QSV_JIT_TILE_BLOCK" not in os.environ:
-            os.environ["QSV_JIT_PAIR"] = "0"
-            os.environ["QSV_JIT_TILE_BLOCK"] = "0"
+        # what this path runs by default without having met the hardware yet, most recent first; each level is
+        # switched off (on every rank) only if the check before it failed and the user has not set it explicitly
+        fallbacks = (({"QSV_JIT_PAIR": "0", "QSV_JIT_TILE_BLOCK": "0"}, "paired loads / tile blocks of the pass kernels off"),
+                     ({"QSV_PLAN_SEARCH": "0"}, "greedy stage plan (no seeded search)"))
+        failed = []
+        for env_, what_ in fallbacks:
+            ok = dist_.broadcast_object(None if parity is None else bool(parity["ok"]), src=0)
+            if ok or any(k in os.environ for k in env_):
+                break
+            os.environ.update(env_)
             L.load().qsv_release_cached()
-            first = parity
+            failed.append({"switched_off_after": what_, "env": env_, "failed_check": parity})
             parity = _cross_g_parity(args, world, rank_, local_rank_, dist_, min(30, n))
-            preflight = {"what": "FALLBACK: the parity check failed under the default pass-kernel switches; timed with "
-                                 "QSV_JIT_PAIR=0 QSV_JIT_TILE_BLOCK=0", "first_check": first}
+        if failed:
+            preflight = {"what": "FALLBACK: the parity check failed under the default switches; the run is timed with "
+                                 + " ".join(f"{k}={v}" for f_ in failed for k, v in f_["env"].items()),
+                         "first_check": failed[0]["failed_check"], "levels": failed}
         L.load().qsv_release_cached()
     sim = ShardedSimulator(n, dtype, fused_exchange=True) if args.fused_exchange else ShardedSimulator(n, dtype)
     rank, dist = sim.rank, sim.dist

@@ -89,6 +89,8 @@ class FakeSim:
         got = self.shard.state.download(out)
         if os.environ.get("FAKE_BREAK_PAIRED_LOADS") == "1" and os.environ.get("QSV_JIT_PAIR") != "0":
             got[3] += 1e-3               # stands for a data-movement switch that misbehaves on the sharded path
+        if os.environ.get("FAKE_BREAK_PLAN_SEARCH") == "1" and os.environ.get("QSV_PLAN_SEARCH") != "0":
+            got[5] += 1e-3               # stands for a searched stage plan that misbehaves
         return got
 
     def close(self): pass

@@ -67,22 +67,22 @@ def test_bench_multi_control_flow_on_cpu(tmp_path):
     assert outs[1][0].strip() == ""                                  # only rank 0 prints
 
 
-@pytest.mark.parametrize("broken", [False, True])
+@pytest.mark.parametrize("broken", [None, "pairs", "search"])
 def test_bench_multi_checks_parity_before_it_times(broken):
     """bench.py --gpus 2: the cross-G parity check runs BEFORE the timed region; when it fails under the default
     data-movement switches of the pass kernels the run falls back to QSV_JIT_PAIR=0 / QSV_JIT_TILE_BLOCK=0 on every
     rank, checks again and says so in config.preflight (emulator fakes, real plumbing)."""
     import json
     world = 2
-    port = 30400 + (os.getpid() % 150) + (37 if broken else 0)
+    port = 30400 + (os.getpid() % 150) + {None: 0, "pairs": 37, "search": 74}[broken]
     procs = []
     for rank in range(world):
         env = dict(os.environ, RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world),
                    MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1")
-        env.pop("QSV_JIT_PAIR", None)
-        env.pop("QSV_JIT_TILE_BLOCK", None)
+        for k in ("QSV_JIT_PAIR", "QSV_JIT_TILE_BLOCK", "QSV_PLAN_SEARCH"):
+            env.pop(k, None)
         if broken:
-            env["FAKE_BREAK_PAIRED_LOADS"] = "1"
+            env["FAKE_BREAK_PAIRED_LOADS" if broken == "pairs" else "FAKE_BREAK_PLAN_SEARCH"] = "1"
         procs.append(subprocess.Popen([sys.executable, str(ROOT / "tests" / "bench_multi_fake.py"), str(world), "parity"],
                                       env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
     outs = [p.communicate(timeout=300) for p in procs]
@@ -94,6 +94,9 @@ def test_bench_multi_checks_parity_before_it_times(broken):
         pre = line["config"]["preflight"]
         assert pre["what"].startswith("FALLBACK") and pre["first_check"]["ok"] is False
         assert pre["first_check"]["max_abs_diff"] > 1e-4
+        # the most recent default is switched off first; the planner's search only if that did not help
+        assert len(pre["levels"]) == (1 if broken == "pairs" else 2)
+        assert ("QSV_PLAN_SEARCH=0" in pre["what"]) == (broken == "search") and "QSV_JIT_PAIR=0" in pre["what"]
     else:
         assert line["config"]["preflight"] is None
 
