@@ -35,10 +35,13 @@ def tsan_available() -> bool:
 
 
 def race_check(step, n_local: int, dtype="complex128", grid: int = 1, tile_block: int = 0, tile_range=None,
-               timeout: int = 600, mutate=None, stop_at_first: bool = False) -> tuple[int, str]:
+               timeout: int = 600, mutate=None, stop_at_first: bool = False, sanitizer: str = "thread") -> tuple[int, str]:
     """(number of ThreadSanitizer reports, their text) for one launch of the pass's specialised kernel over a random
     state of 2^n_local amplitudes.  mutate(source) -> source: the positive controls of the test suite break the
-    kernel's synchronisation on purpose and must be reported."""
+    kernel's synchronisation on purpose and must be reported.
+    sanitizer="address,undefined": the same program under AddressSanitizer + UBSan instead — the host-model counterpart of
+    ``compute-sanitizer --tool memcheck``: the state is one heap block of exactly 2^n_local amplitudes and the ring is one
+    heap block, so a global index outside the shard or a slot index outside the ring is reported."""
     import re
     src = kernel_source(step, dtype)
     if mutate is not None:
@@ -46,7 +49,7 @@ def race_check(step, n_local: int, dtype="complex128", grid: int = 1, tile_block
     src = "\n".join(ln for ln in src.splitlines() if "asm volatile" not in ln)
     call = "k_pass_jit((JV *)state, (const double2 *)tables, rank_bits, tile_begin, n_tiles, C, F)"
     full = src + f"\n#define JIT_HOST_CALL {call}\n#include \"jit_tsan_main.inc\"\n"
-    key = hashlib.sha1((full + (HOST_INC / "jit_prelude.cuh").read_text() + (HOST_INC / "jit_tsan_main.inc").read_text()
+    key = hashlib.sha1((sanitizer + full + (HOST_INC / "jit_prelude.cuh").read_text() + (HOST_INC / "jit_tsan_main.inc").read_text()
                         + (HOST_INC / "jit_host_main.inc").read_text() + (CSRC / "pass_ops.cuh").read_text()).encode()).hexdigest()[:20]
     _BUILD.mkdir(exist_ok=True)
     exe = _BUILD / f"k_{key}"
@@ -54,7 +57,7 @@ def race_check(step, n_local: int, dtype="complex128", grid: int = 1, tile_block
         cpp = _BUILD / f"k_{key}.{os.getpid()}.cpp"
         tmp = _BUILD / f"k_{key}.{os.getpid()}"
         cpp.write_text(full)
-        r = subprocess.run(["g++", "-fsanitize=thread", "-O1", "-g", "-std=c++17", "-pthread", "-Wno-unknown-pragmas", "-Wno-attributes",
+        r = subprocess.run(["g++", f"-fsanitize={sanitizer}", "-fno-sanitize-recover=undefined", "-O1", "-g", "-std=c++17", "-pthread", "-Wno-unknown-pragmas", "-Wno-attributes",
                             f"-I{HOST_INC}", f"-I{CSRC}", "-o", str(tmp), str(cpp)], capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("g++ -fsanitize=thread failed on the generated kernel:\n" + r.stderr[-4000:])
@@ -69,10 +72,11 @@ def race_check(step, n_local: int, dtype="complex128", grid: int = 1, tile_block
     blob.write_bytes(struct.pack("<8Q", n_local, grid, nt, tile_block, tb, te, len(coefs), len(tables)) + coefs.tobytes() + tables.tobytes())
     try:
         r = subprocess.run([str(exe), str(blob)], capture_output=True, text=True, timeout=timeout,
-                           env=dict(os.environ, TSAN_OPTIONS=f"halt_on_error={int(stop_at_first)} exitcode=0 report_signal_unsafe=0"))
+                           env=dict(os.environ, TSAN_OPTIONS=f"halt_on_error={int(stop_at_first)} exitcode=0 report_signal_unsafe=0",
+                                    ASAN_OPTIONS="detect_leaks=0 exitcode=0"))
     finally:
         blob.unlink(missing_ok=True)
-    reports = r.stderr.count("WARNING: ThreadSanitizer")
+    reports = r.stderr.count("WARNING: ThreadSanitizer") + r.stderr.count("ERROR: AddressSanitizer") + r.stderr.count("runtime error:")
     if reports == 0 and "done rc=0" not in r.stdout:
         raise RuntimeError(f"race-check run failed (exit {r.returncode}):\n{r.stdout[-500:]}\n{r.stderr[-3000:]}")
     return reports, r.stderr[-6000:]

@@ -107,3 +107,21 @@ def test_tiles_are_closed_address_sets():
             assert s.desc.store_flip & ~inside == 0                # a store flip only permutes addresses INSIDE the tile
             seen += 1
     assert seen > 25
+
+
+def test_kernels_stay_inside_the_shard_and_the_ring(monkeypatch, prog):
+    """The same host build under AddressSanitizer + UBSan (the host-model counterpart of compute-sanitizer memcheck): the
+    state is ONE heap block of exactly 2^n amplitudes, so a global index outside the shard is reported — none for the
+    default kernels, paired loads with tile blocks and an odd chunk-sized launch, complex64; a launch that claims more tiles
+    than the shard holds is the positive control."""
+    san = "address,undefined"
+    for step in prog.passes[:3]:
+        count, text = race_check(step, N, grid=2, sanitizer=san, tile_range=(0, 1) if step.desc.zero_input else None)
+        assert count == 0, text[-3000:]
+    count, text = race_check(prog.passes[1], N, grid=3, tile_block=2, tile_range=(5, 18), sanitizer=san)
+    assert count == 0, text[-3000:]
+    q = compile_circuit(W.qft(N), dtype="complex64", zero_init=False)
+    count, text = race_check(q.passes[0], N, dtype="complex64", grid=2, sanitizer=san)
+    assert count == 0, text[-3000:]
+    count, text = race_check(prog.passes[1], N, grid=2, tile_range=(0, 40), sanitizer=san)     # 32 tiles exist
+    assert count > 0 and "heap-buffer-overflow" in text
