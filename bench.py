@@ -194,6 +194,13 @@ def reference_arm(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to its workers when it is unset, which OpenBLAS honours: give the reference's
+    # BLAS calls every host core again, as in a plain `python bench.py --impl reference` (N = 1)
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count() or 1, user_api="blas")
+    except Exception:
+        pass
     budget = 150.0 / max(args.steps + args.warmup, 1)          # seconds per step
     probe_cd, _ = workload(14)
     rate_guess, _, kind = _cpu_rate(probe_cd)
