@@ -318,7 +318,7 @@ def _search(ir_ops, n_qubits: int, n_local: int, dtype: str, base: Program, plac
     t0 = _estimate_for_search(base, tr0)
     ident = list(range(n_qubits))
     best_seed, best_init, best_t, best_passes = None, None, t0, k0[0]
-    done = accepted = 0
+    done = accepted = fewer = 0
     # half of the budget varies the greedy plan on ITS placement (placements[0]), the rest goes round the others
     order = [(seed, placements[0]) for seed in range(trials // 2 if len(placements) > 1 else trials)]
     seed = 0
@@ -337,6 +337,7 @@ def _search(ir_ops, n_qubits: int, n_local: int, dtype: str, base: Program, plac
             continue
         if prog.stats["passes"] >= k0[0]:
             continue
+        fewer += 1
         tr = plan_transitions(prog, min_chunk_pos=mcp)
         k = _plan_key(prog, tr)
         if k[1] > k0[1] or k[2] > k0[2] or k[3] > k0[3] or k[4] < min(k0[4], 2 * (k[1] - k[3])) or (k0[5] and k[5] < min(k0[5], 3)):
@@ -347,7 +348,8 @@ def _search(ir_ops, n_qubits: int, n_local: int, dtype: str, base: Program, plac
             if t < best_t:
                 best_seed, best_init, best_t, best_passes = seed, init, t, prog.stats["passes"]
     stats = {"search": {"plans_tried": done, "seed": best_seed, "passes_before": k0[0], "passes_after": best_passes,
-                        "estimate_v2_before_s": t0, "estimate_v2_after_s": best_t, "explore": explore or {}}}
+                        "estimate_v2_before_s": t0, "estimate_v2_after_s": best_t, "explore": explore or {},
+                        "plans_with_fewer_passes": fewer}}
     return best_seed, best_init, stats
 
 
@@ -366,7 +368,9 @@ def _search_staged(ir_ops, n_qubits, n_local, dtype, base, placements, compiler_
         tried += stats["search"]["plans_tried"]
         stats["search"]["plans_tried"] = tried
         out = (seed, init, stats)
-        if seed is not None:
+        # a stage that met no plan with fewer passes at all (acceptable or not) says the greedy plan is at the floor of
+        # this family: the wider stage is not worth its ~12 s (the weak-series plans at 32 / 33 qubits)
+        if seed is not None or stats["search"]["plans_with_fewer_passes"] == 0:
             break
     return out
 

@@ -127,8 +127,11 @@ def test_second_stage_explores_wider_only_when_the_first_finds_nothing(monkeypat
     sharding._SEARCHED.clear()
     found = sharding.plan(ir_ops(cd), n, n - g, search=48, **kw)
     assert calls and calls[0][0] == {}
+    first = found.stats["search"] if len(calls) == 1 else None
     if calls[0][1] is not None:
         assert len(calls) == 1                                   # stage 1 found a plan: stage 2 never ran
+    elif len(calls) == 1:
+        assert first["plans_with_fewer_passes"] == 0             # ... or met no shorter plan at all: the greedy plan is at the floor
     else:
         assert len(calls) == 2 and calls[1][0] == {"explore_p": 0.4, "explore_k": 5}
     assert found.stats["search"]["explore"] == calls[-1][0]
